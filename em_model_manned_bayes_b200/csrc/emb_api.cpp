@@ -1,0 +1,472 @@
+// emb_api.cpp -- the C ABI of libemb200.so (include/emb200.h).  No torch, no C++ types across the
+// boundary, no exceptions escape.  There is deliberately no CPU sampling path in this library.
+#include <cuda_runtime_api.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/emb200.h"
+#include "emb_launch.h"
+#include "emb_model.h"
+
+using emb::DevModel;
+using emb::HostModel;
+
+struct emb_model {
+    std::unique_ptr<HostModel> h;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define EMB_TRY try {
+#define EMB_CATCH                                                        \
+    }                                                                    \
+    catch (const emb::Error& e) { return set_err(e.code, e.msg); }       \
+    catch (const std::bad_alloc&) { return set_err(EMB_E_LIMIT, "out of host memory"); } \
+    catch (const std::exception& e) { return set_err(EMB_E_ARG, e.what()); }
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return set_err(EMB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// Upload (or refresh after emb_set_prior) the packed tables of a model to `device`.
+int ensure_device(const HostModel& H, int device, DevModel& D) {
+    std::lock_guard<std::mutex> lk(H.mu);
+    auto& c = H.device_copies[device];
+    if (c.version != H.version) {
+        if (c.thr_initial) cudaFree(c.thr_initial);
+        if (c.thr_transition) cudaFree(c.thr_transition);
+        if (c.edges) cudaFree(c.edges);
+        c.thr_initial = c.thr_transition = nullptr;
+        c.edges = nullptr;
+        auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+            *dst = nullptr;
+            if (!bytes) return 0;
+            CU(cudaMalloc(dst, bytes));
+            CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+            return 0;
+        };
+        int rc;
+        if ((rc = up(H.thr_initial.data(), H.thr_initial.size() * 4, (void**)&c.thr_initial))) return rc;
+        if ((rc = up(H.thr_transition.data(), H.thr_transition.size() * 4, (void**)&c.thr_transition))) return rc;
+        if ((rc = up(H.edges.data(), H.edges.size() * 8, (void**)&c.edges))) return rc;
+        c.version = H.version;
+    }
+    D = H.dev;
+    D.thr_init = c.thr_initial;
+    D.thr_trans = c.thr_transition;
+    D.edges = c.edges;
+    return 0;
+}
+
+int pick_device(const emb_sample_opts* o, int& device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return set_err(EMB_E_CUDA, std::string("no CUDA device available (libemb200 has no CPU path): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    device = o->device;
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= count) return set_err(EMB_E_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+// Device-side staging for host-memory callers.
+struct Staged {
+    void* host = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0;
+    bool owned = false;
+};
+struct Stager {
+    int mem;
+    cudaStream_t stream;
+    std::vector<Staged> items;
+    ~Stager() {
+        for (auto& s : items)
+            if (s.owned && s.dev) cudaFree(s.dev);
+    }
+    // returns the device pointer to use for a caller buffer (nullptr stays nullptr)
+    int out(void* user, size_t bytes, bool zero, void** dev) {
+        *dev = nullptr;
+        if (!user || !bytes) return 0;
+        if (mem == EMB_MEM_DEVICE) {
+            *dev = user;
+            return 0;
+        }
+        Staged s;
+        s.host = user;
+        s.bytes = bytes;
+        s.owned = true;
+        CU(cudaMalloc(&s.dev, bytes));
+        if (zero) CU(cudaMemcpyAsync(s.dev, user, bytes, cudaMemcpyHostToDevice, stream));  // accumulate (+=) semantics
+        items.push_back(s);
+        *dev = s.dev;
+        return 0;
+    }
+    int finish() {
+        for (auto& s : items) CU(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return 0;
+    }
+};
+
+template <class T>
+int64_t copy_out(const std::vector<T>& v, T* buf, int64_t cap) {
+    if (buf) std::memcpy(buf, v.data(), sizeof(T) * (size_t)std::min<int64_t>(cap, (int64_t)v.size()));
+    return (int64_t)v.size();
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int emb_abi_version(void) { return EMB_ABI_VERSION; }
+const char* emb_last_error(void) { return g_err.c_str(); }
+int64_t emb_launch_count(void) { return emb::g_launch_count.load(); }
+
+int emb_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+int emb_host_alloc(void** p, int64_t bytes) {
+    CU(cudaMallocHost(p, (size_t)bytes));
+    return 0;
+}
+int emb_host_free(void* p) {
+    CU(cudaFreeHost(p));
+    return 0;
+}
+
+uint32_t emb_rng_word(uint64_t seed, uint64_t sample, uint32_t attempt, uint32_t purpose, uint32_t index,
+                      uint32_t sub, uint32_t lane) {
+    return emb::keyed_word(seed, sample, attempt, purpose, index, sub, lane & 3u);
+}
+
+int emb_model_load(const char* path, int is_overwrite, const int32_t* idx_zero, int32_t n_idx, emb_model** out) {
+    if (!path || !out) return set_err(EMB_E_ARG, "null argument");
+    *out = nullptr;
+    EMB_TRY
+    std::unique_ptr<emb_model> m(new emb_model());
+    m->h.reset(emb::load_model_file(path, is_overwrite != 0, idx_zero, idx_zero ? n_idx : 0));
+    *out = m.release();
+    return 0;
+    EMB_CATCH
+}
+
+int emb_model_from_arrays(int32_t n_initial, const uint8_t* G_initial, const int32_t* r_initial,
+                          const double* N_initial, int64_t len_N_initial, int32_t n_transition,
+                          const uint8_t* G_transition, const int32_t* r_transition, const double* N_transition,
+                          int64_t len_N_transition, const int32_t* temporal_map, int32_t n_temporal,
+                          const double* boundaries, const int32_t* boundaries_len, const double* resample_rates,
+                          emb_model** out) {
+    if (!out || !G_initial || !r_initial || !N_initial || n_initial <= 0) return set_err(EMB_E_ARG, "null argument");
+    *out = nullptr;
+    EMB_TRY
+    std::unique_ptr<emb_model> m(new emb_model());
+    m->h.reset(new HostModel());
+    HostModel& H = *m->h;
+    H.n_initial = n_initial;
+    H.G_initial.assign(G_initial, G_initial + (size_t)n_initial * n_initial);
+    H.r_initial.assign(r_initial, r_initial + n_initial);
+    for (int i = 0; i < n_initial; ++i) H.labels_initial.push_back("\"x" + std::to_string(i + 1) + "\"");
+    auto fill = [&](const std::vector<uint8_t>& G, const std::vector<int32_t>& r, int n, int first, const double* x,
+                    int64_t len, std::vector<emb::Table>& T, const char* what) {
+        T.assign(n, emb::Table{});
+        int64_t index = 0;
+        for (int i = first; i < n; ++i) {
+            emb::Table& t = T[i];
+            t.r = r[i];
+            t.q = 1;
+            for (int p = 0; p < n; ++p)
+                if (G[(size_t)p * n + i]) {
+                    t.parents.push_back(p);
+                    t.q *= r[p];
+                }
+            const int64_t cnt = (int64_t)t.r * t.q;
+            if (index + cnt > len) throw emb::Error{EMB_E_ARG, std::string(what) + " is shorter than sum(r_i*q_i)"};
+            t.N.assign(x + index, x + index + cnt);
+            t.present = true;
+            index += cnt;
+        }
+        if (index != len) throw emb::Error{EMB_E_ARG, std::string(what) + " is longer than sum(r_i*q_i)"};
+    };
+    fill(H.G_initial, H.r_initial, n_initial, 0, N_initial, len_N_initial, H.T_initial, "N_initial");
+    if (n_transition > 0 && G_transition && r_transition && N_transition) {
+        H.has_transition = true;
+        H.n_transition = n_transition;
+        H.G_transition.assign(G_transition, G_transition + (size_t)n_transition * n_transition);
+        H.r_transition.assign(r_transition, r_transition + n_transition);
+        for (int i = 0; i < n_transition; ++i) H.labels_transition.push_back("\"y" + std::to_string(i + 1) + "\"");
+        fill(H.G_transition, H.r_transition, n_transition, n_initial, N_transition, len_N_transition, H.T_transition,
+             "N_transition");
+        if (!temporal_map || n_temporal <= 0) throw emb::Error{EMB_E_ARG, "temporal_map is required with a transition network"};
+        for (int k = 0; k < n_temporal; ++k) {
+            const int a = temporal_map[2 * k] - 1, b = temporal_map[2 * k + 1] - 1;
+            if (a < 0 || a >= n_initial || b < n_initial || b >= n_transition)
+                throw emb::Error{EMB_E_ARG, "temporal_map entry out of range"};
+            H.temporal_map.push_back({a, b});
+        }
+        H.temporal_map_given = true;
+    }
+    H.boundaries.assign(n_initial, {});
+    if (boundaries && boundaries_len) {
+        const double* b = boundaries;
+        for (int i = 0; i < n_initial; ++i) {
+            H.boundaries[i].assign(b, b + boundaries_len[i]);
+            b += boundaries_len[i];
+        }
+        H.has_boundaries = true;
+    }
+    if (resample_rates) H.resample_rates.assign(resample_rates, resample_rates + n_initial);
+    H.derive();
+    H.pack();
+    *out = m.release();
+    return 0;
+    EMB_CATCH
+}
+
+void emb_model_free(emb_model* m) {
+    if (!m) return;
+    if (m->h) {
+        for (auto& kv : m->h->device_copies) {
+            int cur = 0;
+            if (cudaGetDevice(&cur) == cudaSuccess && cudaSetDevice(kv.first) == cudaSuccess) {
+                if (kv.second.thr_initial) cudaFree(kv.second.thr_initial);
+                if (kv.second.thr_transition) cudaFree(kv.second.thr_transition);
+                if (kv.second.edges) cudaFree(kv.second.edges);
+                cudaSetDevice(cur);
+            }
+        }
+    }
+    delete m;
+}
+
+int emb_model_get_info(const emb_model* m, emb_model_info* info) {
+    if (!m || !info) return set_err(EMB_E_ARG, "null argument");
+    const HostModel& H = *m->h;
+    std::memset(info, 0, sizeof(*info));
+    info->n_initial = H.n_initial;
+    info->n_transition = H.has_transition ? H.n_transition : 0;
+    info->n_dyn = (int32_t)H.temporal_map.size();
+    info->n_gated = (int32_t)H.gated.size();
+    info->is_dynvar_depend = H.is_dynvar_depend ? 1 : 0;
+    info->n_timevarying = (int32_t)H.timevarying.size();
+    for (auto& t : H.T_initial) info->len_N_initial += (int64_t)t.N.size();
+    for (auto& t : H.T_transition) info->len_N_transition += (int64_t)t.N.size();
+    for (int i = 0; i < H.n_initial; ++i) {
+        info->r_initial[i] = H.r_initial[i];
+        info->order_initial[i] = H.order_initial[i] + 1;
+        info->zero_bins[i] = H.zero_bins[i];
+        info->boundaries_len[i] = (int32_t)H.boundaries[i].size();
+        info->resample_rates[i] = H.resample_rates[i];
+        info->bounds_initial[i][0] = H.bounds_initial[i].first;
+        info->bounds_initial[i][1] = H.bounds_initial[i].second;
+    }
+    if (H.has_transition)
+        for (int i = 0; i < H.n_transition; ++i) {
+            info->r_transition[i] = H.r_transition[i];
+            info->order_transition[i] = H.order_transition[i] + 1;
+        }
+    for (size_t k = 0; k < H.temporal_map.size(); ++k) {
+        info->temporal_map[k][0] = H.temporal_map[k].first + 1;
+        info->temporal_map[k][1] = H.temporal_map[k].second + 1;
+    }
+    for (size_t k = 0; k < H.timevarying.size(); ++k) info->timevarying_vars[k] = H.timevarying[k] + 1;
+    return 0;
+}
+
+int64_t emb_model_get_labels(const emb_model* m, int which, char* buf, int64_t cap) {
+    if (!m) return set_err(EMB_E_ARG, "null argument");
+    const auto& L = which ? m->h->labels_transition : m->h->labels_initial;
+    std::string s;
+    for (size_t i = 0; i < L.size(); ++i) {
+        if (i) s.push_back('\n');
+        s += L[i];
+    }
+    if (buf && cap > 0) {
+        const size_t k = std::min<size_t>((size_t)cap - 1, s.size());
+        std::memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int64_t emb_model_get_G(const emb_model* m, int which, uint8_t* buf, int64_t cap) {
+    if (!m) return set_err(EMB_E_ARG, "null argument");
+    return copy_out(which ? m->h->G_transition : m->h->G_initial, buf, cap);
+}
+
+int64_t emb_model_get_N(const emb_model* m, int which, double* buf, int64_t cap) {
+    if (!m) return set_err(EMB_E_ARG, "null argument");
+    std::vector<double> all;
+    for (auto& t : (which ? m->h->T_transition : m->h->T_initial)) all.insert(all.end(), t.N.begin(), t.N.end());
+    return copy_out(all, buf, cap);
+}
+
+int64_t emb_model_get_boundaries(const emb_model* m, double* buf, int64_t cap) {
+    if (!m) return set_err(EMB_E_ARG, "null argument");
+    std::vector<double> all;
+    for (auto& b : m->h->boundaries) all.insert(all.end(), b.begin(), b.end());
+    return copy_out(all, buf, cap);
+}
+
+int64_t emb_model_get_packed(const emb_model* m, int which, uint32_t* buf, int64_t cap) {
+    if (!m) return set_err(EMB_E_ARG, "null argument");
+    return copy_out(which ? m->h->thr_transition : m->h->thr_initial, buf, cap);
+}
+
+int emb_set_prior(emb_model* m, int which, int kind, double value) {
+    if (!m) return set_err(EMB_E_ARG, "null argument");
+    if (kind != EMB_PRIOR_CONSTANT && kind != EMB_PRIOR_DBE && kind != EMB_PRIOR_STAY)
+        return set_err(EMB_E_ARG, "prior:unknown");
+    if (kind == EMB_PRIOR_STAY && which == 0) return set_err(EMB_E_ARG, "stay prior applies to the transition network only");
+    if (kind != EMB_PRIOR_DBE && !(value >= 0.0)) return set_err(EMB_E_ARG, "prior must be >= 0");
+    EMB_TRY
+    HostModel& H = *m->h;
+    std::lock_guard<std::mutex> lk(H.mu);
+    emb::PriorSpec old_i = H.prior_initial, old_t = H.prior_transition;
+    (which ? H.prior_transition : H.prior_initial) = emb::PriorSpec{kind, value};
+    try {
+        H.pack();
+    } catch (...) {
+        H.prior_initial = old_i;
+        H.prior_transition = old_t;
+        H.pack();
+        throw;
+    }
+    return 0;
+    EMB_CATCH
+}
+
+void emb_sample_opts_init(emb_sample_opts* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->device = -1;
+    o->mem = EMB_MEM_HOST;
+    for (int i = 0; i < EMB_MAX_VARS; ++i) {
+        o->box_lo[i] = -1.0 / 0.0;
+        o->box_hi[i] = 1.0 / 0.0;
+    }
+}
+
+int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts, int8_t* bins,
+                       double* values, uint16_t* attempts) {
+    if (!m || !rng || !opts || n < 0) return set_err(EMB_E_ARG, "null or negative argument");
+    const HostModel& H = *m->h;
+    emb::SampleParams P;
+    int rc = 0;
+    try {
+        emb::fill_params(H, rng->seed, rng->first_sample, n, 0, *opts, P);
+    } catch (const emb::Error& e) {
+        return set_err(e.code, e.msg);
+    }
+    if (n == 0) return 0;
+    int device;
+    if ((rc = pick_device(opts, device))) return rc;
+    DevModel D;
+    if ((rc = ensure_device(H, device, D))) return rc;
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    Stager sg{opts->mem, st, {}};
+    int8_t* d_bins;
+    double* d_vals;
+    uint16_t* d_att;
+    if ((rc = sg.out(bins, (size_t)n * H.n_initial, false, (void**)&d_bins))) return rc;
+    if ((rc = sg.out(values, (size_t)n * H.n_initial * 8, false, (void**)&d_vals))) return rc;
+    if ((rc = sg.out(attempts, (size_t)n * 2, false, (void**)&d_att))) return rc;
+    int32_t* d_status = nullptr;
+    CU(cudaMalloc((void**)&d_status, 4));
+    CU(cudaMemsetAsync(d_status, 0, 4, st));
+    cudaError_t e = (cudaError_t)emb::launch_initial(D, P, d_bins, d_vals, d_att, nullptr, d_status, st);
+    if (e != cudaSuccess) {
+        cudaFree(d_status);
+        return cuda_fail(e, "launch k_initial");
+    }
+    int32_t status = 0;
+    e = cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_status);
+    if (e != cudaSuccess) return cuda_fail(e, "k_initial");
+    if ((rc = sg.finish())) return rc;
+    if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+    return 0;
+}
+
+int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T) {
+    if (!m || n < 0 || T < 0) return 0;
+    const int64_t nch16 = (T + 15) / 16;
+    return (int64_t)m->h->temporal_map.size() * nch16 * n * 16;
+}
+int64_t emb_tracks_values_len(const emb_model* m, int64_t n, int32_t T) {
+    if (!m || n < 0 || T < 0) return 0;
+    const int64_t nch16 = (T + 15) / 16;
+    return (int64_t)m->h->timevarying.size() * nch16 * 4 * n * 4;
+}
+
+int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                      const emb_track_out* out) {
+    if (!m || !rng || !opts || !out || n < 0 || T < 1) return set_err(EMB_E_ARG, "null or out-of-range argument");
+    const HostModel& H = *m->h;
+    if (!H.has_transition || H.temporal_map.empty())
+        return set_err(EMB_E_ARG, "dynvar:empty: model has no transition network");
+    if ((int64_t)T * (int64_t)(H.temporal_map.size() + H.gated.size()) >= (1ll << 33))
+        return set_err(EMB_E_LIMIT, "T too large for the 32-bit stream index");
+    emb::SampleParams P;
+    int rc = 0;
+    try {
+        emb::fill_params(H, rng->seed, rng->first_sample, n, T, *opts, P);
+    } catch (const emb::Error& e) {
+        return set_err(e.code, e.msg);
+    }
+    if (n == 0) return 0;
+    int device;
+    if ((rc = pick_device(opts, device))) return rc;
+    DevModel D;
+    if ((rc = ensure_device(H, device, D))) return rc;
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    Stager sg{opts->mem, st, {}};
+    emb::TrackOut O{};
+    const size_t ni = (size_t)H.n_initial;
+    if ((rc = sg.out(out->bins, (size_t)emb_tracks_bins_len(m, n, T), false, (void**)&O.bins))) return rc;
+    if ((rc = sg.out(out->values, (size_t)emb_tracks_values_len(m, n, T) * 4, false, (void**)&O.values))) return rc;
+    if ((rc = sg.out(out->init_bins, (size_t)n * ni, false, (void**)&O.init_bins))) return rc;
+    if ((rc = sg.out(out->init_values, (size_t)n * ni * 8, false, (void**)&O.init_values))) return rc;
+    if ((rc = sg.out(out->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
+    if ((rc = sg.out(out->hist_initial, ni * 64 * 8, true, (void**)&O.hist_initial))) return rc;
+    if ((rc = sg.out(out->hist_transition, H.temporal_map.size() * 64 * 8, true, (void**)&O.hist_transition))) return rc;
+    CU(cudaMalloc((void**)&O.status, 4));
+    CU(cudaMemsetAsync(O.status, 0, 4, st));
+    cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);
+    if (e != cudaSuccess) {
+        cudaFree(O.status);
+        return cuda_fail(e, "launch k_tracks");
+    }
+    int32_t status = 0;
+    e = cudaMemcpyAsync(&status, O.status, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(O.status);
+    if (e != cudaSuccess) return cuda_fail(e, "k_tracks");
+    if ((rc = sg.finish())) return rc;
+    if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+    return 0;
+}
+
+}  // extern "C"

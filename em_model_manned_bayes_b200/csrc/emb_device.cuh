@@ -1,0 +1,390 @@
+// emb_device.cuh -- device-side model layout, keyed Philox stream and the per-sample sampling
+// routines shared by all kernels.  Everything here is integer work except de-discretisation.
+//
+// Word-space inverse CDF ("normalised cumulative CPT"): for a column of weights w (N + alpha,
+// select_random.m:17-20) the reference picks the first bin m with cumsum(w)(m) >= sum(w)*u.  With
+// u = (k + 0.5) 2^-32 for a 32-bit Philox word k, "bin > m" is monotone in k, so the packer
+// (emb_model.cpp: pack_column) stores K_m = min{k : cumsum(w)(m) < fl(sum(w) * u_k)}, found with the
+// reference's own fp64 comparison.  A column occupies rp = 4*ceil(r/4) uint32 slots:
+//     slots 0 .. rp-2 : T'_m = K_m - 1   (0xFFFFFFFF when K_m == 0 or K_m == 2^32 or m >= r-1)
+//     slot  rp-1      : lead = #{m : K_m == 0}
+// and the 0-based bin is  lead + #{m < rp-1 : k > T'_m}.   Bit-identical to the fp64 rule.
+//
+// The functions are __host__ __device__ only so that tests/emu can run the *same* code on the CPU
+// against the oracle when no GPU is present; libemb200.so never executes them on the host.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define EMB_HD __host__ __device__ __forceinline__
+#else
+#define EMB_HD inline
+#endif
+
+namespace emb {
+
+constexpr int MAXV = 24;  // EMB_MAX_VARS
+constexpr int MAXD = 8;   // EMB_MAX_DYN
+constexpr int MAXP = 8;   // EMB_MAX_PARENTS
+constexpr int MAXG = 16;  // EMB_MAX_GATED
+constexpr int MAXX = MAXV + MAXD;
+constexpr int HIST_STRIDE = 64;
+
+// stream spec v1 purposes (oracle/philox.py)
+constexpr uint32_t P_INIT = 1, P_STEP = 2, P_STEP_DD = 3, P_LAYER = 4;
+
+struct Node {
+    int32_t r;               // bins
+    int32_t rp;              // padded column length (multiple of 4)
+    int32_t np;              // number of parents
+    uint32_t off;            // offset of column 0 in the threshold table (uint32 units)
+    uint8_t par[MAXP];       // parent indices into the state vector x (increasing)
+    uint32_t stride_rp[MAXP];// asub2ind stride of that parent times rp
+};
+
+struct DevModel {
+    int32_t n_initial, n_transition, n_dyn, n_gated, n_tv, nw, fast;
+    int32_t order_initial[MAXV];   // 0-based ids, topological
+    int32_t order_dyn[MAXD];       // dynamic ordinals in order_transition order
+    Node init[MAXV];
+    Node dyn[MAXD];
+    int32_t dyn_t[MAXD];           // x index of the variable at time t
+    int32_t dyn_t1[MAXD];          // x index of its (t+1)/(t-1) counterpart
+    int32_t gated_var[MAXG];
+    uint64_t gate_G[MAXG];         // fires iff k < G
+    double gate_inv[MAXG];         // 1.0 / G
+    int32_t tv_var[MAXV];          // time-varying variables (dynamic(t) or gated), ascending
+    int32_t tv_of_var[MAXV];       // inverse map or -1
+    int32_t edge_off[MAXV];        // offset (doubles) into edges of {a,w} pairs, -1 = no boundaries
+    int32_t zero_bin[MAXV];        // 1-based zero bin or 0
+    const uint32_t* thr_init;
+    const uint32_t* thr_trans;
+    const double* edges;
+};
+
+struct SampleParams {
+    uint64_t seed;
+    uint64_t first_sample;
+    int64_t n;
+    int32_t T;
+    int32_t reject_mode;           // EMB_REJECT_*
+    int32_t idx_v, idx_dh, idx_L;  // 0-based, -1 if unused
+    int32_t is_quantize500;
+    int32_t n_layers;
+    int32_t max_attempts;
+    uint8_t start[MAXV];           // preset 1-based bin, 0 = free
+    double layers[8][2];
+    double box_lo[MAXV], box_hi[MAXV];
+};
+
+struct TrackOut {
+    int8_t* bins;
+    float* values;
+    int8_t* init_bins;
+    double* init_values;
+    uint16_t* attempts;
+    unsigned long long* hist_initial;
+    unsigned long long* hist_transition;
+    int32_t* status;               // device flag: set to 1 if any sample exhausted max_attempts
+};
+
+// ---------------------------------------------------------------------------------------------
+// exact fp64 helpers (no FMA contraction, round-to-nearest) so host emulation == device
+EMB_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+EMB_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+EMB_HD double u01(uint32_t k) { return dmul(dadd((double)k, 0.5), 2.3283064365386963e-10); }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11)
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+EMB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// Sequential reader of one (sample, attempt, purpose) word stream: position p -> block p/4, lane p%4.
+// Caches the last block, so monotone access costs one Philox call per 4 words.
+struct WordStream {
+    uint32_t k0, k1, c0, c1, w3;
+    uint32_t blk;
+    uint32_t w[4];
+    EMB_HD void init(uint64_t seed, uint64_t sample, uint32_t attempt, uint32_t purpose) {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        c0 = (uint32_t)sample; c1 = (uint32_t)(sample >> 32);
+        w3 = (attempt << 16) | (purpose << 8);
+        blk = 0xFFFFFFFFu;
+    }
+    EMB_HD uint32_t at(uint32_t p) {
+        const uint32_t b = p >> 2;
+        if (b != blk) {
+            blk = b;
+            philox4x32_10(c0, c1, b, w3, k0, k1, w[0], w[1], w[2], w[3]);
+        }
+        const uint32_t l = p & 3u;
+        return l == 0 ? w[0] : l == 1 ? w[1] : l == 2 ? w[2] : w[3];
+    }
+};
+
+EMB_HD uint32_t keyed_word(uint64_t seed, uint64_t sample, uint32_t attempt, uint32_t purpose, uint32_t index,
+                           uint32_t sub, uint32_t lane) {
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), index, (attempt << 16) | (purpose << 8) | sub,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
+    return lane == 0 ? o0 : lane == 1 ? o1 : lane == 2 ? o2 : o3;
+}
+
+// ---------------------------------------------------------------------------------------------
+EMB_HD uint32_t ldg32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+EMB_HD double ldg64(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// 0-based bin of word k in a packed column (rp slots, 16-byte aligned).
+EMB_HD int select_bin(const uint32_t* col, int rp, uint32_t k) {
+    int bin = 0;
+    for (int q = 0; q < rp; q += 4) {
+#if defined(__CUDA_ARCH__)
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(col + q));
+        const uint32_t a = v.x, b = v.y, c = v.z, d = v.w;
+#else
+        const uint32_t a = col[q], b = col[q + 1], c = col[q + 2], d = col[q + 3];
+#endif
+        bin += (k > a) + (k > b) + (k > c);
+        if (q + 4 < rp) bin += (k > d); else bin += (int)d;   // last slot holds `lead`
+    }
+    return bin;
+}
+
+// column address of a node given the state vector
+EMB_HD const uint32_t* node_column(const Node& nd, const uint32_t* table, const uint8_t* x) {
+    uint32_t o = nd.off;
+    for (int p = 0; p < nd.np; ++p) o += nd.stride_rp[p] * (uint32_t)x[nd.par[p]];
+    return table + o;
+}
+
+// dediscretize.m:22-41 for 0-based bin `b` of variable i given uniform u (only read when needed)
+EMB_HD bool needs_uniform(const DevModel& M, int i, int b) {
+    return M.edge_off[i] >= 0 && M.zero_bin[i] != b + 1;
+}
+EMB_HD double dedisc(const DevModel& M, int i, int b, double u) {
+    if (M.edge_off[i] < 0) return (double)(b + 1);          // dediscretize.m:7-10: return the bin
+    if (M.zero_bin[i] == b + 1) return 0.0;                 // :24-25
+    const double* e = M.edges + M.edge_off[i] + 2 * b;
+    return dadd(ldg64(e), dmul(ldg64(e + 1), u));           // :39  a + (b-a)*rand
+}
+
+EMB_HD double round500(double num) {                        // UncorEncounterModel.m:196
+    double m = ::fmod(num, 500.0);
+    if (m < 0) m += 500.0;
+    const double q = ::floor(num / 500.0);
+    return 500.0 * (q + (m > 250.0 ? 1.0 : 0.0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Initial network: bn_sample.m:39-58 + dbn_hierarchical_sample.m:25-31 (+ rejection of the driver:
+// UncorEncounterModel.m:248-280 / @CorTerminalModel/sample.m:32-72).
+// x: 0-based bins (size >= n_transition, dynamic slots untouched); vals: continuous values.
+// Returns the attempt index that was accepted, or -1 when max_attempts was exhausted.
+EMB_HD int sample_initial(const DevModel& M, const SampleParams& P, uint64_t sample, uint8_t* x, double* vals) {
+    const int n = M.n_initial;
+    for (int attempt = 0; attempt <= P.max_attempts; ++attempt) {
+        WordStream ws;
+        ws.init(P.seed, sample, (uint32_t)attempt, P_INIT);
+        for (int oi = 0; oi < n; ++oi) {
+            const int i = M.order_initial[oi];
+            if (P.start[i]) {
+                x[i] = (uint8_t)(P.start[i] - 1);                                   // bn_sample.m:49
+            } else {
+                const Node& nd = M.init[i];
+                x[i] = (uint8_t)select_bin(node_column(nd, M.thr_init, x), nd.rp, ws.at((uint32_t)i));
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            const int b = x[i];
+            double u = 0.5;
+            if (needs_uniform(M, i, b)) u = u01(ws.at((uint32_t)(n + i)));
+            vals[i] = dedisc(M, i, b, u);
+        }
+        bool good = true;
+        if (P.reject_mode == 1) {
+            if (P.n_layers > 0 || P.is_quantize500) {
+                double h = vals[P.idx_L];
+                if (P.n_layers > 0) {                                               // UncorEncounterModel.m:259-260
+                    const int L = x[P.idx_L];
+                    const uint32_t k = keyed_word(P.seed, sample, (uint32_t)attempt, P_LAYER, 0, 0, 0);
+                    h = dadd(P.layers[L][0], dmul(u01(k), dadd(P.layers[L][1], -P.layers[L][0])));
+                }
+                if (P.is_quantize500 && vals[P.idx_dh] == 0.0) h = round500(h);     // :266-268
+                vals[P.idx_L] = h;                                                  // :270-272
+            }
+            const double a = vals[P.idx_dh] < 0 ? -vals[P.idx_dh] : vals[P.idx_dh];
+            good = dmul(vals[P.idx_v], 1.68781) > a / 60.0;                         // :275
+        } else if (P.reject_mode == 2) {
+            for (int i = 0; i < n; ++i) good = good && (vals[i] >= P.box_lo[i]) && (vals[i] <= P.box_hi[i]);
+        }
+        if (good) return attempt;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic track sampler (any model within the EMB_MAX_* limits, both dbn_sample.m branches).
+// One call = one track.  Dense tiled output, see emb200.h.  `hist` (nullable) is a block-shared
+// [n_dyn][HIST_STRIDE] uint32 scratch on the device.
+template <class HistInc>
+EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackOut& O, int64_t s, HistInc hist_inc) {
+    uint8_t x[MAXX];
+    double vals[MAXV];
+    const uint64_t sample = P.first_sample + (uint64_t)s;
+    const int n = M.n_initial, nd = M.n_dyn, ng = M.n_gated, ntv = M.n_tv, nw = M.nw;
+    const int T = P.T;
+    const int64_t N = P.n;
+    for (int i = 0; i < MAXX; ++i) x[i] = 0;
+
+    int attempt = sample_initial(M, P, sample, x, vals);
+    if (attempt < 0) {
+        if (O.status) *O.status = 1;
+        attempt = P.max_attempts;  // keep the last attempt's state so the outputs are defined
+    }
+    if (O.attempts) O.attempts[s] = (uint16_t)(attempt + 1);
+    for (int i = 0; i < n; ++i) {
+        if (O.init_bins) O.init_bins[(int64_t)i * N + s] = (int8_t)(x[i] + 1);
+        if (O.init_values) O.init_values[(int64_t)i * N + s] = vals[i];
+        if (O.hist_initial) hist_inc(0, i, x[i]);
+    }
+    if (T <= 0 || (!O.bins && !O.values && !O.hist_transition)) return;
+
+    // frozen columns of the fast branch (dbn_sample.m:110-135): parents evaluated once at t = 1
+    const uint32_t* col[MAXD];
+    for (int d = 0; d < nd; ++d) {
+        x[M.dyn_t1[d]] = x[M.dyn_t[d]];
+        col[d] = node_column(M.dyn[d], M.thr_trans, x);
+    }
+
+    WordStream ws, wdd;
+    ws.init(P.seed, sample, (uint32_t)attempt, P_STEP);
+    const int nch16 = (T + 15) >> 4, nch4 = nch16 * 4;
+    uint32_t bpack[MAXD][4];
+    float vbuf[MAXV][4];
+    for (int d = 0; d < MAXD; ++d) bpack[d][0] = bpack[d][1] = bpack[d][2] = bpack[d][3] = 0;
+
+    const int Tpad = nch16 * 16;
+    for (int c = 0; c < Tpad; ++c) {          // column c = state during second c+1; step e = c
+        if (c > 0 && c < T) {
+            const uint32_t base = (uint32_t)(c - 1) * (uint32_t)nw;
+            uint32_t wstep[MAXD + MAXG];
+            for (int q = 0; q < nw; ++q) wstep[q] = ws.at(base + (uint32_t)q);
+            // resample gates on the pre-transition bins (resample_events.m:23-29)
+            for (int g = 0; g < ng; ++g) {
+                const uint32_t k = wstep[nd + g];
+                if ((uint64_t)k < M.gate_G[g]) {
+                    const int v = M.gated_var[g];
+                    vals[v] = dedisc(M, v, x[v], dmul(dadd((double)k, 0.5), M.gate_inv[g]));
+                }
+            }
+            // transitions (dbn_sample.m:69-79 slow / :143-146 fast)
+            for (int od = 0; od < nd; ++od) {
+                const int d = M.fast ? od : M.order_dyn[od];
+                const Node& nd_ = M.dyn[d];
+                const uint32_t* cp = M.fast ? col[d] : node_column(nd_, M.thr_trans, x);
+                x[M.dyn_t1[d]] = (uint8_t)select_bin(cp, nd_.rp, wstep[d]);
+            }
+            // map back + change events (dbn_sample.m:82-92)
+            bool dd_ready = false;
+            uint32_t ddw[4] = {0, 0, 0, 0};
+            int dd_sub = -1;
+            for (int d = 0; d < nd; ++d) {
+                const int vt = M.dyn_t[d];
+                const uint8_t nb = x[M.dyn_t1[d]];
+                if (nb != x[vt]) {
+                    x[vt] = nb;
+                    double u = 0.5;
+                    if (needs_uniform(M, vt, nb)) {
+                        if (!dd_ready || dd_sub != (d >> 2)) {
+                            dd_sub = d >> 2;
+                            philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)c,
+                                          ((uint32_t)attempt << 16) | (P_STEP_DD << 8) | (uint32_t)dd_sub,
+                                          (uint32_t)P.seed, (uint32_t)(P.seed >> 32), ddw[0], ddw[1], ddw[2], ddw[3]);
+                            dd_ready = true;
+                        }
+                        u = u01(ddw[d & 3]);
+                    }
+                    vals[vt] = dedisc(M, vt, nb, u);
+                }
+            }
+        }
+        const bool live = c < T;
+        for (int d = 0; d < nd; ++d) {
+            const uint32_t b = live ? (uint32_t)(x[M.dyn_t[d]] + 1) : 0u;
+            bpack[d][(c >> 2) & 3] |= b << (8 * (c & 3));
+            if (live && c > 0 && O.hist_transition) hist_inc(1, d, x[M.dyn_t[d]]);
+        }
+        for (int tv = 0; tv < ntv; ++tv) vbuf[tv][c & 3] = live ? (float)vals[M.tv_var[tv]] : 0.0f;
+        if ((c & 3) == 3 && O.values) {
+            for (int tv = 0; tv < ntv; ++tv) {
+                float* dst = O.values + (((int64_t)tv * nch4 + (c >> 2)) * N + s) * 4;
+#if defined(__CUDA_ARCH__)
+                *reinterpret_cast<float4*>(dst) = make_float4(vbuf[tv][0], vbuf[tv][1], vbuf[tv][2], vbuf[tv][3]);
+#else
+                dst[0] = vbuf[tv][0]; dst[1] = vbuf[tv][1]; dst[2] = vbuf[tv][2]; dst[3] = vbuf[tv][3];
+#endif
+            }
+        }
+        if ((c & 15) == 15) {
+            if (O.bins) {
+                for (int d = 0; d < nd; ++d) {
+                    int8_t* dst = O.bins + (((int64_t)d * nch16 + (c >> 4)) * N + s) * 16;
+#if defined(__CUDA_ARCH__)
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(bpack[d][0], bpack[d][1], bpack[d][2], bpack[d][3]);
+#else
+                    for (int q = 0; q < 4; ++q)
+                        for (int b = 0; b < 4; ++b) dst[q * 4 + b] = (int8_t)((bpack[d][q] >> (8 * b)) & 0xFF);
+#endif
+                }
+            }
+            for (int d = 0; d < nd; ++d) bpack[d][0] = bpack[d][1] = bpack[d][2] = bpack[d][3] = 0;
+        }
+    }
+}
+
+}  // namespace emb

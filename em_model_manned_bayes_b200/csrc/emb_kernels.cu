@@ -1,0 +1,102 @@
+// emb_kernels.cu -- sm_100a kernels of libemb200.so and their launchers.
+//
+// One thread = one sample (track).  There is no inter-thread communication on the data path; the
+// only shared state is the per-block verification histogram (shared-memory atomics flushed with one
+// global atomic per bin per block).
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "emb_device.cuh"
+#include "emb_launch.h"
+
+namespace emb {
+
+std::atomic<long long> g_launch_count{0};
+
+namespace {
+
+constexpr int BLOCK = 128;
+
+struct SmemHist {
+    uint32_t* sh;
+    __device__ __forceinline__ void operator()(int which, int idx, int bin) const {
+        atomicAdd(&sh[(which ? MAXV * HIST_STRIDE : 0) + idx * HIST_STRIDE + bin], 1u);
+    }
+};
+
+__device__ __forceinline__ void flush_hist(const uint32_t* sh, const DevModel& M, unsigned long long* hi,
+                                           unsigned long long* ht) {
+    __syncthreads();
+    if (hi)
+        for (int q = threadIdx.x; q < M.n_initial * HIST_STRIDE; q += blockDim.x)
+            if (sh[q]) atomicAdd(&hi[q], (unsigned long long)sh[q]);
+    if (ht)
+        for (int q = threadIdx.x; q < M.n_dyn * HIST_STRIDE; q += blockDim.x)
+            if (sh[MAXV * HIST_STRIDE + q]) atomicAdd(&ht[q], (unsigned long long)sh[MAXV * HIST_STRIDE + q]);
+}
+
+// ---- initial network only (bn_sample.m batch; config 2; terminal geometry) ----------------------
+__global__ void __launch_bounds__(BLOCK)
+k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P, int8_t* __restrict__ bins,
+          double* __restrict__ values, uint16_t* __restrict__ attempts, unsigned long long* hist, int32_t* status) {
+    __shared__ uint32_t sh[MAXV * HIST_STRIDE];
+    if (hist) {
+        for (int q = threadIdx.x; q < MAXV * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
+        __syncthreads();
+    }
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n) {
+        uint8_t x[MAXX];
+        double vals[MAXV];
+        int attempt = sample_initial(M, P, P.first_sample + (uint64_t)s, x, vals);
+        if (attempt < 0) {
+            *status = 1;
+            attempt = P.max_attempts;
+        }
+        if (attempts) attempts[s] = (uint16_t)(attempt + 1);
+        for (int i = 0; i < M.n_initial; ++i) {
+            if (bins) bins[(int64_t)i * P.n + s] = (int8_t)(x[i] + 1);
+            if (values) values[(int64_t)i * P.n + s] = vals[i];
+            if (hist) atomicAdd(&sh[i * HIST_STRIDE + x[i]], 1u);
+        }
+    }
+    if (hist) flush_hist(sh, M, hist, nullptr);
+}
+
+// ---- tracks, generic (any model, both dbn_sample.m branches) ------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
+                 const __grid_constant__ TrackOut O) {
+    __shared__ uint32_t sh[(MAXV + MAXD) * HIST_STRIDE];
+    const bool want_hist = O.hist_initial || O.hist_transition;
+    if (want_hist) {
+        for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
+        __syncthreads();
+    }
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n) track_generic(M, P, O, s, SmemHist{sh});
+    if (want_hist) flush_hist(sh, M, O.hist_initial, O.hist_transition);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+int launch_initial(const DevModel& M, const SampleParams& P, int8_t* bins, double* values, uint16_t* attempts,
+                   unsigned long long* hist, int32_t* status, void* stream) {
+    if (P.n <= 0) return 0;
+    const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
+    k_initial<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, bins, values, attempts, hist, status);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream) {
+    if (P.n <= 0) return 0;
+    const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
+    k_tracks_generic<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace emb

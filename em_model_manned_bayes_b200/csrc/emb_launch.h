@@ -1,0 +1,17 @@
+// emb_launch.h -- launchers implemented in emb_kernels.cu, called from the C-ABI layer.
+#pragma once
+#include <atomic>
+#include <cstdint>
+
+#include "emb_device.cuh"
+
+namespace emb {
+
+extern std::atomic<long long> g_launch_count;
+
+// all return a cudaError_t value (0 = success); pointers are device pointers
+int launch_initial(const DevModel& M, const SampleParams& P, int8_t* bins, double* values, uint16_t* attempts,
+                   unsigned long long* hist, int32_t* status, void* stream);
+int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream);
+
+}  // namespace emb

@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's model classes on top of the C ABI.
+
+Mirrors (paths relative to /root/reference/code/matlab/):
+  em_read.m                                  -> EncounterModel(parameters_filename=...)
+  @EncounterModel/EncounterModel.m           -> EncounterModel properties (same names)
+  bn_sample.m                                -> bn_sample(G, r, N, alpha, num_samples, start, order)
+  @UncorEncounterModel/UncorEncounterModel.m -> UncorEncounterModel.sample(n_samples, sample_time, ...)
+  @CorTerminalModel/sample.m                 -> CorTerminalModel.sample(nSamples, ...)
+
+All sampling goes through libemb200.so (CUDA, sm_100a).  Nothing here computes samples on the CPU.
+Values are 1-based (bins, variable ids) exactly as the MATLAB API returns them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _ptr(a):
+    """numpy array / torch tensor / None -> void* (and keepalive)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def untile_bins(buf, n_dyn: int, n: int, T: int):
+    """[n_dyn][Tpad/16][n][16] -> (n, n_dyn, T).  Works on numpy arrays and torch tensors."""
+    nch = (T + 15) // 16
+    a = buf.reshape(n_dyn, nch, n, 16)
+    a = a.transpose(2, 0, 1, 3) if isinstance(a, np.ndarray) else a.permute(2, 0, 1, 3)
+    return a.reshape(n, n_dyn, nch * 16)[:, :, :T]
+
+
+def untile_values(buf, n_tv: int, n: int, T: int):
+    """[n_tv][Tpad/4][n][4] -> (n, n_tv, T)."""
+    nch = ((T + 15) // 16) * 4
+    a = buf.reshape(n_tv, nch, n, 4)
+    a = a.transpose(2, 0, 1, 3) if isinstance(a, np.ndarray) else a.permute(2, 0, 1, 3)
+    return a.reshape(n, n_tv, nch * 4)[:, :, :T]
+
+
+@dataclass
+class TrackResult:
+    """Compact result of `EncounterModel.sample_tracks` (one entry per track, global order)."""
+    n: int
+    T: int
+    dyn_vars: List[int]            # 1-based ids of the dynamic variables (temporal_map(:,1))
+    tv_vars: List[int]             # 1-based ids of the time-varying variables (dynamic or resampled)
+    bins_tiled: Optional[object]
+    values_tiled: Optional[object]
+    init_bins: Optional[object]    # (n_initial, n) int8
+    init_values: Optional[object]  # (n_initial, n) float64 == out_inits'
+    attempts: Optional[object]
+
+    @property
+    def bins(self):
+        """(n, n_dyn, T) int8 1-based bins; [:, d, c] is the bin during second c+1."""
+        return untile_bins(self.bins_tiled, len(self.dyn_vars), self.n, self.T)
+
+    @property
+    def values(self):
+        """(n, n_tv, T) float32 continuous values."""
+        return untile_values(self.values_tiled, len(self.tv_vars), self.n, self.T)
+
+
+class EncounterModel:
+    """@EncounterModel/EncounterModel.m:75-153 (file-backed form) -- same property names."""
+
+    def __init__(self, parameters_filename: str = "", idxZeroBoundaries: Sequence[int] = (),
+                 isOverwriteZeroBoundaries: bool = False, prior=0, _handle=None):
+        self._h = C.c_void_p()
+        lib = L.lib()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            if not parameters_filename:
+                raise L.EmbError(L.EMB_E_ARG, "parameters_filename is required")
+            idx = (C.c_int32 * max(1, len(idxZeroBoundaries)))(*[int(v) for v in idxZeroBoundaries])
+            L.check(lib.emb_model_load(str(parameters_filename).encode(), int(bool(isOverwriteZeroBoundaries)),
+                                       idx, len(idxZeroBoundaries), C.byref(self._h)))
+        self.parameters_filename = parameters_filename
+        self._load_info()
+        self.start = [None] * self.n_initial                 # EncounterModel.m:259-261
+        self._prior = 0
+        if prior != 0:
+            self.prior = prior
+
+    # -- lifetime ----------------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                L.lib().emb_model_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- properties --------------------------------------------------------------------------------
+    def _load_info(self):
+        lib = L.lib()
+        info = L.ModelInfo()
+        L.check(lib.emb_model_get_info(self._h, C.byref(info)))
+        self._info = info
+        n, nt = info.n_initial, info.n_transition
+        self.n_initial, self.n_transition = n, nt
+        self.n_dyn, self.n_gated, self.n_timevarying = info.n_dyn, info.n_gated, info.n_timevarying
+        self.is_dynvar_depend = bool(info.is_dynvar_depend)
+        self.r_initial = np.array(info.r_initial[:n], dtype=np.int64)
+        self.r_transition = np.array(info.r_transition[:nt], dtype=np.int64)
+        self.order_initial = list(info.order_initial[:n])
+        self.order_transition = list(info.order_transition[:nt])
+        self.temporal_map = np.array([[info.temporal_map[k][0], info.temporal_map[k][1]] for k in range(info.n_dyn)],
+                                     dtype=np.int64).reshape(-1, 2)
+        self.zero_bins = [[int(z)] if z else [] for z in info.zero_bins[:n]]
+        self.resample_rates = np.array(info.resample_rates[:n], dtype=np.float64)
+        self.bounds_initial = np.array([[info.bounds_initial[i][0], info.bounds_initial[i][1]] for i in range(n)])
+        self.timevarying_vars = list(info.timevarying_vars[:info.n_timevarying])
+        self.labels_initial = self._labels(0)
+        self.labels_transition = self._labels(1) if nt else []
+        G = np.zeros(n * n, dtype=np.uint8)
+        lib.emb_model_get_G(self._h, 0, G.ctypes.data, G.size)
+        self.G_initial = G.reshape(n, n).astype(bool)
+        if nt:
+            G = np.zeros(nt * nt, dtype=np.uint8)
+            lib.emb_model_get_G(self._h, 1, G.ctypes.data, G.size)
+            self.G_transition = G.reshape(nt, nt).astype(bool)
+        else:
+            self.G_transition = np.zeros((0, 0), dtype=bool)
+        blen = list(info.boundaries_len[:n])
+        flat = np.zeros(max(1, sum(blen)))
+        lib.emb_model_get_boundaries(self._h, flat.ctypes.data, flat.size)
+        self.boundaries, o = [], 0
+        for k in blen:
+            self.boundaries.append(flat[o:o + k].copy())
+            o += k
+        self.cutpoints_initial = [np.arange(2, self.r_initial[i] + 1, dtype=np.float64) if blen[i] == 0
+                                  else self.boundaries[i][1:-1].copy() for i in range(n)]   # em_read.m:128-136
+
+    def _labels(self, which):
+        lib = L.lib()
+        need = lib.emb_model_get_labels(self._h, which, None, 0)
+        buf = C.create_string_buffer(int(need))
+        lib.emb_model_get_labels(self._h, which, buf, need)
+        s = buf.value.decode("utf-8")
+        return s.split("\n") if s else []
+
+    def _tables(self, which):
+        lib = L.lib()
+        total = int(self._info.len_N_transition if which else self._info.len_N_initial)
+        flat = np.zeros(max(1, total))
+        lib.emb_model_get_N(self._h, which, flat.ctypes.data, flat.size)
+        G = self.G_transition if which else self.G_initial
+        r = self.r_transition if which else self.r_initial
+        nvar = G.shape[0]
+        first = self.n_initial if which else 0
+        out: List[Optional[np.ndarray]] = [None] * nvar
+        o = 0
+        for i in range(first, nvar):
+            q = int(np.prod(r[G[:, i]])) if G[:, i].any() else 1
+            cnt = int(r[i]) * q
+            out[i] = flat[o:o + cnt].reshape((int(r[i]), q), order="F").copy()
+            o += cnt
+        return out
+
+    @property
+    def N_initial(self):
+        return self._tables(0)
+
+    @property
+    def N_transition(self):
+        return self._tables(1)
+
+    @property
+    def dediscretize_parameters(self):
+        return self.boundaries
+
+    @property
+    def prior(self):
+        return self._prior
+
+    @prior.setter
+    def prior(self, value):
+        """EncounterModel.m:194-203: numeric constant or 'dbe' (bn_dirichlet_prior.m:17-38)."""
+        lib = L.lib()
+        if isinstance(value, str):
+            if value.lower() != "dbe":
+                raise L.EmbError(L.EMB_E_ARG, "prior:notdbe Unknown prior of %s, if char expecting prior = 'dbe'" % value)
+            kind, v = L.EMB_PRIOR_DBE, 0.0
+        else:
+            kind, v = L.EMB_PRIOR_CONSTANT, float(value)
+        L.check(lib.emb_set_prior(self._h, 0, kind, v))
+        if self.n_transition:
+            L.check(lib.emb_set_prior(self._h, 1, kind, v))
+        self._prior = value
+
+    def set_transition_stay_prior(self, value: float = 1.0):
+        """setTransitionPriors.m:12-33 (terminal trajectory DBNs)."""
+        L.check(L.lib().emb_set_prior(self._h, 1, L.EMB_PRIOR_STAY, float(value)))
+
+    def packed(self, which: int) -> np.ndarray:
+        lib = L.lib()
+        n = lib.emb_model_get_packed(self._h, which, None, 0)
+        buf = np.zeros(max(1, int(n)), dtype=np.uint32)
+        lib.emb_model_get_packed(self._h, which, buf.ctypes.data, buf.size)
+        return buf[:int(n)]
+
+    # -- option plumbing ---------------------------------------------------------------------------
+    def _opts(self, start=None, device=None, stream=None, mem=L.EMB_MEM_HOST, max_attempts=0):
+        o = L.SampleOpts()
+        L.lib().emb_sample_opts_init(C.byref(o))
+        start = self.start if start is None else start
+        if len(start) != self.n_initial:
+            raise L.EmbError(L.EMB_E_ARG, "start must have n_initial entries")
+        for i, s in enumerate(start):
+            free = s is None or (isinstance(s, (list, tuple, np.ndarray)) and len(s) == 0) or \
+                (isinstance(s, float) and math.isnan(s))
+            o.start[i] = 0 if free else int(s)
+        o.mem = mem
+        o.device = -1 if device is None else int(device)
+        o.stream = None if stream is None else int(stream)
+        o.max_attempts = int(max_attempts)
+        return o
+
+    @staticmethod
+    def _alloc(shape, dtype, like):
+        """Allocate an output buffer: numpy (host) or torch on `like` device."""
+        if like is None:
+            return np.zeros(shape, dtype=dtype)
+        import torch
+        tdt = {np.int8: torch.int8, np.float32: torch.float32, np.float64: torch.float64, np.uint16: torch.int16,
+               np.uint64: torch.int64}[dtype]
+        return torch.zeros(shape, dtype=tdt, device=like)
+
+    # -- sampling ----------------------------------------------------------------------------------
+    def sample_initial(self, n: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
+                       want_values=True, want_attempts=True):
+        """bn_sample.m:25-58 over n samples + de-discretisation.  Returns (bins (n, n_initial) int8,
+        values (n, n_initial) float64 or None, attempts (n,) or None).  `device`: torch device string
+        to keep the outputs in HBM; default host numpy."""
+        o = opts if opts is not None else self._opts(start=start)
+        stream = None
+        if device is not None:
+            import torch
+            dev = torch.device(device)
+            o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            o.stream = stream
+        ni = self.n_initial
+        bins = self._alloc((ni, n), np.int8, device)
+        vals = self._alloc((ni, n), np.float64, device) if want_values else None
+        att = self._alloc((n,), np.uint16, device) if want_attempts else None
+        rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
+        L.check(L.lib().emb_sample_initial(self._h, C.byref(rng), n, C.byref(o), _ptr(bins), _ptr(vals), _ptr(att)))
+        return bins.T, (vals.T if vals is not None else None), att
+
+    def sample_tracks(self, n: int, T: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
+                      want_bins=True, want_values=True, want_init=True, hist_initial=None, hist_transition=None,
+                      out: Optional[TrackResult] = None) -> TrackResult:
+        """Dense compact tracks (emb200.h: emb_sample_tracks)."""
+        lib = L.lib()
+        o = opts if opts is not None else self._opts(start=start)
+        if device is not None:
+            import torch
+            dev = torch.device(device)
+            o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+            o.stream = torch.cuda.current_stream(dev).cuda_stream
+        ni = self.n_initial
+        if out is None:
+            nb = int(lib.emb_tracks_bins_len(self._h, n, T))
+            nv = int(lib.emb_tracks_values_len(self._h, n, T))
+            out = TrackResult(
+                n=n, T=T, dyn_vars=[int(v) for v in self.temporal_map[:, 0]], tv_vars=list(self.timevarying_vars),
+                bins_tiled=self._alloc((nb,), np.int8, device) if want_bins else None,
+                values_tiled=self._alloc((nv,), np.float32, device) if want_values else None,
+                init_bins=self._alloc((ni, n), np.int8, device) if want_init else None,
+                init_values=self._alloc((ni, n), np.float64, device) if want_init else None,
+                attempts=self._alloc((n,), np.uint16, device) if want_init else None)
+        to = L.TrackOut(_ptr(out.bins_tiled), _ptr(out.values_tiled), _ptr(out.init_bins), _ptr(out.init_values),
+                        _ptr(out.attempts), _ptr(hist_initial), _ptr(hist_transition))
+        rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
+        L.check(lib.emb_sample_tracks(self._h, C.byref(rng), n, T, C.byref(o), C.byref(to)))
+        return out
+
+
+def _find(labels, name):
+    for i, l in enumerate(labels):
+        if l == name:
+            return i + 1
+    return 0
+
+
+class UncorEncounterModel(EncounterModel):
+    """@UncorEncounterModel/UncorEncounterModel.m (file input_type)."""
+
+    def __init__(self, parameters_filename: str, idxZeroBoundaries: Sequence[int] = (1, 2, 3),
+                 isOverwriteZeroBoundaries: bool = False, prior=0):
+        super().__init__(parameters_filename, idxZeroBoundaries, isOverwriteZeroBoundaries, prior)
+        self.isRotorcraft = "rotorcraft" in str(parameters_filename)          # UncorEncounterModel.m:179-183
+        self.idxL = _find(self.labels_initial, '"L"')                          # :225-229
+        self.idxV = _find(self.labels_initial, '"v"')
+        self.idxDV = _find(self.labels_initial, '"\\dot v"')
+        self.idxDH = _find(self.labels_initial, '"\\dot h"')
+        self.idxDPsi = _find(self.labels_initial, '"\\dot \\psi"')
+
+    def uncor_opts(self, isQuantize500=False, layers=None, start=None, max_attempts=0):
+        if not (self.idxDV and self.idxDH and self.idxDPsi):                   # :231-234
+            raise L.EmbError(L.EMB_E_ARG, "dynvar:empty Model does not have a dynamic variable for either "
+                             "acceleration, vertical rate, or turn rate")
+        o = self._opts(start=start, max_attempts=max_attempts)
+        o.reject_mode = L.EMB_REJECT_UNCOR
+        o.idx_v, o.idx_dh, o.idx_L = self.idxV, self.idxDH, self.idxL
+        o.is_quantize500 = int(bool(isQuantize500))
+        if layers is not None and len(layers):
+            layers = np.asarray(layers, dtype=np.float64).reshape(-1, 2)
+            o.n_layers = layers.shape[0]
+            for k in range(layers.shape[0]):
+                o.layers[k][0], o.layers[k][1] = layers[k, 0], layers[k, 1]
+        return o
+
+    def sample_compact(self, n_samples: int, sample_time: int, seed: int = 0, first_sample: int = 0,
+                       isQuantize500=False, layers=None, device=None, **kw) -> TrackResult:
+        """The batch form of UncorEncounterModel.m:244-307 with compact dense outputs."""
+        o = self.uncor_opts(isQuantize500, layers)
+        return self.sample_tracks(n_samples, sample_time, seed=seed, first_sample=first_sample, opts=o,
+                                  device=device, **kw)
+
+    def sample(self, n_samples: int, sample_time: int, seed=float("nan"), isQuantize500=False, layers=None):
+        """UncorEncounterModel.m:192-313 -> (out_inits n x n_initial, out_samples list of n_initial x T).
+        `seed` NaN draws a fresh 64-bit seed (the reference keeps the global stream; here streams are keyed)."""
+        if isinstance(seed, float) and math.isnan(seed):
+            seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
+        res = self.sample_compact(n_samples, sample_time, seed=int(seed), isQuantize500=isQuantize500, layers=layers)
+        out_inits = np.ascontiguousarray(res.init_values.T)
+        vals = res.values
+        out_samples = []
+        tv0 = [v - 1 for v in res.tv_vars]
+        for k in range(n_samples):
+            d = np.repeat(out_inits[k][:, None], sample_time, axis=1)
+            d[tv0, :] = vals[k].astype(np.float64)
+            out_samples.append(d)
+        return out_inits, out_samples, res

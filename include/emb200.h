@@ -1,0 +1,173 @@
+/* emb200.h -- C ABI of libemb200.so, the B200-native sampler for the hot path of
+ * Airspace-Encounter-Models/em-model-manned-bayes.
+ *
+ * The reference is pure MATLAB and has no FFI boundary of its own; the
+ * boundary therefore sits at the MATLAB signatures that take a *batch* argument.  Each entry point
+ * below names the reference interface it replaces (paths relative to /root/reference/).  A MATLAB
+ * user reaches these through the MEX gateway in matlab/emb_mex.cpp; the tests and the Python
+ * mirror (em_model_manned_bayes_b200/) reach them through ctypes.  INTEGRATION.md shows both.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative EMB_E_* code, and
+ *    emb_last_error() returns a thread-local message whose text starts with the reference's error
+ *    identifier/message where one exists (e.g. "Unknown field: ...", em_read.m:105).
+ *  - bins are 1-based (MATLAB values); variable ids in arrays are 1-based too.
+ *  - sample indices are 0-based *global* indices; the random stream is keyed by them, so any shard
+ *    [first, first+n) of a job gives the same numbers on any GPU count.
+ *  - the caller owns every output buffer; `mem` says whether buffers are host or device pointers.
+ *    Host buffers should be pinned (emb_host_alloc) for full PCIe speed.
+ *  - there is NO CPU fallback: sampling entry points fail with EMB_E_CUDA if no sm_100 device or
+ *    kernel image is available.
+ */
+#ifndef EMB200_H
+#define EMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMB_ABI_VERSION 1
+
+/* status codes */
+#define EMB_OK 0
+#define EMB_E_IO (-1)        /* cannot open/read file */
+#define EMB_E_PARSE (-2)     /* malformed model file ("Unknown field: %s", em_read.m:105) */
+#define EMB_E_MODEL (-3)     /* inconsistent model ("Network could not be hierarchically sorted", bn_sort.m:23) */
+#define EMB_E_ARG (-4)       /* bad argument ("Attempt to preset a dependent variable", bn_sample.m:47; "dynvar:empty", UncorEncounterModel.m:231) */
+#define EMB_E_CUDA (-5)      /* CUDA error / no device */
+#define EMB_E_LIMIT (-6)     /* model exceeds a compiled limit (EMB_MAX_*) */
+#define EMB_E_REJECT (-7)    /* a sample exhausted the rejection budget */
+
+#define EMB_MAX_VARS 24      /* initial-network variables */
+#define EMB_MAX_DYN 8        /* dynamic variables */
+#define EMB_MAX_PARENTS 8
+#define EMB_MAX_GATED 16
+
+/* memory kind of caller buffers */
+#define EMB_MEM_HOST 0
+#define EMB_MEM_DEVICE 1
+
+/* prior kinds: bn_dirichlet_prior.m:17-38 and setTransitionPriors.m:12-33 */
+#define EMB_PRIOR_CONSTANT 0 /* alpha = value everywhere (EncounterModel.m:45 default 0) */
+#define EMB_PRIOR_DBE 1      /* alpha = 1/(r*q) */
+#define EMB_PRIOR_STAY 2     /* transition only: alpha = value where child bin == own previous bin */
+
+typedef struct emb_model emb_model; /* opaque; immutable after load except emb_set_prior */
+
+/* ---- model reader: replaces em_read.m:1-141 + bn_sort.m:14-24 + the packing the kernels need --- */
+int emb_model_load(const char* parameters_filename, int is_overwrite_zero_boundaries,
+                   const int32_t* idx_zero_boundaries, int32_t n_idx, emb_model** out);
+/* Build a model from arrays (bn_sample.m:1 functional form and synthetic models).  G is row-major
+ * n x n with G[parent*n + child]; N_* are the concatenated column-major count tables in variable
+ * order (em_read.m:191-198); transition arguments may be NULL/0 for an initial-only network;
+ * boundaries are concatenated, boundaries_len[i] entries each (0 = '*'). */
+int emb_model_from_arrays(int32_t n_initial, const uint8_t* G_initial, const int32_t* r_initial,
+                          const double* N_initial, int64_t len_N_initial,
+                          int32_t n_transition, const uint8_t* G_transition, const int32_t* r_transition,
+                          const double* N_transition, int64_t len_N_transition,
+                          const int32_t* temporal_map /* k x 2, 1-based, row-major */, int32_t n_temporal,
+                          const double* boundaries, const int32_t* boundaries_len,
+                          const double* resample_rates, emb_model** out);
+void emb_model_free(emb_model* m);
+
+typedef struct emb_model_info {
+    int32_t n_initial, n_transition, n_dyn, n_gated;
+    int32_t is_dynvar_depend;   /* dbn_sample.m:55: 1 = "slow" branch, 0 = frozen-parent "fast" branch */
+    int32_t n_timevarying;      /* variables whose continuous value can change over a track */
+    int64_t len_N_initial, len_N_transition;
+    int32_t r_initial[EMB_MAX_VARS];
+    int32_t r_transition[EMB_MAX_VARS + EMB_MAX_DYN];
+    int32_t order_initial[EMB_MAX_VARS];                       /* 1-based, bn_sort order */
+    int32_t order_transition[EMB_MAX_VARS + EMB_MAX_DYN];
+    int32_t temporal_map[EMB_MAX_DYN][2];                      /* 1-based [var(t), var(t+1|t-1)] */
+    int32_t zero_bins[EMB_MAX_VARS];                           /* 0 = none (em_read.m:143-156) */
+    int32_t boundaries_len[EMB_MAX_VARS];
+    int32_t timevarying_vars[EMB_MAX_VARS];                    /* 1-based ids, ascending */
+    double resample_rates[EMB_MAX_VARS];
+    double bounds_initial[EMB_MAX_VARS][2];                    /* em_read.m:124-136 */
+} emb_model_info;
+int emb_model_get_info(const emb_model* m, emb_model_info* info);
+/* copies; `which`: 0 initial, 1 transition.  Returns the needed length when buf is NULL. */
+int64_t emb_model_get_labels(const emb_model* m, int which, char* buf, int64_t cap); /* '\n'-joined */
+int64_t emb_model_get_G(const emb_model* m, int which, uint8_t* buf, int64_t cap);
+int64_t emb_model_get_N(const emb_model* m, int which, double* buf, int64_t cap);
+int64_t emb_model_get_boundaries(const emb_model* m, double* buf, int64_t cap);
+/* packed word-space thresholds actually uploaded to the GPU (for tests): column-padded tables */
+int64_t emb_model_get_packed(const emb_model* m, int which, uint32_t* buf, int64_t cap);
+
+/* ---- priors: replaces EncounterModel.m:249-257 -> bn_dirichlet_prior.m, setTransitionPriors.m --- */
+int emb_set_prior(emb_model* m, int which /*0 initial, 1 transition*/, int kind, double value);
+
+/* ---- random stream --------------------------------------------------------------------------- */
+typedef struct emb_rng {
+    uint64_t seed;          /* replaces rng(seed,'twister') (UncorEncounterModel.m:213-216) */
+    uint64_t first_sample;  /* global index of this call's sample 0 */
+} emb_rng;
+/* the keyed Philox4x32-10 word for tests / injection hooks (stream spec v1) */
+uint32_t emb_rng_word(uint64_t seed, uint64_t sample, uint32_t attempt, uint32_t purpose,
+                      uint32_t index, uint32_t sub, uint32_t lane);
+
+/* ---- sampling options ------------------------------------------------------------------------ */
+#define EMB_REJECT_NONE 0
+#define EMB_REJECT_UNCOR 1 /* v*1.68781 > |dh|/60 (UncorEncounterModel.m:275) */
+#define EMB_REJECT_BOX 2   /* lo <= value <= hi per variable (@CorTerminalModel/sample.m:45-70) */
+
+typedef struct emb_sample_opts {
+    int32_t start[EMB_MAX_VARS]; /* preset bins, 0 = free (bn_sample.m:45, `start` cell) */
+    int32_t reject_mode;
+    int32_t idx_v, idx_dh, idx_L;             /* 1-based variable ids for EMB_REJECT_UNCOR / layers */
+    double box_lo[EMB_MAX_VARS], box_hi[EMB_MAX_VARS]; /* EMB_REJECT_BOX */
+    int32_t is_quantize500;                   /* UncorEncounterModel.m:266-268 */
+    int32_t n_layers;                         /* 0 = no layers; else rows of `layers` (UncorEncounterModel.m:259-263) */
+    double layers[8][2];
+    int32_t max_attempts;                     /* 0 -> 65535 */
+    int32_t mem;                              /* EMB_MEM_HOST / EMB_MEM_DEVICE for all output buffers */
+    int32_t device;                           /* CUDA device ordinal; -1 = current */
+    void* stream;                             /* cudaStream_t or NULL */
+} emb_sample_opts;
+void emb_sample_opts_init(emb_sample_opts* o);
+
+/* ---- initial network: replaces bn_sample.m:25-58 (batch over num_samples) followed by the
+ *      initial half of dbn_hierarchical_sample.m:25-31 / @CorTerminalModel/sample.m:29-77 ------- */
+/* bins   : int8  [n_initial][n]   (1-based bins)                 nullable
+ * values : double[n_initial][n]   (dediscretised; bin for '*')   nullable
+ * attempts: uint16[n]             (rejection attempts used)      nullable */
+int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts,
+                       int8_t* bins, double* values, uint16_t* attempts);
+
+/* ---- tracks: replaces UncorEncounterModel.m:244-307 loop around dbn_hierarchical_sample.m:9-37
+ *      (dbn_sample.m both branches, resample_events.m, dediscretize.m, events2samples.m) ---------- */
+typedef struct emb_track_out {
+    /* dense, tiled for coalesced 16-byte stores; Tpad = 16*ceil(T/16); column c (0-based) is the
+     * state during second c+1, i.e. out_samples{ii}(:, c+1) (events2samples.m:9-27) */
+    int8_t* bins;        /* [n_dyn][Tpad/16][n][16]  1-based bins of the dynamic variables   nullable */
+    float* values;       /* [n_timevarying][Tpad/4][n][4] continuous values                  nullable */
+    /* per track */
+    int8_t* init_bins;   /* [n_initial][n]                                                   nullable */
+    double* init_values; /* [n_initial][n]  out_inits (after layers/quantize500)             nullable */
+    uint16_t* attempts;  /* [n]                                                              nullable */
+    /* verification histograms, accumulated (+=) on the device: counts[var][bin-1], stride 64 */
+    unsigned long long* hist_initial;    /* [n_initial][64]                                  nullable */
+    unsigned long long* hist_transition; /* [n_dyn][64] over all columns 2..T                nullable */
+} emb_track_out;
+int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T,
+                      const emb_sample_opts* opts, const emb_track_out* out);
+/* sizes (in elements) of the dense buffers for given n, T */
+int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T);
+int64_t emb_tracks_values_len(const emb_model* m, int64_t n, int32_t T);
+
+/* ---- misc ------------------------------------------------------------------------------------- */
+int emb_host_alloc(void** p, int64_t bytes); /* pinned host memory */
+int emb_host_free(void* p);
+int emb_device_count(void);
+const char* emb_last_error(void);
+int emb_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t emb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMB200_H */

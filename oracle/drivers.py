@@ -1,0 +1,160 @@
+"""TEST INFRASTRUCTURE (oracle) -- not product code.
+
+Restatement of the reference's sampling drivers:
+  @UncorEncounterModel/UncorEncounterModel.m:192-313  (sample)
+  @CorTerminalModel/sample.m:1-82                      (terminal encounter geometry)
+  bn_sample.m:39 batch loop                            (initial-network-only sampling, config 2)
+  em_sample.m:41-104                                   (legacy file writer)
+
+`sample ids` are 0-based global indices (they key the Philox stream); everything else is 1-based
+like MATLAB.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import sampler as sp
+
+
+@dataclass
+class UncorSample:
+    initial: np.ndarray            # out_inits(ii,:)  continuous (bin index for '*' variables)
+    events: np.ndarray             # out_events{ii}   k x 3 [dt var value]
+    samples: np.ndarray            # out_samples{ii}  n_initial x T
+    controls: np.ndarray           # EncounterModelEvents.event  [t dh dpsi dv] in EME units
+    initial_bins: np.ndarray       # (oracle extra) sampled bins of the accepted attempt
+    sample_bins: np.ndarray        # (oracle extra) n_initial x T bins, same expansion as samples
+    event_bins: np.ndarray         # (oracle extra) k bins aligned with events rows
+    prov: list = field(default_factory=list)
+    attempts: int = 1
+
+
+def _find_label(labels, name):
+    for i, l in enumerate(labels):
+        if l == name:
+            return i + 1
+    return None
+
+
+def round500(num):
+    """UncorEncounterModel.m:196"""
+    return 500.0 * (np.floor(num / 500.0) + (np.mod(num, 500.0) > 250.0))
+
+
+def uncor_sample(parms, n_samples, sample_time, U, *, first_sample=0, prior=0, isQuantize500=False,
+                 layers=None, start=None, strict_quirks=False, max_attempts=65535) -> List[UncorSample]:
+    """UncorEncounterModel.m:192-313 (rng seeding is the provider's business)."""
+    labels = parms.labels_initial
+    idxL = _find_label(labels, '"L"')
+    idxV = _find_label(labels, '"v"')
+    idxDV = _find_label(labels, '"\\dot v"')
+    idxDH = _find_label(labels, '"\\dot h"')
+    idxDPsi = _find_label(labels, '"\\dot \\psi"')
+    if idxDV is None or idxDH is None or idxDPsi is None:
+        raise sp.OracleError("dynvar:empty")                                    # :231-234
+    alpha_i = sp.bn_dirichlet_prior(parms.N_initial, prior)
+    alpha_t = sp.bn_dirichlet_prior(parms.N_transition, prior)
+    start = parms.start if start is None else start
+    U.bind(parms.n_initial, parms.temporal_map, parms.resample_rates)
+    out = []
+    tm = np.asarray(parms.temporal_map)
+    for ii in range(n_samples):
+        attempt = 0
+        while True:                                                              # :248
+            U.begin(first_sample + ii, attempt)
+            initial, events, prov, ibins, ebins = sp.dbn_hierarchical_sample(
+                parms, alpha_i, alpha_t, sample_time, parms.boundaries, parms.zero_bins,
+                parms.resample_rates, start, U, strict_quirks)
+            if layers is not None and len(layers):                               # :259-263
+                L = int(initial[idxL - 1])
+                h_ft = layers[L - 1][0] + U.layer() * (layers[L - 1][1] - layers[L - 1][0])
+            else:
+                h_ft = initial[idxL - 1]
+            if initial[idxDH - 1] == 0 and isQuantize500:                        # :266-268
+                h_ft = round500(h_ft)
+            if (layers is not None and len(layers)) or isQuantize500:           # :270-272
+                initial[idxL - 1] = h_ft
+            if initial[idxV - 1] * 1.68781 > abs(initial[idxDH - 1]) / 60:       # :275
+                break
+            attempt += 1
+            if attempt > max_attempts:
+                raise sp.OracleError("rejection loop exceeded max_attempts")
+        samples = sp.events2samples(initial, events)                             # :283
+        controls = sp.events2controls(initial, events, tm)                       # :286
+        dynt = list(tm[:, 0])
+        idxEME = [dynt.index(idxDH) + 1, dynt.index(idxDPsi) + 1, dynt.index(idxDV) + 1]   # :291 (+1 -> col)
+        controls = controls[:, [0] + idxEME]
+        controls[:, 1] = controls[:, 1] / 60                                     # :295
+        controls[:, 2] = np.deg2rad(controls[:, 2])                              # :296
+        controls[:, 3] = controls[:, 3] * 1.68780972222222                       # :297
+        bin_events = [[e[0], e[1], b] for e, b in zip(events, ebins)]
+        sample_bins = sp.events2samples(ibins, bin_events)
+        out.append(UncorSample(initial=np.array(initial), events=np.asarray(events, dtype=np.float64).reshape(-1, 3),
+                               samples=samples, controls=controls, initial_bins=np.array(ibins),
+                               sample_bins=sample_bins, event_bins=np.asarray(ebins, dtype=np.float64),
+                               prov=prov, attempts=attempt + 1))
+    return out
+
+
+def initial_sample(parms, num_samples, U, *, first_sample=0, prior=0, start=None, dediscretize=True):
+    """Config 2: bn_sample.m:39-58 over `num_samples`, then the initial-vector half of
+    dbn_hierarchical_sample.m:25-31.  Returns (bins num_samples x n, values num_samples x n)."""
+    alpha_i = sp.bn_dirichlet_prior(parms.N_initial, prior)
+    start = parms.start if start is None else start
+    U.bind(parms.n_initial, parms.temporal_map, parms.resample_rates)
+    ids = [first_sample + k for k in range(num_samples)]
+    S = sp.bn_sample(parms.G_initial, parms.r_initial, parms.N_initial, alpha_i, num_samples, start,
+                     parms.order_initial, U, sample_ids=ids)
+    V = S.copy()
+    if dediscretize:
+        for k in range(num_samples):
+            U.begin(ids[k], 0)
+            for ii in range(1, parms.n_initial + 1):
+                V[k, ii - 1] = sp.dediscretize_u(S[k, ii - 1], parms.boundaries[ii - 1], parms.zero_bins[ii - 1],
+                                                 lambda v=ii: U.dedisc_init(v))
+    return S, V
+
+
+def terminal_sample(parms, n_samples, U, *, first_sample=0, prior=0, start=None, bounds_sample=None,
+                    dyn_limits1=(50.0, 506.0), dyn_limits2=(50.0, 506.0), max_attempts=65535):
+    """@CorTerminalModel/sample.m:29-77.  dyn_limits = (minVel_ft_s, maxVel_ft_s) of the GENERIC
+    aircraft type (@CorTerminalModel/getDynamicLimits.m:15-17).  Returns (outInits, bins, attempts)."""
+    alpha_i = sp.bn_dirichlet_prior(parms.N_initial, prior)
+    start = parms.start if start is None else start
+    U.bind(parms.n_initial, None, None)
+    i_own = _find_label(parms.labels_initial, '"own_speed"')
+    i_int = _find_label(parms.labels_initial, '"int_speed"')
+    n = parms.n_initial
+    out_inits = np.zeros((n_samples, n))
+    out_bins = np.zeros((n_samples, n))
+    attempts = np.zeros(n_samples, dtype=np.int64)
+    for ii in range(n_samples):
+        attempt = 0
+        while True:
+            U.begin(first_sample + ii, attempt)
+            bins = sp.bn_sample(parms.G_initial, parms.r_initial, parms.N_initial, alpha_i, 1, start,
+                                parms.order_initial, U)[0]                        # sample.m:34
+            initial = bins.copy()
+            for kk in range(1, n + 1):                                            # sample.m:37-42
+                if len(parms.boundaries[kk - 1]):
+                    initial[kk - 1] = sp.dediscretize_u(initial[kk - 1], parms.boundaries[kk - 1],
+                                                        parms.zero_bins[kk - 1], lambda v=kk: U.dedisc_init(v))
+            good = True
+            if bounds_sample is not None and len(bounds_sample):                  # sample.m:45-53
+                good = bool(np.all((initial >= bounds_sample[:, 0]) & (initial <= bounds_sample[:, 1])))
+            if good:                                                              # sample.m:57-71
+                s1 = dyn_limits1[0] <= initial[i_own - 1] <= dyn_limits1[1]
+                s2 = dyn_limits2[0] <= initial[i_int - 1] <= dyn_limits2[1]
+                good = s1 and s2
+            if good:
+                break
+            attempt += 1
+            if attempt > max_attempts:
+                raise sp.OracleError("rejection loop exceeded max_attempts")
+        out_inits[ii] = initial
+        out_bins[ii] = bins
+        attempts[ii] = attempt + 1
+    return out_inits, out_bins, attempts

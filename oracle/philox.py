@@ -1,0 +1,139 @@
+"""TEST INFRASTRUCTURE (oracle) -- not product code.
+
+Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy
+as 1, 2, 3", SC'11; the Random123 `philox4x32_R(10, ctr, key)` function) and the keyed
+stream layout ("stream spec v1") shared by the oracle and the CUDA sampler.
+
+The reference (`/root/reference/code/matlab/select_random.m:14`, `dbn_sample.m:133`,
+`resample_events.m:24`, `dediscretize.m:39`) draws from MATLAB's global `rand`.  The B200
+sampler replaces *when* a uniform is consumed by *what it is for*: every uniform is a pure
+function of (seed, sample, attempt, purpose, index, lane).  The oracle is fed exactly these
+uniforms (uniform-injection), so bin indices must be bit-identical.
+
+Stream spec v1
+--------------
+key     = (seed & 0xffffffff, seed >> 32)
+counter = (sample & 0xffffffff, sample >> 32, index, (attempt << 16) | (purpose << 8) | sub)
+A call returns four 32-bit words; `lane` picks one.
+
+purpose INIT (1):    word position p;  p = i            -> select word of initial variable i (0-based)
+                                      p = n_initial + i -> dediscretize word of initial variable i
+                     index = p // 4, lane = p % 4
+purpose STEP (2):    word position p = (e - 1) * nw + slot, e = 1..T the event second,
+                     nw = n_dyn + n_gated; slot d (< n_dyn) -> transition select of the d-th
+                     dynamic variable (temporal_map row d) for loop index t = e + 1;
+                     slot n_dyn + g -> resample gate of the g-th variable with rate > 0 at
+                     second e.   index = p // 4, lane = p % 4
+purpose STEP_DD (3): index = e, sub = d // 4, lane = d % 4 -> dediscretize word of a transition
+                     event of dynamic variable d at second e
+purpose LAYER (4):   index = 0, lane = 0 -> altitude-layer draw (UncorEncounterModel.m:260)
+purpose TERM_* (5+): terminal trajectory chains, see oracle/terminal.py
+
+word -> uniform: u = (k + 0.5) * 2**-32  (strictly inside (0,1), exact in fp64).
+gate: fires iff u < rate  <=>  k < G, G = #{k : (k + 0.5) 2**-32 < rate}.  The within-bin
+resample that follows a fired gate re-uses the residual of the same word:
+u' = (k + 0.5) * (1.0 / G)   (uniform on (0,1) given k < G; independent of the decision).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK32 = np.uint64(0xFFFFFFFF)
+
+P_INIT = 1
+P_STEP = 2
+P_STEP_DD = 3
+P_LAYER = 4
+P_TERM_SEL = 5
+P_TERM_DD = 6
+
+TWO_M32 = 2.0 ** -32
+
+
+def philox4x32_10(ctr, key):
+    """ctr: uint32 array (..., 4); key: (k0, k1) python ints.  Returns uint32 (..., 4)."""
+    ctr = np.asarray(ctr, dtype=np.uint32)
+    c0 = ctr[..., 0].astype(np.uint64)
+    c1 = ctr[..., 1].astype(np.uint64)
+    c2 = ctr[..., 2].astype(np.uint64)
+    c3 = ctr[..., 3].astype(np.uint64)
+    k0 = int(key[0]) & 0xFFFFFFFF
+    k1 = int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0  # 32x32 -> 64, no overflow in uint64
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK32
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    out = np.stack([c0, c1, c2, c3], axis=-1)
+    return out.astype(np.uint32)
+
+
+def make_counter(sample, index, attempt, purpose, sub=0):
+    """Vectorised counter builder (broadcasts its arguments)."""
+    sample = np.asarray(sample, dtype=np.uint64)
+    index = np.asarray(index, dtype=np.uint64)
+    attempt = np.asarray(attempt, dtype=np.uint64)
+    sub = np.asarray(sub, dtype=np.uint64)
+    w3 = (attempt << np.uint64(16)) | np.uint64(purpose << 8) | sub
+    sample, index, w3 = np.broadcast_arrays(sample, index, w3)
+    ctr = np.empty(sample.shape + (4,), dtype=np.uint32)
+    ctr[..., 0] = (sample & MASK32).astype(np.uint32)
+    ctr[..., 1] = (sample >> np.uint64(32)).astype(np.uint32)
+    ctr[..., 2] = (index & MASK32).astype(np.uint32)
+    ctr[..., 3] = (w3 & MASK32).astype(np.uint32)
+    return ctr
+
+
+def seed_key(seed: int):
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return (seed & 0xFFFFFFFF, seed >> 32)
+
+
+def word(seed, sample, attempt, purpose, index, lane, sub=0):
+    """One 32-bit word of the keyed stream (scalar or broadcast)."""
+    out = philox4x32_10(make_counter(sample, index, attempt, purpose, sub), seed_key(seed))
+    lane = np.asarray(lane)
+    if lane.ndim == 0:
+        return out[..., int(lane)]
+    return np.take_along_axis(out, lane[..., None].astype(np.int64), axis=-1)[..., 0]
+
+
+def word_at(seed, sample, attempt, purpose, position):
+    """Word at linear position p of a (sample, attempt, purpose) stream: index=p//4, lane=p%4."""
+    position = np.asarray(position, dtype=np.int64)
+    return word(seed, sample, attempt, purpose, position // 4, position % 4)
+
+
+def u01(k):
+    """32-bit word -> uniform strictly inside (0,1), exact in fp64."""
+    return (np.asarray(k, dtype=np.float64) + 0.5) * TWO_M32
+
+
+def gate_threshold(rate: float) -> int:
+    """G = number of words k in [0, 2^32) with (k + 0.5) * 2^-32 < rate, via the literal fp64 test
+    the reference performs (`rand(size(rates)) < rates`, resample_events.m:24)."""
+    rate = float(rate)
+    if not rate > 0.0:
+        return 0
+    if rate >= 1.0:
+        return 1 << 32
+    g = int(np.floor(rate * 4294967296.0))
+    g = max(0, min(g, (1 << 32) - 1))
+
+    def fires(k):  # literal comparison
+        return (float(k) + 0.5) * TWO_M32 < rate
+
+    while g > 0 and not fires(g - 1):
+        g -= 1
+    while g < (1 << 32) and fires(g):
+        g += 1
+    return g

@@ -1,0 +1,119 @@
+// tests/emu/emu.cpp -- TEST-ONLY host emulation of the device sampling routines.
+//
+// emb_device.cuh is written __host__ __device__; this file instantiates the *same* per-sample code
+// on the CPU (one loop iteration per CUDA thread) so the `-m "not gpu"` test-suite can check the
+// device logic against the oracle without a GPU.  It is NOT part of libemb200.so, is not reachable
+// from the C ABI, and is never used by bench.py or the product path.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../em_model_manned_bayes_b200/csrc/emb_model.h"
+#include "../../include/emb200.h"
+
+using namespace emb;
+
+static thread_local std::string g_err;
+
+struct HostHist {
+    unsigned long long* hi;
+    unsigned long long* ht;
+    void operator()(int which, int idx, int bin) const {
+        unsigned long long* h = which ? ht : hi;
+        if (h) h[idx * HIST_STRIDE + bin] += 1;
+    }
+};
+
+extern "C" {
+
+const char* emu_last_error() { return g_err.c_str(); }
+
+int emu_model_load(const char* path, int overwrite, const int32_t* idx, int32_t n_idx, void** out) {
+    try {
+        *out = load_model_file(path, overwrite != 0, idx, idx ? n_idx : 0);
+        return 0;
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+}
+void emu_model_free(void* h) { delete static_cast<HostModel*>(h); }
+
+int emu_set_prior(void* h, int which, int kind, double value) {
+    HostModel& H = *static_cast<HostModel*>(h);
+    try {
+        (which ? H.prior_transition : H.prior_initial) = PriorSpec{kind, value};
+        H.pack();
+        return 0;
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+}
+
+static DevModel host_dev(const HostModel& H) {
+    DevModel D = H.dev;
+    D.thr_init = H.thr_initial.data();
+    D.thr_trans = H.thr_transition.data();
+    D.edges = H.edges.data();
+    return D;
+}
+
+int emu_sample_initial(void* h, uint64_t seed, uint64_t first, int64_t n, const emb_sample_opts* o, int8_t* bins,
+                       double* values, uint16_t* attempts) {
+    const HostModel& H = *static_cast<HostModel*>(h);
+    SampleParams P;
+    try {
+        fill_params(H, seed, first, n, 0, *o, P);
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+    const DevModel D = host_dev(H);
+    int status = 0;
+    for (int64_t s = 0; s < n; ++s) {
+        uint8_t x[MAXX];
+        double vals[MAXV];
+        int attempt = sample_initial(D, P, P.first_sample + (uint64_t)s, x, vals);
+        if (attempt < 0) {
+            status = 1;
+            attempt = P.max_attempts;
+        }
+        if (attempts) attempts[s] = (uint16_t)(attempt + 1);
+        for (int i = 0; i < D.n_initial; ++i) {
+            if (bins) bins[(int64_t)i * n + s] = (int8_t)(x[i] + 1);
+            if (values) values[(int64_t)i * n + s] = vals[i];
+        }
+    }
+    return status ? EMB_E_REJECT : 0;
+}
+
+int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t T, const emb_sample_opts* o,
+                      const emb_track_out* out) {
+    const HostModel& H = *static_cast<HostModel*>(h);
+    SampleParams P;
+    try {
+        fill_params(H, seed, first, n, T, *o, P);
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+    const DevModel D = host_dev(H);
+    int32_t status = 0;
+    TrackOut O{};
+    O.bins = out->bins;
+    O.values = out->values;
+    O.init_bins = out->init_bins;
+    O.init_values = out->init_values;
+    O.attempts = out->attempts;
+    O.hist_initial = out->hist_initial;
+    O.hist_transition = out->hist_transition;
+    O.status = &status;
+    HostHist hh{out->hist_initial, out->hist_transition};
+    for (int64_t s = 0; s < n; ++s) track_generic(D, P, O, s, hh);
+    return status ? EMB_E_REJECT : 0;
+}
+
+}  // extern "C"
