@@ -194,6 +194,7 @@ HostModel* load_model_file(const char* path, bool overwrite_zero_boundaries, con
             M->n_initial = (int32_t)M->labels_initial.size();
         } else if (name == "# G_initial") {
             parse_matrix(lines, row, M->n_initial, M->G_initial, "G_initial");
+            M->order_initial = topo_sort(M->G_initial, M->n_initial);  // em_read.m:74: bn_sort at parse time
         } else if (name == "# r_initial") {
             need(1);
             xs.clear();
@@ -213,6 +214,7 @@ HostModel* load_model_file(const char* path, bool overwrite_zero_boundaries, con
             M->has_transition = true;
         } else if (name == "# G_transition") {
             parse_matrix(lines, row, M->n_transition, M->G_transition, "G_transition");
+            M->order_transition = topo_sort(M->G_transition, M->n_transition);  // em_read.m:87
         } else if (name == "# r_transition") {
             need(1);
             xs.clear();

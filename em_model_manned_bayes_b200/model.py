@@ -347,3 +347,46 @@ class UncorEncounterModel(EncounterModel):
             d[tv0, :] = vals[k].astype(np.float64)
             out_samples.append(d)
         return out_inits, out_samples, res
+
+
+class CorTerminalModel(EncounterModel):
+    """@CorTerminalModel/CorTerminalModel.m + sample.m: the terminal encounter *geometry* model.
+    (The 20 trajectory DBN files are missing from the public checkout -- SURVEY.md F5.)"""
+
+    # @CorTerminalModel/getDynamicLimits.m:14-62 (minVel_ft_s, maxVel_ft_s)
+    DYN_LIMITS = {"GENERIC": (50.0, 506.0), "RTCA228_A1": (169.0, 491.0), "RTCA228_A2": (68.0, 338.0),
+                  "RTCA228_A3": (68.0, 186.0), "TEST": (68.0, 186.0)}
+
+    def __init__(self, parameters_filename: str, acType1: str = "GENERIC", acType2: str = "GENERIC"):
+        super().__init__(parameters_filename)
+        self.acType1, self.acType2 = acType1, acType2
+        self.bounds_sample = np.stack([np.full(self.n_initial, -np.inf), np.full(self.n_initial, np.inf)], axis=1)
+        self.idx_own_speed = _find(self.labels_initial, '"own_speed"')
+        self.idx_int_speed = _find(self.labels_initial, '"int_speed"')
+
+    def _terminal_opts(self, start=None, max_attempts=0):
+        o = self._opts(start=start, max_attempts=max_attempts)
+        o.reject_mode = L.EMB_REJECT_BOX
+        lo, hi = self.bounds_sample[:, 0].copy(), self.bounds_sample[:, 1].copy()
+        for idx, ac in ((self.idx_own_speed, self.acType1), (self.idx_int_speed, self.acType2)):   # sample.m:64-65
+            if idx:
+                vmin, vmax = self.DYN_LIMITS[ac.upper()]
+                lo[idx - 1], hi[idx - 1] = max(lo[idx - 1], vmin), min(hi[idx - 1], vmax)
+        for i in range(self.n_initial):
+            o.box_lo[i], o.box_hi[i] = lo[i], hi[i]
+        return o
+
+    def sample_raw(self, nSamples: int, seed: int = 0, first_sample: int = 0, device=None):
+        """-> (outInits (n, 15) float64, bins (n, 15) int8, attempts)."""
+        bins, vals, att = self.sample_initial(nSamples, seed=seed, first_sample=first_sample,
+                                              opts=self._terminal_opts(), device=device)
+        return vals, bins, att
+
+    def sample(self, nSamples: int, seed=float("nan")):
+        """@CorTerminalModel/sample.m:1-82 -> (outInits, outSamples list of dict(field -> value))."""
+        if isinstance(seed, float) and math.isnan(seed):
+            seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
+        out_inits, _, _ = self.sample_raw(nSamples, seed=int(seed))
+        names = [l.replace('"', "") for l in self.labels_initial]                                   # sample.m:59
+        out_samples = [dict(zip(names, row)) for row in out_inits]
+        return out_inits, out_samples

@@ -158,3 +158,31 @@ def terminal_sample(parms, n_samples, U, *, first_sample=0, prior=0, start=None,
         out_bins[ii] = bins
         attempts[ii] = attempt + 1
     return out_inits, out_bins, attempts
+
+
+def dbn_tracks(parms, n_samples, sample_time, U, *, first_sample=0, prior=0, start=None, strict_quirks=False):
+    """The sampling loop of em_sample.m:78-85 (dbn_hierarchical_sample + events2samples, no
+    rejection) for any model with a transition network, e.g. the correlated model cor_v1.txt.
+    `prior` follows bn_dirichlet_prior (number or 'dbe'); pass prior='stay' for the terminal
+    trajectory priors of createEncounter.m:128-129."""
+    if prior == "stay":
+        alpha_i = sp.bn_dirichlet_prior(parms.N_initial, 0)
+        alpha_t = sp.set_transition_priors(parms.G_transition, parms.r_transition, parms.temporal_map, 1)
+    else:
+        alpha_i = sp.bn_dirichlet_prior(parms.N_initial, prior)
+        alpha_t = sp.bn_dirichlet_prior(parms.N_transition, prior)
+    start = parms.start if start is None else start
+    U.bind(parms.n_initial, parms.temporal_map, parms.resample_rates)
+    out = []
+    for ii in range(n_samples):
+        U.begin(first_sample + ii, 0)
+        initial, events, prov, ibins, ebins = sp.dbn_hierarchical_sample(
+            parms, alpha_i, alpha_t, sample_time, parms.boundaries, parms.zero_bins, parms.resample_rates, start, U,
+            strict_quirks)
+        samples = sp.events2samples(initial, events)
+        bin_events = [[e[0], e[1], b] for e, b in zip(events, ebins)]
+        out.append(UncorSample(initial=np.array(initial), events=np.asarray(events, dtype=np.float64).reshape(-1, 3),
+                               samples=samples, controls=sp.events2controls(initial, events, parms.temporal_map),
+                               initial_bins=np.array(ibins), sample_bins=sp.events2samples(ibins, bin_events),
+                               event_bins=np.asarray(ebins, dtype=np.float64), prov=prov, attempts=1))
+    return out

@@ -1,0 +1,55 @@
+"""The C-ABI library loads and exports every symbol include/emb200.h declares (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from em_model_manned_bayes_b200 import _lib as L
+from helpers import ROOT
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "emb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(emb_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(L.EXPORTED) == names
+    assert lib.emb_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes computed from the header's field list (natural alignment)
+    assert C.sizeof(L.Rng) == 16
+    assert C.sizeof(L.TrackOut) == 7 * 8
+    assert C.sizeof(L.SampleOpts) == 24 * 4 + 4 * 4 + 2 * 24 * 8 + 4 + 4 + 8 * 2 * 8 + 4 * 3 + 4 + 8
+    assert C.sizeof(L.ModelInfo) % 8 == 0
+
+
+def test_rng_word_matches_oracle_stream():
+    from oracle import philox as px
+    lib = L.lib()
+    for (seed, sample, attempt, purpose, index, sub, lane) in [(1, 0, 0, 1, 0, 0, 0), (2 ** 63 + 5, 12345678901, 3, 2, 77, 0, 3),
+                                                             (42, 2 ** 40, 65535, 3, 599, 1, 2)]:
+        got = lib.emb_rng_word(seed, sample, attempt, purpose, index, sub, lane)
+        want = int(px.word(seed, sample, attempt, purpose, index, lane, sub=sub))
+        assert got == want
+
+
+def test_no_cpu_fallback_without_gpu(model_paths):
+    """Sampling must fail loudly (EMB_E_CUDA) when no device is present -- never silently compute on the CPU."""
+    lib = L.lib()
+    if lib.emb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from em_model_manned_bayes_b200.model import EncounterModel
+    m = EncounterModel(model_paths["balloon_v1"])
+    with pytest.raises(L.EmbError) as ei:
+        m.sample_initial(4, seed=1)
+    assert ei.value.code == L.EMB_E_CUDA

@@ -1,0 +1,97 @@
+"""CPU suite: the device sampling routines (emb_device.cuh), executed on the host by the TEST-ONLY
+emulation in tests/emu, against the oracle's golden vectors.  The GPU suite (test_gpu_parity.py) runs
+the same cases through libemb200.so on a B200."""
+import numpy as np
+import pytest
+
+import cases
+from em_model_manned_bayes_b200 import _lib as L
+from helpers import EmuModel
+from oracle.em_read import em_read
+
+
+def _run_tracks(model_paths, c):
+    path = model_paths[c["model"]]
+    ow = c.get("overwrite", ())
+    p = em_read(path, isOverwriteZeroBoundaries=bool(ow), idxZeroBoundaries=ow or (1, 2, 3))
+    em = EmuModel(path, idx_zero=ow, overwrite=bool(ow))
+    if c.get("prior") == "dbe":
+        em.set_prior(0, L.EMB_PRIOR_DBE, 0.0)
+        em.set_prior(1, L.EMB_PRIOR_DBE, 0.0)
+    kw = {}
+    if c["uncor"]:
+        lab = p.labels_initial
+        kw.update(reject_mode=L.EMB_REJECT_UNCOR, idx_v=cases.label_index(lab, '"v"'),
+                  idx_dh=cases.label_index(lab, '"\\dot h"'), idx_L=cases.label_index(lab, '"L"'))
+        if c.get("q500"):
+            kw["is_quantize500"] = 1
+        if c.get("layers") is not None:
+            kw["layers"] = c["layers"]
+    o = EmuModel.opts(p.n_initial, start=c.get("start"), **kw)
+    nd = p.temporal_map.shape[0]
+    ntv = len(set(p.temporal_map[:, 0]) | {i + 1 for i in range(p.n_initial) if p.resample_rates[i] > 0})
+    return em.sample_tracks(p.n_initial, nd, ntv, c["n"], c["T"], c["seed"], c.get("first", 0), o)
+
+
+@pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
+def test_tracks_match_golden(model_paths, golden, name):
+    got = _run_tracks(model_paths, cases.TRACK_CASES[name])
+    cases.check_tracks(got, golden[name])
+
+
+@pytest.mark.parametrize("name", sorted(cases.INITIAL_CASES))
+def test_initial_matches_golden(model_paths, golden, name):
+    c = cases.INITIAL_CASES[name]
+    p = em_read(model_paths[c["model"]])
+    em = EmuModel(model_paths[c["model"]])
+    bins, vals, att = em.sample_initial(p.n_initial, c["n"], c["seed"], c["first"], EmuModel.opts(p.n_initial))
+    assert np.array_equal(bins, golden[name]["bins"])
+    assert np.array_equal(vals, golden[name]["values"])
+    assert np.all(att == 1)
+
+
+@pytest.mark.parametrize("name", sorted(cases.TERMINAL_CASES))
+def test_terminal_geometry_matches_golden(model_paths, golden, name):
+    c = cases.TERMINAL_CASES[name]
+    p = em_read(model_paths[c["model"]])
+    em = EmuModel(model_paths[c["model"]])
+    lo, hi = [-np.inf] * p.n_initial, [np.inf] * p.n_initial
+    for lab in ('"own_speed"', '"int_speed"'):
+        i = p.labels_initial.index(lab)
+        lo[i], hi[i] = cases.GENERIC_VEL
+    o = EmuModel.opts(p.n_initial, start=c["start"], reject_mode=L.EMB_REJECT_BOX, box_lo=lo, box_hi=hi)
+    bins, vals, att = em.sample_initial(p.n_initial, c["n"], c["seed"], 0, o)
+    assert np.array_equal(bins, golden[name]["bins"])
+    assert np.array_equal(vals, golden[name]["values"])
+    assert np.array_equal(att.astype(np.int64), golden[name]["attempts"].astype(np.int64))
+
+
+def test_shard_invariance(model_paths):
+    """Results are keyed by the global sample index: [0,40) == [0,13) + [13,40)."""
+    c = dict(cases.TRACK_CASES["uncor_v2p1_n24_T300_seed1"], n=40, T=64)
+    whole = _run_tracks(model_paths, c)
+    a = _run_tracks(model_paths, dict(c, n=13))
+    b = _run_tracks(model_paths, dict(c, n=27, first=13))
+    for k in ("bins", "values", "init_bins", "init_values"):
+        assert np.array_equal(np.concatenate([a[k], b[k]]), whole[k]), k
+
+
+def test_histograms_count_every_column(model_paths):
+    path = model_paths["uncor_1200code_v2p1"]
+    p = em_read(path)
+    em = EmuModel(path)
+    o = EmuModel.opts(p.n_initial)
+    r = em.sample_tracks(p.n_initial, 3, 4, 50, 37, 9, 0, o, hist=True)
+    assert r["hist_initial"].sum(axis=1).tolist() == [50] * 7
+    assert r["hist_transition"].sum(axis=1).tolist() == [50 * 36] * 3
+    for d in range(3):
+        cnt = np.bincount(r["bins"][:, d, 1:].ravel() - 1, minlength=64)
+        assert np.array_equal(cnt, r["hist_transition"][d])
+
+
+def test_preset_dependent_variable_is_rejected(model_paths):
+    p = em_read(model_paths["uncor_1200code_v2p1"])
+    em = EmuModel(model_paths["uncor_1200code_v2p1"])
+    o = EmuModel.opts(p.n_initial, start=[None, 2, None, None, None, None, None])
+    with pytest.raises(L.EmbError, match="Attempt to preset a dependent variable"):
+        em.sample_initial(p.n_initial, 4, 1, 0, o)

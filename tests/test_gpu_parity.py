@@ -1,0 +1,190 @@
+"""GPU suite (`-m gpu`, run on the B200): libemb200.so through the C ABI against the oracle's golden
+vectors, against the oracle run live on small seeded inputs, and -- at BASELINE.json's full sizes --
+through size-independent properties (shard invariance, determinism, histogram == dense counts,
+chi-square of node marginals against the normalised count tables)."""
+import numpy as np
+import pytest
+
+import cases
+from em_model_manned_bayes_b200 import _lib as L
+from em_model_manned_bayes_b200.model import CorTerminalModel, EncounterModel, UncorEncounterModel
+from oracle.drivers import uncor_sample
+from oracle.em_read import em_read
+from oracle.uniforms import KeyedPhilox
+from helpers import oracle_dense
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(model_paths, c):
+    path = model_paths[c["model"]]
+    ow = c.get("overwrite", ())
+    cls = UncorEncounterModel if c["uncor"] else EncounterModel
+    m = cls(path, idxZeroBoundaries=ow or (1, 2, 3), isOverwriteZeroBoundaries=bool(ow))
+    if c.get("prior") is not None:
+        m.prior = c["prior"]
+    return m
+
+
+def _run_tracks(model_paths, c, device=None):
+    m = _model(model_paths, c)
+    if c["uncor"]:
+        o = m.uncor_opts(isQuantize500=c.get("q500", False), layers=c.get("layers"), start=c.get("start"))
+    else:
+        o = m._opts(start=c.get("start"))
+    res = m.sample_tracks(c["n"], c["T"], seed=c["seed"], first_sample=c.get("first", 0), opts=o, device=device)
+    cpu = (lambda a: a.cpu().numpy()) if device is not None else (lambda a: a)
+    return dict(bins=cpu(res.bins), values=cpu(res.values), init_bins=cpu(res.init_bins).T,
+                init_values=cpu(res.init_values).T, attempts=cpu(res.attempts))
+
+
+@pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
+def test_tracks_match_golden(model_paths, golden, name):
+    cases.check_tracks(_run_tracks(model_paths, cases.TRACK_CASES[name]), golden[name])
+
+
+def test_tracks_device_buffers_match_host_buffers(model_paths, golden):
+    name = "uncor_v2p1_n24_T300_seed1"
+    got = _run_tracks(model_paths, cases.TRACK_CASES[name], device="cuda:0")
+    cases.check_tracks(got, golden[name])
+
+
+@pytest.mark.parametrize("name", sorted(cases.INITIAL_CASES))
+def test_initial_matches_golden(model_paths, golden, name):
+    c = cases.INITIAL_CASES[name]
+    m = EncounterModel(model_paths[c["model"]])
+    bins, vals, att = m.sample_initial(c["n"], seed=c["seed"], first_sample=c["first"])
+    assert np.array_equal(bins, golden[name]["bins"])
+    assert np.array_equal(vals, golden[name]["values"])
+    assert np.all(att == 1)
+
+
+@pytest.mark.parametrize("name", sorted(cases.TERMINAL_CASES))
+def test_terminal_geometry_matches_golden(model_paths, golden, name):
+    c = cases.TERMINAL_CASES[name]
+    m = CorTerminalModel(model_paths[c["model"]])
+    if c["start"] is not None:
+        m.start = c["start"]
+    out_inits, bins, att = m.sample_raw(c["n"], seed=c["seed"])
+    assert np.array_equal(bins, golden[name]["bins"])
+    assert np.array_equal(out_inits, golden[name]["values"])
+    assert np.array_equal(att.astype(np.int64), golden[name]["attempts"].astype(np.int64))
+
+
+@pytest.mark.parametrize("model,n,T,seed", [("uncor_1200code_v2p1", 40, 97, 21), ("glider_v1", 33, 61, 22)])
+def test_tracks_match_live_oracle(model_paths, model, n, T, seed):
+    """Fresh seeds (not in the golden file): oracle computed here, on the box's CPU."""
+    p = em_read(model_paths[model])
+    bins, vals, dyn, tv = oracle_dense(p, uncor_sample(p, n, T, KeyedPhilox(seed), first_sample=5))
+    m = UncorEncounterModel(model_paths[model])
+    res = m.sample_compact(n, T, seed=seed, first_sample=5)
+    assert res.dyn_vars == dyn and res.tv_vars == tv
+    assert np.array_equal(res.bins, bins)
+    assert np.all(np.abs(res.values.astype(np.float64) - vals) <= 1e-6 * np.abs(vals))
+
+
+def test_shard_invariance_and_determinism(model_paths):
+    """Global-index keying: any split of [0, n) gives identical results, twice."""
+    m = UncorEncounterModel(model_paths["uncor_allcode_fwsingle_v1"])
+    n, T = 5000, 600
+    whole = m.sample_compact(n, T, seed=7)
+    again = m.sample_compact(n, T, seed=7)
+    assert np.array_equal(whole.bins_tiled, again.bins_tiled) and np.array_equal(whole.values_tiled, again.values_tiled)
+    parts = [m.sample_compact(k, T, seed=7, first_sample=f) for f, k in ((0, 1250), (1250, 1250), (2500, 2499), (4999, 1))]
+    assert np.array_equal(np.concatenate([p.bins for p in parts]), whole.bins)
+    assert np.array_equal(np.concatenate([p.values for p in parts]), whole.values)
+    assert np.array_equal(np.concatenate([p.init_values for p in parts], axis=1), whole.init_values)
+    other = m.sample_compact(64, T, seed=8)
+    assert not np.array_equal(other.bins, whole.bins[:64])
+
+
+def test_ragged_and_tiny_sizes(model_paths):
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    ref = m.sample_compact(131, 49, seed=3)
+    for n, T in [(1, 1), (1, 2), (3, 15), (3, 16), (3, 17), (129, 49)]:
+        r = m.sample_compact(n, T, seed=3)
+        assert r.bins.shape == (n, 3, T) and r.values.shape == (n, 4, T)
+        assert np.array_equal(r.bins, ref.bins[:n, :, :T])          # prefix property in n and T
+        assert np.array_equal(r.values, ref.values[:n, :, :T])
+    z = m.sample_compact(0, 10, seed=3)
+    assert z.bins.shape[0] == 0
+
+
+def test_full_size_properties_config3(model_paths):
+    """uncor_allcode_fwsingle_v1, T = 600 at a large sample count, outputs resident in HBM: histograms ==
+    dense counts, initial-node marginals pass a chi-square test against the normalised count tables."""
+    import torch
+    m = UncorEncounterModel(model_paths["uncor_allcode_fwsingle_v1"])
+    n, T = 200_000, 600
+    hi = torch.zeros((m.n_initial, 64), dtype=torch.int64, device="cuda:0")
+    ht = torch.zeros((m.n_dyn, 64), dtype=torch.int64, device="cuda:0")
+    res = m.sample_compact(n, T, seed=11, device="cuda:0", hist_initial=hi, hist_transition=ht)
+    torch.cuda.synchronize()
+    bins = res.bins
+    assert int(bins.min()) >= 1
+    for d in range(m.n_dyn):
+        cnt = torch.bincount(bins[:, d, 1:].reshape(-1).to(torch.int64) - 1, minlength=64)
+        assert torch.equal(cnt, ht[d])
+    assert hi.sum(dim=1).tolist() == [n] * m.n_initial
+    # root variable G: exact marginal from the table
+    N = m.N_initial
+    pG = N[0][:, 0] / N[0][:, 0].sum()
+    obs = hi[0, : len(pG)].cpu().numpy().astype(np.float64)
+    # rejection (v*1.68781 > |dh|/60) removes a negligible fraction; chi-square with generous bound
+    chi2 = ((obs - n * pG) ** 2 / np.maximum(n * pG, 1e-9)).sum()
+    assert chi2 < 40.0, chi2
+    # transition bins must stay inside [1, r]
+    for d, v in enumerate(res.dyn_vars):
+        assert int(bins[:, d, :].max()) <= int(m.r_initial[v - 1])
+    vals = res.values
+    assert bool(torch.isfinite(vals).all())
+
+
+def test_initial_full_size_chi_square_config2(model_paths):
+    """glider_v1 initial network, 4M samples on the device: every node marginal against exact enumeration."""
+    import torch
+    m = EncounterModel(model_paths["glider_v1"])
+    n = 4_000_000
+    bins, vals, _ = m.sample_initial(n, seed=5, device="cuda:0", want_attempts=False)
+    torch.cuda.synchronize()
+    # exact joint by enumeration of the 5-node network (4*8*5*7*7 = 7840 states)
+    N, G, r = m.N_initial, m.G_initial, m.r_initial
+    dims = [int(x) for x in r]
+    grids = np.indices(dims)
+    joint = np.ones(dims)
+    for i0 in range(len(dims)):
+        par = np.nonzero(G[:, i0])[0]
+        j = np.zeros(dims, dtype=np.int64)
+        stride = 1
+        for p_ in par:                                   # asub2ind.m:13 strides
+            j += stride * grids[p_]
+            stride *= dims[p_]
+        tab = N[i0] / np.maximum(N[i0].sum(axis=0, keepdims=True), 1e-300)
+        joint = joint * tab[grids[i0], j]
+    assert abs(joint.sum() - 1.0) < 1e-9
+    for i in range(len(r)):
+        marg = joint.sum(axis=tuple(k for k in range(len(r)) if k != i))
+        obs = torch.bincount(bins[:, i].to(torch.int64) - 1, minlength=int(r[i])).cpu().numpy().astype(np.float64)
+        keep = marg > 0
+        assert obs[~keep].sum() == 0
+        chi2 = ((obs[keep] - n * marg[keep]) ** 2 / (n * marg[keep])).sum()
+        assert chi2 < 50.0, (i, chi2)
+
+
+def test_errors_through_the_abi(model_paths):
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    with pytest.raises(L.EmbError, match="Attempt to preset a dependent variable"):
+        m.sample_tracks(4, 10, seed=1, start=[None, 2, None, None, None, None, None])
+    b = UncorEncounterModel(model_paths["balloon_v1"])
+    with pytest.raises(L.EmbError, match="dynvar:empty"):
+        b.sample_compact(4, 10, seed=1)
+    t = EncounterModel(model_paths["terminal_v3_radar_encounter_model"])
+    with pytest.raises(L.EmbError, match="dynvar:empty"):
+        t.sample_tracks(4, 10, seed=1)
+
+
+def test_kernels_actually_launched(model_paths):
+    lib = L.lib()
+    before = lib.emb_launch_count()
+    UncorEncounterModel(model_paths["uncor_1200code_v2p1"]).sample_compact(8, 8, seed=1)
+    assert lib.emb_launch_count() == before + 1

@@ -1,0 +1,53 @@
+"""Scratch timing helper for gpurun sessions (not the bench contract; see bench.py)."""
+import os
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from em_model_manned_bayes_b200.model import EncounterModel, UncorEncounterModel  # noqa: E402
+from em_model_manned_bayes_b200.model_archive import materialize  # noqa: E402
+
+paths = materialize(tempfile.mkdtemp(prefix="emb_models_"))
+dev = "cuda:0"
+
+
+def time_tracks(name, n, T, reps=3):
+    m = UncorEncounterModel(paths[name])
+    res = m.sample_compact(n, T, seed=1, device=dev, want_init=False)
+    torch.cuda.synchronize()
+    best = 1e9
+    for r in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.sample_compact(n, T, seed=2 + r, device=dev, out=res)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print("%s n=%d T=%d: %.3f ms  %.3e track-timesteps/s" % (name, n, T, best, n * T / best * 1e3), flush=True)
+
+
+def time_initial(name, n, reps=3):
+    m = EncounterModel(paths[name])
+    m.sample_initial(n, seed=1, device=dev, want_attempts=False)
+    torch.cuda.synchronize()
+    best = 1e9
+    for r in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.sample_initial(n, seed=2 + r, device=dev, want_attempts=False)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print("%s initial n=%d: %.3f ms  %.3e samples/s" % (name, n, best, n / best * 1e3), flush=True)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    time_tracks("uncor_1200code_v2p1", 1 << 20, 300)
+    time_tracks("uncor_allcode_fwsingle_v1", 1 << 20, 600)
+    time_tracks("glider_v1", 1 << 20, 300)
+    time_initial("glider_v1", 1 << 24)
