@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2] per-GPU shard -- UncorEncounterModel.sample on
+`uncor_allcode_fwsingle_v1.txt`, 1.25e6 tracks x 600 s per GPU (10M tracks over 8 GPUs; weak scaling).
+A "step" is one pass of the hot path (emb_sample_tracks: initial network, 599 transition steps, 600
+resample gates, de-discretisation, dense compact outputs) over one batch of 1.25e6 tracks.
+  value : track-timesteps/s over all ranks, outputs resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the C ABI with pinned HOST output buffers, D2H inside the timed region
+  roofline / cpu_baseline : see the task statement; cpu_baseline = oracle/oracle_c.c ("port") on host cores
+The model tables (about 1 MB) are read-only inputs that legitimately live in L2; every step writes a
+fresh 14.5 GB of outputs (>> 126 MB L2) with a new seed, so no step can reuse another's cache lines.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MODEL = "uncor_allcode_fwsingle_v1"
+TRACKS_PER_GPU = 1_250_000
+T = 600
+# bytes(track) = T*n_dyn*(1+4) + n_initial*(1+4) + 4*(sum r_initial + sum r_dyn)
+ALGO_BYTES_PER_TRACK = T * 3 * 5 + 7 * 5 + 4 * (39 + 19)
+ALGO_BYTES_PER_UNIT = ALGO_BYTES_PER_TRACK / T          # 15.445 B per track-timestep at T = 600
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def materialise_model():
+    from em_model_manned_bayes_b200.model_archive import materialize
+    d = os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid())
+    return materialize(d, names=[MODEL])[MODEL]
+
+
+def cpu_port(path, n_tracks, threads):
+    """Time oracle/oracle_c.c on `threads` host threads over n_tracks x T; returns track-timesteps/s."""
+    import ctypes as C
+    from oracle.c_oracle import COracle, lib
+    from oracle.em_read import em_read
+    co = COracle(em_read(path), uncor=True)
+    import numpy as np
+    ib = np.zeros((n_tracks, 7), dtype=np.int8)
+    lib().oc_sample_tracks(C.byref(co.m), 1, 0, min(n_tracks, 256), T, threads, ib.ctypes.data, None, None, None, None, None)
+    t0 = time.perf_counter()
+    rc = lib().oc_sample_tracks(C.byref(co.m), 1, 0, n_tracks, T, threads, ib.ctypes.data, None, None, None, None, None)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return n_tracks * T / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (the oracle's C port -- the
+    reference itself is MATLAB and cannot run here) on all host threads, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.c_oracle import lib
+    threads = lib().oc_num_threads()
+    path = materialise_model()
+    per_thread = 30000
+    n = per_thread * threads
+    cpu_port(path, min(n, 512), threads)
+    vals, t_all = [], 0.0
+    for _ in range(args.warmup):
+        cpu_port(path, max(256, n // 8), threads)
+    for _ in range(args.steps):
+        v, dt = cpu_port(path, n, threads)
+        vals.append(v)
+        t_all += dt
+    value = n * T * args.steps / t_all
+    sample = "%d tracks x %d s per step (%d per thread), oracle/oracle_c.c, OpenMP" % (n, T, per_thread)
+    print(json.dumps({
+        "impl": "reference", "metric": "sampled track-timesteps/sec", "value": value, "unit": "track-timesteps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "UncorEncounterModel.sample, %s, %d tracks x %d s per GPU (bounded CPU sample: %s)"
+                   % (MODEL, TRACKS_PER_GPU, T, sample)},
+        "cpu_baseline": {"value": value, "unit": "track-timesteps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--tracks", type=int, default=TRACKS_PER_GPU, help="tracks per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from em_model_manned_bayes_b200 import _lib as L
+    from em_model_manned_bayes_b200.model import UncorEncounterModel
+    from em_model_manned_bayes_b200.shard import allreduce_histograms
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    n = args.tracks
+    lib = L.lib()
+    path = materialise_model()
+    m = UncorEncounterModel(path)
+    hi = torch.zeros((m.n_initial, 64), dtype=torch.int64, device=dev)
+    ht = torch.zeros((m.n_dyn, 64), dtype=torch.int64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    res = m.sample_compact(n, T, seed=1, first_sample=rank * n, device=dev)           # allocates outputs once
+    for w in range(args.warmup):
+        m.sample_compact(n, T, seed=100 + w, first_sample=rank * n, device=dev, out=res)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.emb_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        last = k == args.steps - 1
+        m.sample_compact(n, T, seed=1000 + k, first_sample=rank * n, device=dev, out=res,
+                         hist_initial=hi if last else None, hist_transition=ht if last else None)
+        ev[k + 1].record()
+    allreduce_histograms(hi, ht)          # the single collective of the job (verification only)
+    barrier()
+    launches = lib.emb_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    units_per_step = world * n * T
+    value = units_per_step * args.steps / (total_ms * 1e-3)
+    assert int(hi.sum().item()) == world * n * m.n_initial, "verification histogram lost samples"
+    assert int(ht.sum().item()) == world * n * (T - 1) * m.n_dyn
+
+    # ---- end-to-end arm: C ABI with pinned host buffers, D2H inside the timed region --------------
+    nb = int(lib.emb_tracks_bins_len(m._h, n, T))
+    nv = int(lib.emb_tracks_values_len(m._h, n, T))
+    h_bins = torch.empty(nb, dtype=torch.int8).pin_memory()
+    h_vals = torch.empty(nv, dtype=torch.float32).pin_memory()
+    h_iv = torch.empty((m.n_initial, n), dtype=torch.float64).pin_memory()
+    from em_model_manned_bayes_b200.model import TrackResult
+    host_out = TrackResult(n=n, T=T, dyn_vars=res.dyn_vars, tv_vars=res.tv_vars, bins_tiled=h_bins, values_tiled=h_vals,
+                           init_bins=None, init_values=h_iv, attempts=None)
+    del res
+    torch.cuda.empty_cache()
+    o = m.uncor_opts()
+    o.mem, o.device = L.EMB_MEM_HOST, local
+    m.sample_tracks(n, T, seed=5, first_sample=rank * n, opts=o, out=host_out)      # warm-up (allocations, page faults)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        m.sample_tracks(n, T, seed=2000 + k, first_sample=rank * n, opts=o, out=host_out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * args.e2e_steps / float(t.item())
+    d2h = nb + nv * 4 + h_iv.numel() * 8 + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    k_ms = statistics.mean(kern_ms)
+    achieved = ALGO_BYTES_PER_UNIT * n * T / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("bytes_per_unit") * n * T
+        except Exception:
+            traffic = None
+    out = {
+        "metric": "sampled track-timesteps/sec", "value": value, "unit": "track-timesteps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "UncorEncounterModel.sample (BASELINE configs[2] per-GPU shard): %s, %d tracks x %d s per GPU, "
+                               "start all-free, prior 0, dense compact outputs (int8 bins of 3 dynamic variables + fp32 "
+                               "values of 4 time-varying variables)" % (MODEL, n, T),
+                   "cache": "each step writes %.1f GB of fresh outputs (>> L2); the 1 MB model tables are the only re-read input"
+                            % ((nb + nv * 4) / 1e9),
+                   "sharding": "global sample index, rank r owns [r*n, (r+1)*n); one NCCL all-reduce of verification histograms"},
+        "e2e": {"value": e2e_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400, "d2h_bytes_per_step": d2h,
+                "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": ALGO_BYTES_PER_UNIT,
+                     "written_bytes_per_unit": (nb + nv * 4) / (n * T), "kernel_ms": k_ms},
+        "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu:
+        from oracle.c_oracle import lib as olib
+        threads = olib().oc_num_threads()
+        ntr = 80000 * threads
+        v, dt = cpu_port(path, ntr, threads)
+        out["cpu_baseline"] = {"value": v, "unit": "track-timesteps/s", "cores": threads, "kind": "port",
+                               "sample": "%d tracks x %d s, oracle/oracle_c.c (plain-C restatement of the MATLAB path), OpenMP, %.1f s"
+                                         % (ntr, T, dt)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,14 +66,20 @@ static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t 
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
-typedef struct { uint64_t seed, sample; uint32_t attempt; int nd, nw, n_initial; } ukey;
-static uint32_t word(const ukey* k, uint32_t purpose, uint32_t index, uint32_t sub, uint32_t lane) {
-    uint32_t o[4];
-    philox((uint32_t)k->sample, (uint32_t)(k->sample >> 32), index, (k->attempt << 16) | (purpose << 8) | sub,
-           (uint32_t)k->seed, (uint32_t)(k->seed >> 32), o);
-    return o[lane];
+/* one cached block per purpose so that the port does not pay 4x for its uniforms (the reference's
+ * MT19937 draw is cheap; the CPU baseline should not be inflated by the keyed generator) */
+typedef struct { uint64_t seed, sample; uint32_t attempt; int nd, nw, n_initial;
+                 uint32_t c_idx[8], c_w3[8], c_o[8][4]; int c_ok[8]; } ukey;
+static uint32_t word(ukey* k, uint32_t purpose, uint32_t index, uint32_t sub, uint32_t lane) {
+    const uint32_t w3 = (k->attempt << 16) | (purpose << 8) | sub;
+    const int q = (int)(purpose & 7);
+    if (!k->c_ok[q] || k->c_idx[q] != index || k->c_w3[q] != w3) {
+        philox((uint32_t)k->sample, (uint32_t)(k->sample >> 32), index, w3, (uint32_t)k->seed, (uint32_t)(k->seed >> 32), k->c_o[q]);
+        k->c_idx[q] = index; k->c_w3[q] = w3; k->c_ok[q] = 1;
+    }
+    return k->c_o[q][lane];
 }
-static uint32_t word_at(const ukey* k, uint32_t purpose, uint64_t p) { return word(k, purpose, (uint32_t)(p >> 2), 0, (uint32_t)(p & 3)); }
+static uint32_t word_at(ukey* k, uint32_t purpose, uint64_t p) { return word(k, purpose, (uint32_t)(p >> 2), 0, (uint32_t)(p & 3)); }
 static double u01(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
 
 /* ---- select_random.m:17-20 --------------------------------------------------------------------- */
@@ -117,7 +123,12 @@ static double dediscretize(const oc_model* M, int var, double d, double rnd) {
 static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, event* ev, event* ev2,
                       double* init_bins, double* initial, double* dense_vals, double* dense_bins, int* n_events_out) {
     const int n = M->n_initial, nt = M->n_transition, nd = M->n_dyn;
-    ukey K = {seed, sample, 0, nd, nd + M->n_gated, n};
+    ukey K;
+    memset(&K, 0, sizeof(K));
+    K.seed = seed; K.sample = sample; K.nd = nd; K.nw = nd + M->n_gated; K.n_initial = n;
+    int gate_of_var[MAXV + 1];
+    for (int i = 0; i <= n; ++i) gate_of_var[i] = -1;
+    for (int g = 0; g < M->n_gated; ++g) gate_of_var[M->gated[g]] = g;
     for (int attempt = 0; attempt <= M->max_attempts; ++attempt) {
         K.attempt = (uint32_t)attempt;
         double x[MAXV + 8];
@@ -199,8 +210,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                     delta_t += 1;
                     for (int i = 1; i <= n; ++i) { /* changes = find(rand(size(rates)) < rates) */
                         double u = 0.5;
-                        for (int g = 0; g < M->n_gated; ++g)
-                            if (M->gated[g] == i) u = u01(word_at(&K, 2, (uint64_t)(second - 1) * K.nw + nd + g));
+                        if (gate_of_var[i] >= 0) u = u01(word_at(&K, 2, (uint64_t)(second - 1) * K.nw + nd + gate_of_var[i]));
                         if (u < M->rates[i - 1]) {
                             ev2[n2].dt = first ? delta_t : 0; ev2[n2].var = i; ev2[n2].val = xr[i - 1];
                             ev2[n2].kind = 1; ev2[n2].second = second; ++n2;
@@ -346,7 +356,9 @@ int oc_sample_initial(const oc_model* M, uint64_t seed, uint64_t first_sample, i
 #endif
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t s = 0; s < n; ++s) {
-        ukey K = {seed, first_sample + (uint64_t)s, 0, 0, 0, ni};
+        ukey K;
+        memset(&K, 0, sizeof(K));
+        K.seed = seed; K.sample = first_sample + (uint64_t)s; K.n_initial = ni;
         double x[MAXV], v[MAXV];
         int a;
         for (a = 0; a <= M->max_attempts; ++a) {
