@@ -91,6 +91,8 @@ def lib():
         "emb_abi_version": (C.c_int, []),
         "emb_last_error": (C.c_char_p, []),
         "emb_launch_count": (i64, []),
+        "emb_debug_force_generic": (None, [C.c_int]),
+        "emb_debug_last_kernel_fast": (C.c_int, []),
         "emb_device_count": (C.c_int, []),
         "emb_host_alloc": (C.c_int, [P(vp), i64]),
         "emb_host_free": (C.c_int, [vp]),
@@ -120,7 +122,7 @@ def lib():
 
 
 EXPORTED = [
-    "emb_abi_version", "emb_last_error", "emb_launch_count", "emb_device_count", "emb_host_alloc", "emb_host_free",
+    "emb_abi_version", "emb_last_error", "emb_launch_count", "emb_debug_force_generic", "emb_debug_last_kernel_fast", "emb_device_count", "emb_host_alloc", "emb_host_free",
     "emb_rng_word", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",

@@ -141,6 +141,8 @@ extern "C" {
 int emb_abi_version(void) { return EMB_ABI_VERSION; }
 const char* emb_last_error(void) { return g_err.c_str(); }
 int64_t emb_launch_count(void) { return emb::g_launch_count.load(); }
+void emb_debug_force_generic(int on) { emb::g_force_generic = on; }
+int emb_debug_last_kernel_fast(void) { return emb::g_last_kernel_fast; }
 
 int emb_device_count(void) {
     int c = 0;

@@ -311,7 +311,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     const int Tpad = nch16 * 16;
     for (int c = 0; c < Tpad; ++c) {          // column c = state during second c+1; step e = c
         if (c > 0 && c < T) {
-            const uint32_t base = (uint32_t)(c - 1) * (uint32_t)nw;
+            const uint32_t base = (uint32_t)c * (uint32_t)nw;   // stream spec v1: p = e*nw + slot
             uint32_t wstep[MAXD + MAXG];
             for (int q = 0; q < nw; ++q) wstep[q] = ws.at(base + (uint32_t)q);
             // resample gates on the pre-transition bins (resample_events.m:23-29)

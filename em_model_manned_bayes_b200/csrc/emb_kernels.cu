@@ -8,11 +8,14 @@
 #include <atomic>
 
 #include "emb_device.cuh"
+#include "emb_fast.cuh"
 #include "emb_launch.h"
 
 namespace emb {
 
 std::atomic<long long> g_launch_count{0};
+int g_force_generic = 0;      // emb_debug_force_generic(): tests compare both kernels
+int g_last_kernel_fast = 0;
 
 namespace {
 
@@ -79,6 +82,23 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
     if (want_hist) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
+// ---- tracks, register-resident specialisation (emb_fast.cuh) --------------------------------------
+template <uint32_t RS, int NG, bool FAST>
+__global__ void __launch_bounds__(BLOCK)
+k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
+              const __grid_constant__ TrackOut O) {
+    __shared__ FastShared S;
+    __shared__ uint32_t sh[(MAXV + MAXD) * HIST_STRIDE];
+    const bool want_hist = O.hist_initial || O.hist_transition;
+    fast_fill_shared(M, S, threadIdx.x, blockDim.x);
+    if (want_hist)
+        for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n) track_fast<RS, NG, FAST>(M, P, O, s, S, SmemHist{sh});
+    if (want_hist) flush_hist(sh, M, O.hist_initial, O.hist_transition);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -94,7 +114,18 @@ int launch_initial(const DevModel& M, const SampleParams& P, int8_t* bins, doubl
 int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream) {
     if (P.n <= 0) return 0;
     const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
-    k_tracks_generic<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);
+    const uint32_t rs = g_force_generic ? 0u : fast_shape_of(M);
+    const bool fast = M.fast != 0;
+    bool done = false;
+#define EMB_X(RS_, NG_, FAST_)                                                             \
+    if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_)) {                   \
+        k_tracks_fast<RS_, NG_, FAST_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
+        done = true;                                                                       \
+    }
+    EMB_FAST_SHAPES(EMB_X)
+#undef EMB_X
+    if (!done) k_tracks_generic<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);
+    g_last_kernel_fast = done ? 1 : 0;
     g_launch_count.fetch_add(1);
     return (int)cudaGetLastError();
 }

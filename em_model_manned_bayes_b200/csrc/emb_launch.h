@@ -8,6 +8,8 @@
 namespace emb {
 
 extern std::atomic<long long> g_launch_count;
+extern int g_force_generic;
+extern int g_last_kernel_fast;
 
 // all return a cudaError_t value (0 = success); pointers are device pointers
 int launch_initial(const DevModel& M, const SampleParams& P, int8_t* bins, double* values, uint16_t* attempts,

@@ -166,6 +166,10 @@ const char* emb_last_error(void);
 int emb_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t emb_launch_count(void);
+/* test hooks: force the generic kernel (1) so the specialised and generic kernels can be compared;
+ * whether the last emb_sample_tracks ran a specialised (1) or the generic (0) kernel */
+void emb_debug_force_generic(int on);
+int emb_debug_last_kernel_fast(void);
 
 #ifdef __cplusplus
 }

@@ -170,14 +170,14 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                         for (int d = 0; d < nd; ++d) if (M->temporal_map[2 * d + 1] == i) {
                             int64_t j = parent_index(M->G_transition, nt, i - 1, M->r, x);
                             const double* w = M->W_transition + M->off_transition[i - 1] + (j - 1) * M->r[i - 1];
-                            double rnd = u01(word_at(&K, 2, (uint64_t)(t - 2) * K.nw + d));
+                            double rnd = u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + d));
                             x[i - 1] = (double)select_random(w, M->r[i - 1], rnd);
                         }
                     }
                 } else { /* :143-146 */
                     for (int d = 0; d < nd; ++d) {
                         int ii = M->temporal_map[2 * d + 1];
-                        volatile double sthres = s[d][rdyn[d] - 1] * u01(word_at(&K, 2, (uint64_t)(t - 2) * K.nw + d));
+                        volatile double sthres = s[d][rdyn[d] - 1] * u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + d));
                         int m = 0;
                         while (!(s[d][m] >= sthres)) ++m;
                         x[ii - 1] = (double)(m + 1);
@@ -210,7 +210,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                     delta_t += 1;
                     for (int i = 1; i <= n; ++i) { /* changes = find(rand(size(rates)) < rates) */
                         double u = 0.5;
-                        if (gate_of_var[i] >= 0) u = u01(word_at(&K, 2, (uint64_t)(second - 1) * K.nw + nd + gate_of_var[i]));
+                        if (gate_of_var[i] >= 0) u = u01(word_at(&K, 2, (uint64_t)second * K.nw + nd + gate_of_var[i]));
                         if (u < M->rates[i - 1]) {
                             ev2[n2].dt = first ? delta_t : 0; ev2[n2].var = i; ev2[n2].val = xr[i - 1];
                             ev2[n2].kind = 1; ev2[n2].second = second; ++n2;
@@ -236,7 +236,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                 if (ev2[e].kind == 1) {
                     int g = 0;
                     while (M->gated[g] != var) ++g;
-                    uint32_t k = word_at(&K, 2, (uint64_t)(ev2[e].second - 1) * K.nw + nd + g);
+                    uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + nd + g);
                     rnd = ((double)k + 0.5) * (1.0 / (double)M->gate_G[g]);
                 } else {
                     int d = 0;

@@ -19,7 +19,8 @@ A call returns four 32-bit words; `lane` picks one.
 purpose INIT (1):    word position p;  p = i            -> select word of initial variable i (0-based)
                                       p = n_initial + i -> dediscretize word of initial variable i
                      index = p // 4, lane = p % 4
-purpose STEP (2):    word position p = (e - 1) * nw + slot, e = 1..T the event second,
+purpose STEP (2):    word position p = e * nw + slot, e = 1..T the event second (the nw positions
+                     of e = 0 are unused, which keeps groups of four seconds aligned to nw blocks),
                      nw = n_dyn + n_gated; slot d (< n_dyn) -> transition select of the d-th
                      dynamic variable (temporal_map row d) for loop index t = e + 1;
                      slot n_dyn + g -> resample gate of the g-th variable with rate > 0 at

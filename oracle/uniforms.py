@@ -76,7 +76,7 @@ class KeyedPhilox(_Base):
     def _sel_word(self, t, var_t1):
         d = self.dyn_vars_t1.index(int(var_t1))
         e = t - 1
-        return self._w(px.P_STEP, (e - 1) * self.nw + d)
+        return self._w(px.P_STEP, e * self.nw + d)
 
     def select_trans(self, t, var_t1):               # dbn_sample.m:77 (slow branch)
         return self._rec(("trans_sel", t, var_t1), px.u01(self._sel_word(t, var_t1)))
@@ -91,7 +91,7 @@ class KeyedPhilox(_Base):
     def gates(self, second):                         # resample_events.m:24  rand(size(rates))
         u = np.full(self.n_initial, 0.5)
         for g, v in enumerate(self.gated):
-            u[v - 1] = px.u01(self._w(px.P_STEP, (second - 1) * self.nw + self.nd + g))
+            u[v - 1] = px.u01(self._w(px.P_STEP, second * self.nw + self.nd + g))
         if self.record:
             for v in range(1, self.n_initial + 1):
                 self.tape.append((("gate", second, v), float(u[v - 1])))
@@ -100,7 +100,7 @@ class KeyedPhilox(_Base):
     def dedisc_event(self, kind, second, var):       # dbn_hierarchical_sample.m:35
         if kind == "gate":       # residual of the gate word (see philox.py)
             g = self.gated.index(int(var))
-            k = self._w(px.P_STEP, (second - 1) * self.nw + self.nd + g)
+            k = self._w(px.P_STEP, second * self.nw + self.nd + g)
             G = self.G[int(var)]
             assert k < G
             u = (float(k) + 0.5) * (1.0 / float(G))

@@ -10,12 +10,14 @@
 #include <string>
 #include <vector>
 
+#include "../../em_model_manned_bayes_b200/csrc/emb_fast.cuh"
 #include "../../em_model_manned_bayes_b200/csrc/emb_model.h"
 #include "../../include/emb200.h"
 
 using namespace emb;
 
 static thread_local std::string g_err;
+static int g_use_fast = 0, g_last_fast = 0;
 
 struct HostHist {
     unsigned long long* hi;
@@ -29,6 +31,8 @@ struct HostHist {
 extern "C" {
 
 const char* emu_last_error() { return g_err.c_str(); }
+void emu_use_fast(int on) { g_use_fast = on; }
+int emu_last_fast() { return g_last_fast; }
 
 int emu_model_load(const char* path, int overwrite, const int32_t* idx, int32_t n_idx, void** out) {
     try {
@@ -112,7 +116,23 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
     O.hist_transition = out->hist_transition;
     O.status = &status;
     HostHist hh{out->hist_initial, out->hist_transition};
-    for (int64_t s = 0; s < n; ++s) track_generic(D, P, O, s, hh);
+    bool done = false;
+    if (g_use_fast) {
+        const uint32_t rs = fast_shape_of(D);
+        const bool fast = D.fast != 0;
+        static FastShared S;
+        fast_fill_shared(D, S, 0, 1);
+#define EMB_X(RS_, NG_, FAST_)                                                         \
+    if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_)) {               \
+        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_>(D, P, O, s, S, hh); \
+        done = true;                                                                   \
+    }
+        EMB_FAST_SHAPES(EMB_X)
+#undef EMB_X
+    }
+    g_last_fast = done ? 1 : 0;
+    if (!done)
+        for (int64_t s = 0; s < n; ++s) track_generic(D, P, O, s, hh);
     return status ? EMB_E_REJECT : 0;
 }
 

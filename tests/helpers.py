@@ -49,7 +49,7 @@ def emu_lib():
     here = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(here, "libemb_emu.so")
     srcs = [os.path.join(here, "emu.cpp"), os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", "emb_model.cpp")]
-    deps = srcs + [os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", f) for f in ("emb_device.cuh", "emb_model.h")]
+    deps = srcs + [os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", f) for f in ("emb_device.cuh", "emb_fast.cuh", "emb_model.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         cuda_inc = "/usr/local/cuda/include"
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared",
@@ -63,6 +63,8 @@ def emu_lib():
     lib.emu_set_prior.argtypes = [vp, C.c_int, C.c_int, C.c_double]
     lib.emu_sample_initial.argtypes = [vp, u64, u64, i64, C.POINTER(L.SampleOpts), vp, vp, vp]
     lib.emu_sample_tracks.argtypes = [vp, u64, u64, i64, i32, C.POINTER(L.SampleOpts), C.POINTER(L.TrackOut)]
+    lib.emu_use_fast.argtypes = [C.c_int]
+    lib.emu_last_fast.restype = C.c_int
     _emu = lib
     return lib
 

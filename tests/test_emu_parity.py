@@ -33,10 +33,20 @@ def _run_tracks(model_paths, c):
     return em.sample_tracks(p.n_initial, nd, ntv, c["n"], c["T"], c["seed"], c.get("first", 0), o)
 
 
+@pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
 @pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
-def test_tracks_match_golden(model_paths, golden, name):
-    got = _run_tracks(model_paths, cases.TRACK_CASES[name])
+def test_tracks_match_golden(model_paths, golden, name, fast):
+    """Both device code paths (track_generic and the register-resident track_fast) against the oracle."""
+    from helpers import emu_lib
+    lib = emu_lib()
+    lib.emu_use_fast(fast)
+    try:
+        got = _run_tracks(model_paths, cases.TRACK_CASES[name])
+        used_fast = lib.emu_last_fast()
+    finally:
+        lib.emu_use_fast(0)
     cases.check_tracks(got, golden[name])
+    assert used_fast == fast, "every golden model shape is expected to have a specialised kernel"
 
 
 @pytest.mark.parametrize("name", sorted(cases.INITIAL_CASES))

@@ -38,9 +38,35 @@ def _run_tracks(model_paths, c, device=None):
                 init_values=cpu(res.init_values).T, attempts=cpu(res.attempts))
 
 
+@pytest.mark.parametrize("generic", [0, 1], ids=["specialised", "generic"])
 @pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
-def test_tracks_match_golden(model_paths, golden, name):
-    cases.check_tracks(_run_tracks(model_paths, cases.TRACK_CASES[name]), golden[name])
+def test_tracks_match_golden(model_paths, golden, name, generic):
+    """Both kernels (k_tracks_fast<...> and k_tracks_generic) against the oracle's golden vectors."""
+    lib = L.lib()
+    lib.emb_debug_force_generic(generic)
+    try:
+        got = _run_tracks(model_paths, cases.TRACK_CASES[name])
+        was_fast = lib.emb_debug_last_kernel_fast()
+    finally:
+        lib.emb_debug_force_generic(0)
+    cases.check_tracks(got, golden[name])
+    assert was_fast == (0 if generic else 1)
+
+
+def test_specialised_equals_generic_at_scale(model_paths):
+    """100k tracks x 600 s: the two kernels must agree bit-for-bit on every output byte."""
+    lib = L.lib()
+    m = UncorEncounterModel(model_paths["uncor_allcode_fwsingle_v1"])
+    a = m.sample_compact(100_000, 600, seed=99, device="cuda:0")
+    lib.emb_debug_force_generic(1)
+    try:
+        b = m.sample_compact(100_000, 600, seed=99, device="cuda:0")
+    finally:
+        lib.emb_debug_force_generic(0)
+    import torch
+    assert torch.equal(a.bins_tiled, b.bins_tiled)
+    assert torch.equal(a.values_tiled.view(torch.int32), b.values_tiled.view(torch.int32))
+    assert torch.equal(a.init_values, b.init_values)
 
 
 def test_tracks_device_buffers_match_host_buffers(model_paths, golden):
