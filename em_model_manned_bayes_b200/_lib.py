@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libemb200.so")
+LIB_PATH = os.environ.get("EMB200_LIB") or os.path.join(HERE, "libemb200.so")   # EMB200_LIB: tuning variants (build.py --variant)
 
 EMB_MAX_VARS = 24
 EMB_MAX_DYN = 8

@@ -59,6 +59,21 @@ def _run(cmd, verbose):
     return r
 
 
+def build_variant(name: str, defines) -> str:
+    """Scratch builds for kernel tuning: libemb200_<name>.so with extra -D flags (load it with EMB200_LIB=<path>)."""
+    out = os.path.join(HERE, "libemb200_%s.so" % name)
+    objs = []
+    os.makedirs(OBJ, exist_ok=True)
+    for src in CU_SOURCES:
+        o = os.path.join(OBJ, "%s.%s.o" % (src, name))
+        _run([_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o], False)
+        objs.append(o)
+    for src in CXX_SOURCES:
+        objs.append(os.path.join(OBJ, src + ".o"))
+    _run([_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"], False)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
@@ -89,5 +104,9 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        build()
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_info="--ptxas" in sys.argv)
     print(path)

@@ -52,8 +52,10 @@ int ensure_device(const HostModel& H, int device, DevModel& D) {
         if (c.thr_initial) cudaFree(c.thr_initial);
         if (c.thr_transition) cudaFree(c.thr_transition);
         if (c.edges) cudaFree(c.edges);
+        if (c.dd32) cudaFree(c.dd32);
         c.thr_initial = c.thr_transition = nullptr;
         c.edges = nullptr;
+        c.dd32 = nullptr;
         auto up = [&](const void* src, size_t bytes, void** dst) -> int {
             *dst = nullptr;
             if (!bytes) return 0;
@@ -65,12 +67,14 @@ int ensure_device(const HostModel& H, int device, DevModel& D) {
         if ((rc = up(H.thr_initial.data(), H.thr_initial.size() * 4, (void**)&c.thr_initial))) return rc;
         if ((rc = up(H.thr_transition.data(), H.thr_transition.size() * 4, (void**)&c.thr_transition))) return rc;
         if ((rc = up(H.edges.data(), H.edges.size() * 8, (void**)&c.edges))) return rc;
+        if ((rc = up(H.dd32.data(), H.dd32.size() * 4, (void**)&c.dd32))) return rc;
         c.version = H.version;
     }
     D = H.dev;
     D.thr_init = c.thr_initial;
     D.thr_trans = c.thr_transition;
     D.edges = c.edges;
+    D.dd32 = c.dd32;
     return 0;
 }
 
@@ -256,6 +260,7 @@ void emb_model_free(emb_model* m) {
                 if (kv.second.thr_initial) cudaFree(kv.second.thr_initial);
                 if (kv.second.thr_transition) cudaFree(kv.second.thr_transition);
                 if (kv.second.edges) cudaFree(kv.second.edges);
+                if (kv.second.dd32) cudaFree(kv.second.dd32);
                 cudaSetDevice(cur);
             }
         }
@@ -414,13 +419,13 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
 
 int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T) {
     if (!m || n < 0 || T < 0) return 0;
-    const int64_t nch16 = (T + 15) / 16;
-    return (int64_t)m->h->temporal_map.size() * nch16 * n * 16;
+    const int64_t nch4 = (T + 3) / 4;
+    return (int64_t)m->h->temporal_map.size() * nch4 * n * 4;
 }
 int64_t emb_tracks_values_len(const emb_model* m, int64_t n, int32_t T) {
     if (!m || n < 0 || T < 0) return 0;
-    const int64_t nch16 = (T + 15) / 16;
-    return (int64_t)m->h->timevarying.size() * nch16 * 4 * n * 4;
+    const int64_t nch4 = (T + 3) / 4;
+    return (int64_t)m->h->timevarying.size() * nch4 * n * 4;
 }
 
 int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,

@@ -31,8 +31,9 @@ constexpr int MAXG = 16;  // EMB_MAX_GATED
 constexpr int MAXX = MAXV + MAXD;
 constexpr int HIST_STRIDE = 64;
 
-// stream spec v1 purposes (oracle/philox.py)
-constexpr uint32_t P_INIT = 1, P_STEP = 2, P_STEP_DD = 3, P_LAYER = 4;
+// stream spec v2 purposes (oracle/philox.py)
+constexpr uint32_t P_INIT = 1, P_STEP = 2, P_LAYER = 4;
+constexpr uint32_t DD_MULT = 0x9E3779B1u;   // value word -> de-discretisation uniform (spec v2)
 
 struct Node {
     int32_t r;               // bins
@@ -51,9 +52,12 @@ struct DevModel {
     Node dyn[MAXD];
     int32_t dyn_t[MAXD];           // x index of the variable at time t
     int32_t dyn_t1[MAXD];          // x index of its (t+1)/(t-1) counterpart
-    int32_t gated_var[MAXG];
-    uint64_t gate_G[MAXG];         // fires iff k < G
-    double gate_inv[MAXG];         // 1.0 / G
+    int32_t gated_var[MAXG];       // variables with a value word: rate > 0 or dynamic, ascending (spec v2)
+    uint64_t gate_G[MAXG];         // fires iff k < G (0 for rate 0)
+    int32_t gate_of_dyn[MAXD];     // gated ordinal of the d-th dynamic variable
+    int32_t dd_off[MAXG];          // first entry of gated ordinal g in dd32
+    int32_t fast32_ok;             // every gated bin can be de-discretised in fp32 within 1e-6 relative
+    int32_t two23;                 // 2^23 as a run-time value (keeps IMAD.HI from being strength-reduced)
     int32_t tv_var[MAXV];          // time-varying variables (dynamic(t) or gated), ascending
     int32_t tv_of_var[MAXV];       // inverse map or -1
     int32_t edge_off[MAXV];        // offset (doubles) into edges of {a,w} pairs, -1 = no boundaries
@@ -61,6 +65,7 @@ struct DevModel {
     const uint32_t* thr_init;
     const uint32_t* thr_trans;
     const double* edges;
+    const float* dd32;             // per (gated ordinal, bin): {slope, base, s, c}  (emb_model.cpp: pack)
 };
 
 struct SampleParams {
@@ -73,6 +78,7 @@ struct SampleParams {
     int32_t is_quantize500;
     int32_t n_layers;
     int32_t max_attempts;
+    uint32_t rk[20];               // Philox round keys (k0 + i*W0, k1 + i*W1), read from the constant bank
     uint8_t start[MAXV];           // preset 1-based bin, 0 = free
     double layers[8][2];
     double box_lo[MAXV], box_hi[MAXV];
@@ -114,20 +120,50 @@ EMB_HD double u01(uint32_t k) { return dmul(dadd((double)k, 0.5), 2.328306436538
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
+// 32x32 -> 64 multiply as ONE IMAD.WIDE.U32 (the C++ form is lowered through a 64-bit multiply that
+// leaves a dead add per product in SASS)
+EMB_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    uint64_t p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+#else
+    const uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+
 EMB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                           uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
-        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1;
-        c3 = (uint32_t)p0;
-        c0 = n0;
-        c2 = n2;
+        uint32_t h0, l0, h1, l1;
+        mulhilo(PHILOX_M0, c0, h0, l0);
+        mulhilo(PHILOX_M1, c2, h1, l1);
+        c0 = h1 ^ c1 ^ k0;
+        c2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
         k0 += PHILOX_W0;
         k1 += PHILOX_W1;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// same function with the ten round keys precomputed (SampleParams::rk lives in the constant bank, so the
+// key injection is a constant operand of the LOP3 and costs no instruction)
+EMB_HD void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20],
+                             uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(PHILOX_M0, c0, h0, l0);
+        mulhilo(PHILOX_M1, c2, h1, l1);
+        c0 = h1 ^ c1 ^ rk[2 * i];
+        c2 = h0 ^ c3 ^ rk[2 * i + 1];
+        c1 = l1;
+        c3 = l0;
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
@@ -164,6 +200,9 @@ EMB_HD uint32_t keyed_word(uint64_t seed, uint64_t sample, uint32_t attempt, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// stream spec v2: de-discretisation uniform of a value word, (((k*A) mod 2^32 >> 9) + 0.5) 2^-23
+EMB_HD double u_dd(uint32_t k) { return dmul(dadd((double)((k * DD_MULT) >> 9), 0.5), 1.1920928955078125e-07); }
+
 EMB_HD uint32_t ldg32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
@@ -276,7 +315,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     uint8_t x[MAXX];
     double vals[MAXV];
     const uint64_t sample = P.first_sample + (uint64_t)s;
-    const int n = M.n_initial, nd = M.n_dyn, ng = M.n_gated, ntv = M.n_tv, nw = M.nw;
+    const int n = M.n_initial, nd = M.n_dyn, ng = M.n_gated, nw = M.nw;
     const int T = P.T;
     const int64_t N = P.n;
     for (int i = 0; i < MAXX; ++i) x[i] = 0;
@@ -301,17 +340,17 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
         col[d] = node_column(M.dyn[d], M.thr_trans, x);
     }
 
-    WordStream ws, wdd;
+    WordStream ws;
     ws.init(P.seed, sample, (uint32_t)attempt, P_STEP);
-    const int nch16 = (T + 15) >> 4, nch4 = nch16 * 4;
-    uint32_t bpack[MAXD][4];
+    const int nch4 = (T + 3) >> 2;
+    uint32_t bpack[MAXD];
     float vbuf[MAXV][4];
-    for (int d = 0; d < MAXD; ++d) bpack[d][0] = bpack[d][1] = bpack[d][2] = bpack[d][3] = 0;
+    for (int d = 0; d < MAXD; ++d) bpack[d] = 0;
 
-    const int Tpad = nch16 * 16;
+    const int Tpad = nch4 * 4;
     for (int c = 0; c < Tpad; ++c) {          // column c = state during second c+1; step e = c
         if (c > 0 && c < T) {
-            const uint32_t base = (uint32_t)c * (uint32_t)nw;   // stream spec v1: p = e*nw + slot
+            const uint32_t base = (uint32_t)c * (uint32_t)nw;   // stream spec v2: p = e*nw + slot
             uint32_t wstep[MAXD + MAXG];
             for (int q = 0; q < nw; ++q) wstep[q] = ws.at(base + (uint32_t)q);
             // resample gates on the pre-transition bins (resample_events.m:23-29)
@@ -319,7 +358,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 const uint32_t k = wstep[nd + g];
                 if ((uint64_t)k < M.gate_G[g]) {
                     const int v = M.gated_var[g];
-                    vals[v] = dedisc(M, v, x[v], dmul(dadd((double)k, 0.5), M.gate_inv[g]));
+                    vals[v] = dedisc(M, v, x[v], u_dd(k));
                 }
             }
             // transitions (dbn_sample.m:69-79 slow / :143-146 fast)
@@ -329,60 +368,45 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 const uint32_t* cp = M.fast ? col[d] : node_column(nd_, M.thr_trans, x);
                 x[M.dyn_t1[d]] = (uint8_t)select_bin(cp, nd_.rp, wstep[d]);
             }
-            // map back + change events (dbn_sample.m:82-92)
-            bool dd_ready = false;
-            uint32_t ddw[4] = {0, 0, 0, 0};
-            int dd_sub = -1;
+            // map back + change events (dbn_sample.m:82-92); the new value reads the same value word
             for (int d = 0; d < nd; ++d) {
                 const int vt = M.dyn_t[d];
                 const uint8_t nb = x[M.dyn_t1[d]];
                 if (nb != x[vt]) {
                     x[vt] = nb;
-                    double u = 0.5;
-                    if (needs_uniform(M, vt, nb)) {
-                        if (!dd_ready || dd_sub != (d >> 2)) {
-                            dd_sub = d >> 2;
-                            philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)c,
-                                          ((uint32_t)attempt << 16) | (P_STEP_DD << 8) | (uint32_t)dd_sub,
-                                          (uint32_t)P.seed, (uint32_t)(P.seed >> 32), ddw[0], ddw[1], ddw[2], ddw[3]);
-                            dd_ready = true;
-                        }
-                        u = u01(ddw[d & 3]);
-                    }
-                    vals[vt] = dedisc(M, vt, nb, u);
+                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[nd + M.gate_of_dyn[d]]));
                 }
             }
         }
         const bool live = c < T;
         for (int d = 0; d < nd; ++d) {
             const uint32_t b = live ? (uint32_t)(x[M.dyn_t[d]] + 1) : 0u;
-            bpack[d][(c >> 2) & 3] |= b << (8 * (c & 3));
+            bpack[d] |= b << (8 * (c & 3));
             if (live && c > 0 && O.hist_transition) hist_inc(1, d, x[M.dyn_t[d]]);
         }
-        for (int tv = 0; tv < ntv; ++tv) vbuf[tv][c & 3] = live ? (float)vals[M.tv_var[tv]] : 0.0f;
-        if ((c & 3) == 3 && O.values) {
-            for (int tv = 0; tv < ntv; ++tv) {
-                float* dst = O.values + (((int64_t)tv * nch4 + (c >> 2)) * N + s) * 4;
+        for (int g = 0; g < ng; ++g) vbuf[g][c & 3] = live ? (float)vals[M.gated_var[g]] : 0.0f;
+        if ((c & 3) == 3) {
+            if (O.values) {
+                for (int g = 0; g < ng; ++g) {
+                    float* dst = O.values + (((int64_t)g * nch4 + (c >> 2)) * N + s) * 4;
 #if defined(__CUDA_ARCH__)
-                *reinterpret_cast<float4*>(dst) = make_float4(vbuf[tv][0], vbuf[tv][1], vbuf[tv][2], vbuf[tv][3]);
+                    *reinterpret_cast<float4*>(dst) = make_float4(vbuf[g][0], vbuf[g][1], vbuf[g][2], vbuf[g][3]);
 #else
-                dst[0] = vbuf[tv][0]; dst[1] = vbuf[tv][1]; dst[2] = vbuf[tv][2]; dst[3] = vbuf[tv][3];
-#endif
-            }
-        }
-        if ((c & 15) == 15) {
-            if (O.bins) {
-                for (int d = 0; d < nd; ++d) {
-                    int8_t* dst = O.bins + (((int64_t)d * nch16 + (c >> 4)) * N + s) * 16;
-#if defined(__CUDA_ARCH__)
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(bpack[d][0], bpack[d][1], bpack[d][2], bpack[d][3]);
-#else
-                    for (int q = 0; q < 4; ++q)
-                        for (int b = 0; b < 4; ++b) dst[q * 4 + b] = (int8_t)((bpack[d][q] >> (8 * b)) & 0xFF);
+                    dst[0] = vbuf[g][0]; dst[1] = vbuf[g][1]; dst[2] = vbuf[g][2]; dst[3] = vbuf[g][3];
 #endif
                 }
             }
-            for (int d = 0; d < nd; ++d) bpack[d][0] = bpack[d][1] = bpack[d][2] = bpack[d][3] = 0;
+            if (O.bins) {
+                for (int d = 0; d < nd; ++d) {
+                    int8_t* dst = O.bins + (((int64_t)d * nch4 + (c >> 2)) * N + s) * 4;
+#if defined(__CUDA_ARCH__)
+                    *reinterpret_cast<uint32_t*>(dst) = bpack[d];
+#else
+                    for (int b = 0; b < 4; ++b) dst[b] = (int8_t)((bpack[d] >> (8 * b)) & 0xFF);
+#endif
+                }
+            }
+            for (int d = 0; d < nd; ++d) bpack[d] = 0;
         }
     }
 }

@@ -1,21 +1,27 @@
-// emb_fast.cuh -- register-resident track sampler for the common model shapes.
+// emb_fast.cuh -- register-resident, branch-free track sampler for the common model shapes.
 //
-// Same semantics and same keyed stream as track_generic (emb_device.cuh); what changes is where the
-// state lives.  Template parameters fix the number of bins of every dynamic variable (RS packs up to
-// four of them, one per byte, in temporal_map order) and the number of gated variables NG, so that
+// Same semantics and same keyed stream (spec v2, oracle/philox.py) as track_generic (emb_device.cuh);
+// what changes is where the state lives and that nothing in the per-second loop diverges.  Template
+// parameters fix the number of bins of every dynamic variable (RS packs up to four of them, one per
+// byte, in temporal_map order) and the number of gated variables NG, so that
 //   * the frozen inverse-CDF thresholds of the fast branch (dbn_sample.m:110-135) sit in registers,
 //   * the nw = ND + NG words of four consecutive seconds come from exactly nw Philox calls whose
-//     outputs are indexed statically (stream spec v1: p = e*nw + slot, so 4 seconds = nw blocks),
-//   * bins are packed 16 per uint4 store and values 4 per float4 store ([var][t/16][sample][16]).
-// Requirements checked on the host (emb_kernels.cu: pick_fast): every dynamic variable is gated and
-// the gated list ends with the dynamic variables in temporal_map order (true for every shipped
-// model); all gate thresholds G are in [1, 2^32 - 1].
+//     outputs are indexed statically (p = e*nw + slot, so 4 seconds = nw blocks),
+//   * a second costs, per gated variable, one compare (gate), one compare (bin changed), and one
+//     predicated fp32 de-discretisation  value = fma(slope, fma(f, s, c), base)  whose operands come
+//     from a 16-byte shared-memory entry indexed by the bin (no fp64, no int->float conversion: the
+//     23-bit value-word fraction is placed in the mantissa of f in [1,2)),
+//   * bins and values leave as 4-second tiles: one 4-byte store per dynamic variable and one 16-byte
+//     store per gated variable per thread, contiguous across the warp.
+// Requirements checked on the host (fast_shape_of): the gated list ends with the dynamic variables in
+// temporal_map order (true for every shipped model); all gate thresholds G < 2^32; no gated bin
+// straddles zero without being the zero bin (DevModel::fast32_ok).
 #pragma once
 #include "emb_device.cuh"
 
 namespace emb {
 
-constexpr int FAST_MAX_EDGES = 160;  // sum of bins over the gated variables (shared-memory edge table)
+constexpr int FAST_MAX_EDGES = 160;  // sum of bins over the gated variables (shared-memory entry table)
 
 template <uint32_t RS>
 struct DynShape {
@@ -27,40 +33,199 @@ struct DynShape {
     static constexpr int RPMAX = (RMAX + 3) & ~3;
 };
 
+struct DdEntry {
+    float slope, base, s, c;
+};
+
 // per-block constants of the fast kernel (shared memory on the device)
-struct FastShared {
-    double edges[2 * FAST_MAX_EDGES];  // {a, w} per (gated ordinal, bin)
+struct alignas(16) FastShared {
+    DdEntry ent[FAST_MAX_EDGES];  // per (gated ordinal, bin), DevModel::dd32
 };
 
 // fill FastShared (called by all threads of a block with their index, or by the host with tid=0,nthreads=1)
 EMB_HD void fast_fill_shared(const DevModel& M, FastShared& S, int tid, int nthreads) {
-    int base = 0;
-    for (int g = 0; g < M.n_gated; ++g) {
-        const int v = M.gated_var[g];
-        const int r = M.init[v].r;
-        if (M.edge_off[v] >= 0)
-            for (int q = tid; q < 2 * r; q += nthreads) S.edges[2 * base + q] = ldg64(M.edges + M.edge_off[v] + q);
-        base += r;
-    }
+    int total = 0;
+    for (int g = 0; g < M.n_gated; ++g) total += M.init[M.gated_var[g]].r;
+    float* dst = reinterpret_cast<float*>(S.ent);
+    for (int q = tid; q < 4 * total; q += nthreads) dst[q] = M.dd32[q];
 }
 
-template <uint32_t RS, int NG, bool FAST, class HistInc>
+// the 23 fraction bits of a value word as a float in [1,2)   (stream spec v2: u_dd = (f - 1) + 2^-24):
+// one IMAD (hash) + one funnel shift that drops the exponent of 1.0f on top of the fraction
+EMB_HD float dd_fraction(uint32_t k) {
+    const uint32_t h = k * DD_MULT;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__funnelshift_r(h, 0x7Fu, 9));
+#else
+    const uint32_t b = (h >> 9) | 0x3F800000u;
+    float f;
+    __builtin_memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// ---- counting compare:  acc + [k > t]  with nt = ~t ---------------------------------------------------
+// k > t  <=>  k + ~t carries out of 32 bits.  Written as add.cc / addc so that SASS is one IADD3 that
+// only produces the carry predicate (alu pipe) plus one carry-consuming add that ptxas is free to emit
+// as IMAD.X on the fma pipe -- the plain C form (ISETP + increment + predicated move) costs three
+// instructions, two of them on the alu pipe that the Philox LOP3s already saturate.
+EMB_HD uint32_t add_gt(uint32_t acc, uint32_t k, uint32_t nt) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(acc) : "r"(k), "r"(nt));
+    return acc;
+#else
+    return acc + (k > ~nt ? 1u : 0u);
+#endif
+}
+
+EMB_HD float fmaf_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+
+template <uint32_t RS, int NG, bool FAST, bool HIST, class HistInc>
+struct FastTrack {
+    using SH = DynShape<RS>;
+    static constexpr int ND = SH::ND;
+    static constexpr int NS = NG - ND;   // gated variables that are not dynamic (their bin never changes)
+    static constexpr int NW = ND + NG;
+    static constexpr int RPM = SH::RPMAX;
+
+    const DevModel& M;
+    const SampleParams& P;
+    const FastShared& S;
+    HistInc hist_inc;
+    uint32_t bin[ND];         // current bins of the dynamic variables as entry-table indices: ebase + 0-based bin
+    float val[NG];            // current continuous values of the gated variables
+    DdEntry sent[NS > 0 ? NS : 1];   // entries of the static gated variables
+    uint32_t thr[ND][RPM];    // fast branch: frozen thresholds, complemented (~t); [RP-1] = lead
+    uint32_t cbase[ND];       // slow branch: column offset from the parents that never change
+    uint32_t ct[ND][ND], c1[ND][ND];   // slow branch: strides of the dynamic parents (uniform)
+    int ebase[NG];            // entry-table bases (uniform)
+    uint32_t G[NG];           // gate thresholds (uniform)
+    uint32_t c0, c1w, w3;
+
+    EMB_HD FastTrack(const DevModel& M_, const SampleParams& P_, const FastShared& S_, HistInc h)
+        : M(M_), P(P_), S(S_), hist_inc(h) {}
+
+    // one group of four seconds e = 4*grp .. 4*grp+3; CHECK = the group may contain e == 0 or e >= T
+    template <bool CHECK>
+    EMB_HD void group(int grp, int T, uint32_t (&bout)[ND], float (&vout)[NG][4]) {
+        uint32_t W[4 * NW];
+#pragma unroll
+        for (int c = 0; c < NW; ++c)
+            philox4x32_10_rk(c0, c1w, (uint32_t)(grp * NW + c), w3, P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) bout[d] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = 4 * grp + j;
+            const bool act = !CHECK || (e > 0 && e < T);
+            const bool live = !CHECK || e < T;
+            // ---- transitions: new bins from the words of this second --------------------------------
+            uint32_t nb[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) nb[d] = bin[d];
+            if (FAST) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const uint32_t k = W[j * NW + d];
+                    uint32_t b = thr[d][SH::RP(d) - 1];
+#pragma unroll
+                    for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gt(b, k, thr[d][m]);
+                    nb[d] = act ? b : bin[d];
+                }
+            } else if (act) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) nb[d] = 0;
+#pragma unroll
+                for (int od = 0; od < ND; ++od) {
+                    const int dsel = M.order_dyn[od];   // uniform: which variable is sampled od-th
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        if (dsel == d) {
+                            uint32_t o = cbase[d];
+#pragma unroll
+                            for (int e2 = 0; e2 < ND; ++e2) o += ct[d][e2] * bin[e2] + c1[d][e2] * nb[e2];   // cbase absorbs ebase
+                            const uint32_t* col = M.thr_trans + o;
+                            uint32_t t[RPM];
+#pragma unroll
+                            for (int q = 0; q < SH::RP(d); q += 4) {
+#if defined(__CUDA_ARCH__)
+                                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(col + q));
+                                t[q] = v4.x; t[q + 1] = v4.y; t[q + 2] = v4.z; t[q + 3] = v4.w;
+#else
+                                t[q] = col[q]; t[q + 1] = col[q + 1]; t[q + 2] = col[q + 2]; t[q + 3] = col[q + 3];
+#endif
+                            }
+                            const uint32_t k = W[j * NW + d];
+                            uint32_t b = t[SH::RP(d) - 1] + (uint32_t)ebase[NS + d];
+#pragma unroll
+                            for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gt(b, k, ~t[m]);
+                            nb[d] = b;
+                        }
+                    }
+                }
+            }
+            // ---- values: gate (resample_events.m:23-29) and/or bin change (dbn_sample.m:82-92) ------
+            // bin[] / nb[] hold entry-table indices (ebase + bin), see track_fast
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t k = W[j * NW + ND + g];
+                const int d = g - NS;
+                DdEntry en;
+                if (g >= NS) en = S.ent[nb[d >= 0 ? d : 0]];
+                else en = sent[g < NS ? g : 0];
+                const float gp = fmaf_rn(dd_fraction(k), en.s, en.c);
+#if defined(__CUDA_ARCH__)
+                // val = (k < G || nb != bin) ? fma(slope, gp, base) : val   as a predicated FFMA (no FSEL)
+                if (!CHECK) {
+                    if (g >= NS)
+                        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %4, %5;\n\tsetp.ne.or.u32 q, %6, %7, q;\n\t"
+                            "@q fma.rn.f32 %0, %1, %2, %3;\n\t}"
+                            : "+f"(val[g]) : "f"(en.slope), "f"(gp), "f"(en.base), "r"(k), "r"(G[g]), "r"(nb[d >= 0 ? d : 0]), "r"(bin[d >= 0 ? d : 0]));
+                    else
+                        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %4, %5;\n\t@q fma.rn.f32 %0, %1, %2, %3;\n\t}"
+                            : "+f"(val[g]) : "f"(en.slope), "f"(gp), "f"(en.base), "r"(k), "r"(G[g]));
+                } else
+#endif
+                {
+                    bool p = k < G[g];
+                    if (g >= NS) p = p || (nb[d >= 0 ? d : 0] != bin[d >= 0 ? d : 0]);
+                    if (p && act) val[g] = fmaf_rn(en.slope, gp, en.base);
+                }
+                if (g >= NS) bin[d >= 0 ? d : 0] = nb[d >= 0 ? d : 0];
+                vout[g][j] = live ? val[g] : 0.0f;
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                if (CHECK) bout[d] |= (live ? bin[d] - (uint32_t)ebase[NS + d] + 1u : 0u) << (8 * j);
+                else bout[d] += bin[d] << (8 * j);     // (1 - ebase) of all four seconds is added once below
+                if (HIST && act) hist_inc(1, d, (int)bin[d] - ebase[NS + d]);
+            }
+        }
+        if (!CHECK) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) bout[d] += 0x01010101u * (1u - (uint32_t)ebase[NS + d]);
+        }
+    }
+};
+
+template <uint32_t RS, int NG, bool FAST, bool HIST, class HistInc>
 EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut& O, int64_t s, const FastShared& S,
                        HistInc hist_inc) {
+    using FT = FastTrack<RS, NG, FAST, HIST, HistInc>;
     using SH = DynShape<RS>;
-    constexpr int ND = SH::ND;
-    constexpr int NW = ND + NG;
-    constexpr int RPM = SH::RPMAX;
+    constexpr int ND = FT::ND, NS = FT::NS;
     const uint64_t sample = P.first_sample + (uint64_t)s;
     const int T = P.T;
     const int64_t N = P.n;
+    FT ft(M, P, S, hist_inc);
 
-    // ---- initial network (once per track; generic code, cost amortised over T steps) ------------
-    uint32_t bin[ND];        // current 0-based bins of the dynamic variables
-    uint32_t gbin[NG];       // current 0-based bins of the gated variables (last ND mirror bin[])
-    float val[NG];           // current continuous values of the gated (= time-varying) variables
-    uint32_t thr[ND][RPM];   // fast branch: frozen thresholds, [RP-1] = lead
-    uint32_t cbase[ND];      // slow branch: column offset from the parents that never change
+    // ---- initial network (once per track; generic code, cost amortised over T seconds) -----------
     int attempt;
     {
         uint8_t x[MAXX];
@@ -78,22 +243,29 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
             if (O.hist_initial) hist_inc(0, i, x[i]);
         }
         if (T <= 0 || (!O.bins && !O.values && !O.hist_transition)) return;
+        {
+            int b = 0;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            bin[d] = x[M.dyn_t[d]];
-            x[M.dyn_t1[d]] = x[M.dyn_t[d]];
+            for (int g = 0; g < NG; ++g) {
+                ft.ebase[g] = b;
+                b += M.init[M.gated_var[g]].r;
+                ft.G[g] = (uint32_t)M.gate_G[g];
+                ft.val[g] = (float)vals[M.gated_var[g]];
+                if (g < NS) ft.sent[g] = S.ent[ft.ebase[g] + (int)x[M.gated_var[g]]];
+            }
         }
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            gbin[g] = x[M.gated_var[g]];
-            val[g] = (float)vals[M.gated_var[g]];
+        for (int d = 0; d < ND; ++d) {
+            ft.bin[d] = (uint32_t)ft.ebase[NS + d] + x[M.dyn_t[d]];
+            x[M.dyn_t1[d]] = x[M.dyn_t[d]];
         }
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             if (FAST) {
                 const uint32_t* col = node_column(M.dyn[d], M.thr_trans, x);
 #pragma unroll
-                for (int m = 0; m < SH::RP(d); ++m) thr[d][m] = ldg32(col + m);
+                for (int m = 0; m < SH::RP(d); ++m)
+                    ft.thr[d][m] = m < SH::RP(d) - 1 ? ~ldg32(col + m) : ldg32(col + m) + (uint32_t)ft.ebase[NS + d];
             } else {
                 // column offset contributed by parents that are neither X(t) nor X(t+1) of a dynamic variable
                 const Node& nd = M.dyn[d];
@@ -103,179 +275,63 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                     for (int e = 0; e < ND; ++e) isdyn = isdyn || nd.par[p] == M.dyn_t[e] || nd.par[p] == M.dyn_t1[e];
                     if (!isdyn) o += nd.stride_rp[p] * (uint32_t)x[nd.par[p]];
                 }
-                cbase[d] = o;
+                ft.cbase[d] = o;
             }
         }
     }
-    // slow branch: coefficients of the dynamic parents (uniform across threads)
-    uint32_t ct[ND][ND], c1[ND][ND];
-    if (!FAST) {
+    if (!FAST) {   // strides of the dynamic parents (uniform across threads)
 #pragma unroll
         for (int d = 0; d < ND; ++d)
 #pragma unroll
             for (int e = 0; e < ND; ++e) {
-                ct[d][e] = 0;
-                c1[d][e] = 0;
+                ft.ct[d][e] = 0;
+                ft.c1[d][e] = 0;
                 for (int p = 0; p < M.dyn[d].np; ++p) {
-                    if (M.dyn[d].par[p] == M.dyn_t[e]) ct[d][e] = M.dyn[d].stride_rp[p];
-                    if (M.dyn[d].par[p] == M.dyn_t1[e]) c1[d][e] = M.dyn[d].stride_rp[p];
+                    if (M.dyn[d].par[p] == M.dyn_t[e]) ft.ct[d][e] = M.dyn[d].stride_rp[p];
+                    if (M.dyn[d].par[p] == M.dyn_t1[e]) ft.c1[d][e] = M.dyn[d].stride_rp[p];
                 }
+                // bin[] / nb[] carry ebase: take it out of the column offset once
+                ft.cbase[d] -= (ft.ct[d][e] + ft.c1[d][e]) * (uint32_t)ft.ebase[NS + e];
             }
     }
-    // edge-table bases of the gated variables (uniform)
-    int ebase[NG];
-    {
-        int b = 0;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            ebase[g] = b;
-            b += M.init[M.gated_var[g]].r;
-        }
-    }
+    ft.c0 = (uint32_t)sample;
+    ft.c1w = (uint32_t)(sample >> 32);
+    ft.w3 = ((uint32_t)attempt << 16) | (P_STEP << 8);
 
-    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
-    const uint32_t c0 = (uint32_t)sample, c1w = (uint32_t)(sample >> 32);
-    const uint32_t w3 = ((uint32_t)attempt << 16) | (P_STEP << 8);
-    const uint32_t w3dd = ((uint32_t)attempt << 16) | (P_STEP_DD << 8);
-    const int nch16 = (T + 15) >> 4, nch4 = nch16 * 4;
-
-    uint32_t bpack[ND][4];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) bpack[d][0] = bpack[d][1] = bpack[d][2] = bpack[d][3] = 0;
-
+    const int nch4 = (T + 3) >> 2;
+    const int nfull = T >> 2;       // groups 1 .. nfull-1 contain only seconds 1 <= e < T
+    // [var][grp][n][4]: per-thread running pointers, one uniform stride per variable
+    int8_t* pb = O.bins ? O.bins + s * 4 : nullptr;
+    float* pv = O.values ? O.values + s * 4 : nullptr;
+    const int64_t var_stride = (int64_t)nch4 * N * 4;   // elements between consecutive variables
     for (int grp = 0; grp < nch4; ++grp) {
-        // ---- the 4*NW words of seconds e = 4*grp .. 4*grp+3 : NW Philox calls ------------------
-        uint32_t W[4 * NW];
-#pragma unroll
-        for (int c = 0; c < NW; ++c)
-            philox4x32_10(c0, c1w, (uint32_t)(grp * NW + c), w3, k0, k1, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
-        float vb[NG][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int e = 4 * grp + j;
-            if (e > 0 && e < T) {
-                // ---- resample gates on the pre-transition bins (resample_events.m:23-29) ---------
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const uint32_t k = W[j * NW + ND + g];
-                    if (k < (uint32_t)M.gate_G[g]) {
-                        const int v = M.gated_var[g];
-                        double x;
-                        if (M.edge_off[v] < 0) x = (double)(gbin[g] + 1);
-                        else if ((uint32_t)M.zero_bin[v] == gbin[g] + 1) x = 0.0;
-                        else {
-                            const double u = dmul(dadd((double)k, 0.5), M.gate_inv[g]);
-                            const double* ed = S.edges + 2 * (ebase[g] + (int)gbin[g]);
-                            x = dadd(ed[0], dmul(ed[1], u));
-                        }
-                        val[g] = (float)x;
-                    }
-                }
-                // ---- transitions ------------------------------------------------------------------
-                uint32_t nb[ND];
-#pragma unroll
-                for (int d = 0; d < ND; ++d) nb[d] = 0;
-                if (FAST) {
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        const uint32_t k = W[j * NW + d];
-                        uint32_t b = thr[d][SH::RP(d) - 1];
-#pragma unroll
-                        for (int m = 0; m < SH::R(d) - 1; ++m) b += (k > thr[d][m]) ? 1u : 0u;
-                        nb[d] = b;
-                    }
-                } else {
-#pragma unroll
-                    for (int od = 0; od < ND; ++od) {
-                        const int dsel = M.order_dyn[od];   // uniform: which variable is sampled od-th
-#pragma unroll
-                        for (int d = 0; d < ND; ++d) {
-                            if (dsel == d) {
-                                uint32_t o = cbase[d];
-#pragma unroll
-                                for (int e2 = 0; e2 < ND; ++e2) o += ct[d][e2] * bin[e2] + c1[d][e2] * nb[e2];
-                                const uint32_t* col = M.thr_trans + o;
-                                uint32_t t[RPM];
-#pragma unroll
-                                for (int q = 0; q < SH::RP(d); q += 4) {
-#if defined(__CUDA_ARCH__)
-                                    const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(col + q));
-                                    t[q] = v4.x; t[q + 1] = v4.y; t[q + 2] = v4.z; t[q + 3] = v4.w;
-#else
-                                    t[q] = col[q]; t[q + 1] = col[q + 1]; t[q + 2] = col[q + 2]; t[q + 3] = col[q + 3];
-#endif
-                                }
-                                const uint32_t k = W[j * NW + d];
-                                uint32_t b = t[SH::RP(d) - 1];
-#pragma unroll
-                                for (int m = 0; m < SH::R(d) - 1; ++m) b += (k > t[m]) ? 1u : 0u;
-                                nb[d] = b;
-                            }
-                        }
-                    }
-                }
-                // ---- map back + change events (dbn_sample.m:82-92) --------------------------------
-                bool any = false;
-#pragma unroll
-                for (int d = 0; d < ND; ++d) any = any || (nb[d] != bin[d]);
-                if (any) {
-                    uint32_t dd0, dd1, dd2, dd3;
-                    philox4x32_10(c0, c1w, (uint32_t)e, w3dd, k0, k1, dd0, dd1, dd2, dd3);
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        if (nb[d] != bin[d]) {
-                            const int g = NG - ND + d;
-                            const int v = M.gated_var[g];
-                            bin[d] = nb[d];
-                            gbin[g] = nb[d];
-                            double x;
-                            if (M.edge_off[v] < 0) x = (double)(nb[d] + 1);
-                            else if ((uint32_t)M.zero_bin[v] == nb[d] + 1) x = 0.0;
-                            else {
-                                const uint32_t kk = d == 0 ? dd0 : d == 1 ? dd1 : d == 2 ? dd2 : dd3;
-                                const double* ed = S.edges + 2 * (ebase[g] + (int)nb[d]);
-                                x = dadd(ed[0], dmul(ed[1], u01(kk)));
-                            }
-                            val[g] = (float)x;
-                        }
-                    }
-                }
-            }
-            const bool live = e < T;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                bpack[d][grp & 3] |= (live ? bin[d] + 1u : 0u) << (8 * j);
-                if (live && e > 0 && O.hist_transition) hist_inc(1, d, (int)bin[d]);
-            }
-#pragma unroll
-            for (int g = 0; g < NG; ++g) vb[g][j] = live ? val[g] : 0.0f;
-        }
+        uint32_t bout[ND];
+        float vout[NG][4];
+        if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout);
+        else ft.template group<true>(grp, T, bout, vout);
         if (O.values) {
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                float* dst = O.values + (((int64_t)g * nch4 + grp) * N + s) * 4;
+                float* dst = pv + g * var_stride;
 #if defined(__CUDA_ARCH__)
-                __stcs(reinterpret_cast<float4*>(dst), make_float4(vb[g][0], vb[g][1], vb[g][2], vb[g][3]));
+                __stcs(reinterpret_cast<float4*>(dst), make_float4(vout[g][0], vout[g][1], vout[g][2], vout[g][3]));
 #else
-                dst[0] = vb[g][0]; dst[1] = vb[g][1]; dst[2] = vb[g][2]; dst[3] = vb[g][3];
+                dst[0] = vout[g][0]; dst[1] = vout[g][1]; dst[2] = vout[g][2]; dst[3] = vout[g][3];
 #endif
             }
+            pv += N * 4;
         }
-        if ((grp & 3) == 3) {
-            if (O.bins) {
+        if (O.bins) {
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    int8_t* dst = O.bins + (((int64_t)d * nch16 + (grp >> 2)) * N + s) * 16;
+            for (int d = 0; d < ND; ++d) {
+                int8_t* dst = pb + d * var_stride;
 #if defined(__CUDA_ARCH__)
-                    __stcs(reinterpret_cast<uint4*>(dst), make_uint4(bpack[d][0], bpack[d][1], bpack[d][2], bpack[d][3]));
+                __stcs(reinterpret_cast<uint32_t*>(dst), bout[d]);
 #else
-                    for (int q = 0; q < 4; ++q)
-                        for (int b = 0; b < 4; ++b) dst[q * 4 + b] = (int8_t)((bpack[d][q] >> (8 * b)) & 0xFF);
+                for (int b = 0; b < 4; ++b) dst[b] = (int8_t)((bout[d] >> (8 * b)) & 0xFF);
 #endif
-                }
             }
-#pragma unroll
-            for (int d = 0; d < ND; ++d) bpack[d][0] = bpack[d][1] = bpack[d][2] = bpack[d][3] = 0;
+            pb += N * 4;
         }
     }
 }
@@ -285,10 +341,10 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
 // kernel's structural requirements, else 0.
 inline uint32_t fast_shape_of(const DevModel& M) {
     const int nd = M.n_dyn, ng = M.n_gated;
-    if (nd < 1 || nd > 4 || ng < nd) return 0;
+    if (nd < 1 || nd > 4 || ng < nd || !M.fast32_ok) return 0;
     int edges = 0;
     for (int g = 0; g < ng; ++g) {
-        if (M.gate_G[g] < 1 || M.gate_G[g] > 0xFFFFFFFFull) return 0;
+        if (M.gate_G[g] > 0xFFFFFFFFull) return 0;
         edges += M.init[M.gated_var[g]].r;
     }
     if (edges > FAST_MAX_EDGES) return 0;

@@ -19,7 +19,13 @@ int g_last_kernel_fast = 0;
 
 namespace {
 
-constexpr int BLOCK = 128;
+#ifndef EMB_BLOCK
+#define EMB_BLOCK 128
+#endif
+#ifndef EMB_MINBLOCKS
+#define EMB_MINBLOCKS 4
+#endif
+constexpr int BLOCK = EMB_BLOCK;
 
 struct SmemHist {
     uint32_t* sh;
@@ -83,20 +89,19 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
 }
 
 // ---- tracks, register-resident specialisation (emb_fast.cuh) --------------------------------------
-template <uint32_t RS, int NG, bool FAST>
-__global__ void __launch_bounds__(BLOCK)
+template <uint32_t RS, int NG, bool FAST, bool HIST>
+__global__ void __launch_bounds__(BLOCK, EMB_MINBLOCKS)
 k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
               const __grid_constant__ TrackOut O) {
     __shared__ FastShared S;
-    __shared__ uint32_t sh[(MAXV + MAXD) * HIST_STRIDE];
-    const bool want_hist = O.hist_initial || O.hist_transition;
+    __shared__ uint32_t sh[HIST ? (MAXV + MAXD) * HIST_STRIDE : 1];
     fast_fill_shared(M, S, threadIdx.x, blockDim.x);
-    if (want_hist)
+    if (HIST)
         for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) track_fast<RS, NG, FAST>(M, P, O, s, S, SmemHist{sh});
-    if (want_hist) flush_hist(sh, M, O.hist_initial, O.hist_transition);
+    if (s < P.n) track_fast<RS, NG, FAST, HIST>(M, P, O, s, S, SmemHist{sh});
+    if (HIST) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
 }  // namespace
@@ -116,11 +121,13 @@ int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, v
     const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
     const uint32_t rs = g_force_generic ? 0u : fast_shape_of(M);
     const bool fast = M.fast != 0;
+    const bool hist = O.hist_initial || O.hist_transition;
     bool done = false;
-#define EMB_X(RS_, NG_, FAST_)                                                             \
-    if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_)) {                   \
-        k_tracks_fast<RS_, NG_, FAST_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
-        done = true;                                                                       \
+#define EMB_X(RS_, NG_, FAST_)                                                                          \
+    if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_)) {                                \
+        if (hist) k_tracks_fast<RS_, NG_, FAST_, true><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
+        else k_tracks_fast<RS_, NG_, FAST_, false><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);   \
+        done = true;                                                                                    \
     }
     EMB_FAST_SHAPES(EMB_X)
 #undef EMB_X

@@ -307,10 +307,14 @@ void HostModel::derive() {
         for (int i = 0; i < n; ++i)
             if (r_transition[i] != r_initial[i]) fail(EMB_E_MODEL, "r_transition(1:n_initial) differs from r_initial");
     }
+    // stream spec v2: a variable owns a value word per second iff its value can change (rate > 0 or dynamic)
     gated.clear();
-    for (int i = 0; i < n; ++i)
-        if (resample_rates[i] > 0.0) gated.push_back(i);
-    if ((int)gated.size() > MAXG) fail(EMB_E_LIMIT, "more than EMB_MAX_GATED variables with resample rate > 0");
+    for (int i = 0; i < n; ++i) {
+        bool g = resample_rates[i] > 0.0;
+        for (auto& a : temporal_map) g = g || a.first == i;
+        if (g) gated.push_back(i);
+    }
+    if ((int)gated.size() > MAXG) fail(EMB_E_LIMIT, "more than EMB_MAX_GATED resampled or dynamic variables");
     timevarying.clear();
     for (int i = 0; i < n; ++i) {
         bool tv = resample_rates[i] > 0.0;
@@ -378,6 +382,7 @@ void HostModel::pack() {
     D.n_tv = (int32_t)timevarying.size();
     D.nw = D.n_dyn + D.n_gated;
     D.fast = is_dynvar_depend ? 0 : 1;
+    D.two23 = 1 << 23;
     for (int i = 0; i < n; ++i) D.order_initial[i] = order_initial[i];
 
     thr_initial.clear();
@@ -418,8 +423,10 @@ void HostModel::pack() {
     for (int g = 0; g < D.n_gated; ++g) {
         D.gated_var[g] = gated[g];
         D.gate_G[g] = gate_threshold(resample_rates[gated[g]]);
-        D.gate_inv[g] = D.gate_G[g] ? 1.0 / (double)D.gate_G[g] : 0.0;
     }
+    for (int d = 0; d < D.n_dyn; ++d)
+        for (int g = 0; g < D.n_gated; ++g)
+            if (gated[g] == temporal_map[d].first) D.gate_of_dyn[d] = g;
     for (int i = 0; i < MAXV; ++i) D.tv_of_var[i] = -1;
     for (int k = 0; k < D.n_tv; ++k) {
         D.tv_var[k] = timevarying[k];
@@ -440,6 +447,39 @@ void HostModel::pack() {
             edges.push_back((double)w);
         }
     }
+    // fp32 de-discretisation entries of the gated variables, {slope, base, s, c} per bin:
+    //   f in [1,2) carries the 23-bit value-word fraction g = f - 1;  g' = fma(f, s, c);  value = fma(slope, g', base)
+    //   bins on the positive side: (s, c) = (1, -1), g' = g,            value = (a + w 2^-24) + w g
+    //   bins on the negative side: (s, c) = (-1, 2 - 2^-23), g' = 1 - 2^-23 - g, value = (b - w 2^-24) - w g'
+    // so that every term has the sign of the result and fp32 rounding stays <= ~2e-7 relative.
+    dd32.clear();
+    D.fast32_ok = 1;
+    for (int g = 0; g < D.n_gated; ++g) {
+        const int v = gated[g];
+        D.dd_off[g] = (int32_t)(dd32.size() / 4);
+        for (int b = 0; b < r_initial[v]; ++b) {
+            float e[4] = {0.0f, 0.0f, 1.0f, -1.0f};
+            if (boundaries[v].empty()) {
+                e[1] = (float)(b + 1);                                  // dediscretize.m:7-10: the bin itself
+            } else if (zero_bins[v] == b + 1) {
+                e[1] = 0.0f;                                            // :24-25
+            } else {
+                const double a = boundaries[v][b], bb = boundaries[v][b + 1];
+                volatile double w = bb - a;
+                if (a < 0.0 && bb > 0.0) D.fast32_ok = 0;               // value can cancel to ~0: fp64 only
+                if (a + bb < 0.0) {
+                    e[0] = (float)(-(double)w);
+                    e[1] = (float)(bb - (double)w * 5.9604644775390625e-08);
+                    e[2] = -1.0f;
+                    e[3] = 1.99999988079071044921875f;                  // 2 - 2^-23
+                } else {
+                    e[0] = (float)(double)w;
+                    e[1] = (float)(a + (double)w * 5.9604644775390625e-08);
+                }
+            }
+            dd32.insert(dd32.end(), e, e + 4);
+        }
+    }
     ++version;
 }
 
@@ -449,6 +489,10 @@ void fill_params(const HostModel& H, uint64_t seed, uint64_t first_sample, int64
     const emb_sample_opts* o = &opts;
     std::memset(&P, 0, sizeof(P));
     P.seed = seed;
+    for (int i = 0; i < 10; ++i) {
+        P.rk[2 * i] = (uint32_t)seed + (uint32_t)i * PHILOX_W0;
+        P.rk[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * PHILOX_W1;
+    }
     P.first_sample = first_sample;
     P.n = n;
     P.T = T;

@@ -49,7 +49,7 @@ struct HostModel {
     std::vector<int32_t> zero_bins;                        // 1-based bin or 0
     std::vector<std::pair<double, double>> bounds_initial;
     bool is_dynvar_depend = false;                         // dbn_sample.m:55
-    std::vector<int32_t> gated;                            // 0-based ids with rate > 0
+    std::vector<int32_t> gated;                            // 0-based ids with rate > 0 or dynamic (value words)
     std::vector<int32_t> timevarying;                      // 0-based ids: dynamic(t) or gated
     // ---- priors ----
     PriorSpec prior_initial, prior_transition;
@@ -57,6 +57,7 @@ struct HostModel {
     DevModel dev{};                    // metadata with null table pointers
     std::vector<uint32_t> thr_initial, thr_transition;
     std::vector<double> edges;         // per variable: a[bin], w[bin] interleaved
+    std::vector<float> dd32;           // per (gated ordinal, bin): {slope, base, s, c}
     uint64_t version = 0;
 
     // ---- device copies ----
@@ -65,6 +66,7 @@ struct HostModel {
         uint32_t* thr_initial = nullptr;
         uint32_t* thr_transition = nullptr;
         double* edges = nullptr;
+        float* dd32 = nullptr;
     };
     mutable std::mutex mu;
     mutable std::map<int, DeviceCopy> device_copies;

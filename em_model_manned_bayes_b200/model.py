@@ -33,16 +33,16 @@ def _ptr(a):
 
 
 def untile_bins(buf, n_dyn: int, n: int, T: int):
-    """[n_dyn][Tpad/16][n][16] -> (n, n_dyn, T).  Works on numpy arrays and torch tensors."""
-    nch = (T + 15) // 16
-    a = buf.reshape(n_dyn, nch, n, 16)
+    """[n_dyn][ceil(T/4)][n][4] -> (n, n_dyn, T).  Works on numpy arrays and torch tensors."""
+    nch = (T + 3) // 4
+    a = buf.reshape(n_dyn, nch, n, 4)
     a = a.transpose(2, 0, 1, 3) if isinstance(a, np.ndarray) else a.permute(2, 0, 1, 3)
-    return a.reshape(n, n_dyn, nch * 16)[:, :, :T]
+    return a.reshape(n, n_dyn, nch * 4)[:, :, :T]
 
 
 def untile_values(buf, n_tv: int, n: int, T: int):
-    """[n_tv][Tpad/4][n][4] -> (n, n_tv, T)."""
-    nch = ((T + 15) // 16) * 4
+    """[n_tv][ceil(T/4)][n][4] -> (n, n_tv, T)."""
+    nch = (T + 3) // 4
     a = buf.reshape(n_tv, nch, n, 4)
     a = a.transpose(2, 0, 1, 3) if isinstance(a, np.ndarray) else a.permute(2, 0, 1, 3)
     return a.reshape(n, n_tv, nch * 4)[:, :, :T]

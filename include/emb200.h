@@ -140,10 +140,11 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
 /* ---- tracks: replaces UncorEncounterModel.m:244-307 loop around dbn_hierarchical_sample.m:9-37
  *      (dbn_sample.m both branches, resample_events.m, dediscretize.m, events2samples.m) ---------- */
 typedef struct emb_track_out {
-    /* dense, tiled for coalesced 16-byte stores; Tpad = 16*ceil(T/16); column c (0-based) is the
-     * state during second c+1, i.e. out_samples{ii}(:, c+1) (events2samples.m:9-27) */
-    int8_t* bins;        /* [n_dyn][Tpad/16][n][16]  1-based bins of the dynamic variables   nullable */
-    float* values;       /* [n_timevarying][Tpad/4][n][4] continuous values                  nullable */
+    /* dense, in tiles of four seconds so that a warp stores contiguous memory; column c (0-based)
+     * is the state during second c+1, i.e. out_samples{ii}(:, c+1) (events2samples.m:9-27); the
+     * padding seconds of the last tile are 0 */
+    int8_t* bins;        /* [n_dyn][ceil(T/4)][n][4]  1-based bins of the dynamic variables  nullable */
+    float* values;       /* [n_timevarying][ceil(T/4)][n][4] continuous values               nullable */
     /* per track */
     int8_t* init_bins;   /* [n_initial][n]                                                   nullable */
     double* init_values; /* [n_initial][n]  out_inits (after layers/quantize500)             nullable */

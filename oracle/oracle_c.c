@@ -12,7 +12,7 @@
  * reference's data flow -- event lists, resample pass, de-discretisation pass, dense expansion --
  * and uses none of the product's tricks (no word-space thresholds: every draw is a cumsum + fp64
  * compare exactly like select_random.m).  The model arrays come from the oracle's own reader
- * (oracle/em_read.py); nothing is shared with libemb200.so.  Uniforms: keyed Philox, stream spec v1
+ * (oracle/em_read.py); nothing is shared with libemb200.so.  Uniforms: keyed Philox, stream spec v2
  * (oracle/philox.py).
  *
  * PARITY UNPINNED: validated only against the Python oracle (tests/test_oracle_c.py), which in turn
@@ -56,7 +56,7 @@ typedef struct {
     int32_t max_attempts;
 } oc_model;
 
-/* ---- keyed Philox4x32-10 (stream spec v1) ----------------------------------------------------- */
+/* ---- keyed Philox4x32-10 (stream spec v2) ----------------------------------------------------- */
 static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* o) {
     for (int i = 0; i < 10; ++i) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -233,16 +233,12 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
             int var = (int)ev2[e].var;
             double rnd = 0.5;
             if (dd_needs_u(M, var, ev2[e].val)) {
-                if (ev2[e].kind == 1) {
-                    int g = 0;
-                    while (M->gated[g] != var) ++g;
-                    uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + nd + g);
-                    rnd = ((double)k + 0.5) * (1.0 / (double)M->gate_G[g]);
-                } else {
-                    int d = 0;
-                    while (M->temporal_map[2 * d] != var) ++d;
-                    rnd = u01(word(&K, 3, (uint32_t)ev2[e].second, (uint32_t)(d >> 2), (uint32_t)(d & 3)));
-                }
+                /* stream spec v2: fired-gate and transition values both read the variable's value word */
+                int g = 0;
+                while (M->gated[g] != var) ++g;
+                uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + nd + g);
+                uint32_t h = k * 0x9E3779B1u;
+                rnd = ((double)(h >> 9) + 0.5) * 1.1920928955078125e-07; /* 2^-23 */
             }
             /* keep the bin for the dense bin expansion in .second's place holder */
             double bin = ev2[e].val;

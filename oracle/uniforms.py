@@ -4,7 +4,7 @@ Uniform providers for the restated reference sampler.  The restatement (oracle/s
 provider for a uniform at every place the reference calls `rand`, passing the *context* of the
 draw.  Two providers:
 
-* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v1"): the uniform is a pure
+* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v2"): the uniform is a pure
   function of the context.  This is the uniform-injection hook of BASELINE.json's north star: the
   reference algorithm, fed these uniforms, must give bit-identical bins to the CUDA sampler.
 * MTStream     -- MATLAB's `rng(seed,'twister'); rand` emulation (MT19937 `genrand_res53`, which
@@ -36,7 +36,7 @@ class _Base:
 
 class KeyedPhilox(_Base):
     """Context-keyed uniforms.  `bind(parms)` must be called once per model so that the dynamic and
-    gated ordinals (stream spec v1) are known."""
+    gated ordinals (stream spec v2) are known."""
 
     def __init__(self, seed: int, record: bool = False):
         super().__init__()
@@ -53,7 +53,7 @@ class KeyedPhilox(_Base):
         self.dyn_vars_t1 = [int(v) for v in tm[:, 1]]      # their (t+1)/(t-1) counterparts
         rates = np.zeros(self.n_initial) if resample_rates is None else np.asarray(resample_rates, dtype=np.float64)
         self.rates = rates
-        self.gated = [i + 1 for i in range(rates.size) if rates[i] > 0]
+        self.gated = [i + 1 for i in range(rates.size) if rates[i] > 0 or (i + 1) in self.dyn_vars_t]
         self.G = {v: px.gate_threshold(rates[v - 1]) for v in self.gated}
         self.nd = len(self.dyn_vars_t)
         self.nw = self.nd + len(self.gated)
@@ -98,16 +98,12 @@ class KeyedPhilox(_Base):
         return u
 
     def dedisc_event(self, kind, second, var):       # dbn_hierarchical_sample.m:35
-        if kind == "gate":       # residual of the gate word (see philox.py)
-            g = self.gated.index(int(var))
-            k = self._w(px.P_STEP, second * self.nw + self.nd + g)
-            G = self.G[int(var)]
-            assert k < G
-            u = (float(k) + 0.5) * (1.0 / float(G))
-        else:                    # transition event of dynamic variable `var` (id at time t)
-            d = self.dyn_vars_t.index(int(var))
-            u = px.u01(int(px.word(self.seed, self.sample, self.attempt, px.P_STEP_DD, second, d % 4, sub=d // 4)))
-        return self._rec(("event_dd", kind, second, var), u)
+        # both kinds (re-emitted bin of a fired gate, new bin of a transition) read the value word
+        g = self.gated.index(int(var))
+        k = self._w(px.P_STEP, second * self.nw + self.nd + g)
+        if kind == "gate":
+            assert k < self.G[int(var)]
+        return self._rec(("event_dd", kind, second, var), px.dd_uniform(k))
 
     def layer(self):                                 # UncorEncounterModel.m:260
         return self._rec(("layer",), px.u01(self._w(px.P_LAYER, 0)))

@@ -62,6 +62,7 @@ static DevModel host_dev(const HostModel& H) {
     D.thr_init = H.thr_initial.data();
     D.thr_trans = H.thr_transition.data();
     D.edges = H.edges.data();
+    D.dd32 = H.dd32.data();
     return D;
 }
 
@@ -124,7 +125,7 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
         fast_fill_shared(D, S, 0, 1);
 #define EMB_X(RS_, NG_, FAST_)                                                         \
     if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_)) {               \
-        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_>(D, P, O, s, S, hh); \
+        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_, true>(D, P, O, s, S, hh); \
         done = true;                                                                   \
     }
         EMB_FAST_SHAPES(EMB_X)

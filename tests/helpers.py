@@ -31,7 +31,7 @@ def oracle_dense(parms, samples):
     tm = np.asarray(parms.temporal_map)
     dyn = [int(v) for v in tm[:, 0]]
     rates = np.asarray(parms.resample_rates)
-    tv = sorted(set(dyn) | {i + 1 for i in range(parms.n_initial) if rates[i] > 0})
+    tv = sorted(set(dyn) | {i + 1 for i in range(parms.n_initial) if rates[i] > 0})   # = the gated variables
     bins = np.stack([s.sample_bins[[d - 1 for d in dyn], :] for s in samples]).astype(np.int8)
     vals = np.stack([s.samples[[v - 1 for v in tv], :] for s in samples])
     return bins, vals, dyn, tv
@@ -126,9 +126,9 @@ class EmuModel:
         return bins.T, vals.T, att
 
     def sample_tracks(self, n_initial, n_dyn, n_tv, n, T, seed, first, opts, hist=False):
-        nch = (T + 15) // 16
-        bins = np.zeros(n_dyn * nch * n * 16, dtype=np.int8)
-        vals = np.zeros(n_tv * nch * 4 * n * 4, dtype=np.float32)
+        nch = (T + 3) // 4
+        bins = np.zeros(n_dyn * nch * n * 4, dtype=np.int8)
+        vals = np.zeros(n_tv * nch * n * 4, dtype=np.float32)
         ib = np.zeros((n_initial, n), dtype=np.int8)
         iv = np.zeros((n_initial, n), dtype=np.float64)
         att = np.zeros(n, dtype=np.uint16)

@@ -47,6 +47,9 @@ def time_initial(name, n, reps=3):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    if len(sys.argv) > 1 and sys.argv[1] == "tracks":
+        time_tracks("uncor_allcode_fwsingle_v1", 1250000, 600, reps=5)
+        sys.exit(0)
     time_tracks("uncor_1200code_v2p1", 1 << 20, 300)
     time_tracks("uncor_allcode_fwsingle_v1", 1 << 20, 600)
     time_tracks("glider_v1", 1 << 20, 300)
