@@ -1,0 +1,166 @@
+// emb_mex.cpp -- thin MEX gateway from MATLAB to the C ABI of libemb200.so (include/emb200.h).
+//
+// SOURCE ONLY: this image has no MATLAB (no mex.h), so the file is never compiled by build() and no
+// test links it; it documents the binding a maintainer adds:
+//     mex -R2018a matlab/emb_mex.cpp -Iinclude -Lem_model_manned_bayes_b200 -lemb200
+//
+//   h    = emb_mex('load', parameters_filename, isOverwriteZeroBoundaries, idxZeroBoundaries)
+//   s    = emb_mex('info', h)                       % struct mirroring emb_model_info (1-based ids)
+//          emb_mex('set_prior', h, which, kind, value)
+//   [bins, values, attempts] = emb_mex('sample_initial', h, seed, first, n, opts)
+//   [out_inits, bins, values, attempts] = emb_mex('sample_tracks', h, seed, first, n, T, opts)
+//          emb_mex('free', h)
+// opts: struct with optional fields start (1 x n_initial, 0/NaN = free), reject_mode, idx_v, idx_dh,
+// idx_L, is_quantize500, layers (r_L x 2), box_lo, box_hi, max_attempts, device.
+// Errors become mexErrMsgIdAndTxt with the reference's identifiers where the reference has one
+// ('dynvar:empty', UncorEncounterModel.m:231-234; 'prior:notdbe', EncounterModel.m:200).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "emb200.h"
+#include "mex.h"
+
+namespace {
+
+void fail(int rc) {
+    const char* msg = emb_last_error();
+    const char* id = "emb200:error";
+    if (std::strstr(msg, "dynvar:empty")) id = "dynvar:empty";
+    else if (std::strstr(msg, "prior:")) id = "prior:notdbe";
+    else if (rc == EMB_E_CUDA) id = "emb200:cuda";
+    else if (rc == EMB_E_REJECT) id = "emb200:reject";
+    mexErrMsgIdAndTxt(id, "%s", msg);
+}
+#define CHECK(call) do { int rc__ = (call); if (rc__ != 0) fail(rc__); } while (0)
+
+emb_model* handle(const mxArray* a) {
+    if (!mxIsUint64(a) || mxGetNumberOfElements(a) != 1) mexErrMsgIdAndTxt("emb200:arg", "bad model handle");
+    return reinterpret_cast<emb_model*>(*static_cast<uint64_t*>(mxGetData(a)));
+}
+
+double field_or(const mxArray* s, const char* name, double dflt) {
+    const mxArray* f = s && mxIsStruct(s) ? mxGetField(s, 0, name) : nullptr;
+    return f && !mxIsEmpty(f) ? mxGetScalar(f) : dflt;
+}
+
+void fill_opts(const mxArray* s, int n_initial, emb_sample_opts* o) {
+    emb_sample_opts_init(o);
+    o->mem = EMB_MEM_HOST;
+    o->device = (int)field_or(s, "device", -1);
+    o->reject_mode = (int)field_or(s, "reject_mode", EMB_REJECT_NONE);
+    o->idx_v = (int)field_or(s, "idx_v", 0);
+    o->idx_dh = (int)field_or(s, "idx_dh", 0);
+    o->idx_L = (int)field_or(s, "idx_L", 0);
+    o->is_quantize500 = (int)field_or(s, "is_quantize500", 0);
+    o->max_attempts = (int)field_or(s, "max_attempts", 0);
+    if (!s || !mxIsStruct(s)) return;
+    if (const mxArray* st = mxGetField(s, 0, "start")) {          // bn_sample.m:45: empty/NaN = free
+        const double* p = mxGetPr(st);
+        for (size_t i = 0; i < mxGetNumberOfElements(st) && (int)i < n_initial; ++i)
+            o->start[i] = std::isnan(p[i]) ? 0 : (int32_t)p[i];
+    }
+    if (const mxArray* ly = mxGetField(s, 0, "layers")) {         // UncorEncounterModel.m:259-263, r_L x 2 column-major
+        const size_t r = mxGetM(ly);
+        const double* p = mxGetPr(ly);
+        o->n_layers = (int32_t)r;
+        for (size_t k = 0; k < r && k < 8; ++k) { o->layers[k][0] = p[k]; o->layers[k][1] = p[r + k]; }
+    }
+    for (const char* nm : {"box_lo", "box_hi"})
+        if (const mxArray* b = mxGetField(s, 0, nm)) {
+            const double* p = mxGetPr(b);
+            double* dst = nm[4] == 'l' ? o->box_lo : o->box_hi;
+            for (size_t i = 0; i < mxGetNumberOfElements(b) && (int)i < n_initial; ++i) dst[i] = p[i];
+        }
+}
+
+}  // namespace
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("emb200:arg", "first argument must be a command string");
+    char cmd[32];
+    mxGetString(prhs[0], cmd, sizeof(cmd));
+    const std::string c(cmd);
+
+    if (c == "load") {                                            // replaces em_read.m:1-141
+        char path[4096];
+        mxGetString(prhs[1], path, sizeof(path));
+        const int overwrite = nrhs > 2 ? (int)mxGetScalar(prhs[2]) : 0;
+        std::vector<int32_t> idx;
+        if (nrhs > 3)
+            for (size_t i = 0; i < mxGetNumberOfElements(prhs[3]); ++i) idx.push_back((int32_t)mxGetPr(prhs[3])[i]);
+        emb_model* m = nullptr;
+        CHECK(emb_model_load(path, overwrite, idx.data(), (int32_t)idx.size(), &m));
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *static_cast<uint64_t*>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(m);
+        return;
+    }
+    emb_model* m = handle(prhs[1]);
+    emb_model_info info;
+    CHECK(emb_model_get_info(m, &info));
+    const int ni = info.n_initial;
+
+    if (c == "free") {
+        emb_model_free(m);
+    } else if (c == "info") {
+        const char* names[] = {"n_initial", "n_transition", "n_dyn", "is_dynvar_depend", "r_initial", "order_initial",
+                               "temporal_map", "zero_bins", "resample_rates", "timevarying_vars"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 10, names);
+        auto scalar = [&](const char* f, double v) { mxSetField(plhs[0], 0, f, mxCreateDoubleScalar(v)); };
+        auto vec = [&](const char* f, int n, auto get) {
+            mxArray* a = mxCreateDoubleMatrix(1, n, mxREAL);
+            for (int i = 0; i < n; ++i) mxGetPr(a)[i] = (double)get(i);
+            mxSetField(plhs[0], 0, f, a);
+        };
+        scalar("n_initial", ni); scalar("n_transition", info.n_transition); scalar("n_dyn", info.n_dyn);
+        scalar("is_dynvar_depend", info.is_dynvar_depend);
+        vec("r_initial", ni, [&](int i) { return info.r_initial[i]; });
+        vec("order_initial", ni, [&](int i) { return info.order_initial[i]; });
+        vec("zero_bins", ni, [&](int i) { return info.zero_bins[i]; });
+        vec("resample_rates", ni, [&](int i) { return info.resample_rates[i]; });
+        vec("timevarying_vars", info.n_timevarying, [&](int i) { return info.timevarying_vars[i]; });
+        mxArray* tm = mxCreateDoubleMatrix(info.n_dyn, 2, mxREAL);
+        for (int k = 0; k < info.n_dyn; ++k) { mxGetPr(tm)[k] = info.temporal_map[k][0]; mxGetPr(tm)[info.n_dyn + k] = info.temporal_map[k][1]; }
+        mxSetField(plhs[0], 0, "temporal_map", tm);
+    } else if (c == "set_prior") {                                // EncounterModel.m:194-203, setTransitionPriors.m
+        CHECK(emb_set_prior(m, (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), mxGetScalar(prhs[4])));
+    } else if (c == "sample_initial") {                           // bn_sample.m:39 batch / @CorTerminalModel/sample.m
+        emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
+        const int64_t n = (int64_t)mxGetScalar(prhs[4]);
+        emb_sample_opts o;
+        fill_opts(nrhs > 5 ? prhs[5] : nullptr, ni, &o);
+        // MATLAB is column-major: an n x n_initial matrix IS the [n_initial][n] layout of the ABI
+        plhs[0] = mxCreateNumericMatrix(n, ni, mxINT8_CLASS, mxREAL);
+        mxArray* vals = mxCreateDoubleMatrix(n, ni, mxREAL);
+        mxArray* att = mxCreateNumericMatrix(n, 1, mxUINT16_CLASS, mxREAL);
+        CHECK(emb_sample_initial(m, &rng, n, &o, (int8_t*)mxGetData(plhs[0]), mxGetPr(vals), (uint16_t*)mxGetData(att)));
+        if (nlhs > 1) plhs[1] = vals; else mxDestroyArray(vals);
+        if (nlhs > 2) plhs[2] = att; else mxDestroyArray(att);
+    } else if (c == "sample_tracks") {                            // UncorEncounterModel.m:244-307
+        emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
+        const int64_t n = (int64_t)mxGetScalar(prhs[4]);
+        const int32_t T = (int32_t)mxGetScalar(prhs[5]);
+        emb_sample_opts o;
+        fill_opts(nrhs > 6 ? prhs[6] : nullptr, ni, &o);
+        const mwSize nch = (mwSize)((T + 3) / 4);
+        // tiles [var][ceil(T/4)][n][4] == column-major MATLAB arrays of size 4 x n x nch x var
+        const mwSize db[4] = {4, (mwSize)n, nch, (mwSize)info.n_dyn};
+        const mwSize dv[4] = {4, (mwSize)n, nch, (mwSize)info.n_timevarying};
+        plhs[0] = mxCreateDoubleMatrix(n, ni, mxREAL);            // out_inits
+        mxArray* bins = mxCreateNumericArray(4, db, mxINT8_CLASS, mxREAL);
+        mxArray* vals = mxCreateNumericArray(4, dv, mxSINGLE_CLASS, mxREAL);
+        mxArray* att = mxCreateNumericMatrix(n, 1, mxUINT16_CLASS, mxREAL);
+        emb_track_out out{};
+        out.bins = (int8_t*)mxGetData(bins);
+        out.values = (float*)mxGetData(vals);
+        out.init_values = mxGetPr(plhs[0]);
+        out.attempts = (uint16_t*)mxGetData(att);
+        CHECK(emb_sample_tracks(m, &rng, n, T, &o, &out));
+        if (nlhs > 1) plhs[1] = bins; else mxDestroyArray(bins);
+        if (nlhs > 2) plhs[2] = vals; else mxDestroyArray(vals);
+        if (nlhs > 3) plhs[3] = att; else mxDestroyArray(att);
+    } else {
+        mexErrMsgIdAndTxt("emb200:arg", "unknown command '%s'", cmd);
+    }
+}

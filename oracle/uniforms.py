@@ -83,6 +83,7 @@ class KeyedPhilox(_Base):
 
     def trans_column(self, var_t1, t_max):           # dbn_sample.m:133  rand(t_max,1); row 1 unused
         col = np.full(t_max, np.nan)
+        self._rec(("trans_sel", 1, var_t1), 0.5)     # row 1 of rand(t_max,1) is drawn but never used (tape padding)
         for t in range(2, t_max + 1):
             col[t - 1] = px.u01(self._sel_word(t, var_t1))
             self._rec(("trans_sel", t, var_t1), col[t - 1])
