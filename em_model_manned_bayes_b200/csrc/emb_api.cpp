@@ -402,7 +402,7 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     int32_t* d_status = nullptr;
     CU(cudaMalloc((void**)&d_status, 4));
     CU(cudaMemsetAsync(d_status, 0, 4, st));
-    cudaError_t e = (cudaError_t)emb::launch_initial(D, P, d_bins, d_vals, d_att, nullptr, d_status, st);
+    cudaError_t e = (cudaError_t)emb::launch_initial(D, P, (int)H.thr_initial.size(), d_bins, d_vals, d_att, nullptr, d_status, st);
     if (e != cudaSuccess) {
         cudaFree(d_status);
         return cuda_fail(e, "launch k_initial");

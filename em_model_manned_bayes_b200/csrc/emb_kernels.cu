@@ -5,10 +5,12 @@
 // global atomic per bin per block).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "emb_device.cuh"
 #include "emb_fast.cuh"
+#include "emb_initial.cuh"
 #include "emb_launch.h"
 
 namespace emb {
@@ -73,6 +75,28 @@ k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SamplePara
     if (hist) flush_hist(sh, M, hist, nullptr);
 }
 
+// ---- initial network, register-resident (emb_initial.cuh): 4 consecutive samples per thread -------
+// SMEM: the whole threshold table (glider family 42 KB, balloons, HAA transition-free models ...) is
+// staged in shared memory once per persistent block, so the per-lane column gathers are LDS.128
+// instead of 32-sector L1 lookups; larger tables (7-variable uncor: 0.6-1.1 MB) are gathered from L1/L2.
+template <int NV, bool VALUES, bool SMEM>
+__global__ void __launch_bounds__(256)
+k_initial_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
+               const __grid_constant__ InitStrides ST, int table_words, int8_t* __restrict__ bins,
+               double* __restrict__ values, uint16_t* __restrict__ attempts) {
+    extern __shared__ uint4 smem_table[];
+    const uint32_t* table = M.thr_init;
+    if (SMEM) {
+        const uint4* src = reinterpret_cast<const uint4*>(M.thr_init);
+        for (int q = threadIdx.x; q < table_words / 4; q += blockDim.x) smem_table[q] = __ldg(src + q);
+        __syncthreads();
+        table = reinterpret_cast<const uint32_t*>(smem_table);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * INIT_SPT;
+    for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * INIT_SPT; s0 < P.n; s0 += stride)
+        initial_fast4<NV, VALUES>(M, P, ST, table, s0, bins, values, attempts);
+}
+
 // ---- tracks, generic (any model, both dbn_sample.m branches) ------------------------------------
 __global__ void __launch_bounds__(BLOCK)
 k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
@@ -107,9 +131,49 @@ k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sample
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-int launch_initial(const DevModel& M, const SampleParams& P, int8_t* bins, double* values, uint16_t* attempts,
-                   unsigned long long* hist, int32_t* status, void* stream) {
+int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
+                   uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream) {
     if (P.n <= 0) return 0;
+    if (!g_force_generic && !hist && initial_fast_ok(M, P)) {
+        InitStrides st;
+        fill_init_strides(M, st);
+        const int64_t need = (P.n + 256 * INIT_SPT - 1) / (256 * INIT_SPT);
+        const size_t tbytes = (size_t)table_words * 4;
+        const bool smem = tbytes > 0 && tbytes <= 96 * 1024 && need >= 2 * 148;   // staging pays only for large batches
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        bool done = false;
+#define EMB_LAUNCH_INIT(NV_, VAL_, SM_)                                                                          \
+    do {                                                                                                         \
+        auto kern = k_initial_fast<NV_, VAL_, SM_>;                                                              \
+        unsigned g4 = (unsigned)need;                                                                            \
+        if (SM_) {   /* persistent grid: one table copy per resident block */                                    \
+            int occ = 1;                                                                                         \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);                \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, tbytes);                              \
+            g4 = (unsigned)std::min<int64_t>(need, (int64_t)sms * std::max(occ, 1));                             \
+        }                                                                                                        \
+        kern<<<g4, 256, SM_ ? tbytes : 0, (cudaStream_t)stream>>>(M, P, st, table_words, bins, values, attempts); \
+    } while (0)
+#define EMB_X(NV_)                                                          \
+    if (!done && M.n_initial == (NV_)) {                                    \
+        if (values && smem) EMB_LAUNCH_INIT(NV_, true, true);               \
+        else if (values) EMB_LAUNCH_INIT(NV_, true, false);                 \
+        else if (smem) EMB_LAUNCH_INIT(NV_, false, true);                   \
+        else EMB_LAUNCH_INIT(NV_, false, false);                            \
+        done = true;                                                        \
+    }
+        EMB_INIT_SHAPES(EMB_X)
+#undef EMB_X
+#undef EMB_LAUNCH_INIT
+        if (done) {
+            g_last_kernel_fast = 1;
+            g_launch_count.fetch_add(1);
+            return (int)cudaGetLastError();
+        }
+    }
+    g_last_kernel_fast = 0;
     const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
     k_initial<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, bins, values, attempts, hist, status);
     g_launch_count.fetch_add(1);

@@ -12,8 +12,9 @@ extern int g_force_generic;
 extern int g_last_kernel_fast;
 
 // all return a cudaError_t value (0 = success); pointers are device pointers
-int launch_initial(const DevModel& M, const SampleParams& P, int8_t* bins, double* values, uint16_t* attempts,
-                   unsigned long long* hist, int32_t* status, void* stream);
+// table_words = length of the initial threshold table (decides shared-memory staging)
+int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
+                   uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream);
 int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream);
 
 }  // namespace emb

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../em_model_manned_bayes_b200/csrc/emb_fast.cuh"
+#include "../../em_model_manned_bayes_b200/csrc/emb_initial.cuh"
 #include "../../em_model_manned_bayes_b200/csrc/emb_model.h"
 #include "../../include/emb200.h"
 
@@ -78,6 +79,26 @@ int emu_sample_initial(void* h, uint64_t seed, uint64_t first, int64_t n, const 
     }
     const DevModel D = host_dev(H);
     int status = 0;
+    g_last_fast = 0;
+    if (g_use_fast && initial_fast_ok(D, P)) {
+        InitStrides st;
+        fill_init_strides(D, st);
+        bool done = false;
+#define EMB_X(NV_)                                                                                      \
+    if (!done && D.n_initial == (NV_)) {                                                                \
+        for (int64_t s0 = 0; s0 < n; s0 += INIT_SPT) {                                                  \
+            if (values) initial_fast4<NV_, true>(D, P, st, D.thr_init, s0, bins, values, attempts);                 \
+            else initial_fast4<NV_, false>(D, P, st, D.thr_init, s0, bins, values, attempts);                       \
+        }                                                                                               \
+        done = true;                                                                                    \
+    }
+        EMB_INIT_SHAPES(EMB_X)
+#undef EMB_X
+        if (done) {
+            g_last_fast = 1;
+            return 0;
+        }
+    }
     for (int64_t s = 0; s < n; ++s) {
         uint8_t x[MAXX];
         double vals[MAXV];

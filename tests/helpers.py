@@ -49,7 +49,7 @@ def emu_lib():
     here = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(here, "libemb_emu.so")
     srcs = [os.path.join(here, "emu.cpp"), os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", "emb_model.cpp")]
-    deps = srcs + [os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", f) for f in ("emb_device.cuh", "emb_fast.cuh", "emb_model.h")]
+    deps = srcs + [os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", f) for f in ("emb_device.cuh", "emb_fast.cuh", "emb_initial.cuh", "emb_model.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         cuda_inc = "/usr/local/cuda/include"
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared",

@@ -49,15 +49,46 @@ def test_tracks_match_golden(model_paths, golden, name, fast):
     assert used_fast == fast, "every golden model shape is expected to have a specialised kernel"
 
 
+@pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
 @pytest.mark.parametrize("name", sorted(cases.INITIAL_CASES))
-def test_initial_matches_golden(model_paths, golden, name):
+def test_initial_matches_golden(model_paths, golden, name, fast):
+    from helpers import emu_lib
+    lib = emu_lib()
     c = cases.INITIAL_CASES[name]
     p = em_read(model_paths[c["model"]])
     em = EmuModel(model_paths[c["model"]])
-    bins, vals, att = em.sample_initial(p.n_initial, c["n"], c["seed"], c["first"], EmuModel.opts(p.n_initial))
+    lib.emu_use_fast(fast)
+    try:
+        bins, vals, att = em.sample_initial(p.n_initial, c["n"], c["seed"], c["first"], EmuModel.opts(p.n_initial))
+        assert lib.emu_last_fast() == fast
+    finally:
+        lib.emu_use_fast(0)
     assert np.array_equal(bins, golden[name]["bins"])
     assert np.array_equal(vals, golden[name]["values"])
     assert np.all(att == 1)
+
+
+@pytest.mark.parametrize("model,n,start", [
+    ("balloon_v1", 37, None), ("glider_v1", 1001, None), ("glider_v1", 64, [2, None, None, None, None]),
+    ("littoral_uncor_v1", 130, None), ("uncor_1200code_v2p1", 203, [1, 4, 2, None, None, None, None]),
+    ("terminal_v3_radar_encounter_model", 95, None), ("cor_v1", 50, None)])
+def test_initial_specialised_equals_generic(model_paths, model, n, start):
+    """initial_fast4 (4 samples per thread, register state) == sample_initial, ragged n and presets included;
+    cor_v1 has a non-identity topological order and must fall back to the generic routine."""
+    from helpers import emu_lib
+    lib = emu_lib()
+    p = em_read(model_paths[model])
+    em = EmuModel(model_paths[model])
+    o = EmuModel.opts(p.n_initial, start=start)
+    ref = em.sample_initial(p.n_initial, n, 21, 5, o)
+    lib.emu_use_fast(1)
+    try:
+        got = em.sample_initial(p.n_initial, n, 21, 5, o)
+        assert lib.emu_last_fast() == (0 if model == "cor_v1" else 1)
+    finally:
+        lib.emu_use_fast(0)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("name", sorted(cases.TERMINAL_CASES))

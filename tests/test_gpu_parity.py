@@ -72,6 +72,25 @@ def test_specialised_equals_generic_at_scale(model_paths):
     assert torch.equal(a.init_values, b.init_values)
 
 
+@pytest.mark.parametrize("model,n", [("glider_v1", 1_000_003), ("uncor_allcode_fwsingle_v1", 400_000),
+                                     ("terminal_v3_radar_encounter_model", 100_000)])
+def test_initial_specialised_equals_generic_at_scale(model_paths, model, n):
+    """k_initial_fast (4 samples per thread) against k_initial on every output byte, ragged n included."""
+    import torch
+    lib = L.lib()
+    m = EncounterModel(model_paths[model])
+    a = m.sample_initial(n, seed=17, first_sample=3, device="cuda:0")
+    assert lib.emb_debug_last_kernel_fast() == 1
+    lib.emb_debug_force_generic(1)
+    try:
+        b = m.sample_initial(n, seed=17, first_sample=3, device="cuda:0")
+        assert lib.emb_debug_last_kernel_fast() == 0
+    finally:
+        lib.emb_debug_force_generic(0)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
 def test_tracks_device_buffers_match_host_buffers(model_paths, golden):
     name = "uncor_v2p1_n24_T300_seed1"
     got = _run_tracks(model_paths, cases.TRACK_CASES[name], device="cuda:0")

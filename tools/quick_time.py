@@ -30,19 +30,19 @@ def time_tracks(name, n, T, reps=3):
     print("%s n=%d T=%d: %.3f ms  %.3e track-timesteps/s" % (name, n, T, best, n * T / best * 1e3), flush=True)
 
 
-def time_initial(name, n, reps=3):
+def time_initial(name, n, reps=3, want_values=True):
     m = EncounterModel(paths[name])
-    m.sample_initial(n, seed=1, device=dev, want_attempts=False)
+    m.sample_initial(n, seed=1, device=dev, want_attempts=False, want_values=want_values)
     torch.cuda.synchronize()
     best = 1e9
     for r in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        m.sample_initial(n, seed=2 + r, device=dev, want_attempts=False)
+        m.sample_initial(n, seed=2 + r, device=dev, want_attempts=False, want_values=want_values)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    print("%s initial n=%d: %.3f ms  %.3e samples/s" % (name, n, best, n / best * 1e3), flush=True)
+    print("%s initial n=%d values=%s: %.3f ms  %.3e samples/s" % (name, n, want_values, best, n / best * 1e3), flush=True)
 
 
 if __name__ == "__main__":
@@ -54,3 +54,6 @@ if __name__ == "__main__":
     time_tracks("uncor_allcode_fwsingle_v1", 1 << 20, 600)
     time_tracks("glider_v1", 1 << 20, 300)
     time_initial("glider_v1", 1 << 24)
+    time_initial("glider_v1", 1 << 24, want_values=False)
+    time_initial("uncor_allcode_fwsingle_v1", 1 << 24, want_values=False)
+    time_initial("terminal_v3_radar_encounter_model", 1 << 22)
