@@ -110,6 +110,7 @@ def lib():
         "emb_sample_opts_init": (None, [P(SampleOpts)]),
         "emb_sample_initial": (C.c_int, [vp, P(Rng), i64, P(SampleOpts), vp, vp, vp]),
         "emb_sample_tracks": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), P(TrackOut)]),
+        "emb_sample_track_events": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i64, vp, vp, P(TrackOut), P(i64)]),
         "emb_tracks_bins_len": (i64, [vp, i64, i32]),
         "emb_tracks_values_len": (i64, [vp, i64, i32]),
     }
@@ -126,8 +127,11 @@ EXPORTED = [
     "emb_rng_word", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
-    "emb_tracks_bins_len", "emb_tracks_values_len",
+    "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",
 ]
+
+# numpy view of emb_event (include/emb200.h)
+EVENT_DTYPE = [("dt", "<u2"), ("var", "u1"), ("bin", "u1"), ("value", "<f4")]
 
 
 def check(rc):

@@ -476,4 +476,84 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     return 0;
 }
 
+int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                            int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
+                            int64_t* total_rows) {
+    if (!m || !rng || !opts || !offsets || n < 0 || T < 1 || capacity < 0 || (capacity > 0 && !events))
+        return set_err(EMB_E_ARG, "null or out-of-range argument");
+    if (T > 65535) return set_err(EMB_E_LIMIT, "event rows store dt in 16 bits: T must be <= 65535");
+    if (init && (init->bins || init->values || init->hist_initial || init->hist_transition))
+        return set_err(EMB_E_ARG, "emb_sample_track_events: dense outputs and histograms belong to emb_sample_tracks");
+    const HostModel& H = *m->h;
+    if (!H.has_transition || H.temporal_map.empty())
+        return set_err(EMB_E_ARG, "dynvar:empty: model has no transition network");
+    emb::SampleParams P;
+    int rc = 0;
+    try {
+        emb::fill_params(H, rng->seed, rng->first_sample, n, T, *opts, P);
+    } catch (const emb::Error& e) {
+        return set_err(e.code, e.msg);
+    }
+    int device;
+    if ((rc = pick_device(opts, device))) return rc;
+    DevModel D;
+    if ((rc = ensure_device(H, device, D))) return rc;
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    if (total_rows) *total_rows = 0;
+    if (n == 0) {
+        const int64_t zero = 0;
+        if (opts->mem == EMB_MEM_DEVICE) CU(cudaMemcpyAsync(offsets, &zero, 8, cudaMemcpyHostToDevice, st));
+        else offsets[0] = 0;
+        return 0;
+    }
+    Stager sg{opts->mem, st, {}};
+    const size_t ni = (size_t)H.n_initial;
+    emb::TrackOut O{};
+    long long* d_off = nullptr;
+    if ((rc = sg.out(offsets, (size_t)(n + 1) * 8, false, (void**)&d_off))) return rc;
+    if (init) {
+        if ((rc = sg.out(init->init_bins, (size_t)n * ni, false, (void**)&O.init_bins))) return rc;
+        if ((rc = sg.out(init->init_values, (size_t)n * ni * 8, false, (void**)&O.init_values))) return rc;
+        if ((rc = sg.out(init->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
+    }
+    struct Scratch {
+        void* p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } counts, status;
+    CU(cudaMalloc(&counts.p, (size_t)n * 4));
+    CU(cudaMalloc(&status.p, 4));
+    CU(cudaMemsetAsync(status.p, 0, 4, st));
+    O.status = (int32_t*)status.p;
+    // pass 1: rows per track (also writes the per-track initial outputs), then the prefix sum
+    O.ev_counts = (uint32_t*)counts.p;
+    cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event count)");
+    e = (cudaError_t)emb::launch_scan_counts((const uint32_t*)counts.p, d_off, n, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch k_scan_counts");
+    long long total = 0;
+    int32_t flag = 0;
+    CU(cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&flag, status.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (total_rows) *total_rows = total;
+    if (flag) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+    if (total > capacity) {
+        if ((rc = sg.finish())) return rc;   // offsets and the initial outputs are valid
+        return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
+    }
+    // pass 2: write the rows (the keyed stream reproduces pass 1 exactly)
+    uint2* d_ev = nullptr;
+    if ((rc = sg.out(events, (size_t)total * 8, false, (void**)&d_ev))) return rc;
+    O.ev_counts = nullptr;
+    O.ev_offsets = d_off;
+    O.events = d_ev;
+    O.init_bins = nullptr;
+    O.init_values = nullptr;
+    O.attempts = nullptr;
+    e = (cudaError_t)emb::launch_tracks(D, P, O, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
+    CU(cudaStreamSynchronize(st));
+    return sg.finish();
+}
+
 }  // extern "C"

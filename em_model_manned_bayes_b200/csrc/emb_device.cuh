@@ -16,6 +16,8 @@
 #include <cmath>
 #include <cstdint>
 
+#include <vector_types.h>   // uint2 / uint4 (host and device)
+
 #if defined(__CUDACC__)
 #define EMB_HD __host__ __device__ __forceinline__
 #else
@@ -93,6 +95,10 @@ struct TrackOut {
     unsigned long long* hist_initial;
     unsigned long long* hist_transition;
     int32_t* status;               // device flag: set to 1 if any sample exhausted max_attempts
+    // sparse event list (emb200.h: emb_event), two passes: count rows per track, then write them
+    uint32_t* ev_counts;           // pass 1: [n] rows of each track (including the closing row)
+    const long long* ev_offsets;   // pass 2: [n] first row of each track
+    uint2* events;                 // pass 2: rows
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -331,7 +337,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
         if (O.init_values) O.init_values[(int64_t)i * N + s] = vals[i];
         if (O.hist_initial) hist_inc(0, i, x[i]);
     }
-    if (T <= 0 || (!O.bins && !O.values && !O.hist_transition)) return;
+    if (T <= 0 || (!O.bins && !O.values && !O.hist_transition && !O.ev_counts && !O.events)) return;
 
     // frozen columns of the fast branch (dbn_sample.m:110-135): parents evaluated once at t = 1
     const uint32_t* col[MAXD];
@@ -339,6 +345,26 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
         x[M.dyn_t1[d]] = x[M.dyn_t[d]];
         col[d] = node_column(M.dyn[d], M.thr_trans, x);
     }
+
+    // event list (emb200.h: emb_event): pass 1 counts rows, pass 2 writes them
+    const bool ev = O.ev_counts || O.events;
+    uint2* ev_ptr = O.events ? O.events + O.ev_offsets[s] : nullptr;
+    uint32_t ev_last = 0, ev_n = 0;
+    auto emit = [&](uint32_t e, uint32_t var1, uint32_t bin1, double value) {
+        if (ev_ptr) {
+            const float f = (float)value;
+            uint2 row;
+            row.x = (e - ev_last) | (var1 << 16) | (bin1 << 24);
+#if defined(__CUDA_ARCH__)
+            row.y = __float_as_uint(f);
+#else
+            __builtin_memcpy(&row.y, &f, 4);
+#endif
+            *ev_ptr++ = row;
+        }
+        ev_last = e;
+        ++ev_n;
+    };
 
     WordStream ws;
     ws.init(P.seed, sample, (uint32_t)attempt, P_STEP);
@@ -359,6 +385,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 if ((uint64_t)k < M.gate_G[g]) {
                     const int v = M.gated_var[g];
                     vals[v] = dedisc(M, v, x[v], u_dd(k));
+                    if (ev) emit((uint32_t)c, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, vals[v]);
                 }
             }
             // transitions (dbn_sample.m:69-79 slow / :143-146 fast)
@@ -375,6 +402,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 if (nb != x[vt]) {
                     x[vt] = nb;
                     vals[vt] = dedisc(M, vt, nb, u_dd(wstep[nd + M.gate_of_dyn[d]]));
+                    if (ev) emit((uint32_t)c, (uint32_t)vt + 1u, (uint32_t)nb + 1u, vals[vt]);
                 }
             }
         }
@@ -408,6 +436,18 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
             }
             for (int d = 0; d < nd; ++d) bpack[d] = 0;
         }
+    }
+    if (ev) {
+        // gates of the last held second T (resample_events.m:23-29), then the closing row (dbn_hierarchical_sample.m:15-19)
+        for (int g = 0; g < ng; ++g) {
+            const uint32_t k = ws.at((uint32_t)T * (uint32_t)nw + (uint32_t)(nd + g));
+            if ((uint64_t)k < M.gate_G[g]) {
+                const int v = M.gated_var[g];
+                emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k)));
+            }
+        }
+        emit((uint32_t)T, 0u, 0u, 0.0);
+        if (O.ev_counts) O.ev_counts[s] = ev_n;
     }
 }
 

@@ -86,7 +86,8 @@ EMB_HD float fmaf_rn(float a, float b, float c) {
 #endif
 }
 
-template <uint32_t RS, int NG, bool FAST, bool HIST, class HistInc>
+// EV: 0 = dense outputs only, 1 = also count the rows of the event list, 2 = also write them (see emb200.h: emb_event)
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, class HistInc>
 struct FastTrack {
     using SH = DynShape<RS>;
     static constexpr int ND = SH::ND;
@@ -107,9 +108,30 @@ struct FastTrack {
     int ebase[NG];            // entry-table bases (uniform)
     uint32_t G[NG];           // gate thresholds (uniform)
     uint32_t c0, c1w, w3;
+    uint32_t sbin1[NS > 0 ? NS : 1];   // EV: 1-based bins of the static gated variables
+    uint32_t ev_last, ev_n;            // EV: second of the last row, rows so far
+    uint2* ev_ptr;                     // EV == 2: next row of this track
 
     EMB_HD FastTrack(const DevModel& M_, const SampleParams& P_, const FastShared& S_, HistInc h)
         : M(M_), P(P_), S(S_), hist_inc(h) {}
+
+    // one row [dt, var, value] of out_events (dbn_hierarchical_sample.m:9-37 after resample_events.m:11-37):
+    // dt = seconds since the previous row, 0 for further rows of the same second
+    EMB_HD void emit(bool on, uint32_t e, uint32_t var1, uint32_t bin1, float value) {
+        if (!on) return;
+        if (EV == 2) {
+            uint2 row;
+            row.x = (e - ev_last) | (var1 << 16) | (bin1 << 24);
+#if defined(__CUDA_ARCH__)
+            row.y = __float_as_uint(value);
+#else
+            __builtin_memcpy(&row.y, &value, 4);
+#endif
+            *ev_ptr++ = row;
+        }
+        ev_last = e;
+        ++ev_n;
+    }
 
     // one group of four seconds e = 4*grp .. 4*grp+3; CHECK = the group may contain e == 0 or e >= T
     template <bool CHECK>
@@ -125,6 +147,7 @@ struct FastTrack {
             const int e = 4 * grp + j;
             const bool act = !CHECK || (e > 0 && e < T);
             const bool live = !CHECK || e < T;
+            const bool act_gate = !CHECK || (e > 0 && e <= T);   // EV: second T still draws its gates (resample_events.m:23)
             // ---- transitions: new bins from the words of this second --------------------------------
             uint32_t nb[ND];
 #pragma unroll
@@ -172,6 +195,8 @@ struct FastTrack {
             }
             // ---- values: gate (resample_events.m:23-29) and/or bin change (dbn_sample.m:82-92) ------
             // bin[] / nb[] hold entry-table indices (ebase + bin), see track_fast
+            bool ev_chg[ND];
+            float ev_val[ND];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const uint32_t k = W[j * NW + ND + g];
@@ -180,25 +205,32 @@ struct FastTrack {
                 if (g >= NS) en = S.ent[nb[d >= 0 ? d : 0]];
                 else en = sent[g < NS ? g : 0];
                 const float gp = fmaf_rn(dd_fraction(k), en.s, en.c);
-#if defined(__CUDA_ARCH__)
-                // val = (k < G || nb != bin) ? fma(slope, gp, base) : val   as a predicated FFMA (no FSEL)
-                if (!CHECK) {
-                    if (g >= NS)
-                        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %4, %5;\n\tsetp.ne.or.u32 q, %6, %7, q;\n\t"
-                            "@q fma.rn.f32 %0, %1, %2, %3;\n\t}"
-                            : "+f"(val[g]) : "f"(en.slope), "f"(gp), "f"(en.base), "r"(k), "r"(G[g]), "r"(nb[d >= 0 ? d : 0]), "r"(bin[d >= 0 ? d : 0]));
-                    else
-                        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %4, %5;\n\t@q fma.rn.f32 %0, %1, %2, %3;\n\t}"
-                            : "+f"(val[g]) : "f"(en.slope), "f"(gp), "f"(en.base), "r"(k), "r"(G[g]));
-                } else
-#endif
-                {
-                    bool p = k < G[g];
-                    if (g >= NS) p = p || (nb[d >= 0 ? d : 0] != bin[d >= 0 ? d : 0]);
-                    if (p && act) val[g] = fmaf_rn(en.slope, gp, en.base);
+                const float cand = fmaf_rn(en.slope, gp, en.base);
+                const bool fired = k < G[g];
+                const bool changed = g >= NS && nb[d >= 0 ? d : 0] != bin[d >= 0 ? d : 0];
+                if ((fired || changed) && act) val[g] = cand;
+                if (EV) {
+                    // gate row: the re-emitted *current* bin (resample_events.m:26-29); when the variable also changes
+                    // in this second the row is hidden in the dense output but present in the list
+                    float gv = cand;
+                    uint32_t b1 = g >= NS ? bin[d >= 0 ? d : 0] - (uint32_t)ebase[g] + 1u : sbin1[g < NS ? g : 0];
+                    if (g >= NS && fired && changed) {
+                        const DdEntry eo = S.ent[bin[d >= 0 ? d : 0]];
+                        gv = fmaf_rn(eo.slope, fmaf_rn(dd_fraction(k), eo.s, eo.c), eo.base);
+                    }
+                    emit(fired && act_gate, (uint32_t)e, (uint32_t)M.gated_var[g] + 1u, b1, gv);
+                    if (g >= NS) {
+                        ev_chg[d >= 0 ? d : 0] = changed && act;
+                        ev_val[d >= 0 ? d : 0] = cand;
+                    }
                 }
                 if (g >= NS) bin[d >= 0 ? d : 0] = nb[d >= 0 ? d : 0];
                 vout[g][j] = live ? val[g] : 0.0f;
+            }
+            if (EV) {   // transition rows follow the gate rows of the same second, variables ascending (dbn_sample.m:84-92)
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    emit(ev_chg[d], (uint32_t)e, (uint32_t)M.dyn_t[d] + 1u, bin[d] - (uint32_t)ebase[NS + d] + 1u, ev_val[d]);
             }
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
@@ -214,10 +246,10 @@ struct FastTrack {
     }
 };
 
-template <uint32_t RS, int NG, bool FAST, bool HIST, class HistInc>
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, class HistInc>
 EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut& O, int64_t s, const FastShared& S,
                        HistInc hist_inc) {
-    using FT = FastTrack<RS, NG, FAST, HIST, HistInc>;
+    using FT = FastTrack<RS, NG, FAST, HIST, EV, HistInc>;
     using SH = DynShape<RS>;
     constexpr int ND = FT::ND, NS = FT::NS;
     const uint64_t sample = P.first_sample + (uint64_t)s;
@@ -242,7 +274,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
             if (O.init_values) O.init_values[(int64_t)i * N + s] = vals[i];
             if (O.hist_initial) hist_inc(0, i, x[i]);
         }
-        if (T <= 0 || (!O.bins && !O.values && !O.hist_transition)) return;
+        if (T <= 0 || (!EV && !O.bins && !O.values && !O.hist_transition)) return;
         {
             int b = 0;
 #pragma unroll
@@ -251,9 +283,15 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                 b += M.init[M.gated_var[g]].r;
                 ft.G[g] = (uint32_t)M.gate_G[g];
                 ft.val[g] = (float)vals[M.gated_var[g]];
-                if (g < NS) ft.sent[g] = S.ent[ft.ebase[g] + (int)x[M.gated_var[g]]];
+                if (g < NS) {
+                    ft.sent[g] = S.ent[ft.ebase[g] + (int)x[M.gated_var[g]]];
+                    ft.sbin1[g] = (uint32_t)x[M.gated_var[g]] + 1u;
+                }
             }
         }
+        ft.ev_last = 0;
+        ft.ev_n = 0;
+        ft.ev_ptr = EV == 2 ? O.events + O.ev_offsets[s] : nullptr;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             ft.bin[d] = (uint32_t)ft.ebase[NS + d] + x[M.dyn_t[d]];
@@ -304,11 +342,13 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     int8_t* pb = O.bins ? O.bins + s * 4 : nullptr;
     float* pv = O.values ? O.values + s * 4 : nullptr;
     const int64_t var_stride = (int64_t)nch4 * N * 4;   // elements between consecutive variables
-    for (int grp = 0; grp < nch4; ++grp) {
+    const int ngrp = EV ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
+    for (int grp = 0; grp < ngrp; ++grp) {
         uint32_t bout[ND];
         float vout[NG][4];
         if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout);
         else ft.template group<true>(grp, T, bout, vout);
+        if (EV && grp >= nch4) break;
         if (O.values) {
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -333,6 +373,10 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
             }
             pb += N * 4;
         }
+    }
+    if (EV) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
+        ft.emit(true, (uint32_t)T, 0u, 0u, 0.0f);
+        if (EV == 1) O.ev_counts[s] = ft.ev_n;
     }
 }
 

@@ -113,7 +113,7 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
 }
 
 // ---- tracks, register-resident specialisation (emb_fast.cuh) --------------------------------------
-template <uint32_t RS, int NG, bool FAST, bool HIST>
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV>
 __global__ void __launch_bounds__(BLOCK, EMB_MINBLOCKS)
 k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
               const __grid_constant__ TrackOut O) {
@@ -124,11 +124,55 @@ k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sample
         for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) track_fast<RS, NG, FAST, HIST>(M, P, O, s, S, SmemHist{sh});
+    if (s < P.n) track_fast<RS, NG, FAST, HIST, EV>(M, P, O, s, S, SmemHist{sh});
     if (HIST) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
+// ---- exclusive prefix sum of the per-track row counts (one block; n is at most a few 10^7) -------
+__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict__ counts, long long* __restrict__ offsets,
+                                                      long long n) {
+    __shared__ long long warp_sum[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const long long v = i < n ? (long long)counts[i] : 0;
+        long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            long long t = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(0xFFFFFFFFu, t, o);
+                if (lane >= o) t += y;
+            }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        const long long before = carry + (w ? warp_sum[w - 1] : 0) + x - v;
+        if (i < n) offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
 }  // namespace
+
+int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, void* stream) {
+    k_scan_counts<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, offsets, n);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------------
 int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
@@ -186,11 +230,14 @@ int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, v
     const uint32_t rs = g_force_generic ? 0u : fast_shape_of(M);
     const bool fast = M.fast != 0;
     const bool hist = O.hist_initial || O.hist_transition;
+    const int ev = O.ev_counts ? 1 : O.events ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
     bool done = false;
 #define EMB_X(RS_, NG_, FAST_)                                                                          \
     if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_)) {                                \
-        if (hist) k_tracks_fast<RS_, NG_, FAST_, true><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
-        else k_tracks_fast<RS_, NG_, FAST_, false><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);   \
+        if (ev == 1) k_tracks_fast<RS_, NG_, FAST_, false, 1><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);      \
+        else if (ev == 2) k_tracks_fast<RS_, NG_, FAST_, false, 2><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
+        else if (hist) k_tracks_fast<RS_, NG_, FAST_, true, 0><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);     \
+        else k_tracks_fast<RS_, NG_, FAST_, false, 0><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);              \
         done = true;                                                                                    \
     }
     EMB_FAST_SHAPES(EMB_X)

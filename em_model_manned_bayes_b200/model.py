@@ -290,11 +290,107 @@ class EncounterModel:
         return out
 
 
+@dataclass
+class EventResult:
+    """Sparse result of `EncounterModel.sample_events`: row k of track s is events[offsets[s] + k]."""
+    n: int
+    T: int
+    events: object        # structured array (host) or int64 tensor viewing emb_event rows (device)
+    offsets: object       # int64 [n + 1]
+    init_bins: Optional[object]
+    init_values: Optional[object]
+    attempts: Optional[object]
+    total: int
+
+    def track(self, s: int) -> np.ndarray:
+        """out_events{s+1} as a k x 3 float64 matrix [dt, var, value] (host results only)."""
+        o = np.asarray(self.offsets)
+        e = np.asarray(self.events)[int(o[s]):int(o[s + 1])]
+        return np.stack([e["dt"].astype(np.float64), e["var"].astype(np.float64), e["value"].astype(np.float64)], axis=1)
+
+
+def events2samples(initial, events) -> np.ndarray:
+    """events2samples.m:9-27 (host-side expansion of one track's event list to n_initial x T)."""
+    n = len(initial)
+    T = int(sum(e[0] for e in events))
+    d = np.zeros((n, T))
+    x = np.array(initial, dtype=np.float64)
+    t = 0
+    for (delta_t, var, val) in events:
+        delta_t = int(delta_t)
+        if var == 0:
+            t = t + 1
+            d[:, t - 1: t - 1 + delta_t] = x[:, None]
+        else:
+            if delta_t > 0:
+                d[:, t: t + delta_t] = x[:, None]
+                t = t + delta_t
+            x[int(var) - 1] = val
+    return d
+
+
+def events2controls(initial, events, temporal_map) -> np.ndarray:
+    """events2controls.m:9-31: one row [t, x(temporal_map(:,1))] per event with dt > 0, before applying it."""
+    vars_ = np.asarray(temporal_map)[:, 0] - 1
+    x = np.array(initial, dtype=np.float64)
+    rows = []
+    t = 0
+    for (delta_t, var, val) in events:
+        if delta_t > 0:
+            rows.append(np.concatenate(([t], x[vars_])))
+            t = t + delta_t
+        if var > 0:
+            x[int(var) - 1] = val
+    return np.asarray(rows).reshape(-1, 1 + len(vars_))
+
+
 def _find(labels, name):
     for i, l in enumerate(labels):
         if l == name:
             return i + 1
     return 0
+
+
+def _sample_events(self, n: int, T: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
+                   want_init=True, capacity: Optional[int] = None) -> EventResult:
+    """Sparse tracks (emb200.h: emb_sample_track_events): the reference's out_events lists."""
+    lib = L.lib()
+    o = opts if opts is not None else self._opts(start=start)
+    if device is not None:
+        import torch
+        dev = torch.device(device)
+        o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+        o.stream = torch.cuda.current_stream(dev).cuda_stream
+    ni = self.n_initial
+    ib = self._alloc((ni, n), np.int8, device) if want_init else None
+    iv = self._alloc((ni, n), np.float64, device) if want_init else None
+    att = self._alloc((n,), np.uint16, device) if want_init else None
+    init = L.TrackOut(None, None, _ptr(ib), _ptr(iv), _ptr(att), None, None)
+    rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
+    total = C.c_int64(0)
+    if capacity is None:   # expected rows: T * (sum of rates + a transition allowance) + slack
+        capacity = int(n * (T * (float(np.sum(self.resample_rates)) + 0.15) + 8)) + 1024
+
+    def alloc(cap):
+        if device is None:
+            return np.zeros(max(cap, 1), dtype=L.EVENT_DTYPE), np.zeros(n + 1, dtype=np.int64)
+        import torch
+        return torch.zeros(max(cap, 1), dtype=torch.int64, device=device), torch.zeros(n + 1, dtype=torch.int64, device=device)
+
+    ev, off = alloc(capacity)
+    rc = lib.emb_sample_track_events(self._h, C.byref(rng), n, T, C.byref(o), capacity, _ptr(ev), _ptr(off), C.byref(init),
+                                     C.byref(total))
+    if rc == L.EMB_E_LIMIT and total.value > capacity:
+        capacity = int(total.value)
+        ev, off = alloc(capacity)
+        rc = lib.emb_sample_track_events(self._h, C.byref(rng), n, T, C.byref(o), capacity, _ptr(ev), _ptr(off),
+                                         C.byref(init), C.byref(total))
+    L.check(rc)
+    return EventResult(n=n, T=T, events=ev[:total.value], offsets=off, init_bins=ib, init_values=iv, attempts=att,
+                       total=int(total.value))
+
+
+EncounterModel.sample_events = _sample_events
 
 
 class UncorEncounterModel(EncounterModel):
@@ -332,21 +428,35 @@ class UncorEncounterModel(EncounterModel):
         return self.sample_tracks(n_samples, sample_time, seed=seed, first_sample=first_sample, opts=o,
                                   device=device, **kw)
 
+    def sample_events_uncor(self, n_samples: int, sample_time: int, seed: int = 0, first_sample: int = 0,
+                            isQuantize500=False, layers=None, device=None, **kw) -> EventResult:
+        """The batch form of UncorEncounterModel.m:244-307 with the reference's sparse outputs."""
+        return self.sample_events(n_samples, sample_time, seed=seed, first_sample=first_sample,
+                                  opts=self.uncor_opts(isQuantize500, layers), device=device, **kw)
+
     def sample(self, n_samples: int, sample_time: int, seed=float("nan"), isQuantize500=False, layers=None):
-        """UncorEncounterModel.m:192-313 -> (out_inits n x n_initial, out_samples list of n_initial x T).
-        `seed` NaN draws a fresh 64-bit seed (the reference keeps the global stream; here streams are keyed)."""
+        """UncorEncounterModel.m:192-313 -> (out_inits n x n_initial, out_events list of k x 3 [dt var value],
+        out_samples list of n_initial x T, out_EME list of controls [t, dh ft/s, dpsi rad/s, dv ft/s^2]).
+        `seed` NaN draws a fresh 64-bit seed (the reference keeps the global stream; here streams are keyed).
+        out_samples is expanded on the host from the event lists exactly as events2samples.m does."""
         if isinstance(seed, float) and math.isnan(seed):
             seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
-        res = self.sample_compact(n_samples, sample_time, seed=int(seed), isQuantize500=isQuantize500, layers=layers)
+        res = self.sample_events_uncor(n_samples, sample_time, seed=int(seed), isQuantize500=isQuantize500, layers=layers)
         out_inits = np.ascontiguousarray(res.init_values.T)
-        vals = res.values
-        out_samples = []
-        tv0 = [v - 1 for v in res.tv_vars]
+        out_events, out_samples, out_EME = [], [], []
+        order = [self.idxDH, self.idxDPsi, self.idxDV]                       # UncorEncounterModel.m:291-292
+        cols = [1 + list(self.temporal_map[:, 0]).index(v) for v in order]
         for k in range(n_samples):
-            d = np.repeat(out_inits[k][:, None], sample_time, axis=1)
-            d[tv0, :] = vals[k].astype(np.float64)
-            out_samples.append(d)
-        return out_inits, out_samples, res
+            ev = res.track(k)
+            out_events.append(ev)
+            out_samples.append(events2samples(out_inits[k], ev))
+            c = events2controls(out_inits[k], ev, self.temporal_map)
+            c = c[:, [0] + cols]
+            c[:, 1] = c[:, 1] / 60.0                                          # :295 ft/min -> ft/s
+            c[:, 2] = np.deg2rad(c[:, 2])                                     # :296
+            c[:, 3] = c[:, 3] * 1.68780972222222                              # :297 kt/s -> ft/s^2
+            out_EME.append(c)
+        return out_inits, out_events, out_samples, out_EME
 
 
 class CorTerminalModel(EncounterModel):

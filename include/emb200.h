@@ -159,6 +159,24 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
 int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T);
 int64_t emb_tracks_values_len(const emb_model* m, int64_t n, int32_t T);
 
+/* ---- tracks as sparse event lists: the reference's own track representation, out_events{ii} of
+ *      UncorEncounterModel.m:253-300 = dbn_hierarchical_sample.m:9-37 (dbn_sample.m:84-92/151-161 change
+ *      rows, resample_events.m:17-36 re-emitted bins, closing row :15-19), already de-discretised ----- */
+typedef struct emb_event {
+    uint16_t dt;   /* seconds since the previous row (0 for further rows of the same second) */
+    uint8_t var;   /* 1-based variable id, 0 in the closing row */
+    uint8_t bin;   /* 1-based bin the value was drawn in (oracle extra), 0 in the closing row */
+    float value;   /* de-discretised value (the bin itself for '*' variables) */
+} emb_event;       /* 8 bytes; row k of track s is events[offsets[s] + k] */
+/* Two device passes (count rows per track, prefix-sum, write).  offsets: int64 [n+1] (offsets[n] = total rows),
+ * events: capacity rows.  *total_rows (host, nullable) always receives the number of rows; if it exceeds
+ * `capacity` nothing is written to `events` and EMB_E_LIMIT is returned -- call again with a larger buffer
+ * (the stream is keyed, the result is the same).  `init` (nullable) may carry init_bins / init_values /
+ * attempts; its dense fields and histograms must be NULL.  Requires T <= 65535. */
+int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                            int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
+                            int64_t* total_rows);
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 int emb_host_alloc(void** p, int64_t bytes); /* pinned host memory */
 int emb_host_free(void* p);

@@ -49,3 +49,16 @@ def check_tracks(got, want, rtol=1e-6):
     gv, wv = np.asarray(got["values"], dtype=np.float64), want["values"]
     assert gv.shape == wv.shape
     assert np.all(np.abs(gv - wv) <= rtol * np.abs(wv)), "continuous values differ by more than 1e-6 relative"
+
+
+def check_events(ev, off, want, rtol=1e-6):
+    """ev: structured emb_event rows, off: int64 [n+1]; want: golden case dict (events k x 3, event_bins, event_offsets).
+    dt, var and bin must be identical row by row; values within rtol (fp32 on the device)."""
+    ev, off = np.asarray(ev), np.asarray(off)
+    assert np.array_equal(off, want["event_offsets"]), "rows per track differ"
+    w = want["events"]
+    assert np.array_equal(ev["dt"].astype(np.float64), w[:, 0]), "event dt differ"
+    assert np.array_equal(ev["var"].astype(np.float64), w[:, 1]), "event variables differ"
+    assert np.array_equal(ev["bin"].astype(np.float64), want["event_bins"]), "event bins differ"
+    gv = ev["value"].astype(np.float64)
+    assert np.all(np.abs(gv - w[:, 2]) <= rtol * np.abs(w[:, 2])), "event values differ by more than 1e-6 relative"

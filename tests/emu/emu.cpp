@@ -146,7 +146,7 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
         fast_fill_shared(D, S, 0, 1);
 #define EMB_X(RS_, NG_, FAST_)                                                         \
     if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_)) {               \
-        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_, true>(D, P, O, s, S, hh); \
+        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_, true, 0>(D, P, O, s, S, hh); \
         done = true;                                                                   \
     }
         EMB_FAST_SHAPES(EMB_X)
@@ -155,6 +155,63 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
     g_last_fast = done ? 1 : 0;
     if (!done)
         for (int64_t s = 0; s < n; ++s) track_generic(D, P, O, s, hh);
+    return status ? EMB_E_REJECT : 0;
+}
+
+// host emulation of emb_sample_track_events: pass 1 counts, prefix sum, pass 2 writes (same device code)
+int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t T, const emb_sample_opts* o,
+                            int64_t capacity, emb_event* events, int64_t* offsets, int64_t* total_rows) {
+    const HostModel& H = *static_cast<HostModel*>(h);
+    SampleParams P;
+    try {
+        fill_params(H, seed, first, n, T, *o, P);
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+    const DevModel D = host_dev(H);
+    int32_t status = 0;
+    std::vector<uint32_t> counts((size_t)n);
+    std::vector<long long> off((size_t)n + 1);
+    HostHist hh{nullptr, nullptr};
+    static FastShared S;
+    fast_fill_shared(D, S, 0, 1);
+    const uint32_t rs = g_use_fast ? fast_shape_of(D) : 0;
+    const bool fast = D.fast != 0;
+    for (int pass = 1; pass <= 2; ++pass) {
+        TrackOut O{};
+        O.status = &status;
+        if (pass == 1) O.ev_counts = counts.data();
+        else {
+            O.ev_offsets = off.data();
+            O.events = reinterpret_cast<uint2*>(events);
+        }
+        bool done = false;
+#define EMB_X(RS_, NG_, FAST_)                                                                          \
+    if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_)) {                                \
+        for (int64_t s = 0; s < n; ++s) {                                                               \
+            if (pass == 1) track_fast<RS_, NG_, FAST_, false, 1>(D, P, O, s, S, hh);                    \
+            else track_fast<RS_, NG_, FAST_, false, 2>(D, P, O, s, S, hh);                              \
+        }                                                                                               \
+        done = true;                                                                                    \
+    }
+        EMB_FAST_SHAPES(EMB_X)
+#undef EMB_X
+        g_last_fast = done ? 1 : 0;
+        if (!done)
+            for (int64_t s = 0; s < n; ++s) track_generic(D, P, O, s, hh);
+        if (pass == 1) {
+            long long acc = 0;
+            for (int64_t s = 0; s < n; ++s) {
+                off[(size_t)s] = acc;
+                acc += counts[(size_t)s];
+            }
+            off[(size_t)n] = acc;
+            for (int64_t s = 0; s <= n; ++s) offsets[s] = off[(size_t)s];
+            *total_rows = acc;
+            if (acc > capacity) return EMB_E_LIMIT;
+        }
+    }
     return status ? EMB_E_REJECT : 0;
 }
 

@@ -65,7 +65,11 @@ def pack_model(p):
 
 def tracks_case(p, out):
     bins, vals, dyn, tv = oracle_dense(p, out)
-    return dict(bins=bins, values=vals, dyn=np.array(dyn), tv=np.array(tv),
+    # sparse event lists (out_events) of all tracks, concatenated: [dt, var, value] + the bin each value was drawn in
+    ev = np.concatenate([np.asarray(s.events, dtype=np.float64).reshape(-1, 3) for s in out])
+    evb = np.concatenate([np.asarray(s.event_bins, dtype=np.float64).ravel() for s in out])
+    evo = np.concatenate([[0], np.cumsum([len(s.events) for s in out])]).astype(np.int64)
+    return dict(bins=bins, values=vals, dyn=np.array(dyn), tv=np.array(tv), events=ev, event_bins=evb, event_offsets=evo,
                 init_bins=np.stack([s.initial_bins for s in out]).astype(np.int8),
                 init_values=np.stack([s.initial for s in out]),
                 attempts=np.array([s.attempts for s in out], dtype=np.int32))

@@ -63,6 +63,7 @@ def emu_lib():
     lib.emu_set_prior.argtypes = [vp, C.c_int, C.c_int, C.c_double]
     lib.emu_sample_initial.argtypes = [vp, u64, u64, i64, C.POINTER(L.SampleOpts), vp, vp, vp]
     lib.emu_sample_tracks.argtypes = [vp, u64, u64, i64, i32, C.POINTER(L.SampleOpts), C.POINTER(L.TrackOut)]
+    lib.emu_sample_track_events.argtypes = [vp, u64, u64, i64, i32, C.POINTER(L.SampleOpts), i64, vp, vp, C.POINTER(i64)]
     lib.emu_use_fast.argtypes = [C.c_int]
     lib.emu_last_fast.restype = C.c_int
     _emu = lib
@@ -124,6 +125,18 @@ class EmuModel:
         if rc:
             raise L.EmbError(rc, self.lib.emu_last_error().decode())
         return bins.T, vals.T, att
+
+    def sample_events(self, n, T, seed, first, opts, capacity=None):
+        """-> (events structured array, offsets int64 [n+1])"""
+        cap = capacity if capacity is not None else n * (8 * T + 8)
+        ev = np.zeros(max(cap, 1), dtype=L.EVENT_DTYPE)
+        off = np.zeros(n + 1, dtype=np.int64)
+        total = C.c_int64(0)
+        rc = self.lib.emu_sample_track_events(self.h, seed, first, n, T, C.byref(opts), cap, ev.ctypes.data, off.ctypes.data,
+                                              C.byref(total))
+        if rc:
+            raise L.EmbError(rc, self.lib.emu_last_error().decode())
+        return ev[:total.value], off
 
     def sample_tracks(self, n_initial, n_dyn, n_tv, n, T, seed, first, opts, hist=False):
         nch = (T + 3) // 4

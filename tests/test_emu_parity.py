@@ -10,7 +10,7 @@ from helpers import EmuModel
 from oracle.em_read import em_read
 
 
-def _run_tracks(model_paths, c):
+def _model_and_opts(model_paths, c):
     path = model_paths[c["model"]]
     ow = c.get("overwrite", ())
     p = em_read(path, isOverwriteZeroBoundaries=bool(ow), idxZeroBoundaries=ow or (1, 2, 3))
@@ -27,7 +27,11 @@ def _run_tracks(model_paths, c):
             kw["is_quantize500"] = 1
         if c.get("layers") is not None:
             kw["layers"] = c["layers"]
-    o = EmuModel.opts(p.n_initial, start=c.get("start"), **kw)
+    return p, em, EmuModel.opts(p.n_initial, start=c.get("start"), **kw)
+
+
+def _run_tracks(model_paths, c):
+    p, em, o = _model_and_opts(model_paths, c)
     nd = p.temporal_map.shape[0]
     ntv = len(set(p.temporal_map[:, 0]) | {i + 1 for i in range(p.n_initial) if p.resample_rates[i] > 0})
     return em.sample_tracks(p.n_initial, nd, ntv, c["n"], c["T"], c["seed"], c.get("first", 0), o)
@@ -47,6 +51,23 @@ def test_tracks_match_golden(model_paths, golden, name, fast):
         lib.emu_use_fast(0)
     cases.check_tracks(got, golden[name])
     assert used_fast == fast, "every golden model shape is expected to have a specialised kernel"
+
+
+@pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
+@pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
+def test_event_lists_match_golden(model_paths, golden, name, fast):
+    """out_events (dbn_hierarchical_sample.m:9-37): rows, order, dt, variable and bin identical to the oracle."""
+    from helpers import emu_lib
+    lib = emu_lib()
+    c = cases.TRACK_CASES[name]
+    p, em, o = _model_and_opts(model_paths, c)
+    lib.emu_use_fast(fast)
+    try:
+        ev, off = em.sample_events(c["n"], c["T"], c["seed"], c.get("first", 0), o)
+        assert lib.emu_last_fast() == fast
+    finally:
+        lib.emu_use_fast(0)
+    cases.check_events(ev, off, golden[name])
 
 
 @pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])

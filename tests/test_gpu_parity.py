@@ -53,6 +53,78 @@ def test_tracks_match_golden(model_paths, golden, name, generic):
     assert was_fast == (0 if generic else 1)
 
 
+def _opts_of(m, c):
+    if c["uncor"]:
+        return m.uncor_opts(isQuantize500=c.get("q500", False), layers=c.get("layers"), start=c.get("start"))
+    return m._opts(start=c.get("start"))
+
+
+@pytest.mark.parametrize("generic", [0, 1], ids=["specialised", "generic"])
+@pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
+def test_event_lists_match_golden(model_paths, golden, name, generic):
+    """emb_sample_track_events (count pass, device prefix sum, write pass) against the oracle's out_events:
+    same rows in the same order, dt / variable / bin identical, values within 1e-6."""
+    lib = L.lib()
+    c = cases.TRACK_CASES[name]
+    m = _model(model_paths, c)
+    lib.emb_debug_force_generic(generic)
+    try:
+        res = m.sample_events(c["n"], c["T"], seed=c["seed"], first_sample=c.get("first", 0), opts=_opts_of(m, c))
+        assert lib.emb_debug_last_kernel_fast() == (0 if generic else 1)
+    finally:
+        lib.emb_debug_force_generic(0)
+    cases.check_events(res.events, res.offsets, golden[name])
+    assert np.array_equal(res.init_values.T, golden[name]["init_values"])
+    assert np.array_equal(res.attempts.astype(np.int64), golden[name]["attempts"].astype(np.int64))
+
+
+def test_event_buffer_too_small_is_reported_and_retried(model_paths):
+    c = cases.TRACK_CASES["uncor_v2p1_n24_T300_seed1"]
+    m = _model(model_paths, c)
+    a = m.sample_events(c["n"], c["T"], seed=c["seed"], opts=_opts_of(m, c), capacity=10)      # forces the retry
+    b = m.sample_events(c["n"], c["T"], seed=c["seed"], opts=_opts_of(m, c))
+    assert a.total == b.total and np.array_equal(a.events, b.events) and np.array_equal(a.offsets, b.offsets)
+
+
+def test_events_expand_to_the_dense_output_at_scale(model_paths):
+    """200k tracks x 600 s on the device: events2samples(event list) == dense tiles, bit for bit (same fp32 values),
+    and both kernels give the same rows."""
+    import torch
+    from em_model_manned_bayes_b200.model import events2samples
+    lib = L.lib()
+    n, T = 200_000, 600
+    m = UncorEncounterModel(model_paths["uncor_allcode_fwsingle_v1"])
+    ev = m.sample_events_uncor(n, T, seed=5, device="cuda:0")
+    dense = m.sample_compact(n, T, seed=5, device="cuda:0")
+    lib.emb_debug_force_generic(1)
+    try:
+        evg = m.sample_events_uncor(n, T, seed=5, device="cuda:0")
+    finally:
+        lib.emb_debug_force_generic(0)
+    assert torch.equal(ev.offsets, evg.offsets)
+    a = ev.events.cpu().numpy().view(L.EVENT_DTYPE)
+    g = evg.events.cpu().numpy().view(L.EVENT_DTYPE)
+    for f in ("dt", "var", "bin"):
+        assert np.array_equal(a[f], g[f])
+    assert np.all(np.abs(a["value"].astype(np.float64) - g["value"]) <= 1e-6 * np.abs(g["value"].astype(np.float64)))
+    off = ev.offsets.cpu().numpy()
+    assert off[-1] == ev.total and np.all(np.diff(off) >= 1)
+    # every track: sum(dt) == T, closing row has var 0
+    last = a[off[1:] - 1]
+    assert np.all(last["var"] == 0)
+    assert np.array_equal(np.add.reduceat(a["dt"].astype(np.int64), off[:-1]), np.full(n, T))
+    iv = dense.init_values.cpu().numpy().T
+    tv0 = [v - 1 for v in dense.tv_vars]
+    vals = dense.values[:64].cpu().numpy()
+    for k in range(64):
+        rows = a[off[k]:off[k + 1]]
+        ev3 = np.stack([rows["dt"].astype(np.float64), rows["var"].astype(np.float64), rows["value"].astype(np.float64)], 1)
+        init32 = iv[k].copy()
+        init32[tv0] = vals[k][:, 0]                       # dense values are fp32
+        d = events2samples(init32, ev3)
+        assert np.array_equal(d[tv0, :].astype(np.float32), vals[k])
+
+
 def test_specialised_equals_generic_at_scale(model_paths):
     """100k tracks x 600 s: the two kernels must agree bit-for-bit on every bin and, because the
     specialised kernel de-discretises in fp32 and the generic one in fp64, within 1e-6 relative on values."""

@@ -30,6 +30,23 @@ def time_tracks(name, n, T, reps=3):
     print("%s n=%d T=%d: %.3f ms  %.3e track-timesteps/s" % (name, n, T, best, n * T / best * 1e3), flush=True)
 
 
+def time_events(name, n, T, reps=3):
+    m = UncorEncounterModel(paths[name])
+    r = m.sample_events_uncor(n, T, seed=1, device=dev, want_init=False)
+    cap = int(r.total * 1.05)
+    torch.cuda.synchronize()
+    best = 1e9
+    for k in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = m.sample_events_uncor(n, T, seed=2 + k, device=dev, want_init=False, capacity=cap)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print("%s events n=%d T=%d: %.3f ms  %.3e track-timesteps/s  (%.1f rows/track, %.1f MB)" %
+          (name, n, T, best, n * T / best * 1e3, r.total / n, r.total * 8 / 1e6), flush=True)
+
+
 def time_initial(name, n, reps=3, want_values=True):
     m = EncounterModel(paths[name])
     m.sample_initial(n, seed=1, device=dev, want_attempts=False, want_values=want_values)
@@ -53,6 +70,7 @@ if __name__ == "__main__":
     time_tracks("uncor_1200code_v2p1", 1 << 20, 300)
     time_tracks("uncor_allcode_fwsingle_v1", 1 << 20, 600)
     time_tracks("glider_v1", 1 << 20, 300)
+    time_events("uncor_allcode_fwsingle_v1", 1 << 20, 600)
     time_initial("glider_v1", 1 << 24)
     time_initial("glider_v1", 1 << 24, want_values=False)
     time_initial("uncor_allcode_fwsingle_v1", 1 << 24, want_values=False)
