@@ -194,7 +194,7 @@ def main():
         ev[k + 1].record()
     allreduce_histograms(hi, ht)          # the single collective of the job (verification only)
     barrier()
-    launches = lib.emb_launch_count() - launches0
+    launches = lib.emb_launch_count() - launches0          # kernels of libemb200.so inside the timed region
     clk = clocks.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
@@ -232,6 +232,56 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = units_per_step * args.e2e_steps / float(t.item())
     d2h = nb + nv * 4 + h_iv.numel() * 8 + 4
+    del h_bins, h_vals, host_out
+
+    # ---- end-to-end, sparse contract: the reference's own track representation (out_events) ------------
+    # emb_sample_track_events with pinned host buffers: count pass, prefix sum, write pass, D2H of rows + offsets + inits
+    probe = m.sample_events(n, T, seed=6, first_sample=rank * n, opts=m.uncor_opts(), device=dev, want_init=False)
+    cap = int(probe.total * 1.03)
+    del probe
+    torch.cuda.empty_cache()
+    h_ev = torch.empty(cap, dtype=torch.int64).pin_memory()
+    h_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    import ctypes as C
+    tot = C.c_int64(0)
+    init_only = L.TrackOut(None, None, None, h_iv.data_ptr(), None, None, None)
+
+    def events_call(seed):
+        rng = L.Rng(seed, rank * n)
+        L.check(lib.emb_sample_track_events(m._h, C.byref(rng), n, T, C.byref(o), cap, h_ev.data_ptr(), h_off.data_ptr(),
+                                            C.byref(init_only), C.byref(tot)))
+    events_call(7)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        events_call(3000 + k)
+    barrier()
+    ev_s = time.perf_counter() - t0
+    t = torch.tensor([ev_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_events_value = units_per_step * args.e2e_steps / float(t.item())
+    ev_d2h = int(tot.value) * 8 + (n + 1) * 8 + h_iv.numel() * 8 + 12
+
+    # ---- the other single-GPU configuration of BASELINE.json, for the record (rank 0, device-resident) -----
+    other = {}
+    if rank == 0:
+        from em_model_manned_bayes_b200.model import EncounterModel
+        from em_model_manned_bayes_b200.model_archive import materialize
+        gp = materialize(os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid()), names=["glider_v1"])["glider_v1"]
+        g = EncounterModel(gp)
+        n2 = 100_000_000
+        g.sample_initial(n2, seed=1, device=dev, want_values=False, want_attempts=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for k in range(3):
+            g.sample_initial(n2, seed=2 + k, device=dev, want_values=False, want_attempts=False)
+        e1.record()
+        torch.cuda.synchronize()
+        other["configs[1] glider_v1 initial network only, 100M samples, int8 bins"] = {
+            "value": 3 * n2 / (e0.elapsed_time(e1) * 1e-3), "unit": "samples/s"}
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -240,7 +290,7 @@ def main():
     peak, peak_src = peaks()
     k_ms = statistics.mean(kern_ms)
     achieved = ALGO_BYTES_PER_UNIT * n * T / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per unit from the committed ncu --set full capture
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
@@ -258,7 +308,11 @@ def main():
                             % ((nb + nv * 4) / 1e9),
                    "sharding": "global sample index, rank r owns [r*n, (r+1)*n); one NCCL all-reduce of verification histograms"},
         "e2e": {"value": e2e_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400, "d2h_bytes_per_step": d2h,
-                "steps": args.e2e_steps},
+                "steps": args.e2e_steps, "contract": "dense compact tiles (same call as `value`); PCIe-bound at 19.25 B/unit"},
+        "e2e_events": {"value": e2e_events_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400,
+                       "d2h_bytes_per_step": ev_d2h, "steps": args.e2e_steps,
+                       "contract": "sparse out_events rows (8 B) + offsets + out_inits, emb_sample_track_events"},
+        "other_configs": other,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": ALGO_BYTES_PER_UNIT,

@@ -12,4 +12,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu --e2e-steps 1 > gpurun_out/bench_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_tracks -s 1 -c 1 -f -o gpurun_out/prof_tracks \
     python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 1 --tracks 262144 > gpurun_out/prof_tracks.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/quick_time.log gpurun_out/bench.json
+tail -n 3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/quick_time.log gpurun_out/bench.json
