@@ -66,6 +66,20 @@ class SampleOpts(C.Structure):
     ]
 
 
+class DynLimits(C.Structure):
+    _fields_ = [("minVel_ft_s", C.c_double), ("maxVel_ft_s", C.c_double), ("maxTurnRate_deg_s", C.c_double),
+                ("maxAltitude_ft", C.c_double), ("maxVertRate_ft_s", C.c_double)]
+
+
+class TerminalModels(C.Structure):
+    _fields_ = [("own_fwd", C.c_void_p * 2), ("own_bck", C.c_void_p * 2), ("int_fwd", C.c_void_p * 3),
+                ("int_bck", C.c_void_p * 3)]
+
+
+class TrajOut(C.Structure):
+    _fields_ = [("traj", C.c_void_p), ("len", C.c_void_p)]
+
+
 class TrackOut(C.Structure):
     _fields_ = [
         ("bins", C.c_void_p), ("values", C.c_void_p), ("init_bins", C.c_void_p), ("init_values", C.c_void_p),
@@ -111,6 +125,10 @@ def lib():
         "emb_sample_initial": (C.c_int, [vp, P(Rng), i64, P(SampleOpts), vp, vp, vp]),
         "emb_sample_tracks": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), P(TrackOut)]),
         "emb_sample_track_events": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i64, vp, vp, P(TrackOut), P(i64)]),
+        "emb_dyn_limits_named": (C.c_int, [C.c_char_p, P(DynLimits)]),
+        "emb_terminal_propagate": (C.c_int, [P(TerminalModels), P(Rng), i64, vp, i64, P(i32), C.c_double, P(DynLimits),
+                                             P(SampleOpts), P(TrajOut)]),
+        "emb_terminal_traj_len": (i64, [i64, C.c_double]),
         "emb_tracks_bins_len": (i64, [vp, i64, i32]),
         "emb_tracks_values_len": (i64, [vp, i64, i32]),
     }
@@ -128,7 +146,9 @@ EXPORTED = [
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
     "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",
+    "emb_dyn_limits_named", "emb_terminal_propagate", "emb_terminal_traj_len",
 ]
+TRAJ_FIELDS = ("x_nm", "y_nm", "z_ft", "heading_deg", "v_ft_s")
 
 # numpy view of emb_event (include/emb200.h)
 EVENT_DTYPE = [("dt", "<u2"), ("var", "u1"), ("bin", "u1"), ("value", "<f4")]

@@ -2,6 +2,7 @@
 // boundary, no exceptions escape.  There is deliberately no CPU sampling path in this library.
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -554,6 +555,94 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
     CU(cudaStreamSynchronize(st));
     return sg.finish();
+}
+
+int emb_dyn_limits_named(const char* ac_type, emb_dyn_limits* out) {
+    if (!ac_type || !out) return set_err(EMB_E_ARG, "null argument");
+    emb::TermLimits l;
+    if (!emb::named_dyn_limits(ac_type, l)) return set_err(EMB_E_ARG, std::string("getDynamicLimits: unknown aircraft type ") + ac_type);
+    *out = emb_dyn_limits{l.minVel, l.maxVel, l.maxTurn, l.maxAlt, l.maxVR};
+    return 0;
+}
+
+int64_t emb_terminal_traj_len(int64_t n, double tmax_s) {
+    if (n < 0 || !(tmax_s >= 0.0) || tmax_s >= 32767.0) return 0;
+    return (int64_t)EMB_TRAJ_FIELDS * 2 * (2 * (int64_t)tmax_s + 1) * n;
+}
+
+int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng, int64_t n, const double* geo,
+                           int64_t geo_stride, const int32_t* geo_rows, double tmax_s, const emb_dyn_limits* limits,
+                           const emb_sample_opts* opts, const emb_traj_out* out) {
+    if (!models || !rng || !geo_rows || !limits || !opts || !out || n < 0 || (n > 0 && !geo) || geo_stride < n)
+        return set_err(EMB_E_ARG, "null or out-of-range argument");
+    if (!(tmax_s >= 0.0) || tmax_s >= 32767.0) return set_err(EMB_E_ARG, "tmax_s must be in [0, 32767)");
+    emb::TermParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.seed = rng->seed;
+    P.first_sample = rng->first_sample;
+    P.n = n;
+    P.tmax_s = tmax_s;
+    P.tmax = (int32_t)tmax_s;
+    P.max_attempts = opts->max_attempts > 0 ? std::min(opts->max_attempts, 65535) : 65535;
+    P.geo_stride = geo_stride;
+    int max_row = 0;
+    for (int k = 0; k < 12; ++k) {
+        if (geo_rows[k] < 0) return set_err(EMB_E_ARG, "geo_rows: negative row");
+        P.geo_row[k] = geo_rows[k];
+        max_row = std::max(max_row, (int)geo_rows[k]);
+    }
+    for (int a = 0; a < 2; ++a)
+        P.lim[a] = emb::TermLimits{limits[a].minVel_ft_s, limits[a].maxVel_ft_s, limits[a].maxTurnRate_deg_s,
+                                   limits[a].maxAltitude_ft, limits[a].maxVertRate_ft_s};
+    const emb_model* slot[emb::TERM_NMODELS] = {
+        models->own_fwd[0], models->own_bck[0], models->own_fwd[1], models->own_bck[1], models->int_fwd[0],
+        models->int_bck[0], models->int_fwd[1], models->int_bck[1], models->int_fwd[2], models->int_bck[2]};
+    try {
+        for (int k = 0; k < emb::TERM_NMODELS; ++k) {
+            if (!slot[k]) return set_err(EMB_E_ARG, "emb_terminal_models: null model");
+            emb::make_term_model(*slot[k]->h, P.lim[k < 4 ? 0 : 1], P.m[k]);
+        }
+    } catch (const emb::Error& e) {
+        return set_err(e.code, e.msg);
+    }
+    if (n == 0) return 0;
+    int device, rc = 0;
+    if ((rc = pick_device(opts, device))) return rc;
+    for (int k = 0; k < emb::TERM_NMODELS; ++k) {
+        DevModel D;
+        if ((rc = ensure_device(*slot[k]->h, device, D))) return rc;
+        P.m[k].thr = D.thr_trans;
+        P.m[k].edges = D.edges;
+    }
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    Stager sg{opts->mem, st, {}};
+    struct Scratch {
+        void* p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } d_geo, d_status;
+    if (opts->mem == EMB_MEM_DEVICE) {
+        P.geo = geo;
+    } else {   // stage the rows that are read
+        const size_t bytes = (size_t)(max_row + 1) * (size_t)geo_stride * 8;
+        CU(cudaMalloc(&d_geo.p, bytes));
+        CU(cudaMemcpyAsync(d_geo.p, geo, bytes, cudaMemcpyHostToDevice, st));
+        P.geo = (const double*)d_geo.p;
+    }
+    emb::TermOut O{};
+    if ((rc = sg.out(out->traj, (size_t)emb_terminal_traj_len(n, tmax_s) * 4, false, (void**)&O.traj))) return rc;
+    if ((rc = sg.out(out->len, (size_t)n * 4 * 2, false, (void**)&O.len))) return rc;
+    CU(cudaMalloc(&d_status.p, 4));
+    CU(cudaMemsetAsync(d_status.p, 0, 4, st));
+    O.status = (int32_t*)d_status.p;
+    cudaError_t e = (cudaError_t)emb::launch_terminal(P, O, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch k_terminal_chains");
+    int32_t status = 0;
+    CU(cudaMemcpyAsync(&status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((rc = sg.finish())) return rc;
+    if (status & 2) return set_err(EMB_E_ARG, "Unknown int_intent: own_intent must be 1..2 and int_intent 1..3 (createEncounter.m:22,37)");
+    if (status & 1) return set_err(EMB_E_REJECT, "a trajectory state exhausted max_attempts in the dynamic-limit resample loop");
+    return 0;
 }
 
 }  // extern "C"

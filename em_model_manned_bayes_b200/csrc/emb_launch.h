@@ -19,4 +19,9 @@ int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, v
 // offsets[0..n] = exclusive prefix sums of counts[0..n), offsets[n] = total
 int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, void* stream);
 
+// terminal trajectory chains (emb_terminal.cu): 4 chains per encounter
+struct TermParams;
+struct TermOut;
+int launch_terminal(const TermParams& P, const TermOut& O, void* stream);
+
 }  // namespace emb

@@ -7,6 +7,7 @@
 #include "emb_model.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
@@ -540,5 +541,78 @@ void fill_params(const HostModel& H, uint64_t seed, uint64_t first_sample, int64
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+bool named_dyn_limits(const char* ac_type, TermLimits& out) {
+    std::string t(ac_type ? ac_type : "");
+    for (auto& c : t) c = (char)std::toupper((unsigned char)c);
+    // minVel_ft_s, maxVel_ft_s, maxTurnRate_deg_s, maxAltitude_ft, maxVertRate_ft_s (getDynamicLimits.m:14-62)
+    if (t == "GENERIC") out = TermLimits{50.0, 506.0, 12.0, 5000.0, 6000.0 / 60.0};
+    else if (t == "RTCA228_A1") out = TermLimits{169.0, 491.0, 1.5, 5000.0, 2500.0 / 60.0};
+    else if (t == "RTCA228_A2") out = TermLimits{68.0, 338.0, 3.0, 5000.0, 1500.0 / 60.0};
+    else if (t == "RTCA228_A3") out = TermLimits{68.0, 186.0, 7.0, 5000.0, 500.0 / 60.0};
+    else if (t == "TEST") out = TermLimits{68.0, 186.0, 7.0, 1200.0, 500.0 / 60.0};
+    else return false;
+    return true;
+}
+
+void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M) {
+    std::memset(&M, 0, sizeof(M));
+    auto find = [&](const char* name) {
+        const std::string q = std::string("\"") + name + "\"";
+        for (int i = 0; i < H.n_initial; ++i)
+            if (H.labels_initial[i] == q) return i;
+        fail(EMB_E_MODEL, std::string("createEncounter: trajectory model has no variable ") + q);
+        return -1;
+    };
+    if (H.n_initial != 6 || !H.has_transition)
+        fail(EMB_E_MODEL, "createEncounter: a trajectory model has six initial variables and a transition network");
+    find("intent");
+    M.i_dist = find("distance");
+    M.i_bear = find("bearing");
+    if (find("heading") != 3 || find("altitude") != 4 || find("speed") != 5)                 // createEncounter.m:107-109
+        fail(EMB_E_MODEL, "createEncounter: variables 4-6 must be \"heading\", \"altitude\", \"speed\"");
+    if (H.temporal_map.size() != 3 || H.temporal_map[0].first != 3 || H.temporal_map[1].first != 4 ||
+        H.temporal_map[2].first != 5)
+        fail(EMB_E_MODEL, "createEncounter: the dynamic variables must be heading, altitude and speed");
+    if (H.is_dynvar_depend)
+        fail(EMB_E_MODEL, "createEncounter: trajectory models have no dynamic->dynamic edge (dbn_sample.m:95-166 branch)");
+    if (H.prior_transition.kind != EMB_PRIOR_STAY || H.prior_transition.value != 1.0)
+        fail(EMB_E_ARG, "createEncounter: set the stay prior first, emb_set_prior(m, 1, EMB_PRIOR_STAY, 1.0) "
+                        "(setTransitionPriors, createEncounter.m:129)");
+    if (H.prior_initial.kind != EMB_PRIOR_CONSTANT || H.prior_initial.value != 0.0)
+        fail(EMB_E_ARG, "createEncounter: the initial prior must be 0 (createEncounter.m:128)");
+    for (int d = 0; d < 3; ++d) {
+        M.dyn[d] = H.dev.dyn[d];
+        for (int p = 0; p < M.dyn[d].np; ++p)
+            if (M.dyn[d].par[p] >= 6) fail(EMB_E_MODEL, "createEncounter: parent outside the initial variables");
+    }
+    for (int i = 0; i < 6; ++i) {
+        M.edge_off[i] = H.dev.edge_off[i];
+        M.r[i] = H.r_initial[i];
+    }
+    for (int i : {3, 4, 5})
+        if (H.boundaries[i].empty()) fail(EMB_E_MODEL, "createEncounter: heading, altitude and speed need boundaries");
+    // :120  discreteValidAlt = 1:find(edges <= maxAltitude_ft, 1, 'last')
+    const auto& ea = H.boundaries[4];
+    M.alt_hi = 0;
+    for (size_t j = 0; j < ea.size(); ++j)
+        if (ea[j] <= lim.maxAlt) M.alt_hi = (int32_t)j + 1;
+    // :123-125  s = find((edges >= minVel) == false, 1, 'last'); e = find(edges <= maxVel, 1, 'last'); s:e
+    const auto& es = H.boundaries[5];
+    int s1 = 0, e1 = 0;
+    for (size_t j = 0; j < es.size(); ++j) {
+        if (!(es[j] >= lim.minVel)) s1 = (int)j + 1;
+        if (es[j] <= lim.maxVel) e1 = (int)j + 1;
+    }
+    if (s1 == 0 || e1 == 0) {   // an empty find() makes s:e empty
+        M.spd_lo = 1;
+        M.spd_hi = 0;
+    } else {
+        M.spd_lo = s1;
+        M.spd_hi = e1;
+    }
+    M.dist_max = H.bounds_initial[M.i_dist].second;
+}
 
 }  // namespace emb

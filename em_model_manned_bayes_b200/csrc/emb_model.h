@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "emb_device.cuh"
+#include "emb_terminal.cuh"
 
 struct emb_sample_opts;
 
@@ -87,5 +88,11 @@ void fill_params(const HostModel& H, uint64_t seed, uint64_t first_sample, int64
 
 // G = #{k in [0,2^32) : (k+0.5)*2^-32 < rate}  (resample_events.m:24 under the word->uniform map)
 uint64_t gate_threshold(double rate);
+
+// Terminal trajectory chains: checks the layout createEncounter.m:107-116 asserts and fills the per-chain model
+// descriptor (table pointers left null; valid altitude/speed bins of :118-125 for `lim`); throws Error.
+void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M);
+// @CorTerminalModel/getDynamicLimits.m:14-62; false if the aircraft type is unknown
+bool named_dyn_limits(const char* ac_type, TermLimits& out);
 
 }  // namespace emb

@@ -1,0 +1,34 @@
+// emb_terminal.cu -- sm_100a kernel of the terminal trajectory chains (emb_terminal.cuh).
+//
+// Thread = chain.  blockIdx.y is the chain id (aircraft, direction), so a warp holds 32 consecutive
+// encounters of the same chain: its stores are 128 contiguous bytes per field per step, and the only
+// divergence is between lanes whose intents pick different models and lanes whose chains ended early.
+// The ten models' descriptors travel in the kernel parameter block (constant bank); their threshold
+// tables (a few MB each) are gathered from L2.
+#include <cuda_runtime.h>
+
+#include "emb_launch.h"
+#include "emb_terminal.cuh"
+
+namespace emb {
+namespace {
+
+constexpr int TERM_BLOCK = 128;
+
+__global__ void __launch_bounds__(TERM_BLOCK)
+k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ TermOut O) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n) terminal_chain(P, O, s, (int)blockIdx.y);
+}
+
+}  // namespace
+
+int launch_terminal(const TermParams& P, const TermOut& O, void* stream) {
+    if (P.n <= 0) return 0;
+    const dim3 grid((unsigned)((P.n + TERM_BLOCK - 1) / TERM_BLOCK), 4, 1);
+    k_terminal_chains<<<grid, TERM_BLOCK, 0, (cudaStream_t)stream>>>(P, O);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace emb

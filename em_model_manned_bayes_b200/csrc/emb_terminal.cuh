@@ -1,0 +1,257 @@
+// emb_terminal.cuh -- terminal trajectory chains: @CorTerminalModel/createEncounter.m:93-329
+// (PropagateTrajectory, CreateStartDistribution, CheckTrajectoryConditions) with the fwd/bck
+// concatenation and time sort of :74-84 folded into the output addressing.
+//
+// One call of terminal_chain = one chain = one (encounter, aircraft, direction).  A chain is a
+// sequential walk of at most floor(tmax_s)+1 states; every state costs one dbn_sample(t_max = 2) of the
+// aircraft's trajectory DBN with all six initial variables preset (dbn_sample.m:95-166, frozen-parent
+// branch: three selects from columns addressed by the re-discretised state), the dynamic-limit
+// rejection loop of createEncounter.m:192-243 and the kinematic update of :171-184 / :246-256 in fp64.
+//
+// Uniforms (stream spec v2, terminal part -- oracle/terminal.py): Philox counter
+//   (encounter_lo, encounter_hi, step ii, attempt << 16 | purpose << 8 | chain), chain = 2*aircraft + (0 fwd, 1 bck);
+//   purpose TERM_SEL: lane d = row 2 of the rand(2,1) of the d-th dynamic variable (dbn_sample.m:133,144);
+//   purpose TERM_DD : lane d = the rand of dediscretize for its event (createEncounter.m:203,208,216).
+#pragma once
+#include "emb_device.cuh"
+
+namespace emb {
+
+constexpr uint32_t P_TERM_SEL = 5, P_TERM_DD = 6;
+constexpr int TERM_NMODELS = 10;   // own {landing, takeoff} x {fwd, bck}, intruder {landing, takeoff, transit} x {fwd, bck}
+constexpr int TERM_FIELDS = 5;     // x_nm, y_nm, z_ft, heading_deg, v_ft_s  (t_s is the slot index)
+constexpr double TERM_FT_PER_NM = 6076.1154855643;   // createEncounter.m:172
+
+// what a chain needs from one trajectory model (built on the host from HostModel::dev)
+struct TermModel {
+    Node dyn[3];              // heading', altitude', speed' (temporal_map rows 0..2)
+    const uint32_t* thr;      // word-space threshold table of the transition network
+    const double* edges;      // {a, b-a} pairs (HostModel::edges)
+    int32_t edge_off[6];      // per initial variable: offset into edges (doubles), -1 = no boundaries
+    int32_t r[6];
+    int32_t i_dist, i_bear;   // 0-based positions of "distance" and "bearing" (createEncounter.m:112-113)
+    int32_t alt_hi;           // discreteValidAlt = 1..alt_hi        (createEncounter.m:120), 0 = empty
+    int32_t spd_lo, spd_hi;   // discreteValidV   = spd_lo..spd_hi   (:123-125), lo > hi = empty
+    int32_t pad_;
+    double dist_max;          // bounds_initial(idx.dist, 2)         (:263, :310)
+};
+
+struct TermLimits {           // @CorTerminalModel/getDynamicLimits.m:14-62
+    double minVel, maxVel, maxTurn, maxAlt, maxVR;
+};
+
+struct TermParams {
+    uint64_t seed, first_sample;
+    int64_t n;
+    double tmax_s;
+    int32_t tmax;             // floor(tmax_s): a chain has at most tmax + 1 states
+    int32_t max_attempts;
+    const double* geo;        // sample_geo fields, row geo_row[k] of a [rows][geo_stride] array
+    int64_t geo_stride;
+    int32_t geo_row[12];      // own_{intent, distance, bearing, alt, heading, speed}, int_{...}
+    TermLimits lim[2];
+    TermModel m[TERM_NMODELS];// [aircraft 0: (intent-1)*2 + dir | aircraft 1: 4 + (intent-1)*2 + dir], dir 0 fwd / 1 bck
+};
+
+struct TermOut {
+    float* traj;              // [TERM_FIELDS][2][2*tmax+1][n], slot k <-> t_s = k - tmax, NaN where the aircraft has no state
+    int16_t* len;             // [4][n] states per chain (numel(fwd.t_s), numel(bck.t_s))
+    int32_t* status;          // |= 1: inner resample loop exhausted max_attempts; |= 2: unknown intent (createEncounter.m:22,37)
+};
+
+// ---- MATLAB built-ins as restated by the oracle (oracle/terminal.py) --------------------------------
+EMB_HD void sincosd(double x, double& s, double& c) {
+    const double r = ::fmod(x, 360.0);
+    if (::fmod(r, 90.0) == 0.0) {                       // exact at multiples of 90 degrees (cosd/sind)
+        const int q = (((int)(r / 90.0)) % 4 + 4) % 4;
+        c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
+        s = q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
+        return;
+    }
+    const double a = dmul(r, 0.017453292519943295);     // pi/180
+#if defined(__CUDA_ARCH__)
+    ::sincos(a, &s, &c);
+#else
+    s = ::sin(a);
+    c = ::cos(a);
+#endif
+}
+EMB_HD double atan2d(double y, double x) { return dmul(::atan2(y, x), 57.29577951308232); }   // 180/pi
+EMB_HD double wrap_to_360(double x) {                   // wrapTo360: mod(x,360), positive multiples of 360 -> 360
+    const bool positive = x > 0.0;
+    x = dadd(x, -dmul(360.0, ::floor(x / 360.0)));
+    if (x == 0.0 && positive) x = 360.0;
+    return x;
+}
+EMB_HD double round2(double x) {                        // round(x, 2), half away from zero
+    const double y = dmul(x, 100.0);
+    const double m = ::floor(dadd(::fabs(y), 0.5));
+    return (y >= 0.0 ? m : -m) / 100.0;
+}
+EMB_HD double norm2(double a, double b) { return ::sqrt(dadd(dmul(a, a), dmul(b, b))); }
+
+// discretize_bayes.m:14-22 against cutpoints_initial{i} (em_read.m:128-136); returns the 0-based bin
+EMB_HD int term_discretize(const TermModel& M, int i, double x) {
+    const int r = M.r[i];
+    if (M.edge_off[i] < 0) {                            // no boundaries: cutpoints 2..r
+        int b = 0;
+        for (int j = 2; j <= r; ++j) b += (x >= (double)j) ? 1 : 0;
+        return b;
+    }
+    const double* e = M.edges + M.edge_off[i];          // lower edge of bin j at e[2j]; cutpoints are e[2], e[4], ...
+    int lo = 0, hi = r - 1;                             // result = #{j in 1..r-1 : x >= cut_j}
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (x >= ldg64(e + 2 * mid)) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // dediscretize.m:39, two-argument call
+    if (M.edge_off[i] < 0) return (double)(b + 1);
+    const double* e = M.edges + M.edge_off[i] + 2 * b;
+    return dadd(ldg64(e), dmul(ldg64(e + 1), u01(k)));
+}
+
+#if defined(__CUDA_ARCH__)
+#define EMB_STREAM_F32(p, v) __stcs((p), (v))
+#define EMB_FLAG_OR(p, v) atomicOr((p), (v))
+#else
+#define EMB_STREAM_F32(p, v) (*(p) = (v))
+#define EMB_FLAG_OR(p, v) (*(p) |= (v))
+#endif
+
+// One chain.  `s` = encounter index within this call, chain = 2*aircraft + direction.
+EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain) {
+    const int ac = chain >> 1, dir = chain & 1;
+    const double dt_s = dir ? -1.0 : 1.0;
+    const int64_t N = P.n;
+    const int K = P.tmax + 1;                           // maximum number of states
+    const int64_t S = 2 * (int64_t)P.tmax + 1;          // slots per aircraft
+    const uint64_t sample = P.first_sample + (uint64_t)s;
+    const double* g = P.geo + s;
+    const int32_t* row = P.geo_row + 6 * ac;
+    const int intent = (int)g[(int64_t)row[0] * P.geo_stride];
+    const double distance = g[(int64_t)row[1] * P.geo_stride], bearing = g[(int64_t)row[2] * P.geo_stride];
+    double z_ft = g[(int64_t)row[3] * P.geo_stride];
+    double heading_deg = g[(int64_t)row[4] * P.geo_stride];
+    const double v0 = g[(int64_t)row[5] * P.geo_stride];
+    const TermLimits& L = P.lim[ac];
+
+    auto put = [&](int f, int64_t slot, float v) {
+        EMB_STREAM_F32(O.traj + (((int64_t)f * 2 + ac) * S + slot) * N + s, v);
+    };
+#if defined(__CUDA_ARCH__)
+    const float qnan = __int_as_float(0x7FC00000);
+#else
+    const float qnan = __builtin_nanf("");
+#endif
+    const bool bad_intent = intent < 1 || intent > (ac ? 3 : 2);                 // createEncounter.m:14-38
+    if (bad_intent && O.status) EMB_FLAG_OR(O.status, 2);
+    const TermModel& M = P.m[(ac ? 4 : 0) + ((bad_intent ? 1 : intent) - 1) * 2 + dir];
+
+    double sb, cb, sh, ch;
+    sincosd(bearing, sb, cb);
+    double x = dmul(distance, cb), y = dmul(distance, sb);                        // :45-46
+    sincosd(heading_deg, sh, ch);
+    double vx = dadd(dmul(ch, v0), -dmul(sh, 0.0)), vy = dadd(dmul(sh, v0), dmul(ch, 0.0));   // :150
+    double t_s = 0.0, z_prev = 0.0;
+    bool go = !bad_intent;
+    int len = 0;
+
+    for (int ii = 1; ii <= K; ++ii) {
+        const int64_t slot = dir ? (int64_t)P.tmax - (ii - 1) : (int64_t)P.tmax + (ii - 1);
+        const bool store = O.traj && !(dir && ii == 1);                          // [fwd, bck(2:end)] (:77)
+        if (!go) {
+            if (store) for (int f = 0; f < TERM_FIELDS; ++f) put(f, slot, qnan);
+            continue;
+        }
+        ++len;
+        // state ii (:163-184)
+        const double curr_hdg = wrap_to_360(atan2d(vy, vx));                      // :176
+        double z_rec = z_ft;
+        if (ii > 1) {                                                             // :180-184
+            const double diff = dadd(z_ft, -z_prev);
+            const double lim = ::fmin(L.maxVR, ::fabs(diff));
+            z_rec = dadd(z_prev, diff > 0.0 ? lim : diff < 0.0 ? -lim : dmul(0.0, lim));
+        }
+        z_prev = z_rec;
+        if (store) {
+            put(0, slot, (float)x);
+            put(1, slot, (float)y);
+            put(2, slot, (float)z_rec);
+            put(3, slot, (float)curr_hdg);
+            put(4, slot, (float)norm2(vx, vy));
+        }
+        x = dadd(x, dmul(vx, dt_s) / TERM_FT_PER_NM);                             // :171-173
+        y = dadd(y, dmul(vy, dt_s) / TERM_FT_PER_NM);
+
+        // CreateStartDistribution (:268-294), 0-based bins
+        uint8_t st[6];
+        st[0] = (uint8_t)(intent - 1);
+        st[1] = (uint8_t)term_discretize(M, M.i_dist, norm2(x, y));              // positional cell, cutpoints by label (:277,:293)
+        st[2] = (uint8_t)term_discretize(M, M.i_bear, wrap_to_360(atan2d(y, x)));
+        st[3] = (uint8_t)term_discretize(M, 3, heading_deg);
+        st[4] = (uint8_t)term_discretize(M, 4, z_ft);
+        st[5] = (uint8_t)term_discretize(M, 5, norm2(vx, vy));
+        const uint32_t* col0 = node_column(M.dyn[0], M.thr, st);                  // frozen parents (dbn_sample.m:110-135)
+        const uint32_t* col1 = node_column(M.dyn[1], M.thr, st);
+        const uint32_t* col2 = node_column(M.dyn[2], M.thr, st);
+
+        for (uint32_t attempt = 0;; ++attempt) {                                  // while is_resample (:192-243)
+            uint32_t w0, w1, w2, w3;
+            philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
+                          (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain, (uint32_t)P.seed,
+                          (uint32_t)(P.seed >> 32), w0, w1, w2, w3);
+            const int nh = select_bin(col0, M.dyn[0].rp, w0);
+            const int na = select_bin(col1, M.dyn[1].rp, w1);
+            const int nv = select_bin(col2, M.dyn[2].rp, w2);
+            bool redo = false;
+            if (nh != st[3] || na != st[4] || nv != st[5]) {                      // events in variable order 4, 5, 6
+                uint32_t d0, d1, d2, d3;
+                philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
+                              (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain, (uint32_t)P.seed,
+                              (uint32_t)(P.seed >> 32), d0, d1, d2, d3);
+                if (nh != st[3]) heading_deg = term_dedisc(M, 3, nh, d0);         // :200-205
+                if (na != st[4]) {                                                // :206-212
+                    if (na + 1 <= M.alt_hi) z_ft = term_dedisc(M, 4, na, d1);
+                    else redo = true;
+                }
+                if (!redo && nv != st[5]) {                                       // :213-233
+                    if (nv + 1 >= M.spd_lo && nv + 1 <= M.spd_hi) {
+                        double v1 = term_dedisc(M, 5, nv, d2);
+                        if (v1 < L.minVel) v1 = L.minVel;
+                        if (v1 > L.maxVel) v1 = L.maxVel;
+                        sincosd(heading_deg, sh, ch);
+                        vx = dadd(dmul(ch, v1), -dmul(sh, 0.0));                  // :228-229
+                        vy = dadd(dmul(sh, v1), dmul(ch, 0.0));
+                    } else {
+                        redo = true;
+                    }
+                }
+            }
+            if (!redo) break;
+            if (attempt >= (uint32_t)P.max_attempts) {
+                if (O.status) EMB_FLAG_OR(O.status, 1);
+                break;
+            }
+        }
+        // turn to the desired heading at the maximum rate (:246-256)
+        const double turn1 = round2(dadd(heading_deg, -curr_hdg));
+        const double mag = ::fmin(::fabs(turn1), L.maxTurn);
+        const double delta = turn1 > 0.0 ? mag : turn1 < 0.0 ? -mag : dmul(mag, 0.0);
+        double sd, cd;
+        sincosd(delta, sd, cd);
+        const double nvx = dadd(dmul(cd, vx), -dmul(sd, vy)), nvy = dadd(dmul(sd, vx), dmul(cd, vy));
+        vx = nvx;
+        vy = nvy;
+        t_s = dadd(t_s, dt_s);
+        // CheckTrajectoryConditions (:296-329)
+        const double d_nm = norm2(x, y);
+        const bool violate = ::fabs(t_s) > P.tmax_s || d_nm > M.dist_max || ((intent == 1 || intent == 2) && d_nm <= 0.25) ||
+                             (ac == 0 && y > 0.25);
+        go = !violate;
+    }
+    if (O.len) O.len[(int64_t)chain * N + s] = (int16_t)len;
+}
+
+}  // namespace emb

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -235,7 +236,7 @@ class EncounterModel:
         if like is None:
             return np.zeros(shape, dtype=dtype)
         import torch
-        tdt = {np.int8: torch.int8, np.float32: torch.float32, np.float64: torch.float64, np.uint16: torch.int16,
+        tdt = {np.int8: torch.int8, np.float32: torch.float32, np.float64: torch.float64, np.uint16: torch.int16, np.int16: torch.int16,
                np.uint64: torch.int64}[dtype]
         return torch.zeros(shape, dtype=tdt, device=like)
 
@@ -459,20 +460,60 @@ class UncorEncounterModel(EncounterModel):
         return out_inits, out_events, out_samples, out_EME
 
 
+@dataclass
+class TrajectoryResult:
+    """Batch result of `CorTerminalModel.create_encounters` (emb200.h: emb_traj_out)."""
+    n: int
+    tmax: int
+    traj: object           # (5, 2, 2*tmax+1, n) float32: field, aircraft, slot (t_s = slot - tmax), encounter; NaN = no state
+    len: object            # (4, n) int16: states of chain 2*aircraft + (0 forward, 1 backward)
+
+    def encounter(self, s: int):
+        """traj(1:2) of createEncounter.m:10,74-84 for encounter s: two dicts of float64 row vectors
+        t_s, x_nm, y_nm, z_ft, heading_deg, v_ft_s (already concatenated and ordered in time)."""
+        ln = np.asarray(self.len.cpu() if hasattr(self.len, "cpu") else self.len)[:, s]
+        col = self.traj[:, :, :, s]
+        col = np.asarray(col.cpu() if hasattr(col, "cpu") else col, dtype=np.float64)
+        out = []
+        for ac in range(2):
+            lo, hi = self.tmax - (int(ln[2 * ac + 1]) - 1), self.tmax + int(ln[2 * ac]) - 1
+            d = {"t_s": np.arange(lo - self.tmax, hi - self.tmax + 1, dtype=np.float64)}
+            for f, name in enumerate(L.TRAJ_FIELDS):
+                d[name] = col[f, ac, lo:hi + 1].copy()
+            out.append(d)
+        return out
+
+
 class CorTerminalModel(EncounterModel):
-    """@CorTerminalModel/CorTerminalModel.m + sample.m: the terminal encounter *geometry* model.
-    (The 20 trajectory DBN files are missing from the public checkout -- SURVEY.md F5.)"""
+    """@CorTerminalModel/CorTerminalModel.m + sample.m + createEncounter.m.
+
+    The encounter *geometry* model is the object itself (CorTerminalModel.m:80).  The ten trajectory DBNs
+    (mdlFwd1_1 ... mdlBck2_3, CorTerminalModel.m:12-30,86-100) are loaded with `load_trajectory_models`; their
+    files are missing from the public checkout, so tests and bench use models of the same layout
+    written by `synthetic.write_terminal_model_set`."""
 
     # @CorTerminalModel/getDynamicLimits.m:14-62 (minVel_ft_s, maxVel_ft_s)
     DYN_LIMITS = {"GENERIC": (50.0, 506.0), "RTCA228_A1": (169.0, 491.0), "RTCA228_A2": (68.0, 338.0),
                   "RTCA228_A3": (68.0, 186.0), "TEST": (68.0, 186.0)}
+    # CorTerminalModel.m:62 file-name stems -> (aircraft, direction, intent)
+    TRAJECTORY_SLOTS = (("ownship_landing_model", "own_fwd", 0), ("ownship_takeoff_model", "own_fwd", 1),
+                        ("ownship_landing_model_reverse", "own_bck", 0), ("ownship_takeoff_model_reverse", "own_bck", 1),
+                        ("intruder_landing_model", "int_fwd", 0), ("intruder_takeoff_model", "int_fwd", 1),
+                        ("intruder_transit_model", "int_fwd", 2), ("intruder_landing_model_reverse", "int_bck", 0),
+                        ("intruder_takeoff_model_reverse", "int_bck", 1), ("intruder_transit_model_reverse", "int_bck", 2))
+    GEO_FIELDS = ("own_intent", "own_distance", "own_bearing", "own_alt", "own_heading", "own_speed",
+                  "int_intent", "int_distance", "int_bearing", "int_alt", "int_heading", "int_speed")
 
-    def __init__(self, parameters_filename: str, acType1: str = "GENERIC", acType2: str = "GENERIC"):
+    def __init__(self, parameters_filename: str, acType1: str = "GENERIC", acType2: str = "GENERIC",
+                 parameters_directory: Optional[str] = None):
         super().__init__(parameters_filename)
         self.acType1, self.acType2 = acType1, acType2
         self.bounds_sample = np.stack([np.full(self.n_initial, -np.inf), np.full(self.n_initial, np.inf)], axis=1)
         self.idx_own_speed = _find(self.labels_initial, '"own_speed"')
         self.idx_int_speed = _find(self.labels_initial, '"int_speed"')
+        self.trajectory_models = {}
+        if parameters_directory is not None:
+            self.load_trajectory_models(parameters_directory)
 
     def _terminal_opts(self, start=None, max_attempts=0):
         o = self._opts(start=start, max_attempts=max_attempts)
@@ -500,3 +541,86 @@ class CorTerminalModel(EncounterModel):
         names = [l.replace('"', "") for l in self.labels_initial]                                   # sample.m:59
         out_samples = [dict(zip(names, row)) for row in out_inits]
         return out_inits, out_samples
+
+    # -- trajectory DBNs -----------------------------------------------------------------------------
+    def load_trajectory_models(self, parameters_directory: str, reference_reverse_quirk: bool = False):
+        """CorTerminalModel.m:56-100: finds `*_<stem>.txt` for the ten trajectory models in the directory and applies
+        the stay prior of createEncounter.m:129.  `reference_reverse_quirk=True` reproduces CorTerminalModel.m:97,100,
+        where mdlBck2_2 and mdlBck2_3 both load the intruder *landing* reverse model."""
+        import glob
+        loaded = {}
+        for stem, group, k in self.TRAJECTORY_SLOTS:
+            use = stem
+            if reference_reverse_quirk and group == "int_bck":
+                use = "intruder_landing_model_reverse"
+            hits = sorted(glob.glob(os.path.join(parameters_directory, "*_" + use + ".txt")))
+            if not hits:
+                raise L.EmbError(L.EMB_E_IO, "trajectory model *_%s.txt not found in %s" % (use, parameters_directory))
+            if hits[0] not in loaded:
+                m = EncounterModel(hits[0])
+                m.set_transition_stay_prior(1.0)
+                loaded[hits[0]] = m
+            self.trajectory_models[(group, k)] = loaded[hits[0]]
+        return self
+
+    def set_trajectory_models(self, models: dict):
+        """models[(group, intent-1)] -> EncounterModel, group in own_fwd/own_bck/int_fwd/int_bck."""
+        for m in set(models.values()):
+            m.set_transition_stay_prior(1.0)
+        self.trajectory_models = dict(models)
+        return self
+
+    def _terminal_models_struct(self):
+        tm = L.TerminalModels()
+        for stem, group, k in self.TRAJECTORY_SLOTS:
+            if (group, k) not in self.trajectory_models:
+                raise L.EmbError(L.EMB_E_ARG, "trajectory models are not loaded (load_trajectory_models); the public "
+                                 "checkout of the reference does not ship them")
+            getattr(tm, group)[k] = self.trajectory_models[(group, k)]._h.value
+        return tm
+
+    def create_encounters(self, geo, tmax_s: float = 120, seed: int = 0, first_sample: int = 0, device=None,
+                          geo_rows: Optional[Sequence[int]] = None, max_attempts: int = 0,
+                          out: Optional[TrajectoryResult] = None) -> TrajectoryResult:
+        """The batch form of createEncounter.m:1-91 (without the em-core smoothing of :88-89).
+
+        geo: (rows, n) float64, numpy or torch-on-`device`; by default the transposed outInits of `sample`, i.e. one
+        row per geometry variable, and `geo_rows` (0-based rows of GEO_FIELDS) is looked up from the labels."""
+        lib = L.lib()
+        if geo_rows is None:
+            geo_rows = []
+            for f in self.GEO_FIELDS:
+                i = _find(self.labels_initial, '"%s"' % f)
+                if not i:
+                    raise L.EmbError(L.EMB_E_ARG, "geometry model has no variable %s" % f)
+                geo_rows.append(i - 1)
+        rows = (C.c_int32 * 12)(*[int(v) for v in geo_rows])
+        n = int(geo.shape[1])
+        tmax = int(math.floor(tmax_s))
+        o = self._opts(max_attempts=max_attempts)
+        if device is not None:
+            import torch
+            dev = torch.device(device)
+            o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+            o.stream = torch.cuda.current_stream(dev).cuda_stream
+            assert geo.is_cuda and geo.dtype == torch.float64 and geo.is_contiguous()
+        else:
+            geo = np.ascontiguousarray(geo, dtype=np.float64)
+        if out is None:
+            out = TrajectoryResult(n=n, tmax=tmax, traj=self._alloc((len(L.TRAJ_FIELDS), 2, 2 * tmax + 1, n), np.float32, device),
+                                   len=self._alloc((4, n), np.int16, device))
+        lim = (L.DynLimits * 2)()
+        L.check(lib.emb_dyn_limits_named(self.acType1.encode(), C.byref(lim[0])))
+        L.check(lib.emb_dyn_limits_named(self.acType2.encode(), C.byref(lim[1])))
+        tm = self._terminal_models_struct()
+        rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
+        to = L.TrajOut(_ptr(out.traj), _ptr(out.len))
+        L.check(lib.emb_terminal_propagate(C.byref(tm), C.byref(rng), n, _ptr(geo), int(geo.shape[1]), rows, float(tmax_s),
+                                           lim, C.byref(o), C.byref(to)))
+        return out
+
+    def createEncounter(self, sample_geo: dict, tmax_s: float = 120, seed: int = 0, sample_index: int = 0):
+        """createEncounter.m:1 for one `sample_geo` struct (a dict as returned in outSamples) -> traj(1:2)."""
+        geo = np.array([[float(sample_geo[f])] for f in self.GEO_FIELDS])
+        res = self.create_encounters(geo, tmax_s, seed=seed, first_sample=sample_index, geo_rows=range(12))
+        return res.encounter(0)

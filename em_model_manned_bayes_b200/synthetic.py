@@ -67,3 +67,25 @@ def terminal_trajectory_model_arrays(seed: int = 0, direction: int = +1):
 def write_terminal_trajectory_model(path: str, seed: int = 0, direction: int = +1) -> str:
     """Write a synthetic forward (`direction=+1`) or reverse (`-1`) trajectory model in the reference's file format."""
     return em_write(path, **terminal_trajectory_model_arrays(seed, direction))
+
+
+# CorTerminalModel.m:62 file-name stems of the ten trajectory models
+TRAJECTORY_STEMS = ("ownship_landing_model", "ownship_takeoff_model", "ownship_landing_model_reverse",
+                    "ownship_takeoff_model_reverse", "intruder_landing_model", "intruder_takeoff_model",
+                    "intruder_transit_model", "intruder_landing_model_reverse", "intruder_takeoff_model_reverse",
+                    "intruder_transit_model_reverse")
+
+
+def write_terminal_model_set(directory: str, prefix: str = "terminal_v3_synthetic", seed: int = 0) -> dict:
+    """Write the ten trajectory models a CorTerminalModel loads (`<prefix>_<stem>.txt`); returns {stem: path}."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    paths = {}
+    for k, stem in enumerate(TRAJECTORY_STEMS):
+        path = os.path.join(directory, "%s_%s.txt" % (prefix, stem))
+        if not os.path.exists(path):
+            tmp = path + ".tmp%d" % os.getpid()
+            write_terminal_trajectory_model(tmp, seed=10 * int(seed) + k, direction=-1 if stem.endswith("_reverse") else +1)
+            os.replace(tmp, path)
+        paths[stem] = path
+    return paths

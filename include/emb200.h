@@ -177,6 +177,48 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
                             int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
                             int64_t* total_rows);
 
+/* ---- terminal trajectory chains: replaces @CorTerminalModel/createEncounter.m:1-329 over a batch of encounters
+ *      (PropagateTrajectory :93-265 = per state one dbn_sample.m:95-166 call with t_max = 2 and every initial
+ *      variable preset by CreateStartDistribution :268-294, the dynamic-limit resample loop :192-243, the kinematic
+ *      update :171-184/:246-256, CheckTrajectoryConditions :296-329) including the forward/backward concatenation
+ *      and time sort of :74-84.  The em-core `local_smooth` of :88-89 is not part of this library. ------------------ */
+typedef struct emb_dyn_limits {   /* @CorTerminalModel/getDynamicLimits.m:14-62 */
+    double minVel_ft_s, maxVel_ft_s, maxTurnRate_deg_s, maxAltitude_ft, maxVertRate_ft_s;
+} emb_dyn_limits;
+/* "GENERIC", "RTCA228_A1", "RTCA228_A2", "RTCA228_A3", "TEST" (case-insensitive); EMB_E_ARG otherwise */
+int emb_dyn_limits_named(const char* ac_type, emb_dyn_limits* out);
+
+typedef struct emb_terminal_models {   /* @CorTerminalModel/CorTerminalModel.m:12-30; index = intent - 1 */
+    const emb_model* own_fwd[2];       /* mdlFwd1_1 (landing), mdlFwd1_2 (takeoff) */
+    const emb_model* own_bck[2];       /* mdlBck1_1, mdlBck1_2 */
+    const emb_model* int_fwd[3];       /* mdlFwd2_1 (landing), mdlFwd2_2 (takeoff), mdlFwd2_3 (transit) */
+    const emb_model* int_bck[3];       /* mdlBck2_1, mdlBck2_2, mdlBck2_3 */
+} emb_terminal_models;
+/* Every model must have labels_initial {"intent","distance","bearing","heading","altitude","speed"} with heading,
+ * altitude, speed in positions 4-6 (createEncounter.m:107-116), exactly those three dynamic variables, no
+ * dynamic->dynamic edge, and the stay prior of createEncounter.m:129 already set:
+ * emb_set_prior(m, 1, EMB_PRIOR_STAY, 1.0).  The same emb_model may appear in several slots. */
+
+#define EMB_TRAJ_FIELDS 5 /* x_nm, y_nm, z_ft, heading_deg, v_ft_s; t_s is the slot index */
+typedef struct emb_traj_out {
+    /* merged, time-sorted trajectories traj(1:2) of createEncounter.m:74-84:
+     * traj[field][aircraft][slot][n] with slot k <-> t_s = k - floor(tmax_s), aircraft 0 = ownship, 1 = intruder;
+     * NaN in the slots an aircraft does not reach */
+    float* traj;     /* [EMB_TRAJ_FIELDS][2][2*floor(tmax_s)+1][n]                                  nullable */
+    /* len[2*aircraft + 0][s] = numel(fwd.t_s), len[2*aircraft + 1][s] = numel(bck.t_s): the aircraft has states for
+     * t_s = -(len_bck-1) .. len_fwd-1 */
+    int16_t* len;    /* [4][n]                                                                      nullable */
+} emb_traj_out;
+/* geo: the encounter-geometry samples (outInits of @CorTerminalModel/sample.m), row-major [rows][geo_stride] doubles,
+ * column s = encounter first_sample + s; geo_rows[12] = 0-based rows of own_intent, own_distance, own_bearing,
+ * own_alt, own_heading, own_speed, int_intent, ... int_speed (sample_geo of createEncounter.m:14-49).  `geo` lives
+ * in opts->mem like the outputs.  opts: mem, device, stream, max_attempts are used; limits[0] ownship, [1] intruder.
+ * An intent outside 1..2 (own) / 1..3 (intruder) gives EMB_E_ARG "Unknown int_intent" after the call completes. */
+int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng, int64_t n, const double* geo,
+                           int64_t geo_stride, const int32_t* geo_rows, double tmax_s, const emb_dyn_limits* limits,
+                           const emb_sample_opts* opts, const emb_traj_out* out);
+int64_t emb_terminal_traj_len(int64_t n, double tmax_s); /* elements of emb_traj_out.traj */
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 int emb_host_alloc(void** p, int64_t bytes); /* pinned host memory */
 int emb_host_free(void* p);

@@ -76,7 +76,7 @@ def round2(x):
 
 
 def sign(x):
-    return (x > 0) - (x < 0)
+    return int(x > 0) - int(x < 0)
 
 
 class TerminalKeyed:
@@ -225,3 +225,35 @@ def create_encounter_chains(models, geo, seed, sample, tmax_s=120, dyn=("GENERIC
         order = np.argsort(np.asarray(tr["t_s"]), kind="stable")                             # :81-84
         merged.append({k: [tr[k][i] for i in order] for k in tr})
     return chains, merged
+
+
+GEO_FIELDS = ("own_intent", "own_distance", "own_bearing", "own_alt", "own_heading", "own_speed",
+              "int_intent", "int_distance", "int_bearing", "int_alt", "int_heading", "int_speed")
+
+
+def create_encounters(model_set, geo, seed, first_sample=0, tmax_s=120, dyn=("GENERIC", "GENERIC")):
+    """Batch driver used by the tests: `model_set[(group, intent-1)]` -> Parms with group in own_fwd / own_bck /
+    int_fwd / int_bck (CorTerminalModel.m:12-30); `geo` (12, n) rows in GEO_FIELDS order.  Returns what
+    emb_terminal_propagate writes: traj (5, 2, 2*tmax+1, n) float64 with NaN where an aircraft has no state
+    (slot k <-> t_s = k - tmax) and len (4, n)."""
+    geo = np.asarray(geo, dtype=np.float64)
+    n = geo.shape[1]
+    tmax = int(math.floor(tmax_s))
+    traj = np.full((5, 2, 2 * tmax + 1, n), np.nan)
+    length = np.zeros((4, n), dtype=np.int16)
+    for s in range(n):
+        g = {k: float(v) for k, v in zip(GEO_FIELDS, geo[:, s])}
+        oi, ii = int(g["own_intent"]), int(g["int_intent"])
+        if oi not in (1, 2) or ii not in (1, 2, 3):                                            # createEncounter.m:14-38
+            raise sp.OracleError("Unknown int_intent")
+        models = {(0, +1): model_set[("own_fwd", oi - 1)], (0, -1): model_set[("own_bck", oi - 1)],
+                  (1, +1): model_set[("int_fwd", ii - 1)], (1, -1): model_set[("int_bck", ii - 1)]}
+        chains, merged = create_encounter_chains(models, g, seed, first_sample + s, tmax_s, dyn)
+        for ac in range(2):
+            length[2 * ac, s] = len(chains[(ac, +1)]["t_s"])
+            length[2 * ac + 1, s] = len(chains[(ac, -1)]["t_s"])
+            m = merged[ac]
+            slots = np.asarray(m["t_s"], dtype=np.int64) + tmax
+            for f, name in enumerate(("x_nm", "y_nm", "z_ft", "heading_deg", "v_ft_s")):
+                traj[f, ac, slots, s] = m[name]
+    return traj, length

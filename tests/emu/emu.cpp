@@ -215,4 +215,42 @@ int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, i
     return status ? EMB_E_REJECT : 0;
 }
 
+// host emulation of emb_terminal_propagate (same per-chain code as k_terminal_chains); models = 10 HostModel* in
+// TermParams::m order, geo = host doubles
+int emu_terminal_propagate(void** models, uint64_t seed, uint64_t first, int64_t n, const double* geo, int64_t geo_stride,
+                           const int32_t* geo_rows, double tmax_s, const emb_dyn_limits* limits, int32_t max_attempts,
+                           float* traj, int16_t* len) {
+    TermParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.seed = seed;
+    P.first_sample = first;
+    P.n = n;
+    P.tmax_s = tmax_s;
+    P.tmax = (int32_t)tmax_s;
+    P.max_attempts = max_attempts > 0 ? max_attempts : 65535;
+    P.geo = geo;
+    P.geo_stride = geo_stride;
+    for (int k = 0; k < 12; ++k) P.geo_row[k] = geo_rows[k];
+    for (int a = 0; a < 2; ++a)
+        P.lim[a] = TermLimits{limits[a].minVel_ft_s, limits[a].maxVel_ft_s, limits[a].maxTurnRate_deg_s,
+                              limits[a].maxAltitude_ft, limits[a].maxVertRate_ft_s};
+    try {
+        for (int k = 0; k < TERM_NMODELS; ++k) {
+            const HostModel& H = *static_cast<HostModel*>(models[k]);
+            make_term_model(H, P.lim[k < 4 ? 0 : 1], P.m[k]);
+            P.m[k].thr = H.thr_transition.data();
+            P.m[k].edges = H.edges.data();
+        }
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+    int32_t status = 0;
+    TermOut O{traj, len, &status};
+    for (int chain = 0; chain < 4; ++chain)
+        for (int64_t s = 0; s < n; ++s) terminal_chain(P, O, s, chain);
+    if (status & 2) return EMB_E_ARG;
+    return (status & 1) ? EMB_E_REJECT : 0;
+}
+
 }  // extern "C"

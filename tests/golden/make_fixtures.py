@@ -134,6 +134,21 @@ def main():
     st = [2, 1, 3] + [None] * 12
     I, B, A = terminal_sample(p, 32, KeyedPhilox(14), start=st)
     put("terminal_geo_start213_n32_seed14", dict(values=I, bins=B.astype(np.int8), attempts=A.astype(np.int32)))
+    # config 5 trajectories: createEncounter.m chains on the synthetic trajectory DBNs
+    # (em_model_manned_bayes_b200/synthetic.py -- the reference's 20 trajectory files are not in the checkout),
+    # geometry = the golden terminal-geometry samples above
+    import tempfile
+    from em_model_manned_bayes_b200.synthetic import write_terminal_model_set
+    from test_terminal_traj import geo_from_golden, oracle_propagate
+    tp = write_terminal_model_set(tempfile.mkdtemp(prefix="traj_models_"))
+    gold = {"terminal_geo_n64_seed13": {"values": vec["terminal_geo_n64_seed13/values"]}}
+    geo = geo_from_golden(gold, 16)
+    tr, ln = oracle_propagate(tp, geo, 31, 9000000000, 120)
+    put("terminal_traj_n16_T120_seed31", dict(geo=geo, traj=tr, len=ln, first=np.int64(9000000000)))
+    geo = geo_from_golden(gold, 12)
+    geo[5] = np.clip(geo[5], 70.0, 180.0)            # own_speed inside the TEST limits (sample.m:64 would have rejected others)
+    tr, ln = oracle_propagate(tp, geo, 32, 17, 45, ("TEST", "RTCA228_A1"))
+    put("terminal_traj_n12_T45_seed32_test_a1", dict(geo=geo, traj=tr, len=ln, first=np.int64(17)))
     np.savez_compressed(os.path.join(HERE, "vectors.npz"), **vec)
     for f in ("models.npz", "vectors.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))

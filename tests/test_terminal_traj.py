@@ -1,0 +1,232 @@
+"""Terminal trajectory chains: @CorTerminalModel/createEncounter.m:93-329.
+
+CPU suite: the host emulation of the device code (tests/emu, same emb_terminal.cuh) against the Python oracle
+(oracle/terminal.py) on the synthetic trajectory DBNs, fed the same keyed uniforms, and against the committed golden
+vectors.  GPU suite: the C ABI (emb_terminal_propagate) against the same goldens plus size-independent properties."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from em_model_manned_bayes_b200 import _lib as L
+from em_model_manned_bayes_b200.synthetic import TRAJECTORY_STEMS, write_terminal_model_set
+
+SLOTS = (("ownship_landing_model", "own_fwd", 0), ("ownship_landing_model_reverse", "own_bck", 0),
+         ("ownship_takeoff_model", "own_fwd", 1), ("ownship_takeoff_model_reverse", "own_bck", 1),
+         ("intruder_landing_model", "int_fwd", 0), ("intruder_landing_model_reverse", "int_bck", 0),
+         ("intruder_takeoff_model", "int_fwd", 1), ("intruder_takeoff_model_reverse", "int_bck", 1),
+         ("intruder_transit_model", "int_fwd", 2), ("intruder_transit_model_reverse", "int_bck", 2))   # TermParams::m order
+
+LIMITS = {"GENERIC": (50.0, 506.0, 12.0, 5000.0, 6000 / 60), "RTCA228_A1": (169.0, 491.0, 1.5, 5000.0, 2500 / 60),
+          "RTCA228_A3": (68.0, 186.0, 7.0, 5000.0, 500 / 60), "TEST": (68.0, 186.0, 7.0, 1200.0, 500 / 60)}
+
+
+@pytest.fixture(scope="session")
+def traj_paths(tmp_path_factory):
+    return write_terminal_model_set(str(tmp_path_factory.mktemp("traj_models")))
+
+
+def geo_from_golden(golden, n):
+    """(12, n) sample_geo rows from the golden terminal-geometry samples (labels of terminal_v3_radar_encounter_model)."""
+    labels = ["airspace_class", "own_intent", "int_intent", "int_type", "int_runway", "own_distance", "own_bearing", "own_alt",
+              "own_speed", "own_heading", "int_distance", "int_bearing", "int_alt", "int_speed", "int_heading"]
+    v = golden["terminal_geo_n64_seed13"]["values"][:n]
+    fields = ("own_intent", "own_distance", "own_bearing", "own_alt", "own_heading", "own_speed",
+              "int_intent", "int_distance", "int_bearing", "int_alt", "int_heading", "int_speed")
+    return np.ascontiguousarray(np.stack([v[:, labels.index(f)] for f in fields]))
+
+
+def emu_propagate(traj_paths, geo, seed, first, tmax_s, types=("GENERIC", "GENERIC"), max_attempts=0):
+    lib = H.emu_lib()
+    models = [H.EmuModel(traj_paths[stem]) for stem, _, _ in SLOTS]
+    for m in models:
+        m.set_prior(1, L.EMB_PRIOR_STAY, 1.0)
+    arr = (C.c_void_p * 10)(*[m.h.value for m in models])
+    n = geo.shape[1]
+    tmax = int(tmax_s)
+    traj = np.zeros((5, 2, 2 * tmax + 1, n), dtype=np.float32)
+    ln = np.zeros((4, n), dtype=np.int16)
+    lim = (L.DynLimits * 2)(*[L.DynLimits(*LIMITS[t]) for t in types])
+    rows = (C.c_int32 * 12)(*range(12))
+    rc = lib.emu_terminal_propagate(arr, seed, first, n, geo.ctypes.data, n, rows, float(tmax_s), lim, max_attempts,
+                                    traj.ctypes.data, ln.ctypes.data)
+    return rc, traj, ln
+
+
+_ORACLE_MODELS = {}
+
+
+def oracle_propagate(traj_paths, geo, seed, first, tmax_s, types=("GENERIC", "GENERIC")):
+    from oracle import terminal as T
+    from oracle.em_read import em_read
+    ms = {}
+    for stem, group, k in SLOTS:
+        if traj_paths[stem] not in _ORACLE_MODELS:
+            _ORACLE_MODELS[traj_paths[stem]] = em_read(traj_paths[stem])
+        ms[(group, k)] = _ORACLE_MODELS[traj_paths[stem]]
+    return T.create_encounters(ms, geo, seed, first, tmax_s, types)
+
+
+def check_traj(got, got_len, want, want_len, rtol=1e-6):
+    assert np.array_equal(np.asarray(got_len), np.asarray(want_len)), "chain lengths differ"
+    got = np.asarray(got, dtype=np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "occupied slots differ"
+    ok = ~np.isnan(want)
+    err = np.abs(got[ok] - want[ok])
+    assert np.all(err <= rtol * np.abs(want[ok]) + 1e-12), "trajectory values differ by more than 1e-6 relative (max %g)" % err.max()
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_oracle_helpers_known_answers():
+    from oracle import terminal as T
+    assert T.cosd(90.0) == 0.0 and T.sind(180.0) == 0.0 and T.cosd(-270.0) == 0.0 and T.sind(-90.0) == -1.0
+    assert T.cosd(360.0) == 1.0 and T.sind(450.0) == 1.0
+    assert T.wrap_to_360(0.0) == 0.0 and T.wrap_to_360(360.0) == 360.0 and T.wrap_to_360(720.0) == 360.0
+    assert T.wrap_to_360(-10.0) == 350.0 and T.wrap_to_360(370.0) == 10.0
+    assert T.round2(1.004) == 1.0 and T.round2(-2.674) == -2.67 and T.round2(2.676) == 2.68 and T.round2(0.125) == 0.13 and T.round2(-0.125) == -0.13
+    from oracle.sampler import discretize_bayes
+    cut = [0.5, 1, 2, 3, 4, 5]                     # distance cutpoints (terminal_v3_radar_encounter_model.txt:29)
+    assert [discretize_bayes(x, cut) for x in (0.0, 0.49, 0.5, 4.99, 5.0, 9.0)] == [1, 1, 2, 6, 7, 7]
+
+
+def test_oracle_chain_invariants(traj_paths, golden):
+    """createEncounter.m semantics on the oracle itself: termination rules, rate limits, merge order."""
+    geo = geo_from_golden(golden, 6)
+    traj, ln = oracle_propagate(traj_paths, geo, seed=21, first=0, tmax_s=60)
+    tmax = 60
+    assert ln.min() >= 1 and ln.max() <= tmax + 1
+    for s in range(geo.shape[1]):
+        for ac in range(2):
+            occ = ~np.isnan(traj[0, ac, :, s])
+            lo, hi = tmax - (ln[2 * ac + 1, s] - 1), tmax + ln[2 * ac, s] - 1
+            assert occ[lo:hi + 1].all() and occ.sum() == hi - lo + 1                   # contiguous in time (:74-84)
+            z = traj[2, ac, lo:hi + 1, s]
+            assert np.all(np.abs(np.diff(z[tmax - lo:])) <= 100.0 + 1e-9)              # maxVertRate (:180-184) forward part
+            v = traj[4, ac, lo:hi + 1, s]
+            assert np.all(v[1:-1] <= 506.0 + 1e-9)
+    # the t = 0 state is the encounter geometry (:45-49)
+    assert np.allclose(traj[2, 0, tmax, :], geo[3]) and np.allclose(traj[2, 1, tmax, :], geo[9])
+    assert np.allclose(np.hypot(traj[0, 0, tmax, :], traj[1, 0, tmax, :]), geo[1])
+
+
+@pytest.mark.parametrize("types,tmax_s,seed,first", [(("GENERIC", "GENERIC"), 120, 21, 0),
+                                                     (("TEST", "RTCA228_A1"), 45, 22, 1234567890123),
+                                                     (("RTCA228_A3", "GENERIC"), 0, 23, 5),
+                                                     (("GENERIC", "TEST"), 30.5, 24, 0)])
+def test_emu_chains_match_oracle(traj_paths, golden, types, tmax_s, seed, first):
+    geo = geo_from_golden(golden, 10)
+    if types[0] != "GENERIC":
+        geo[5] = np.clip(geo[5], 70.0, 180.0)
+    rc, traj, ln = emu_propagate(traj_paths, geo, seed, first, tmax_s, types)
+    assert rc == 0
+    want, want_len = oracle_propagate(traj_paths, geo, seed, first, tmax_s, types)
+    check_traj(traj, ln, want, want_len)
+
+
+def test_emu_chains_match_golden(traj_paths, golden):
+    g = golden["terminal_traj_n16_T120_seed31"]
+    rc, traj, ln = emu_propagate(traj_paths, np.ascontiguousarray(g["geo"]), 31, int(g["first"]), 120)
+    assert rc == 0
+    check_traj(traj, ln, g["traj"], g["len"])
+
+
+def test_emu_unknown_intent_is_an_error(traj_paths, golden):
+    geo = geo_from_golden(golden, 4)
+    geo[0, 2] = 3.0                                   # own_intent = 3 has no ownship model (createEncounter.m:21-22)
+    rc, _, _ = emu_propagate(traj_paths, geo, 1, 0, 10)
+    assert rc == L.EMB_E_ARG
+
+
+def test_stay_prior_is_required(traj_paths):
+    lib = H.emu_lib()
+    models = [H.EmuModel(traj_paths[stem]) for stem, _, _ in SLOTS]
+    arr = (C.c_void_p * 10)(*[m.h.value for m in models])
+    geo = np.zeros((12, 1))
+    lim = (L.DynLimits * 2)(*[L.DynLimits(*LIMITS["GENERIC"])] * 2)
+    rows = (C.c_int32 * 12)(*range(12))
+    rc = lib.emu_terminal_propagate(arr, 1, 0, 1, geo.ctypes.data, 1, rows, 10.0, lim, 0, None, None)
+    assert rc == L.EMB_E_ARG and b"stay prior" in lib.emu_last_error()
+
+
+def test_abi_rejects_bad_arguments_without_gpu(traj_paths):
+    lib = L.lib()
+    lim = (L.DynLimits * 2)()
+    assert lib.emb_dyn_limits_named(b"generic", C.byref(lim[0])) == 0 and lim[0].maxVel_ft_s == 506.0
+    assert lib.emb_dyn_limits_named(b"RTCA228_A2", C.byref(lim[1])) == 0 and lim[1].maxTurnRate_deg_s == 3.0
+    assert lib.emb_dyn_limits_named(b"nope", C.byref(lim[1])) == L.EMB_E_ARG
+    assert lib.emb_terminal_traj_len(10, 120.0) == 5 * 2 * 241 * 10
+    assert lib.emb_terminal_traj_len(10, -1.0) == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def _product_model(model_paths, traj_paths, types=("GENERIC", "GENERIC")):
+    from em_model_manned_bayes_b200.model import CorTerminalModel
+    m = CorTerminalModel(model_paths["terminal_v3_radar_encounter_model"], acType1=types[0], acType2=types[1])
+    m.load_trajectory_models(os.path.dirname(traj_paths[TRAJECTORY_STEMS[0]]))
+    return m
+
+
+@pytest.mark.gpu
+def test_gpu_chains_match_golden(model_paths, traj_paths, golden):
+    g = golden["terminal_traj_n16_T120_seed31"]
+    m = _product_model(model_paths, traj_paths)
+    res = m.create_encounters(np.ascontiguousarray(g["geo"]), 120, seed=31, first_sample=int(g["first"]), geo_rows=range(12))
+    check_traj(res.traj, res.len, g["traj"], g["len"])
+    enc = res.encounter(3)
+    assert enc[0]["t_s"][0] == -(int(g["len"][1, 3]) - 1) and enc[0]["t_s"][-1] == int(g["len"][0, 3]) - 1
+
+
+@pytest.mark.gpu
+def test_gpu_limits_golden(model_paths, traj_paths, golden):
+    g = golden["terminal_traj_n12_T45_seed32_test_a1"]
+    m = _product_model(model_paths, traj_paths, ("TEST", "RTCA228_A1"))
+    res = m.create_encounters(np.ascontiguousarray(g["geo"]), 45, seed=32, first_sample=int(g["first"]), geo_rows=range(12))
+    check_traj(res.traj, res.len, g["traj"], g["len"])
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_properties_and_shard_invariance(model_paths, traj_paths):
+    """geometry sampling -> chains, all on the device; 20 000 encounters; any shard reproduces the same numbers."""
+    import torch
+    m = _product_model(model_paths, traj_paths)
+    n, tmax = 20000, 120
+    vals, _, _ = m.sample_raw(n, seed=5, device="cuda:0")              # (n, 15) view of a (15, n) device tensor
+    geo = vals.T.contiguous()
+    res = m.create_encounters(geo, tmax, seed=6, device="cuda:0")
+    traj, ln = res.traj.cpu().numpy(), res.len.cpu().numpy()
+    assert ln.min() >= 1 and ln.max() <= tmax + 1
+    occ = ~np.isnan(traj[0])                                            # (2, S, n)
+    for ac in range(2):
+        assert np.array_equal(occ[ac].sum(axis=0), ln[2 * ac] + ln[2 * ac + 1] - 1)
+        assert np.array_equal(np.isnan(traj[:, ac]), np.broadcast_to(~occ[ac], traj[:, ac].shape))
+    with np.errstate(invalid="ignore"):
+        dz = np.abs(np.diff(traj[2], axis=1))
+        assert np.nanmax(dz) <= 100.0 * (1 + 1e-6)                      # maxVertRate_ft_s, GENERIC
+        assert np.nanmax(traj[4]) <= max(506.0, float(geo[8].max()), float(geo[13].max())) * (1 + 1e-6)
+        hd = traj[3]
+        assert np.nanmin(hd) >= 0.0 and np.nanmax(hd) <= 360.0
+        assert np.nanmax(np.hypot(traj[0], traj[1])) <= 8.0 + 506.0 / 6076.0 + 1e-3   # one step beyond bounds_initial(dist)
+    # shard [7000, 7000+500) alone
+    part = m.create_encounters(geo[:, 7000:7500].contiguous(), tmax, seed=6, first_sample=7000, device="cuda:0")
+    assert torch.equal(part.len, res.len[:, 7000:7500])
+    a, b = part.traj.cpu().numpy(), traj[:, :, :, 7000:7500]
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    # host-memory call gives the same bytes as the device-memory call
+    host = m.create_encounters(geo[:, :300].cpu().numpy(), tmax, seed=6)
+    assert np.array_equal(np.asarray(host.len), ln[:, :300])
+    assert np.array_equal(np.nan_to_num(np.asarray(host.traj), nan=-1.0), np.nan_to_num(traj[:, :, :, :300], nan=-1.0))
+
+
+@pytest.mark.gpu
+def test_gpu_unknown_intent_and_missing_models(model_paths, traj_paths):
+    from em_model_manned_bayes_b200.model import CorTerminalModel
+    m = _product_model(model_paths, traj_paths)
+    geo = np.array([[3.0], [3.0], [200.0], [1200.0], [45.0], [180.0], [1.0], [4.0], [100.0], [2200.0], [300.0], [250.0]])
+    with pytest.raises(L.EmbError) as e:
+        m.create_encounters(geo, 10, seed=1, geo_rows=range(12))
+    assert e.value.code == L.EMB_E_ARG and "Unknown int_intent" in e.value.message
+    bare = CorTerminalModel(model_paths["terminal_v3_radar_encounter_model"])
+    with pytest.raises(L.EmbError):
+        bare.create_encounters(geo, 10, seed=1, geo_rows=range(12))
