@@ -281,6 +281,51 @@ def main():
         torch.cuda.synchronize()
         other["configs[1] glider_v1 initial network only, 100M samples, int8 bins"] = {
             "value": 3 * n2 / (e0.elapsed_time(e1) * 1e-3), "unit": "samples/s"}
+        del g
+        torch.cuda.empty_cache()
+
+        def timed(fn, reps=3):
+            fn(0)
+            torch.cuda.synchronize()
+            e0.record()
+            for k in range(reps):
+                fn(1 + k)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / reps
+
+        # configs[3]: correlated model (cor_v2p1.txt is missing from the public checkout -> cor_v1.txt, 16 initial + 4 dynamic
+        # variables, dbn_sample.m slow branch), 10M encounters x 60 s (em_sample.m:26)
+        mdir = os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid())
+        cp = materialize(mdir, names=["cor_v1"])["cor_v1"]
+        cm = EncounterModel(cp)
+        n4, T4 = 10_000_000, 60
+        r4 = cm.sample_tracks(n4, T4, seed=1, device=dev)
+        dt = timed(lambda k: cm.sample_tracks(n4, T4, seed=10 + k, device=dev, out=r4))
+        other["configs[3] cor_v1 (stand-in for the missing cor_v2p1), 10M encounters x 60 s, dense compact outputs"] = {
+            "value": n4 * T4 / dt, "unit": "track-timesteps/s", "ms": dt * 1e3}
+        del r4, cm
+        torch.cuda.empty_cache()
+
+        # configs[4]: CorTerminalModel, 1M encounters: geometry sampling (sample.m) + four trajectory chains per encounter
+        # (createEncounter.m) on synthetic trajectory DBNs of the documented layout (the 20 model files are missing upstream)
+        from em_model_manned_bayes_b200.model import CorTerminalModel
+        from em_model_manned_bayes_b200.synthetic import write_terminal_model_set
+        tp_ = materialize(mdir, names=["terminal_v3_radar_encounter_model"])["terminal_v3_radar_encounter_model"]
+        write_terminal_model_set(os.path.join(mdir, "traj"))
+        tm = CorTerminalModel(tp_, parameters_directory=os.path.join(mdir, "traj"))
+        n5, tmax5 = 1_000_000, 120
+        vals, _, _ = tm.sample_raw(n5, seed=1, device=dev)
+        geo = vals.T.contiguous()
+        r5 = tm.create_encounters(geo, tmax5, seed=2, device=dev)
+        dt_geo = timed(lambda k: tm.sample_raw(n5, seed=20 + k, device=dev))
+        dt_traj = timed(lambda k: tm.create_encounters(geo, tmax5, seed=30 + k, device=dev, out=r5))
+        states = int(r5.len.to(torch.int64).sum().item())
+        other["configs[4] CorTerminalModel 1M encounters: sample (geometry) + createEncounter chains, tmax 120 s, synthetic "
+              "trajectory DBNs"] = {"value": states / dt_traj, "unit": "trajectory states/s", "ms_chains": dt_traj * 1e3,
+                                    "ms_geometry": dt_geo * 1e3, "encounters_per_s": n5 / (dt_traj + dt_geo),
+                                    "states_per_encounter": states / n5}
+        del r5, geo, vals, tm
         torch.cuda.empty_cache()
 
     if rank != 0:

@@ -435,7 +435,7 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     const HostModel& H = *m->h;
     if (!H.has_transition || H.temporal_map.empty())
         return set_err(EMB_E_ARG, "dynvar:empty: model has no transition network");
-    if ((int64_t)T * (int64_t)(H.temporal_map.size() + H.gated.size()) >= (1ll << 33))
+    if ((int64_t)T * (int64_t)H.gated.size() >= (1ll << 33))
         return set_err(EMB_E_LIMIT, "T too large for the 32-bit stream index");
     emb::SampleParams P;
     int rc = 0;

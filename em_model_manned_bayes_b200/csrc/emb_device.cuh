@@ -33,9 +33,11 @@ constexpr int MAXG = 16;  // EMB_MAX_GATED
 constexpr int MAXX = MAXV + MAXD;
 constexpr int HIST_STRIDE = 64;
 
-// stream spec v2 purposes (oracle/philox.py)
+// stream spec v3 purposes (oracle/philox.py)
 constexpr uint32_t P_INIT = 1, P_STEP = 2, P_LAYER = 4;
-constexpr uint32_t DD_MULT = 0x9E3779B1u;   // value word -> de-discretisation uniform (spec v2)
+// one word k per (second, gated variable): select on k, gate on k*GATE_MULT, de-discretisation on k*DD_MULT (spec v3)
+constexpr uint32_t GATE_MULT = 0x9E3779B1u;
+constexpr uint32_t DD_MULT = 0x85EBCA6Bu;
 
 struct Node {
     int32_t r;               // bins
@@ -54,8 +56,8 @@ struct DevModel {
     Node dyn[MAXD];
     int32_t dyn_t[MAXD];           // x index of the variable at time t
     int32_t dyn_t1[MAXD];          // x index of its (t+1)/(t-1) counterpart
-    int32_t gated_var[MAXG];       // variables with a value word: rate > 0 or dynamic, ascending (spec v2)
-    uint64_t gate_G[MAXG];         // fires iff k < G (0 for rate 0)
+    int32_t gated_var[MAXG];       // variables with a word per second: rate > 0 or dynamic, ascending (spec v3)
+    uint64_t gate_G[MAXG];         // fires iff k*GATE_MULT mod 2^32 < G (0 for rate 0)
     int32_t gate_of_dyn[MAXD];     // gated ordinal of the d-th dynamic variable
     int32_t dd_off[MAXG];          // first entry of gated ordinal g in dd32
     int32_t fast32_ok;             // every gated bin can be de-discretised in fp32 within 1e-6 relative
@@ -206,7 +208,7 @@ EMB_HD uint32_t keyed_word(uint64_t seed, uint64_t sample, uint32_t attempt, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// stream spec v2: de-discretisation uniform of a value word, (((k*A) mod 2^32 >> 9) + 0.5) 2^-23
+// stream spec v3: de-discretisation uniform of a step word, (((k*B) mod 2^32 >> 9) + 0.5) 2^-23
 EMB_HD double u_dd(uint32_t k) { return dmul(dadd((double)((k * DD_MULT) >> 9), 0.5), 1.1920928955078125e-07); }
 
 EMB_HD uint32_t ldg32(const uint32_t* p) {
@@ -376,24 +378,24 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     const int Tpad = nch4 * 4;
     for (int c = 0; c < Tpad; ++c) {          // column c = state during second c+1; step e = c
         if (c > 0 && c < T) {
-            const uint32_t base = (uint32_t)c * (uint32_t)nw;   // stream spec v2: p = e*nw + slot
-            uint32_t wstep[MAXD + MAXG];
+            const uint32_t base = (uint32_t)c * (uint32_t)nw;   // stream spec v3: p = e*nw + g
+            uint32_t wstep[MAXG];
             for (int q = 0; q < nw; ++q) wstep[q] = ws.at(base + (uint32_t)q);
             // resample gates on the pre-transition bins (resample_events.m:23-29)
             for (int g = 0; g < ng; ++g) {
-                const uint32_t k = wstep[nd + g];
-                if ((uint64_t)k < M.gate_G[g]) {
+                const uint32_t k = wstep[g];
+                if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                     const int v = M.gated_var[g];
                     vals[v] = dedisc(M, v, x[v], u_dd(k));
                     if (ev) emit((uint32_t)c, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, vals[v]);
                 }
             }
-            // transitions (dbn_sample.m:69-79 slow / :143-146 fast)
+            // transitions (dbn_sample.m:69-79 slow / :143-146 fast): the variable's own word selects
             for (int od = 0; od < nd; ++od) {
                 const int d = M.fast ? od : M.order_dyn[od];
                 const Node& nd_ = M.dyn[d];
                 const uint32_t* cp = M.fast ? col[d] : node_column(nd_, M.thr_trans, x);
-                x[M.dyn_t1[d]] = (uint8_t)select_bin(cp, nd_.rp, wstep[d]);
+                x[M.dyn_t1[d]] = (uint8_t)select_bin(cp, nd_.rp, wstep[M.gate_of_dyn[d]]);
             }
             // map back + change events (dbn_sample.m:82-92); the new value reads the same value word
             for (int d = 0; d < nd; ++d) {
@@ -401,7 +403,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 const uint8_t nb = x[M.dyn_t1[d]];
                 if (nb != x[vt]) {
                     x[vt] = nb;
-                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[nd + M.gate_of_dyn[d]]));
+                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[M.gate_of_dyn[d]]));
                     if (ev) emit((uint32_t)c, (uint32_t)vt + 1u, (uint32_t)nb + 1u, vals[vt]);
                 }
             }
@@ -440,8 +442,8 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     if (ev) {
         // gates of the last held second T (resample_events.m:23-29), then the closing row (dbn_hierarchical_sample.m:15-19)
         for (int g = 0; g < ng; ++g) {
-            const uint32_t k = ws.at((uint32_t)T * (uint32_t)nw + (uint32_t)(nd + g));
-            if ((uint64_t)k < M.gate_G[g]) {
+            const uint32_t k = ws.at((uint32_t)T * (uint32_t)nw + (uint32_t)g);
+            if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                 const int v = M.gated_var[g];
                 emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k)));
             }

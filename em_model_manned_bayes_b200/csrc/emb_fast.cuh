@@ -1,12 +1,12 @@
 // emb_fast.cuh -- register-resident, branch-free track sampler for the common model shapes.
 //
-// Same semantics and same keyed stream (spec v2, oracle/philox.py) as track_generic (emb_device.cuh);
+// Same semantics and same keyed stream (spec v3, oracle/philox.py) as track_generic (emb_device.cuh);
 // what changes is where the state lives and that nothing in the per-second loop diverges.  Template
 // parameters fix the number of bins of every dynamic variable (RS packs up to four of them, one per
 // byte, in temporal_map order) and the number of gated variables NG, so that
 //   * the frozen inverse-CDF thresholds of the fast branch (dbn_sample.m:110-135) sit in registers,
-//   * the nw = ND + NG words of four consecutive seconds come from exactly nw Philox calls whose
-//     outputs are indexed statically (p = e*nw + slot, so 4 seconds = nw blocks),
+//   * the nw = NG words of four consecutive seconds (one per gated variable and second) come from exactly nw
+//     Philox calls whose outputs are indexed statically (p = e*nw + g, so 4 seconds = nw blocks),
 //   * a second costs, per gated variable, one compare (gate), one compare (bin changed), and one
 //     predicated fp32 de-discretisation  value = fma(slope, fma(f, s, c), base)  whose operands come
 //     from a 16-byte shared-memory entry indexed by the bin (no fp64, no int->float conversion: the
@@ -50,7 +50,7 @@ EMB_HD void fast_fill_shared(const DevModel& M, FastShared& S, int tid, int nthr
     for (int q = tid; q < 4 * total; q += nthreads) dst[q] = M.dd32[q];
 }
 
-// the 23 fraction bits of a value word as a float in [1,2)   (stream spec v2: u_dd = (f - 1) + 2^-24):
+// the 23 fraction bits of a step word as a float in [1,2)   (stream spec v3: u_dd = (f - 1) + 2^-24):
 // one IMAD (hash) + one funnel shift that drops the exponent of 1.0f on top of the fraction
 EMB_HD float dd_fraction(uint32_t k) {
     const uint32_t h = k * DD_MULT;
@@ -92,7 +92,7 @@ struct FastTrack {
     using SH = DynShape<RS>;
     static constexpr int ND = SH::ND;
     static constexpr int NS = NG - ND;   // gated variables that are not dynamic (their bin never changes)
-    static constexpr int NW = ND + NG;
+    static constexpr int NW = NG;        // stream spec v3: one word per (second, gated variable)
     static constexpr int RPM = SH::RPMAX;
 
     const DevModel& M;
@@ -155,7 +155,7 @@ struct FastTrack {
             if (FAST) {
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    const uint32_t k = W[j * NW + d];
+                    const uint32_t k = W[j * NW + NS + d];
                     uint32_t b = thr[d][SH::RP(d) - 1];
 #pragma unroll
                     for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gt(b, k, thr[d][m]);
@@ -184,7 +184,7 @@ struct FastTrack {
                                 t[q] = col[q]; t[q + 1] = col[q + 1]; t[q + 2] = col[q + 2]; t[q + 3] = col[q + 3];
 #endif
                             }
-                            const uint32_t k = W[j * NW + d];
+                            const uint32_t k = W[j * NW + NS + d];
                             uint32_t b = t[SH::RP(d) - 1] + (uint32_t)ebase[NS + d];
 #pragma unroll
                             for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gt(b, k, ~t[m]);
@@ -199,14 +199,14 @@ struct FastTrack {
             float ev_val[ND];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                const uint32_t k = W[j * NW + ND + g];
+                const uint32_t k = W[j * NW + g];
                 const int d = g - NS;
                 DdEntry en;
                 if (g >= NS) en = S.ent[nb[d >= 0 ? d : 0]];
                 else en = sent[g < NS ? g : 0];
                 const float gp = fmaf_rn(dd_fraction(k), en.s, en.c);
                 const float cand = fmaf_rn(en.slope, gp, en.base);
-                const bool fired = k < G[g];
+                const bool fired = (k * GATE_MULT) < G[g];
                 const bool changed = g >= NS && nb[d >= 0 ? d : 0] != bin[d >= 0 ? d : 0];
                 if ((fired || changed) && act) val[g] = cand;
                 if (EV) {

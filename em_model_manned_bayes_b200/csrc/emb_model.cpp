@@ -308,7 +308,7 @@ void HostModel::derive() {
         for (int i = 0; i < n; ++i)
             if (r_transition[i] != r_initial[i]) fail(EMB_E_MODEL, "r_transition(1:n_initial) differs from r_initial");
     }
-    // stream spec v2: a variable owns a value word per second iff its value can change (rate > 0 or dynamic)
+    // stream spec v3: a variable owns one word per second iff its value can change (rate > 0 or dynamic)
     gated.clear();
     for (int i = 0; i < n; ++i) {
         bool g = resample_rates[i] > 0.0;
@@ -381,7 +381,7 @@ void HostModel::pack() {
     D.n_dyn = (int32_t)temporal_map.size();
     D.n_gated = (int32_t)gated.size();
     D.n_tv = (int32_t)timevarying.size();
-    D.nw = D.n_dyn + D.n_gated;
+    D.nw = D.n_gated;   // stream spec v3: one word per (second, gated variable)
     D.fast = is_dynvar_depend ? 0 : 1;
     D.two23 = 1 << 23;
     for (int i = 0; i < n; ++i) D.order_initial[i] = order_initial[i];
@@ -583,9 +583,13 @@ void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M) {
     if (H.prior_initial.kind != EMB_PRIOR_CONSTANT || H.prior_initial.value != 0.0)
         fail(EMB_E_ARG, "createEncounter: the initial prior must be 0 (createEncounter.m:128)");
     for (int d = 0; d < 3; ++d) {
-        M.dyn[d] = H.dev.dyn[d];
-        for (int p = 0; p < M.dyn[d].np; ++p)
-            if (M.dyn[d].par[p] >= 6) fail(EMB_E_MODEL, "createEncounter: parent outside the initial variables");
+        const Node& nd = H.dev.dyn[d];
+        M.off[d] = nd.off;
+        M.rp[d] = (uint32_t)nd.rp;
+        for (int p = 0; p < nd.np; ++p) {
+            if (nd.par[p] >= 6) fail(EMB_E_MODEL, "createEncounter: parent outside the initial variables");
+            M.stride[d][nd.par[p]] = nd.stride_rp[p];
+        }
     }
     for (int i = 0; i < 6; ++i) {
         M.edge_off[i] = H.dev.edge_off[i];

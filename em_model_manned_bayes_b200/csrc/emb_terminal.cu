@@ -15,7 +15,7 @@ namespace {
 
 constexpr int TERM_BLOCK = 128;
 
-__global__ void __launch_bounds__(TERM_BLOCK)
+__global__ void __launch_bounds__(TERM_BLOCK, 6)
 k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ TermOut O) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s < P.n) terminal_chain(P, O, s, (int)blockIdx.y);

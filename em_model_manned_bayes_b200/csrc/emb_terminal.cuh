@@ -8,7 +8,7 @@
 // branch: three selects from columns addressed by the re-discretised state), the dynamic-limit
 // rejection loop of createEncounter.m:192-243 and the kinematic update of :171-184 / :246-256 in fp64.
 //
-// Uniforms (stream spec v2, terminal part -- oracle/terminal.py): Philox counter
+// Uniforms (stream spec v3, terminal part -- oracle/terminal.py): Philox counter
 //   (encounter_lo, encounter_hi, step ii, attempt << 16 | purpose << 8 | chain), chain = 2*aircraft + (0 fwd, 1 bck);
 //   purpose TERM_SEL: lane d = row 2 of the rand(2,1) of the d-th dynamic variable (dbn_sample.m:133,144);
 //   purpose TERM_DD : lane d = the rand of dediscretize for its event (createEncounter.m:203,208,216).
@@ -24,7 +24,11 @@ constexpr double TERM_FT_PER_NM = 6076.1154855643;   // createEncounter.m:172
 
 // what a chain needs from one trajectory model (built on the host from HostModel::dev)
 struct TermModel {
-    Node dyn[3];              // heading', altitude', speed' (temporal_map rows 0..2)
+    // heading', altitude', speed' (temporal_map rows 0..2): column = off + sum_i stride[i] * bin_i over the six
+    // initial variables (asub2ind.m:13-14 strides times the padded column length; 0 for non-parents)
+    uint32_t off[3];
+    uint32_t rp[3];
+    uint32_t stride[3][6];
     const uint32_t* thr;      // word-space threshold table of the transition network
     const double* edges;      // {a, b-a} pairs (HostModel::edges)
     int32_t edge_off[6];      // per initial variable: offset into edges (doubles), -1 = no boundaries
@@ -62,12 +66,6 @@ struct TermOut {
 // ---- MATLAB built-ins as restated by the oracle (oracle/terminal.py) --------------------------------
 EMB_HD void sincosd(double x, double& s, double& c) {
     const double r = ::fmod(x, 360.0);
-    if (::fmod(r, 90.0) == 0.0) {                       // exact at multiples of 90 degrees (cosd/sind)
-        const int q = (((int)(r / 90.0)) % 4 + 4) % 4;
-        c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
-        s = q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
-        return;
-    }
     const double a = dmul(r, 0.017453292519943295);     // pi/180
 #if defined(__CUDA_ARCH__)
     ::sincos(a, &s, &c);
@@ -75,6 +73,11 @@ EMB_HD void sincosd(double x, double& s, double& c) {
     s = ::sin(a);
     c = ::cos(a);
 #endif
+    if (::fmod(r, 90.0) == 0.0) {                       // exact at multiples of 90 degrees (cosd/sind); selects, no branch
+        const int q = ((int)(r / 90.0)) & 3;            // two's complement: -1 -> 3, -2 -> 2, -3 -> 1
+        c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
+        s = q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
+    }
 }
 EMB_HD double atan2d(double y, double x) { return dmul(::atan2(y, x), 57.29577951308232); }   // 180/pi
 EMB_HD double wrap_to_360(double x) {                   // wrapTo360: mod(x,360), positive multiples of 360 -> 360
@@ -137,9 +140,9 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     const double v0 = g[(int64_t)row[5] * P.geo_stride];
     const TermLimits& L = P.lim[ac];
 
-    auto put = [&](int f, int64_t slot, float v) {
-        EMB_STREAM_F32(O.traj + (((int64_t)f * 2 + ac) * S + slot) * N + s, v);
-    };
+    const int64_t fstride = 2 * S * N;                   // between fields
+    float* slotp = O.traj ? O.traj + ((int64_t)ac * S + P.tmax) * N + s : nullptr;   // slot of t_s = 0, field 0
+    auto put = [&](int f, float v) { EMB_STREAM_F32(slotp + f * fstride, v); };
 #if defined(__CUDA_ARCH__)
     const float qnan = __int_as_float(0x7FC00000);
 #else
@@ -159,10 +162,10 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     int len = 0;
 
     for (int ii = 1; ii <= K; ++ii) {
-        const int64_t slot = dir ? (int64_t)P.tmax - (ii - 1) : (int64_t)P.tmax + (ii - 1);
         const bool store = O.traj && !(dir && ii == 1);                          // [fwd, bck(2:end)] (:77)
+        if (ii > 1 && slotp) slotp += dir ? -N : N;
         if (!go) {
-            if (store) for (int f = 0; f < TERM_FIELDS; ++f) put(f, slot, qnan);
+            if (store) for (int f = 0; f < TERM_FIELDS; ++f) put(f, qnan);
             continue;
         }
         ++len;
@@ -176,47 +179,52 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         }
         z_prev = z_rec;
         if (store) {
-            put(0, slot, (float)x);
-            put(1, slot, (float)y);
-            put(2, slot, (float)z_rec);
-            put(3, slot, (float)curr_hdg);
-            put(4, slot, (float)norm2(vx, vy));
+            put(0, (float)x);
+            put(1, (float)y);
+            put(2, (float)z_rec);
+            put(3, (float)curr_hdg);
+            put(4, (float)norm2(vx, vy));
         }
         x = dadd(x, dmul(vx, dt_s) / TERM_FT_PER_NM);                             // :171-173
         y = dadd(y, dmul(vy, dt_s) / TERM_FT_PER_NM);
 
         // CreateStartDistribution (:268-294), 0-based bins
-        uint8_t st[6];
-        st[0] = (uint8_t)(intent - 1);
-        st[1] = (uint8_t)term_discretize(M, M.i_dist, norm2(x, y));              // positional cell, cutpoints by label (:277,:293)
-        st[2] = (uint8_t)term_discretize(M, M.i_bear, wrap_to_360(atan2d(y, x)));
-        st[3] = (uint8_t)term_discretize(M, 3, heading_deg);
-        st[4] = (uint8_t)term_discretize(M, 4, z_ft);
-        st[5] = (uint8_t)term_discretize(M, 5, norm2(vx, vy));
-        const uint32_t* col0 = node_column(M.dyn[0], M.thr, st);                  // frozen parents (dbn_sample.m:110-135)
-        const uint32_t* col1 = node_column(M.dyn[1], M.thr, st);
-        const uint32_t* col2 = node_column(M.dyn[2], M.thr, st);
+        uint32_t st[6];
+        st[0] = (uint32_t)(intent - 1);
+        st[1] = (uint32_t)term_discretize(M, M.i_dist, norm2(x, y));              // positional cell, cutpoints by label (:277,:293)
+        st[2] = (uint32_t)term_discretize(M, M.i_bear, wrap_to_360(atan2d(y, x)));
+        st[3] = (uint32_t)term_discretize(M, 3, heading_deg);
+        st[4] = (uint32_t)term_discretize(M, 4, z_ft);
+        st[5] = (uint32_t)term_discretize(M, 5, norm2(vx, vy));
+        const uint32_t* col[3];                                                   // frozen parents (dbn_sample.m:110-135)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            uint32_t o = M.off[d];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o += M.stride[d][i] * st[i];
+            col[d] = M.thr + o;
+        }
 
         for (uint32_t attempt = 0;; ++attempt) {                                  // while is_resample (:192-243)
             uint32_t w0, w1, w2, w3;
             philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
                           (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain, (uint32_t)P.seed,
                           (uint32_t)(P.seed >> 32), w0, w1, w2, w3);
-            const int nh = select_bin(col0, M.dyn[0].rp, w0);
-            const int na = select_bin(col1, M.dyn[1].rp, w1);
-            const int nv = select_bin(col2, M.dyn[2].rp, w2);
+            const int nh = select_bin(col[0], (int)M.rp[0], w0);
+            const int na = select_bin(col[1], (int)M.rp[1], w1);
+            const int nv = select_bin(col[2], (int)M.rp[2], w2);
             bool redo = false;
-            if (nh != st[3] || na != st[4] || nv != st[5]) {                      // events in variable order 4, 5, 6
+            if (nh != (int)st[3] || na != (int)st[4] || nv != (int)st[5]) {                      // events in variable order 4, 5, 6
                 uint32_t d0, d1, d2, d3;
                 philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
                               (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain, (uint32_t)P.seed,
                               (uint32_t)(P.seed >> 32), d0, d1, d2, d3);
-                if (nh != st[3]) heading_deg = term_dedisc(M, 3, nh, d0);         // :200-205
-                if (na != st[4]) {                                                // :206-212
+                if (nh != (int)st[3]) heading_deg = term_dedisc(M, 3, nh, d0);         // :200-205
+                if (na != (int)st[4]) {                                                // :206-212
                     if (na + 1 <= M.alt_hi) z_ft = term_dedisc(M, 4, na, d1);
                     else redo = true;
                 }
-                if (!redo && nv != st[5]) {                                       // :213-233
+                if (!redo && nv != (int)st[5]) {                                       // :213-233
                     if (nv + 1 >= M.spd_lo && nv + 1 <= M.spd_hi) {
                         double v1 = term_dedisc(M, 5, nv, d2);
                         if (v1 < L.minVel) v1 = L.minVel;

@@ -15,7 +15,10 @@ of the documented structure (`createEncounter.m:107-116` asserts the variable na
 
 Counts are pseudo-random with a strong stay-in-bin diagonal (deterministic in `seed`); bin edges follow the
 encounter-geometry model (`terminal_v3_radar_encounter_model.txt:29-38`) widened so that the dynamic limits
-of `@CorTerminalModel/getDynamicLimits.m:14-62` both accept and reject bins."""
+of `@CorTerminalModel/getDynamicLimits.m:14-62` both accept and reject bins.  No speed edge coincides with a
+minVel/maxVel of that table: createEncounter.m:221-226 clamps a sampled speed to the limit, the clamped speed is rotated
+and re-discretised through norm() in the next state (:290), and a limit sitting exactly on a bin edge would make that bin
+depend on the last bit of cosd/sind."""
 from __future__ import annotations
 
 import numpy as np
@@ -25,7 +28,7 @@ from .em_write import em_write
 DIST_EDGES = [0, 0.5, 1, 2, 3, 4, 5, 8]
 ANGLE_EDGES = list(range(0, 361, 10))
 ALT_EDGES = [0, 200, 500, 1000, 1500, 2000, 2500, 3000, 5000, 10000]
-SPEED_EDGES = [0, 50, 100, 150, 200, 300, 400, 506, 600]
+SPEED_EDGES = [0, 40, 100, 150, 200, 300, 400, 520, 600]
 
 
 def terminal_trajectory_model_arrays(seed: int = 0, direction: int = +1):

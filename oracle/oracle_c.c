@@ -12,7 +12,7 @@
  * reference's data flow -- event lists, resample pass, de-discretisation pass, dense expansion --
  * and uses none of the product's tricks (no word-space thresholds: every draw is a cumsum + fp64
  * compare exactly like select_random.m).  The model arrays come from the oracle's own reader
- * (oracle/em_read.py); nothing is shared with libemb200.so.  Uniforms: keyed Philox, stream spec v2
+ * (oracle/em_read.py); nothing is shared with libemb200.so.  Uniforms: keyed Philox, stream spec v3
  * (oracle/philox.py).
  *
  * PARITY UNPINNED: validated only against the Python oracle (tests/test_oracle_c.py), which in turn
@@ -56,7 +56,7 @@ typedef struct {
     int32_t max_attempts;
 } oc_model;
 
-/* ---- keyed Philox4x32-10 (stream spec v2) ----------------------------------------------------- */
+/* ---- keyed Philox4x32-10 (stream spec v3) ----------------------------------------------------- */
 static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* o) {
     for (int i = 0; i < 10; ++i) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -125,10 +125,12 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
     const int n = M->n_initial, nt = M->n_transition, nd = M->n_dyn;
     ukey K;
     memset(&K, 0, sizeof(K));
-    K.seed = seed; K.sample = sample; K.nd = nd; K.nw = nd + M->n_gated; K.n_initial = n;
+    K.seed = seed; K.sample = sample; K.nd = nd; K.nw = M->n_gated; K.n_initial = n;
     int gate_of_var[MAXV + 1];
     for (int i = 0; i <= n; ++i) gate_of_var[i] = -1;
     for (int g = 0; g < M->n_gated; ++g) gate_of_var[M->gated[g]] = g;
+    int gate_of_dyn[8];   /* stream spec v3: the word of (second, variable) also selects the variable's transition */
+    for (int d = 0; d < nd; ++d) gate_of_dyn[d] = gate_of_var[M->temporal_map[2 * d]];
     for (int attempt = 0; attempt <= M->max_attempts; ++attempt) {
         K.attempt = (uint32_t)attempt;
         double x[MAXV + 8];
@@ -170,14 +172,14 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                         for (int d = 0; d < nd; ++d) if (M->temporal_map[2 * d + 1] == i) {
                             int64_t j = parent_index(M->G_transition, nt, i - 1, M->r, x);
                             const double* w = M->W_transition + M->off_transition[i - 1] + (j - 1) * M->r[i - 1];
-                            double rnd = u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + d));
+                            double rnd = u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + gate_of_dyn[d]));
                             x[i - 1] = (double)select_random(w, M->r[i - 1], rnd);
                         }
                     }
                 } else { /* :143-146 */
                     for (int d = 0; d < nd; ++d) {
                         int ii = M->temporal_map[2 * d + 1];
-                        volatile double sthres = s[d][rdyn[d] - 1] * u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + d));
+                        volatile double sthres = s[d][rdyn[d] - 1] * u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + gate_of_dyn[d]));
                         int m = 0;
                         while (!(s[d][m] >= sthres)) ++m;
                         x[ii - 1] = (double)(m + 1);
@@ -210,7 +212,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                     delta_t += 1;
                     for (int i = 1; i <= n; ++i) { /* changes = find(rand(size(rates)) < rates) */
                         double u = 0.5;
-                        if (gate_of_var[i] >= 0) u = u01(word_at(&K, 2, (uint64_t)second * K.nw + nd + gate_of_var[i]));
+                        if (gate_of_var[i] >= 0) u = u01(word_at(&K, 2, (uint64_t)second * K.nw + gate_of_var[i]) * 0x9E3779B1u);
                         if (u < M->rates[i - 1]) {
                             ev2[n2].dt = first ? delta_t : 0; ev2[n2].var = i; ev2[n2].val = xr[i - 1];
                             ev2[n2].kind = 1; ev2[n2].second = second; ++n2;
@@ -233,11 +235,11 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
             int var = (int)ev2[e].var;
             double rnd = 0.5;
             if (dd_needs_u(M, var, ev2[e].val)) {
-                /* stream spec v2: fired-gate and transition values both read the variable's value word */
+                /* stream spec v3: fired-gate and transition values both read the variable's word of that second */
                 int g = 0;
                 while (M->gated[g] != var) ++g;
-                uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + nd + g);
-                uint32_t h = k * 0x9E3779B1u;
+                uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + g);
+                uint32_t h = k * 0x85EBCA6Bu;
                 rnd = ((double)(h >> 9) + 0.5) * 1.1920928955078125e-07; /* 2^-23 */
             }
             /* keep the bin for the dense bin expansion in .second's place holder */

@@ -2,7 +2,7 @@
 
 Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy
 as 1, 2, 3", SC'11; the Random123 `philox4x32_R(10, ctr, key)` function) and the keyed
-stream layout ("stream spec v2") shared by the oracle and the CUDA sampler.
+stream layout ("stream spec v3") shared by the oracle and the CUDA sampler.
 
 The reference (`/root/reference/code/matlab/select_random.m:14`, `dbn_sample.m:133`,
 `resample_events.m:24`, `dediscretize.m:39`) draws from MATLAB's global `rand`.  The B200
@@ -10,7 +10,7 @@ sampler replaces *when* a uniform is consumed by *what it is for*: every uniform
 function of (seed, sample, attempt, purpose, index, lane).  The oracle is fed exactly these
 uniforms (uniform-injection), so bin indices must be bit-identical.
 
-Stream spec v2
+Stream spec v3
 --------------
 key     = (seed & 0xffffffff, seed >> 32)
 counter = (sample & 0xffffffff, sample >> 32, index, (attempt << 16) | (purpose << 8) | sub)
@@ -19,28 +19,32 @@ A call returns four 32-bit words; `lane` picks one.
 purpose INIT (1):    word position p;  p = i            -> select word of initial variable i (0-based)
                                       p = n_initial + i -> dediscretize word of initial variable i
                      index = p // 4, lane = p % 4
-purpose STEP (2):    word position p = e * nw + slot, e = 1..T the event second (the nw positions
-                     of e = 0 are unused, which keeps groups of four seconds aligned to nw blocks),
-                     nw = n_dyn + n_gated, where the *gated* variables are, in increasing id, the
-                     initial variables that have a resample rate > 0 or are dynamic (temporal_map
-                     column 1); slot d (< n_dyn) -> transition select of the d-th dynamic variable
-                     (temporal_map row d) for loop index t = e + 1; slot n_dyn + g -> the *value
-                     word* of the g-th gated variable at second e.   index = p // 4, lane = p % 4
+purpose STEP (2):    ONE word per (second, variable): word position p = e * nw + g, e = 1..T the second,
+                     g the ordinal of the variable among the *gated* variables -- in increasing id, the
+                     initial variables that have a resample rate > 0 or are dynamic (temporal_map column
+                     1); nw = their number.  (The nw positions of e = 0 are unused, which keeps groups of
+                     four seconds aligned to nw Philox calls.)   index = p // 4, lane = p % 4
 purpose LAYER (4):   index = 0, lane = 0 -> altitude-layer draw (UncorEncounterModel.m:260)
 purpose TERM_* (5+): terminal trajectory chains, see oracle/terminal.py
 
 word -> uniform: u = (k + 0.5) * 2**-32  (strictly inside (0,1), exact in fp64).
 
-value word k of (second e, gated variable v) -- everything random that can happen to the
-*continuous value* of v in second e comes from this one word:
-  * the resample gate `rand < rate` (resample_events.m:24) sees u = (k + 0.5) 2**-32, i.e. it
-    fires iff k < G, G = #{k : (k + 0.5) 2**-32 < rate}  (G = 0 for rate 0);
-  * every de-discretisation of v that takes effect in second e -- the re-emitted bin of a fired
-    gate and/or the new bin of a transition event (dbn_hierarchical_sample.m:35) -- sees
-        u_dd = (((k * 0x9E3779B1) mod 2**32) >> 9) + 0.5) * 2**-23.
-    The odd multiplier is a bijection of the 32-bit words that spreads any interval of k (in
-    particular [0, G)) evenly over the top bits, so u_dd is uniform given the gate decision; its
-    23-bit resolution makes the word -> float conversion exact in fp32 arithmetic on the GPU.
+Everything random that happens to variable v in second e comes from its one word k, through three
+different bijections of the 32-bit words (A = 0x9E3779B1, B = 0x85EBCA6B, both odd):
+  * transition select of a dynamic variable, loop index t = e + 1 (dbn_sample.m:77 / :133,144):
+        u_sel  = (k + 0.5) 2**-32
+  * resample gate `rand < rate` (resample_events.m:24):
+        u_gate = (((k * A) mod 2**32) + 0.5) 2**-32,   i.e. it fires iff (k * A) mod 2**32 < G,
+        G = #{h : (h + 0.5) 2**-32 < rate}  (G = 0 for rate 0)
+  * every de-discretisation of v that takes effect in second e -- the re-emitted bin of a fired gate
+    and/or the new bin of a transition event (dbn_hierarchical_sample.m:35):
+        u_dd   = ((((k * B) mod 2**32) >> 9) + 0.5) 2**-23
+An odd multiplier is a bijection that spreads any interval of k evenly over the top bits of the
+product (a Kronecker/golden-ratio lattice), so each of the three uniforms is uniform given the
+outcome of the other two decisions up to O(2**-32) in probability; the 23-bit resolution of u_dd
+makes the word -> float conversion exact in fp32 arithmetic on the GPU.
+(spec v1 spent separate Philox calls on event values; spec v2 still drew a separate select word per
+dynamic variable, 7 words per second for the 7-variable uncorrelated models instead of 4.)
 """
 from __future__ import annotations
 
@@ -125,11 +129,17 @@ def u01(k):
     return (np.asarray(k, dtype=np.float64) + 0.5) * TWO_M32
 
 
-DD_MULT = 0x9E3779B1
+GATE_MULT = 0x9E3779B1
+DD_MULT = 0x85EBCA6B
+
+
+def gate_word(k):
+    """step word -> the 32-bit word the resample gate compares (stream spec v3)."""
+    return (int(k) * GATE_MULT) & 0xFFFFFFFF
 
 
 def dd_uniform(k):
-    """value word -> de-discretisation uniform (stream spec v2), exact in fp64."""
+    """step word -> de-discretisation uniform (stream spec v3), exact in fp64."""
     h = (int(k) * DD_MULT) & 0xFFFFFFFF
     return (float(h >> 9) + 0.5) * 2.0 ** -23
 

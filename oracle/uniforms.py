@@ -4,7 +4,7 @@ Uniform providers for the restated reference sampler.  The restatement (oracle/s
 provider for a uniform at every place the reference calls `rand`, passing the *context* of the
 draw.  Two providers:
 
-* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v2"): the uniform is a pure
+* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v3"): the uniform is a pure
   function of the context.  This is the uniform-injection hook of BASELINE.json's north star: the
   reference algorithm, fed these uniforms, must give bit-identical bins to the CUDA sampler.
 * MTStream     -- MATLAB's `rng(seed,'twister'); rand` emulation (MT19937 `genrand_res53`, which
@@ -36,7 +36,7 @@ class _Base:
 
 class KeyedPhilox(_Base):
     """Context-keyed uniforms.  `bind(parms)` must be called once per model so that the dynamic and
-    gated ordinals (stream spec v2) are known."""
+    gated ordinals (stream spec v3) are known."""
 
     def __init__(self, seed: int, record: bool = False):
         super().__init__()
@@ -56,7 +56,7 @@ class KeyedPhilox(_Base):
         self.gated = [i + 1 for i in range(rates.size) if rates[i] > 0 or (i + 1) in self.dyn_vars_t]
         self.G = {v: px.gate_threshold(rates[v - 1]) for v in self.gated}
         self.nd = len(self.dyn_vars_t)
-        self.nw = self.nd + len(self.gated)
+        self.nw = len(self.gated)
         return self
 
     def begin(self, sample: int, attempt: int = 0):
@@ -74,9 +74,9 @@ class KeyedPhilox(_Base):
         return self._rec(("init_dd", var), px.u01(self._w(px.P_INIT, self.n_initial + var - 1)))
 
     def _sel_word(self, t, var_t1):
-        d = self.dyn_vars_t1.index(int(var_t1))
+        g = self.gated.index(self.dyn_vars_t[self.dyn_vars_t1.index(int(var_t1))])
         e = t - 1
-        return self._w(px.P_STEP, e * self.nw + d)
+        return self._w(px.P_STEP, e * self.nw + g)
 
     def select_trans(self, t, var_t1):               # dbn_sample.m:77 (slow branch)
         return self._rec(("trans_sel", t, var_t1), px.u01(self._sel_word(t, var_t1)))
@@ -92,18 +92,18 @@ class KeyedPhilox(_Base):
     def gates(self, second):                         # resample_events.m:24  rand(size(rates))
         u = np.full(self.n_initial, 0.5)
         for g, v in enumerate(self.gated):
-            u[v - 1] = px.u01(self._w(px.P_STEP, second * self.nw + self.nd + g))
+            u[v - 1] = px.u01(px.gate_word(self._w(px.P_STEP, second * self.nw + g)))
         if self.record:
             for v in range(1, self.n_initial + 1):
                 self.tape.append((("gate", second, v), float(u[v - 1])))
         return u
 
     def dedisc_event(self, kind, second, var):       # dbn_hierarchical_sample.m:35
-        # both kinds (re-emitted bin of a fired gate, new bin of a transition) read the value word
+        # both kinds (re-emitted bin of a fired gate, new bin of a transition) read the variable's word of that second
         g = self.gated.index(int(var))
-        k = self._w(px.P_STEP, second * self.nw + self.nd + g)
+        k = self._w(px.P_STEP, second * self.nw + g)
         if kind == "gate":
-            assert k < self.G[int(var)]
+            assert px.gate_word(k) < self.G[int(var)]
         return self._rec(("event_dd", kind, second, var), px.dd_uniform(k))
 
     def layer(self):                                 # UncorEncounterModel.m:260

@@ -291,6 +291,57 @@ def test_initial_full_size_chi_square_config2(model_paths):
         assert chi2 < 50.0, (i, chi2)
 
 
+def test_step_word_statistics_spec_v3(model_paths):
+    """Stream spec v3 derives the transition select, the resample gate and the de-discretisation of a variable in
+    a second from ONE Philox word.  With every initial variable preset the frozen-parent columns are known, so:
+    transition bins ~ the normalised count column (chi-square), rows per variable = gates (rate) + changes
+    (1 - stay probability) within 5 sigma, and the de-discretised values of the gate rows are uniform in their bin."""
+    import torch
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    start = [1, 4, 2, 4, 3, 4, 4]          # SURVEY A.8: columns 3918 / 1960 / 558 of the three dynamic variables
+    n, T = 40_000, 250
+    ht = torch.zeros((m.n_dyn, 64), dtype=torch.int64, device="cuda:0")
+    o = m.uncor_opts(start=start)
+    m.sample_tracks(n, T, seed=77, opts=o, device="cuda:0", hist_transition=ht, want_values=False, want_init=False)
+    ev = m.sample_events(n, T, seed=77, opts=m.uncor_opts(start=start), device="cuda:0", want_init=False)
+    torch.cuda.synchronize()
+    rows = ev.events.cpu().numpy().view(L.EVENT_DTYPE)
+    G, r, Nt = m.G_transition, m.r_transition, m.N_transition
+    x = np.array(start) - 1
+    steps = n * (T - 1)
+    for d, (vt, vt1) in enumerate(m.temporal_map):
+        par = np.nonzero(G[:, vt1 - 1])[0]
+        j, stride = 0, 1
+        for p_ in par:                                       # asub2ind.m:13-14
+            j += stride * x[p_]
+            stride *= int(r[p_])
+        col = Nt[vt1 - 1][:, j]
+        pcol = col / col.sum()
+        obs = ht[d, : len(pcol)].cpu().numpy().astype(np.float64)
+        keep = pcol > 0
+        assert obs[~keep].sum() == 0
+        chi2 = ((obs[keep] - steps * pcol[keep]) ** 2 / (steps * pcol[keep])).sum()
+        assert chi2 < 45.0, (d, chi2)
+        # rows of this variable: fired gates (n*T draws at `rate`) + bin changes (i.i.d. draws: P(new != old))
+        rate = float(m.resample_rates[vt - 1])
+        p_change = 1.0 - float((pcol ** 2).sum())            # consecutive i.i.d. draws differ (first step: vs the preset bin)
+        got = int((rows["var"] == vt).sum())
+        want = n * T * rate + steps * p_change
+        sd = np.sqrt(n * T * rate * (1 - rate) + 3.0 * steps * p_change)
+        assert abs(got - want) < 6 * sd + 0.002 * want, (vt, got, want, sd)
+    # static resampled variable v (4): only gate rows, value uniform in its bin [edges of bin 4]
+    v = 4
+    sel = rows[rows["var"] == v]
+    rate = float(m.resample_rates[v - 1])
+    assert abs(len(sel) - n * T * rate) < 6 * np.sqrt(n * T * rate)
+    a, b = m.boundaries[v - 1][start[v - 1] - 1], m.boundaries[v - 1][start[v - 1]]
+    u = (sel["value"].astype(np.float64) - a) / (b - a)
+    assert u.min() >= 0.0 and u.max() <= 1.0
+    h = np.histogram(u, bins=20, range=(0, 1))[0].astype(np.float64)
+    chi2 = ((h - len(u) / 20) ** 2 / (len(u) / 20)).sum()
+    assert chi2 < 60.0, chi2
+
+
 def test_errors_through_the_abi(model_paths):
     m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
     with pytest.raises(L.EmbError, match="Attempt to preset a dependent variable"):

@@ -125,3 +125,25 @@ def test_fixture_archive_matches_reference_files(model_paths):
         for x, y in zip(a.boundaries, b.boundaries):
             assert np.array_equal(x, y)
         assert np.array_equal(a.resample_rates, b.resample_rates)
+
+
+def test_spec_v3_word_bijections_equidistribute():
+    """Stream spec v3 (oracle/philox.py): select on k, gate on k*A, de-discretisation on k*B.  Over any interval of
+    words (= any bin of a select) the gate must fire at its rate and u_dd must be uniform, also given the gate."""
+    from oracle import philox as px
+    rs = np.random.RandomState(3)
+    A, B, M = np.uint64(px.GATE_MULT), np.uint64(px.DD_MULT), np.uint64(0xFFFFFFFF)
+    assert px.GATE_MULT % 2 == 1 and px.DD_MULT % 2 == 1            # bijections of the 32-bit words
+    for L_ in (20_000, 1_000_000):
+        for rate in (0.0107, 0.0333, 0.6667):
+            lo = rs.randint(0, 2 ** 32 - L_)
+            k = (np.uint64(lo) + np.arange(L_, dtype=np.uint64)) & M
+            fired = ((k * A) & M) < np.uint64(px.gate_threshold(rate))
+            assert abs(fired.mean() - rate) < 4.0 / L_ + 1e-4 * rate      # low-discrepancy lattice, far better than binomial
+            u = (((k * B) & M) >> np.uint64(9)).astype(np.float64) * 2.0 ** -23
+            for sub in (u, u[fired]):
+                h = np.histogram(sub, bins=16, range=(0, 1))[0]
+                assert np.abs(h - sub.size / 16).max() < 0.02 * sub.size / 16 + 12
+    k = int(rs.randint(0, 2 ** 32))
+    assert px.dd_uniform(k) == ((((k * px.DD_MULT) & 0xFFFFFFFF) >> 9) + 0.5) * 2.0 ** -23
+    assert 0.0 < px.dd_uniform(0) < 1.0 and 0.0 < px.dd_uniform(0xFFFFFFFF) < 1.0

@@ -203,7 +203,7 @@ def test_gpu_pipeline_properties_and_shard_invariance(model_paths, traj_paths):
         assert np.array_equal(np.isnan(traj[:, ac]), np.broadcast_to(~occ[ac], traj[:, ac].shape))
     with np.errstate(invalid="ignore"):
         dz = np.abs(np.diff(traj[2], axis=1))
-        assert np.nanmax(dz) <= 100.0 * (1 + 1e-6)                      # maxVertRate_ft_s, GENERIC
+        assert np.nanmax(dz) <= 100.0 + 2e-3                            # maxVertRate_ft_s, GENERIC (fp32 outputs near 1e4 ft)
         assert np.nanmax(traj[4]) <= max(506.0, float(geo[8].max()), float(geo[13].max())) * (1 + 1e-6)
         hd = traj[3]
         assert np.nanmin(hd) >= 0.0 and np.nanmax(hd) <= 360.0
