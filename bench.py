@@ -162,7 +162,18 @@ def main():
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # NCCL may print its version banner on stdout at init; the contract is ONE JSON line on stdout
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n = args.tracks
     lib = L.lib()
     path = materialise_model()

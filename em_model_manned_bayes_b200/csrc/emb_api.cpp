@@ -520,8 +520,9 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     struct Scratch {
         void* p = nullptr;
         ~Scratch() { if (p) cudaFree(p); }
-    } counts, status;
+    } counts, status, tiles;
     CU(cudaMalloc(&counts.p, (size_t)n * 4));
+    CU(cudaMalloc(&tiles.p, (size_t)emb::scan_scratch_len(n) * 8));
     CU(cudaMalloc(&status.p, 4));
     CU(cudaMemsetAsync(status.p, 0, 4, st));
     O.status = (int32_t*)status.p;
@@ -529,7 +530,7 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     O.ev_counts = (uint32_t*)counts.p;
     cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);
     if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event count)");
-    e = (cudaError_t)emb::launch_scan_counts((const uint32_t*)counts.p, d_off, n, st);
+    e = (cudaError_t)emb::launch_scan_counts((const uint32_t*)counts.p, d_off, n, (long long*)tiles.p, st);
     if (e != cudaSuccess) return cuda_fail(e, "launch k_scan_counts");
     long long total = 0;
     int32_t flag = 0;

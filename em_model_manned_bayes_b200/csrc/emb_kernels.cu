@@ -128,49 +128,97 @@ k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sample
     if (HIST) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
-// ---- exclusive prefix sum of the per-track row counts (one block; n is at most a few 10^7) -------
-__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict__ counts, long long* __restrict__ offsets,
-                                                      long long n) {
+// ---- exclusive prefix sum of the per-track row counts: tile sums, scan of the tile sums, tile-local scans ------
+constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* warp_sum, long long* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        long long t = lane < nw ? warp_sum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xFFFFFFFFu, t, o);
+            if (lane >= o) t += y;
+        }
+        warp_sum[lane] = t;
+    }
+    __syncthreads();
+    const long long before = (w ? warp_sum[w - 1] : 0) + x - v;
+    if (total) *total = warp_sum[nw - 1];
+    __syncthreads();
+    return before;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ counts, long long* __restrict__ tile_sum,
+                                                                 long long n) {
+    __shared__ long long warp_sum[32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
+    long long v = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_PER_THREAD; ++q)
+        if (base + q < n) v += counts[base + q];
+    long long total;
+    block_exclusive_scan(v, warp_sum, &total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+// one block: tile_sum[0..m) -> exclusive prefixes in place, grand total to *total_out
+__global__ void __launch_bounds__(1024) k_scan_tile_prefix(long long* __restrict__ tile_sum, long long m, long long* __restrict__ total_out) {
     __shared__ long long warp_sum[32];
     __shared__ long long carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (long long base = 0; base < n; base += 1024) {
+    for (long long base = 0; base < m; base += 1024) {
         const long long i = base + threadIdx.x;
-        const long long v = i < n ? (long long)counts[i] : 0;
-        long long x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_sum[w] = x;
+        const long long v = i < m ? tile_sum[i] : 0;
+        long long total;
+        const long long before = block_exclusive_scan(v, warp_sum, &total);
+        if (i < m) tile_sum[i] = carry + before;
         __syncthreads();
-        if (w == 0) {
-            long long t = warp_sum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long y = __shfl_up_sync(0xFFFFFFFFu, t, o);
-                if (lane >= o) t += y;
-            }
-            warp_sum[lane] = t;
-        }
-        __syncthreads();
-        const long long before = carry + (w ? warp_sum[w - 1] : 0) + x - v;
-        if (i < n) offsets[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == 0) carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) offsets[n] = carry;
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ counts, const long long* __restrict__ tile_prefix,
+                                                             long long* __restrict__ offsets, long long n) {
+    __shared__ long long warp_sum[32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
+    uint32_t c[SCAN_PER_THREAD];
+    long long v = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_PER_THREAD; ++q) {
+        c[q] = base + q < n ? counts[base + q] : 0u;
+        v += c[q];
+    }
+    long long run = tile_prefix[blockIdx.x] + block_exclusive_scan(v, warp_sum, nullptr);
+#pragma unroll
+    for (int q = 0; q < SCAN_PER_THREAD; ++q) {
+        if (base + q < n) offsets[base + q] = run;
+        run += c[q];
+    }
 }
 
 }  // namespace
 
-int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, void* stream) {
-    k_scan_counts<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, offsets, n);
-    g_launch_count.fetch_add(1);
+long long scan_scratch_len(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream) {
+    const long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, scratch, n);
+    k_scan_tile_prefix<<<1, 1024, 0, st>>>(scratch, tiles, offsets + n);
+    k_scan_apply<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, scratch, offsets, n);
+    g_launch_count.fetch_add(3);
     return (int)cudaGetLastError();
 }
 

@@ -16,8 +16,9 @@ extern int g_last_kernel_fast;
 int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
                    uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream);
 int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream);
-// offsets[0..n] = exclusive prefix sums of counts[0..n), offsets[n] = total
-int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, void* stream);
+// offsets[0..n] = exclusive prefix sums of counts[0..n), offsets[n] = total; scratch: scan_scratch_len(n) long longs
+long long scan_scratch_len(long long n);
+int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream);
 
 // terminal trajectory chains (emb_terminal.cu): 4 chains per encounter
 struct TermParams;

@@ -1,34 +1,50 @@
-"""Opcode histogram of the unchecked (steady-state) four-second group of a k_tracks_fast kernel:
-the region from the first uniform branch after the main-loop head to the jump over the checked copy.
-    python tools/loop_hist.py "460549ELi4ELb1ELb0"   """
-import collections, re, subprocess, sys
-pat = sys.argv[1]
-txt = subprocess.run(["cuobjdump", "-sass", "em_model_manned_bayes_b200/libemb200.so"], capture_output=True, text=True).stdout
+"""Opcode histogram of the unchecked (steady-state) four-second group of a k_tracks_fast kernel.
+    python tools/loop_hist.py [mangled-name substring, default the 7-variable uncor shape] [path to .so/.o]
+The main loop is the largest backward branch; its first forward predicated branch jumps to the checked copy of the
+group, the unconditional branch just before that target ends the unchecked copy and lands on the store tail."""
+import collections
+import re
+import subprocess
+import sys
+
+pat = sys.argv[1] if len(sys.argv) > 1 else "460549ELi4ELb1ELb0ELi0"
+so = sys.argv[2] if len(sys.argv) > 2 else "em_model_manned_bayes_b200/libemb200.so"
+txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 fn = [f for f in re.split(r"\n\s*Function : ", txt)[1:] if pat in f.split("\n", 1)[0]][0]
 ins = [(int(a, 16), b.strip()) for a, b in re.findall(r"^\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", fn, re.M)]
-back = [(int(re.search(r"0x([0-9a-f]+)", s).group(1), 16), a) for a, s in ins if "BRA" in s and re.search(r"0x([0-9a-f]+)", s)
-        and int(re.search(r"0x([0-9a-f]+)", s).group(1), 16) < a]
-lo, hi = max(back, key=lambda x: x[1] - x[0])
+
+
+def target(s):
+    m = re.search(r"BRA.*?0x([0-9a-f]+)", s)
+    return int(m.group(1), 16) if m else None
+
+
+back = [(a - target(s), target(s), a) for a, s in ins if target(s) is not None and target(s) < a]
+_, lo, hi = max(back)
 body = [(a, s) for a, s in ins if lo <= a <= hi]
-# first forward BRA.U in the loop jumps to the checked copy; the unconditional BRA before that target ends the unchecked copy
-first = next((a, int(re.search(r"0x([0-9a-f]+)", s).group(1), 16)) for a, s in body if s.startswith("BRA.U") or "BRA.U" in s)
-un = [(a, s) for a, s in body if first[0] < a < first[1]]
-tail_start = next(int(re.search(r"0x([0-9a-f]+)", s).group(1), 16) for a, s in reversed(un) if s.startswith("BRA "))
+fwd = next((a, target(s)) for a, s in body if target(s) is not None and target(s) > a and s.startswith("@"))
+un = [(a, s) for a, s in body if fwd[0] < a < fwd[1]]
+tail_start = next(target(s) for a, s in reversed(un) if s.startswith("BRA "))
 tail = [(a, s) for a, s in body if a >= tail_start]
+
+
 def hist(rows):
     c = collections.Counter()
     for _, s in rows:
         s = re.sub(r"^@!?U?P\d+\s+", "", s)
         op = s.split()[0]
-        op = re.sub(r"\.(U32|LUT|AND|OR|reuse|E|128|64|EF|STRONG|GPU|CONSTANT)", "", op)
-        c[op] += 1
+        c[re.sub(r"\.(U32|LUT|AND|OR|reuse|E|128|64|EF|STRONG|GPU|CONSTANT|W|R|GE|NE|GT|LT|EQ)\b", "", op)] += 1
     return c
+
+
 hu, ht = hist(un), hist(tail)
-print("loop 0x%x..0x%x; unchecked group %d instr + store tail %d instr = %.1f per second" % (lo, hi, len(un), len(tail), (len(un) + len(tail)) / 4))
+n = len(un) + len(tail)
+print("loop 0x%x..0x%x; unchecked group %d instr + store tail %d instr = %.1f per second" % (lo, hi, len(un), len(tail), n / 4))
 print("group:", ", ".join("%s %d" % kv for kv in hu.most_common()))
 print("tail :", ", ".join("%s %d" % kv for kv in ht.most_common()))
-alu = {"LOP3", "IADD3", "VIADD", "ISETP", "ISETP.GE", "ISETP.NE", "ISETP.GT", "FSEL", "LEA", "SEL", "MOV", "PRMT", "SHF", "PLOP3", "IADD3.X", "LEA.HI", "ISETP.LT", "ISETP.EQ"}
 tot = hu + ht
-a = sum(v for k, v in tot.items() if k.split(".")[0] in {x.split(".")[0] for x in alu})
-f = sum(v for k, v in tot.items() if k.split(".")[0] in {"IMAD", "FFMA", "FADD", "FMUL", "HFMA2"})
-print("alu-pipe %d (%.1f/s)  fma-pipe %d (%.1f/s)  other %d" % (a, a / 4, f, f / 4, len(un) + len(tail) - a - f))
+alu = sum(v for k, v in tot.items() if k.split(".")[0] in {"LOP3", "IADD3", "VIADD", "ISETP", "FSEL", "LEA", "SEL", "MOV", "PRMT", "SHF", "PLOP3"})
+wide = sum(v for k, v in tot.items() if k.startswith("IMAD.WIDE") or k.startswith("UIMAD.WIDE"))
+fma = sum(v for k, v in tot.items() if k.split(".")[0] in {"IMAD", "FFMA", "FADD", "FMUL"}) - sum(v for k, v in tot.items() if k.startswith("IMAD.WIDE"))
+print("per second: alu-pipe %.1f instr (x2 cycles = %.0f)   IMAD.WIDE %.1f (x4 = %.0f) + other fma-pipe %.1f   other %.1f"
+      % (alu / 4, alu / 2, wide / 4, wide, fma / 4, (n - alu - wide - fma) / 4))
