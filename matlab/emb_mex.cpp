@@ -9,6 +9,13 @@
 //          emb_mex('set_prior', h, which, kind, value)
 //   [bins, values, attempts] = emb_mex('sample_initial', h, seed, first, n, opts)
 //   [out_inits, bins, values, attempts] = emb_mex('sample_tracks', h, seed, first, n, T, opts)
+//   [events, offsets, out_inits, attempts] = emb_mex('sample_events', h, seed, first, n, T, opts)
+//          events: 4 x rows double [dt; var; value; bin], offsets: (n+1) x 1 (0-based first row of each track)
+//   [traj, len] = emb_mex('terminal_propagate', hs, seed, first, geo, tmax_s, limits, opts)
+//          hs: 1 x 10 uint64 handles {own_fwd(1:2), own_bck(1:2), int_fwd(1:3), int_bck(1:3)}; geo: n x 12 double
+//          [own_intent own_distance own_bearing own_alt own_heading own_speed int_...]; limits: 5 x 2 double
+//          [minVel; maxVel; maxTurnRate; maxAltitude; maxVertRate] per aircraft;
+//          traj: n x (2*tmax+1) x 2 x 5 single (NaN = no state), len: n x 4 int16
 //          emb_mex('free', h)
 // opts: struct with optional fields start (1 x n_initial, 0/NaN = free), reject_mode, idx_v, idx_dh,
 // idx_L, is_quantize500, layers (r_L x 2), box_lo, box_hi, max_attempts, device.
@@ -96,6 +103,32 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         *static_cast<uint64_t*>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(m);
         return;
     }
+    if (c == "terminal_propagate") {                              // @CorTerminalModel/createEncounter.m:1-329 over a batch
+        if (!mxIsUint64(prhs[1]) || mxGetNumberOfElements(prhs[1]) != 10) mexErrMsgIdAndTxt("emb200:arg", "need 10 model handles");
+        const uint64_t* hs = static_cast<const uint64_t*>(mxGetData(prhs[1]));
+        emb_terminal_models tm;
+        for (int k = 0; k < 2; ++k) { tm.own_fwd[k] = reinterpret_cast<emb_model*>(hs[k]); tm.own_bck[k] = reinterpret_cast<emb_model*>(hs[2 + k]); }
+        for (int k = 0; k < 3; ++k) { tm.int_fwd[k] = reinterpret_cast<emb_model*>(hs[4 + k]); tm.int_bck[k] = reinterpret_cast<emb_model*>(hs[7 + k]); }
+        emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
+        const int64_t n = (int64_t)mxGetM(prhs[4]);                // geo is n x 12 column-major == [12][n]
+        const double tmax_s = mxGetScalar(prhs[5]);
+        emb_dyn_limits lim[2];
+        for (int a = 0; a < 2; ++a) {
+            const double* p = mxGetPr(prhs[6]) + 5 * a;
+            lim[a] = emb_dyn_limits{p[0], p[1], p[2], p[3], p[4]};
+        }
+        emb_sample_opts o;
+        fill_opts(nrhs > 7 ? prhs[7] : nullptr, 0, &o);
+        const int32_t rows[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+        const mwSize S = (mwSize)(2 * (int64_t)tmax_s + 1);
+        const mwSize dt[4] = {(mwSize)n, S, 2, EMB_TRAJ_FIELDS};   // [field][aircraft][slot][n] == n x S x 2 x 5 column-major
+        plhs[0] = mxCreateNumericArray(4, dt, mxSINGLE_CLASS, mxREAL);
+        mxArray* len = mxCreateNumericMatrix(n, 4, mxINT16_CLASS, mxREAL);
+        emb_traj_out out{(float*)mxGetData(plhs[0]), (int16_t*)mxGetData(len)};
+        CHECK(emb_terminal_propagate(&tm, &rng, n, mxGetPr(prhs[4]), n, rows, tmax_s, lim, &o, &out));
+        if (nlhs > 1) plhs[1] = len; else mxDestroyArray(len);
+        return;
+    }
     emb_model* m = handle(prhs[1]);
     emb_model_info info;
     CHECK(emb_model_get_info(m, &info));
@@ -159,6 +192,34 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         CHECK(emb_sample_tracks(m, &rng, n, T, &o, &out));
         if (nlhs > 1) plhs[1] = bins; else mxDestroyArray(bins);
         if (nlhs > 2) plhs[2] = vals; else mxDestroyArray(vals);
+        if (nlhs > 3) plhs[3] = att; else mxDestroyArray(att);
+    } else if (c == "sample_events") {                            // out_events of UncorEncounterModel.m:253-300
+        emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
+        const int64_t n = (int64_t)mxGetScalar(prhs[4]);
+        const int32_t T = (int32_t)mxGetScalar(prhs[5]);
+        emb_sample_opts o;
+        fill_opts(nrhs > 6 ? prhs[6] : nullptr, ni, &o);
+        std::vector<int64_t> off((size_t)n + 1);
+        mxArray* inits = mxCreateDoubleMatrix(n, ni, mxREAL);
+        mxArray* att = mxCreateNumericMatrix(n, 1, mxUINT16_CLASS, mxREAL);
+        emb_track_out init{};
+        init.init_values = mxGetPr(inits);
+        init.attempts = (uint16_t*)mxGetData(att);
+        int64_t total = 0;
+        std::vector<emb_event> ev;
+        int rc = emb_sample_track_events(m, &rng, n, T, &o, 0, nullptr, off.data(), &init, &total);   // sizes the list
+        if (rc != 0 && rc != EMB_E_LIMIT) fail(rc);
+        ev.resize((size_t)total + 1);
+        CHECK(emb_sample_track_events(m, &rng, n, T, &o, total, ev.data(), off.data(), &init, &total));
+        plhs[0] = mxCreateDoubleMatrix(4, (mwSize)total, mxREAL);
+        double* e = mxGetPr(plhs[0]);
+        for (int64_t k = 0; k < total; ++k) {
+            e[4 * k] = ev[(size_t)k].dt; e[4 * k + 1] = ev[(size_t)k].var; e[4 * k + 2] = ev[(size_t)k].value; e[4 * k + 3] = ev[(size_t)k].bin;
+        }
+        mxArray* offs = mxCreateDoubleMatrix(n + 1, 1, mxREAL);
+        for (int64_t k = 0; k <= n; ++k) mxGetPr(offs)[k] = (double)off[(size_t)k];
+        if (nlhs > 1) plhs[1] = offs; else mxDestroyArray(offs);
+        if (nlhs > 2) plhs[2] = inits; else mxDestroyArray(inits);
         if (nlhs > 3) plhs[3] = att; else mxDestroyArray(att);
     } else {
         mexErrMsgIdAndTxt("emb200:arg", "unknown command '%s'", cmd);

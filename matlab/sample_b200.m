@@ -21,24 +21,22 @@ opts = struct('reject_mode', 1, 'idx_v', find_lab('"v"'), 'idx_dh', find_lab('"\
 st = nan(1, self.n_initial);
 for i = 1:self.n_initial, if ~isempty(self.start{i}), st(i) = self.start{i}; end, end
 opts.start = st;
-[out_inits, ~, values] = emb_mex('sample_tracks', h, seed, 0, n_samples, sample_time, opts);
-% values: 4 x n x ceil(T/4) x n_timevarying  ->  out_samples{ii} n_initial x T  (events2samples.m:9-27)
-tv = info.timevarying_vars;
-values = reshape(permute(values, [2 4 1 3]), n_samples, numel(tv), []);   % n x tv x (4*nch)
+[events, offsets, out_inits] = emb_mex('sample_events', h, seed, 0, n_samples, sample_time, opts);
+% events: 4 x rows [dt; var; value; bin], rows offsets(ii)+1 : offsets(ii+1) belong to track ii -- the reference's own
+% out_events{ii} (dbn_hierarchical_sample.m:9-37), built on the GPU in the reference's row order
 out_samples = cell(n_samples, 1); out_events = cell(n_samples, 1); out_EME = cell(n_samples, 1);
 map = info.temporal_map(:, 1)';
+order = [find_lab('"\dot h"'), find_lab('"\dot \psi"'), find_lab('"\dot v"')];        % UncorEncounterModel.m:291-292
+[~, cols] = ismember(order, map);
 for ii = 1:n_samples
-    d = repmat(out_inits(ii, :)', 1, sample_time);
-    d(tv, :) = double(squeeze(values(ii, :, 1:sample_time)));
-    out_samples{ii} = d;
-    % events: every change of a time-varying value ([dt var value], dbn_hierarchical_sample.m:9-37).
-    % Re-emissions that leave the value unchanged (zero bins) are not recoverable from the dense form;
-    % the exact sparse list is the "next" row of DESIGN.md section 0.
-    [var, col] = find(diff(d, 1, 2) ~= 0);
-    [col, o] = sort(col); var = var(o);
-    dt = diff([0; col]);
-    out_events{ii} = [[dt, var, d(sub2ind(size(d), var, col + 1))]; sample_time - sum(dt), 0, 0];
-    controls = events2controls(out_inits(ii, :), out_events{ii}, map);
+    ev = events(1:3, offsets(ii) + 1:offsets(ii + 1))';
+    out_events{ii} = ev;
+    out_samples{ii} = events2samples(out_inits(ii, :), ev);                               % events2samples.m:9-27
+    controls = events2controls(out_inits(ii, :), ev, map);                                % events2controls.m:9-31
+    controls = controls(:, [1, 1 + cols]);
+    controls(:, 2) = controls(:, 2) / 60;                                                 % :295
+    controls(:, 3) = deg2rad(controls(:, 3));                                             % :296
+    controls(:, 4) = controls(:, 4) * 1.68780972222222;                                   % :297
     out_EME{ii} = controls;
 end
 end

@@ -53,3 +53,23 @@ def test_no_cpu_fallback_without_gpu(model_paths):
     with pytest.raises(L.EmbError) as ei:
         m.sample_initial(4, seed=1)
     assert ei.value.code == L.EMB_E_CUDA
+
+
+def test_mex_gateway_source_matches_the_header():
+    """matlab/emb_mex.cpp cannot be built here (no MATLAB), but it must at least compile against include/emb200.h:
+    syntax- and type-check it with a declarations-only stand-in for mex.h (tests/stubs/mex.h)."""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "stubs"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "matlab", "emb_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "matlab", "emb_mex.cpp")).read()
+    for fn in ("emb_model_load", "emb_set_prior", "emb_sample_initial", "emb_sample_tracks", "emb_sample_track_events",
+               "emb_terminal_propagate"):
+        assert fn + "(" in src, fn
+
+
+def test_terminal_structs_match_header_sizes():
+    assert C.sizeof(L.DynLimits) == 5 * 8
+    assert C.sizeof(L.TerminalModels) == 10 * 8
+    assert C.sizeof(L.TrajOut) == 2 * 8
