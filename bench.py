@@ -9,7 +9,9 @@ Workload (config.workload): BASELINE.json configs[2] per-GPU shard -- UncorEncou
 A "step" is one pass of the hot path (emb_sample_tracks: initial network, 599 transition steps, 600
 resample gates, de-discretisation, dense compact outputs) over one batch of 1.25e6 tracks.
   value : track-timesteps/s over all ranks, outputs resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the C ABI with pinned HOST output buffers, D2H inside the timed region
+  e2e   : same metric through the reference-facing call (UncorEncounterModel.sample's out_inits + sparse out_events, the
+          reference's own track representation) via the C ABI with pinned HOST buffers, D2H inside the timed region;
+          e2e_dense: the dense compact tiles of `value` copied to host memory instead
   roofline / cpu_baseline : see the task statement; cpu_baseline = oracle/oracle_c.c ("port") on host cores
 The model tables (about 1 MB) are read-only inputs that legitimately live in L2; every step writes a
 fresh 14.5 GB of outputs (>> 126 MB L2) with a new seed, so no step can reuse another's cache lines.
@@ -363,11 +365,15 @@ def main():
                    "cache": "each step writes %.1f GB of fresh outputs (>> L2); the 1 MB model tables are the only re-read input"
                             % ((nb + nv * 4) / 1e9),
                    "sharding": "global sample index, rank r owns [r*n, (r+1)*n); one NCCL all-reduce of verification histograms"},
-        "e2e": {"value": e2e_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400, "d2h_bytes_per_step": d2h,
-                "steps": args.e2e_steps, "contract": "dense compact tiles (same call as `value`); PCIe-bound at 19.25 B/unit"},
-        "e2e_events": {"value": e2e_events_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400,
-                       "d2h_bytes_per_step": ev_d2h, "steps": args.e2e_steps,
-                       "contract": "sparse out_events rows (8 B) + offsets + out_inits, emb_sample_track_events"},
+        # e2e = the reference-facing call: UncorEncounterModel.sample's outputs (out_inits + the sparse out_events lists the
+        # reference itself returns, UncorEncounterModel.m:253-300) through emb_sample_track_events with pinned HOST buffers
+        "e2e": {"value": e2e_events_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400,
+                "d2h_bytes_per_step": ev_d2h, "steps": args.e2e_steps,
+                "contract": "UncorEncounterModel.sample outputs: sparse out_events rows (8 B) + offsets + out_inits in host memory, "
+                            "emb_sample_track_events (count pass, prefix sum, write pass, D2H inside the timed region)"},
+        "e2e_dense": {"value": e2e_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400, "d2h_bytes_per_step": d2h,
+                      "steps": args.e2e_steps,
+                      "contract": "dense compact tiles in host memory (the same emb_sample_tracks call as `value`); PCIe-bound at 19.0 B/unit"},
         "other_configs": other,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -544,18 +544,59 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
     }
     // pass 2: write the rows (the keyed stream reproduces pass 1 exactly)
-    uint2* d_ev = nullptr;
-    if ((rc = sg.out(events, (size_t)total * 8, false, (void**)&d_ev))) return rc;
     O.ev_counts = nullptr;
-    O.ev_offsets = d_off;
-    O.events = d_ev;
     O.init_bins = nullptr;
     O.init_values = nullptr;
     O.attempts = nullptr;
-    e = (cudaError_t)emb::launch_tracks(D, P, O, st);
-    if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
+    if (opts->mem == EMB_MEM_DEVICE || total == 0 || n < 8192) {
+        uint2* d_ev = nullptr;
+        if ((rc = sg.out(events, (size_t)total * 8, false, (void**)&d_ev))) return rc;
+        O.ev_offsets = d_off;
+        O.events = d_ev;
+        e = (cudaError_t)emb::launch_tracks(D, P, O, st);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
+        CU(cudaStreamSynchronize(st));
+        return sg.finish();
+    }
+    // host-memory caller: the write pass runs in chunks of tracks on the caller's stream while a second stream copies
+    // the rows of the previous chunk to the host (rows of a track range are contiguous: [offsets[a], offsets[b]))
+    struct Guard {
+        void* dev = nullptr;
+        cudaStream_t copy = nullptr;
+        cudaEvent_t done[16] = {};
+        ~Guard() {
+            for (auto& d : done) if (d) cudaEventDestroy(d);
+            if (copy) cudaStreamDestroy(copy);
+            if (dev) cudaFree(dev);
+        }
+    } g;
+    CU(cudaMalloc(&g.dev, (size_t)total * 8));
+    CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    std::vector<long long> h_off((size_t)n + 1);
+    CU(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    return sg.finish();
+    const int chunks = 8;
+    for (int c = 0; c < chunks; ++c) {
+        const int64_t a = n * c / chunks, b = n * (c + 1) / chunks;
+        if (b <= a) continue;
+        emb::SampleParams Pc = P;
+        Pc.first_sample = P.first_sample + (uint64_t)a;
+        Pc.n = b - a;
+        emb::TrackOut Oc = O;
+        Oc.ev_offsets = d_off + a;
+        Oc.events = (uint2*)g.dev;
+        e = (cudaError_t)emb::launch_tracks(D, Pc, Oc, st);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
+        CU(cudaEventCreateWithFlags(&g.done[c], cudaEventDisableTiming));
+        CU(cudaEventRecord(g.done[c], st));
+        CU(cudaStreamWaitEvent(g.copy, g.done[c], 0));
+        const long long r0 = h_off[(size_t)a], r1 = h_off[(size_t)b];
+        if (r1 > r0)
+            CU(cudaMemcpyAsync(events + r0, (const char*)g.dev + (size_t)r0 * 8, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, g.copy));
+    }
+    if ((rc = sg.finish())) return rc;          // offsets and per-track outputs, on the caller's stream
+    CU(cudaStreamSynchronize(g.copy));
+    return 0;
 }
 
 int emb_dyn_limits_named(const char* ac_type, emb_dyn_limits* out) {

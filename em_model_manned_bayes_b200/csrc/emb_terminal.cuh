@@ -80,11 +80,11 @@ EMB_HD void sincosd(double x, double& s, double& c) {
     }
 }
 EMB_HD double atan2d(double y, double x) { return dmul(::atan2(y, x), 57.29577951308232); }   // 180/pi
-EMB_HD double wrap_to_360(double x) {                   // wrapTo360: mod(x,360), positive multiples of 360 -> 360
-    const bool positive = x > 0.0;
-    x = dadd(x, -dmul(360.0, ::floor(x / 360.0)));
-    if (x == 0.0 && positive) x = 360.0;
-    return x;
+// wrapTo360(atan2d(y, x)): atan2d lies in [-180, 180], where mod(a, 360) is a + 360 for a < 0 and a otherwise (the
+// general formula a - 360*floor(a/360) gives bit-identical results there), so no division is needed
+EMB_HD double heading_of(double y, double x) {
+    const double a = atan2d(y, x);
+    return a < 0.0 ? dadd(a, 360.0) : a;
 }
 EMB_HD double round2(double x) {                        // round(x, 2), half away from zero
     const double y = dmul(x, 100.0);
@@ -170,7 +170,8 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         }
         ++len;
         // state ii (:163-184)
-        const double curr_hdg = wrap_to_360(atan2d(vy, vx));                      // :176
+        const double curr_hdg = heading_of(vy, vx);                               // :176
+        const double speed = norm2(vx, vy);                                       // :168 and :290 (v does not change in between)
         double z_rec = z_ft;
         if (ii > 1) {                                                             // :180-184
             const double diff = dadd(z_ft, -z_prev);
@@ -183,7 +184,7 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
             put(1, (float)y);
             put(2, (float)z_rec);
             put(3, (float)curr_hdg);
-            put(4, (float)norm2(vx, vy));
+            put(4, (float)speed);
         }
         x = dadd(x, dmul(vx, dt_s) / TERM_FT_PER_NM);                             // :171-173
         y = dadd(y, dmul(vy, dt_s) / TERM_FT_PER_NM);
@@ -192,10 +193,10 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         uint32_t st[6];
         st[0] = (uint32_t)(intent - 1);
         st[1] = (uint32_t)term_discretize(M, M.i_dist, norm2(x, y));              // positional cell, cutpoints by label (:277,:293)
-        st[2] = (uint32_t)term_discretize(M, M.i_bear, wrap_to_360(atan2d(y, x)));
+        st[2] = (uint32_t)term_discretize(M, M.i_bear, heading_of(y, x));
         st[3] = (uint32_t)term_discretize(M, 3, heading_deg);
         st[4] = (uint32_t)term_discretize(M, 4, z_ft);
-        st[5] = (uint32_t)term_discretize(M, 5, norm2(vx, vy));
+        st[5] = (uint32_t)term_discretize(M, 5, speed);
         const uint32_t* col[3];                                                   // frozen parents (dbn_sample.m:110-135)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -247,11 +248,13 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         const double turn1 = round2(dadd(heading_deg, -curr_hdg));
         const double mag = ::fmin(::fabs(turn1), L.maxTurn);
         const double delta = turn1 > 0.0 ? mag : turn1 < 0.0 ? -mag : dmul(mag, 0.0);
-        double sd, cd;
-        sincosd(delta, sd, cd);
-        const double nvx = dadd(dmul(cd, vx), -dmul(sd, vy)), nvy = dadd(dmul(sd, vx), dmul(cd, vy));
-        vx = nvx;
-        vy = nvy;
+        if (delta != 0.0) {                                                       // rotation by 0 degrees is the identity
+            double sd, cd;
+            sincosd(delta, sd, cd);
+            const double nvx = dadd(dmul(cd, vx), -dmul(sd, vy)), nvy = dadd(dmul(sd, vx), dmul(cd, vy));
+            vx = nvx;
+            vy = nvy;
+        }
         t_s = dadd(t_s, dt_s);
         // CheckTrajectoryConditions (:296-329)
         const double d_nm = norm2(x, y);

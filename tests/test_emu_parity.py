@@ -6,6 +6,7 @@ import pytest
 
 import cases
 from em_model_manned_bayes_b200 import _lib as L
+import helpers as H
 from helpers import EmuModel
 from oracle.em_read import em_read
 
@@ -157,3 +158,34 @@ def test_preset_dependent_variable_is_rejected(model_paths):
     o = EmuModel.opts(p.n_initial, start=[None, 2, None, None, None, None, None])
     with pytest.raises(L.EmbError, match="Attempt to preset a dependent variable"):
         em.sample_initial(p.n_initial, 4, 1, 0, o)
+
+
+@pytest.mark.parametrize("model,uncor,n,T", [("uncor_allcode_fwsingle_v1", True, 300, 600), ("glider_v1", True, 400, 150),
+                                             ("cor_v1", False, 300, 60), ("uncor_1200only_fwse_v1p2", True, 300, 100)])
+@pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
+def test_tracks_match_c_oracle(model_paths, model, uncor, n, T, fast):
+    """Host emulation of the device code against the plain-C restatement at a few 10^4..10^5 track-seconds."""
+    from oracle.c_oracle import COracle
+    from oracle.em_read import em_read
+    p = em_read(model_paths[model])
+    ref = COracle(p, uncor=uncor).sample_tracks(n, T, seed=92, first_sample=7 * 10 ** 10, threads=0)
+    assert ref["rc"] == 0
+    lib = H.emu_lib()
+    lib.emu_use_fast(fast)
+    m = H.EmuModel(model_paths[model])
+    kw = {}
+    if uncor:
+        lab = p.labels_initial
+        kw = dict(reject_mode=L.EMB_REJECT_UNCOR, idx_v=cases.label_index(lab, '"v"'), idx_dh=cases.label_index(lab, '"\\dot h"'),
+                  idx_L=cases.label_index(lab, '"L"'))
+    tm = np.asarray(p.temporal_map)
+    dyn = [int(v) - 1 for v in tm[:, 0]]
+    rates = np.asarray(p.resample_rates)
+    tv = sorted(set(dyn) | {i for i in range(p.n_initial) if rates[i] > 0})
+    got = m.sample_tracks(p.n_initial, len(dyn), len(tv), n, T, 92, 7 * 10 ** 10, H.EmuModel.opts(p.n_initial, **kw))
+    lib.emu_use_fast(0)
+    assert np.array_equal(got["init_bins"], ref["init_bins"]) and np.array_equal(got["init_values"], ref["init_values"])
+    assert np.array_equal(got["attempts"].astype(np.int64), ref["attempts"].astype(np.int64))
+    assert np.array_equal(got["bins"], ref["sample_bins"][:, dyn, :])
+    want = ref["samples"][:, tv, :]
+    assert np.all(np.abs(got["values"].astype(np.float64) - want) <= 1e-6 * np.abs(want))

@@ -203,6 +203,32 @@ def test_tracks_match_live_oracle(model_paths, model, n, T, seed):
     assert np.all(np.abs(res.values.astype(np.float64) - vals) <= 1e-6 * np.abs(vals))
 
 
+SWEEP = [("uncor_1200code_v2p1", True, 4000, 300), ("uncor_allcode_fwsingle_v1", True, 2000, 600),
+         ("uncor_1200only_fwse_v1p2", True, 3000, 200), ("glider_v1", True, 3000, 200), ("paramotor_v1", True, 3000, 150),
+         ("littoral_uncor_v1", True, 3000, 120), ("cor_v1", False, 3000, 60), ("balloon_v1", False, 5000, 100)]
+
+
+@pytest.mark.parametrize("model,uncor,n,T", SWEEP)
+def test_tracks_match_c_oracle_mid_scale(model_paths, model, uncor, n, T):
+    """Every packed model at a few 10^5..10^6 track-seconds against the plain-C restatement (oracle/oracle_c.c, the size the
+    oracle finishes in seconds): initial bins, attempts and every dense bin bit-exact, values within 1e-6 relative."""
+    from oracle.c_oracle import COracle
+    p = em_read(model_paths[model])
+    ref = COracle(p, uncor=uncor).sample_tracks(n, T, seed=91, first_sample=10 ** 12, threads=0)
+    assert ref["rc"] == 0
+    m = (UncorEncounterModel if uncor else EncounterModel)(model_paths[model])
+    got = m.sample_compact(n, T, seed=91, first_sample=10 ** 12) if uncor else m.sample_tracks(n, T, seed=91, first_sample=10 ** 12)
+    dyn = [int(v) - 1 for v in np.asarray(p.temporal_map)[:, 0]]
+    tv = [v - 1 for v in got.tv_vars]
+    assert np.array_equal(np.asarray(got.init_bins).T, ref["init_bins"])
+    assert np.array_equal(np.asarray(got.attempts).astype(np.int64), ref["attempts"].astype(np.int64))
+    assert np.array_equal(np.asarray(got.init_values).T, ref["init_values"])
+    assert np.array_equal(np.asarray(got.bins), ref["sample_bins"][:, dyn, :])
+    want = ref["samples"][:, tv, :]
+    gv = np.asarray(got.values, dtype=np.float64)
+    assert np.all(np.abs(gv - want) <= 1e-6 * np.abs(want))
+
+
 def test_shard_invariance_and_determinism(model_paths):
     """Global-index keying: any split of [0, n) gives identical results, twice."""
     m = UncorEncounterModel(model_paths["uncor_allcode_fwsingle_v1"])
