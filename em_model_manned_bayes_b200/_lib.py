@@ -80,6 +80,14 @@ class TrajOut(C.Structure):
     _fields_ = [("traj", C.c_void_p), ("len", C.c_void_p)]
 
 
+class IntegrateOpts(C.Structure):
+    _fields_ = [("idx_altitude", C.c_int32), ("idx_speed", C.c_int32), ("idx_acceleration", C.c_int32),
+                ("idx_vertrate", C.c_int32), ("idx_turnrate", C.c_int32),
+                ("ur_speed", C.c_double), ("ur_vertrate", C.c_double), ("ur_heading", C.c_double),
+                ("min_speed", C.c_double), ("max_speed", C.c_double),
+                ("mem", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p)]
+
+
 class TrackOut(C.Structure):
     _fields_ = [
         ("bins", C.c_void_p), ("values", C.c_void_p), ("init_bins", C.c_void_p), ("init_values", C.c_void_p),
@@ -129,6 +137,7 @@ def lib():
         "emb_terminal_propagate": (C.c_int, [P(TerminalModels), P(Rng), i64, vp, i64, P(i32), C.c_double, P(DynLimits),
                                              P(SampleOpts), P(TrajOut)]),
         "emb_terminal_traj_len": (i64, [i64, C.c_double]),
+        "emb_tracks_integrate": (C.c_int, [vp, i64, i32, vp, vp, P(IntegrateOpts), vp, vp]),
         "emb_tracks_bins_len": (i64, [vp, i64, i32]),
         "emb_tracks_values_len": (i64, [vp, i64, i32]),
     }
@@ -146,7 +155,7 @@ EXPORTED = [
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
     "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",
-    "emb_dyn_limits_named", "emb_terminal_propagate", "emb_terminal_traj_len",
+    "emb_dyn_limits_named", "emb_terminal_propagate", "emb_terminal_traj_len", "emb_tracks_integrate",
 ]
 TRAJ_FIELDS = ("x_nm", "y_nm", "z_ft", "heading_deg", "v_ft_s")
 

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/emb200.h"
+#include "emb_integrate.cuh"
 #include "emb_launch.h"
 #include "emb_model.h"
 
@@ -685,6 +686,67 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
     if (status & 2) return set_err(EMB_E_ARG, "Unknown int_intent: own_intent must be 1..2 and int_intent 1..3 (createEncounter.m:22,37)");
     if (status & 1) return set_err(EMB_E_REJECT, "a trajectory state exhausted max_attempts in the dynamic-limit resample loop");
     return 0;
+}
+
+int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double* init_values, const float* values,
+                         const emb_integrate_opts* opts, float* xyz, uint8_t* is_good) {
+    if (!m || !opts || n < 0 || T < 1 || (n > 0 && (!init_values || !values)))
+        return set_err(EMB_E_ARG, "null or out-of-range argument");
+    const HostModel& H = *m->h;
+    emb::IntegrateParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = n;
+    P.T = T;
+    auto tv_of = [&](int32_t var1) -> int {
+        for (size_t k = 0; k < H.timevarying.size(); ++k)
+            if (H.timevarying[k] == var1 - 1) return (int)k;
+        return -1;
+    };
+    if (opts->idx_altitude < 1 || opts->idx_altitude > H.n_initial || opts->idx_speed < 1 || opts->idx_speed > H.n_initial)
+        return set_err(EMB_E_ARG, "sample2track: idx_altitude / idx_speed must name initial variables");
+    P.i_alt = opts->idx_altitude - 1;
+    P.i_speed = opts->idx_speed - 1;
+    P.g_acc = tv_of(opts->idx_acceleration);
+    P.g_vr = tv_of(opts->idx_vertrate);
+    P.g_turn = tv_of(opts->idx_turnrate);
+    if (P.g_acc < 0 || P.g_vr < 0 || P.g_turn < 0)
+        return set_err(EMB_E_ARG, "sample2track: acceleration, vertical rate and turn rate must be time-varying variables of the model");
+    P.ur_speed = opts->ur_speed;
+    P.ur_vertrate = opts->ur_vertrate;
+    P.ur_heading = opts->ur_heading;
+    P.min_speed = opts->min_speed;
+    P.max_speed = opts->max_speed;
+    if (n == 0) return 0;
+    emb_sample_opts so;
+    emb_sample_opts_init(&so);
+    so.device = opts->device;
+    int device, rc = 0;
+    if ((rc = pick_device(&so, device))) return rc;
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    Stager sg{opts->mem, st, {}};
+    struct Scratch {
+        void* p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } d_init, d_vals;
+    const size_t init_bytes = (size_t)H.n_initial * (size_t)n * 8;
+    const size_t val_bytes = (size_t)emb_tracks_values_len(m, n, T) * 4;
+    if (opts->mem == EMB_MEM_DEVICE) {
+        P.init_values = init_values;
+        P.values = values;
+    } else {
+        CU(cudaMalloc(&d_init.p, init_bytes));
+        CU(cudaMalloc(&d_vals.p, val_bytes));
+        CU(cudaMemcpyAsync(d_init.p, init_values, init_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_vals.p, values, val_bytes, cudaMemcpyHostToDevice, st));
+        P.init_values = (const double*)d_init.p;
+        P.values = (const float*)d_vals.p;
+    }
+    if ((rc = sg.out(xyz, (size_t)3 * (size_t)(T + 1) * (size_t)n * 4, false, (void**)&P.xyz))) return rc;
+    if ((rc = sg.out(is_good, (size_t)n, false, (void**)&P.is_good))) return rc;
+    cudaError_t e = (cudaError_t)emb::launch_integrate(P, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks_integrate");
+    CU(cudaStreamSynchronize(st));
+    return sg.finish();
 }
 
 }  // extern "C"

@@ -1,4 +1,5 @@
-// emb_terminal.cu -- sm_100a kernel of the terminal trajectory chains (emb_terminal.cuh).
+// emb_terminal.cu -- sm_100a kernels of the terminal trajectory chains (emb_terminal.cuh) and of the first-order
+// track integration (emb_integrate.cuh).
 //
 // Thread = chain.  blockIdx.y is the chain id (aircraft, direction), so a warp holds 32 consecutive
 // encounters of the same chain: its stores are 128 contiguous bytes per field per step, and the only
@@ -8,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "emb_launch.h"
+#include "emb_integrate.cuh"
 #include "emb_terminal.cuh"
 
 namespace emb {
@@ -21,7 +23,20 @@ k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ 
     if (s < P.n) terminal_chain(P, O, s, (int)blockIdx.y);
 }
 
+// first-order track integration (emb_integrate.cuh): thread = track, HBM-bound (12 B read + 12 B written per track-second)
+__global__ void __launch_bounds__(256) k_tracks_integrate(const __grid_constant__ IntegrateParams P) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n) integrate_track(P, s);
+}
+
 }  // namespace
+
+int launch_integrate(const IntegrateParams& P, void* stream) {
+    if (P.n <= 0) return 0;
+    k_tracks_integrate<<<(unsigned)((P.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 
 int launch_terminal(const TermParams& P, const TermOut& O, void* stream) {
     if (P.n <= 0) return 0;

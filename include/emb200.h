@@ -219,6 +219,21 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
                            const emb_sample_opts* opts, const emb_traj_out* out);
 int64_t emb_terminal_traj_len(int64_t n, double tmax_s); /* elements of emb_traj_out.traj */
 
+/* ---- first-order track integration: replaces the per-track loop of sample2track.m:188-244 (Euler update :199-218,
+ *      CFIT and speed rejection :234-244) on the dense compact output of emb_sample_tracks ------------------------------ */
+typedef struct emb_integrate_opts {
+    int32_t idx_altitude, idx_speed;                      /* 1-based initial variables: 'L' (initial altitude, ft), 'v' */
+    int32_t idx_acceleration, idx_vertrate, idx_turnrate; /* 1-based ids of the dynamic variables \dot v, \dot h, \dot\psi */
+    double ur_speed, ur_vertrate, ur_heading;             /* unit ratios of sample2track.m:108-125 (kt->ft/s, ft/min->ft/s, 1) */
+    double min_speed, max_speed;                          /* boundaries{v}([1 end]) * ur_speed (:98-99, :140-141) */
+    int32_t mem, device;                                  /* EMB_MEM_*, CUDA ordinal (-1 = current) */
+    void* stream;
+} emb_integrate_opts;
+/* init_values: double [n_initial][n] and values: float [n_timevarying][ceil(T/4)][n][4] as written by emb_sample_tracks;
+ * xyz: float [3][T+1][n] = x_ft, y_ft, z_ft at time_s = 0..T (nullable); is_good: uint8 [n] (nullable). */
+int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double* init_values, const float* values,
+                         const emb_integrate_opts* opts, float* xyz, uint8_t* is_good);
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 int emb_host_alloc(void** p, int64_t bytes); /* pinned host memory */
 int emb_host_free(void* p);

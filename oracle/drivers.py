@@ -186,3 +186,17 @@ def dbn_tracks(parms, n_samples, sample_time, U, *, first_sample=0, prior=0, sta
                                initial_bins=np.array(ibins), sample_bins=sp.events2samples(ibins, bin_events),
                                event_bins=np.asarray(ebins, dtype=np.float64), prov=prov, attempts=1))
     return out
+
+
+def em_sample_text(parms, num_initial_samples, num_transition_samples, U, *, start=None):
+    """em_sample.m:59-100: the text of initial.txt and transition.txt (fprintf %g formatting)."""
+    out = dbn_tracks(parms, num_initial_samples, num_transition_samples, U, start=start)
+    tm = np.asarray(parms.temporal_map)
+    ini = ["id " + "".join("%s " % l for l in parms.labels_initial) + "\n"]
+    tra = ["initial_id t " + "".join("%s " % parms.labels_transition[int(k) - 1] for k in tm[:, 1]) + "\n"]
+    for ii, s in enumerate(out, start=1):
+        ini.append("%d " % ii + "".join("%g " % x for x in s.samples[:-1, 0]) + "%g" % s.samples[-1, 0] + "\n")
+        for j in range(1, num_transition_samples + 1):
+            col = s.samples[[int(v) - 1 for v in tm[:, 0]], j - 1]
+            tra.append("%g %g " % (ii, j - 1) + "".join("%g " % x for x in col[:-1]) + "%g" % col[-1] + "\n")
+    return "".join(ini), "".join(tra)

@@ -12,6 +12,7 @@
 
 #include "../../em_model_manned_bayes_b200/csrc/emb_fast.cuh"
 #include "../../em_model_manned_bayes_b200/csrc/emb_initial.cuh"
+#include "../../em_model_manned_bayes_b200/csrc/emb_integrate.cuh"
 #include "../../em_model_manned_bayes_b200/csrc/emb_model.h"
 #include "../../include/emb200.h"
 
@@ -251,6 +252,20 @@ int emu_terminal_propagate(void** models, uint64_t seed, uint64_t first, int64_t
         for (int64_t s = 0; s < n; ++s) terminal_chain(P, O, s, chain);
     if (status & 2) return EMB_E_ARG;
     return (status & 1) ? EMB_E_REJECT : 0;
+}
+
+// host emulation of emb_tracks_integrate (same per-track code as k_tracks_integrate); g_* = tile ordinals
+int emu_tracks_integrate(int64_t n, int32_t T, int32_t i_alt, int32_t i_speed, int32_t g_acc, int32_t g_vr, int32_t g_turn,
+                         double ur_speed, double ur_vertrate, double ur_heading, double min_speed, double max_speed,
+                         const double* init_values, const float* values, float* xyz, uint8_t* is_good) {
+    IntegrateParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = n; P.T = T; P.i_alt = i_alt; P.i_speed = i_speed; P.g_acc = g_acc; P.g_vr = g_vr; P.g_turn = g_turn;
+    P.ur_speed = ur_speed; P.ur_vertrate = ur_vertrate; P.ur_heading = ur_heading;
+    P.min_speed = min_speed; P.max_speed = max_speed;
+    P.init_values = init_values; P.values = values; P.xyz = xyz; P.is_good = is_good;
+    for (int64_t s = 0; s < n; ++s) integrate_track(P, s);
+    return 0;
 }
 
 }  // extern "C"

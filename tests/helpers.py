@@ -49,7 +49,7 @@ def emu_lib():
     here = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(here, "libemb_emu.so")
     srcs = [os.path.join(here, "emu.cpp"), os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", "emb_model.cpp")]
-    deps = srcs + [os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", f) for f in ("emb_device.cuh", "emb_fast.cuh", "emb_initial.cuh", "emb_terminal.cuh", "emb_model.h")]
+    deps = srcs + [os.path.join(ROOT, "em_model_manned_bayes_b200", "csrc", f) for f in ("emb_device.cuh", "emb_fast.cuh", "emb_initial.cuh", "emb_terminal.cuh", "emb_integrate.cuh", "emb_model.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         cuda_inc = "/usr/local/cuda/include"
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared",
@@ -66,6 +66,7 @@ def emu_lib():
     lib.emu_sample_track_events.argtypes = [vp, u64, u64, i64, i32, C.POINTER(L.SampleOpts), i64, vp, vp, C.POINTER(i64)]
     lib.emu_terminal_propagate.argtypes = [C.POINTER(vp), u64, u64, i64, vp, i64, C.POINTER(i32), C.c_double,
                                            C.POINTER(L.DynLimits), i32, vp, vp]
+    lib.emu_tracks_integrate.argtypes = [i64, i32, i32, i32, i32, i32, i32] + [C.c_double] * 5 + [vp, vp, vp, vp]
     lib.emu_use_fast.argtypes = [C.c_int]
     lib.emu_last_fast.restype = C.c_int
     _emu = lib

@@ -368,6 +368,26 @@ def test_step_word_statistics_spec_v3(model_paths):
     assert chi2 < 60.0, chi2
 
 
+def test_em_sample_files_match_oracle(model_paths, tmp_path):
+    """em_sample.m:59-100: the two legacy text files.  Headers, ids and seconds are identical to the
+    oracle's; numbers are compared after parsing (the dense values are fp32, %g prints 6 digits)."""
+    from em_model_manned_bayes_b200.em_sample import em_sample
+    from oracle.drivers import em_sample_text
+    for model, n, T in (("cor_v1", 12, 60), ("uncor_1200code_v2p1", 9, 35)):
+        fi, ft = str(tmp_path / (model + "_initial.txt")), str(tmp_path / (model + "_transition.txt"))
+        em_sample(model_paths[model], fi, ft, num_initial_samples=n, num_transition_samples=T, rng_seed=42)
+        p = em_read(model_paths[model])
+        want_i, want_t = em_sample_text(p, n, T, KeyedPhilox(42))
+        for got, want in ((open(fi).read(), want_i), (open(ft).read(), want_t)):
+            g, w = got.splitlines(), want.splitlines()
+            assert len(g) == len(w) and g[0] == w[0]
+            a = np.array([[float(x) for x in line.split()] for line in g[1:]])
+            b = np.array([[float(x) for x in line.split()] for line in w[1:]])
+            assert a.shape == b.shape
+            assert np.all(np.abs(a - b) <= 2e-5 * np.abs(b))
+        assert open(fi).read() == want_i          # initial values are fp64 on both sides: identical text
+
+
 def test_errors_through_the_abi(model_paths):
     m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
     with pytest.raises(L.EmbError, match="Attempt to preset a dependent variable"):

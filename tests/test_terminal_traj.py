@@ -179,6 +179,24 @@ def test_gpu_chains_match_golden(model_paths, traj_paths, golden):
 
 
 @pytest.mark.gpu
+def test_gpu_chains_match_live_oracle_mixed_limits(model_paths, traj_paths, golden):
+    """More encounters than the goldens hold, oracle run live (about 0.15 s per encounter): all 64 golden geometry
+    samples under GENERIC limits and 48 under (RTCA228_A2-like narrow turn / TEST altitude) limits, 64-bit encounter ids."""
+    geo = geo_from_golden(golden, 64)
+    m = _product_model(model_paths, traj_paths)
+    res = m.create_encounters(geo, 120, seed=41, first_sample=2 ** 40 + 3, geo_rows=range(12))
+    want, want_len = oracle_propagate(traj_paths, geo, 41, 2 ** 40 + 3, 120)
+    check_traj(res.traj, res.len, want, want_len)
+    geo2 = geo_from_golden(golden, 48)
+    geo2[5] = np.clip(geo2[5], 70.0, 180.0)
+    geo2[11] = np.clip(geo2[11], 70.0, 180.0)
+    m2 = _product_model(model_paths, traj_paths, ("RTCA228_A3", "TEST"))
+    res2 = m2.create_encounters(geo2, 75, seed=42, geo_rows=range(12))
+    want2, want_len2 = oracle_propagate(traj_paths, geo2, 42, 0, 75, ("RTCA228_A3", "TEST"))
+    check_traj(res2.traj, res2.len, want2, want_len2)
+
+
+@pytest.mark.gpu
 def test_gpu_limits_golden(model_paths, traj_paths, golden):
     g = golden["terminal_traj_n12_T45_seed32_test_a1"]
     m = _product_model(model_paths, traj_paths, ("TEST", "RTCA228_A1"))
