@@ -80,6 +80,11 @@ class TrajOut(C.Structure):
     _fields_ = [("traj", C.c_void_p), ("len", C.c_void_p)]
 
 
+class ScreenOut(C.Structure):
+    _fields_ = [("hmd_ft", C.c_void_p), ("vmd_ft", C.c_void_p), ("tcpa", C.c_void_p), ("enc_time_s", C.c_void_p),
+                ("runway", C.c_void_p)]
+
+
 class IntegrateOpts(C.Structure):
     _fields_ = [("idx_altitude", C.c_int32), ("idx_speed", C.c_int32), ("idx_acceleration", C.c_int32),
                 ("idx_vertrate", C.c_int32), ("idx_turnrate", C.c_int32),
@@ -137,6 +142,7 @@ def lib():
         "emb_terminal_propagate": (C.c_int, [P(TerminalModels), P(Rng), i64, vp, i64, P(i32), C.c_double, P(DynLimits),
                                              P(SampleOpts), P(TrajOut)]),
         "emb_terminal_traj_len": (i64, [i64, C.c_double]),
+        "emb_terminal_screen": (C.c_int, [vp, vp, i64, C.c_double, C.c_double, C.c_double, P(SampleOpts), P(ScreenOut)]),
         "emb_tracks_integrate": (C.c_int, [vp, i64, i32, vp, vp, P(IntegrateOpts), vp, vp]),
         "emb_tracks_bins_len": (i64, [vp, i64, i32]),
         "emb_tracks_values_len": (i64, [vp, i64, i32]),
@@ -156,6 +162,7 @@ EXPORTED = [
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
     "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",
     "emb_dyn_limits_named", "emb_terminal_propagate", "emb_terminal_traj_len", "emb_tracks_integrate",
+    "emb_terminal_screen",
 ]
 TRAJ_FIELDS = ("x_nm", "y_nm", "z_ft", "heading_deg", "v_ft_s")
 

@@ -749,4 +749,46 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
     return sg.finish();
 }
 
+int emb_terminal_screen(const float* traj, const int16_t* len, int64_t n, double tmax_s, double thres_dist_ft,
+                        double thres_altlow_ft, const emb_sample_opts* opts, const emb_screen_out* out) {
+    if (!opts || !out || n < 0 || (n > 0 && (!traj || !len))) return set_err(EMB_E_ARG, "null or out-of-range argument");
+    if (!(tmax_s >= 0.0) || tmax_s >= 32767.0) return set_err(EMB_E_ARG, "tmax_s must be in [0, 32767)");
+    if (n == 0) return 0;
+    int device, rc = 0;
+    if ((rc = pick_device(opts, device))) return rc;
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    emb::ScreenParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = n;
+    P.tmax = (int32_t)tmax_s;
+    P.thres_dist_ft = thres_dist_ft;
+    P.thres_altlow_ft = thres_altlow_ft;
+    struct Scratch {
+        void* p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } d_traj, d_len;
+    const size_t tb = (size_t)emb_terminal_traj_len(n, tmax_s) * 4, lb = (size_t)n * 4 * 2;
+    if (opts->mem == EMB_MEM_DEVICE) {
+        P.traj = traj;
+        P.len = len;
+    } else {
+        CU(cudaMalloc(&d_traj.p, tb));
+        CU(cudaMalloc(&d_len.p, lb));
+        CU(cudaMemcpyAsync(d_traj.p, traj, tb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_len.p, len, lb, cudaMemcpyHostToDevice, st));
+        P.traj = (const float*)d_traj.p;
+        P.len = (const int16_t*)d_len.p;
+    }
+    Stager sg{opts->mem, st, {}};
+    if ((rc = sg.out(out->hmd_ft, (size_t)n * 8, false, (void**)&P.hmd_ft))) return rc;
+    if ((rc = sg.out(out->vmd_ft, (size_t)n * 8, false, (void**)&P.vmd_ft))) return rc;
+    if ((rc = sg.out(out->tcpa, (size_t)n * 3 * 2, false, (void**)&P.tcpa))) return rc;
+    if ((rc = sg.out(out->enc_time_s, (size_t)n * 2, false, (void**)&P.enc_time_s))) return rc;
+    if ((rc = sg.out(out->runway, (size_t)n, false, (void**)&P.runway))) return rc;
+    cudaError_t e = (cudaError_t)emb::launch_screen(P, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch k_terminal_screen");
+    CU(cudaStreamSynchronize(st));
+    return sg.finish();
+}
+
 }  // extern "C"

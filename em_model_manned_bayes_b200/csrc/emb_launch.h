@@ -25,6 +25,8 @@ struct TermParams;
 struct TermOut;
 int launch_terminal(const TermParams& P, const TermOut& O, void* stream);
 
+struct ScreenParams;
+int launch_screen(const ScreenParams& P, void* stream);
 // first-order track integration (sample2track.m Euler loop) over the dense tiles
 struct IntegrateParams;
 int launch_integrate(const IntegrateParams& P, void* stream);

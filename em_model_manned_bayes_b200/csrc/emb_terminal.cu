@@ -29,7 +29,20 @@ __global__ void __launch_bounds__(256) k_tracks_integrate(const __grid_constant_
     if (s < P.n) integrate_track(P, s);
 }
 
+// encounter screening (miss distance, overlap, runway proximity): thread = encounter, HBM-bound reads of the trajectories
+__global__ void __launch_bounds__(256) k_terminal_screen(const __grid_constant__ ScreenParams P) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n) screen_encounter(P, s);
+}
+
 }  // namespace
+
+int launch_screen(const ScreenParams& P, void* stream) {
+    if (P.n <= 0) return 0;
+    k_terminal_screen<<<(unsigned)((P.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 
 int launch_integrate(const IntegrateParams& P, void* stream) {
     if (P.n <= 0) return 0;

@@ -265,4 +265,72 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     if (O.len) O.len[(int64_t)chain * N + s] = (int16_t)len;
 }
 
+// ---- encounter screening on the merged trajectories -------------------------------------------------
+// getGeneratedMissDistance (@CorTerminalModel/CorTerminalModel.m:117-133), the overlap length of track.m:88 and
+// CheckRunwayProximity (CorTerminalModel.m:187-210) for one encounter, read from the [field][aircraft][slot][n] output.
+struct ScreenParams {
+    int64_t n;
+    int32_t tmax;
+    double thres_dist_ft, thres_altlow_ft;     // track.m thresDist_ft / thresAltLow_ft
+    const float* traj;
+    const int16_t* len;
+    double* hmd_ft;                            // [n] nullable
+    double* vmd_ft;                            // [n]
+    int16_t* tcpa;                             // [3][n]: tcpa_s, tcpa_index_own, tcpa_index_int (1-based)
+    int16_t* enc_time_s;                       // [n] numel(intersect(t_s1, t_s2))
+    uint8_t* runway;                           // [n] bit0 is_close1, bit1 is_low1, bit2 is_close2, bit3 is_low2
+};
+
+EMB_HD void screen_encounter(const ScreenParams& P, int64_t s) {
+    const int64_t N = P.n, S = 2 * (int64_t)P.tmax + 1, fs = 2 * S * N;
+    int lo[2], hi[2];
+    for (int a = 0; a < 2; ++a) {
+        lo[a] = P.tmax - ((int)P.len[(int64_t)(2 * a + 1) * N + s] - 1);
+        hi[a] = P.tmax + (int)P.len[(int64_t)(2 * a) * N + s] - 1;
+    }
+    const float* t0 = P.traj + s;                 // aircraft 0, field 0
+    const float* t1 = P.traj + S * N + s;         // aircraft 1, field 0
+    // getGeneratedMissDistance: common times, first minimum of the horizontal distance
+    const int clo = lo[0] > lo[1] ? lo[0] : lo[1], chi = hi[0] < hi[1] ? hi[0] : hi[1];
+    double best = 0.0, vmd = 0.0;
+    int kbest = -1;
+    for (int k = clo; k <= chi; ++k) {
+        const int64_t o = (int64_t)k * N;
+        const double dx = dadd((double)t0[o], -(double)t1[o]);                      // :120
+        const double dy = dadd((double)t0[fs + o], -(double)t1[fs + o]);            // :121
+        const double d = dmul(::sqrt(dadd(dmul(dx, dx), dmul(dy, dy))), TERM_FT_PER_NM);   // :122
+        if (kbest < 0 || d < best) {                                                // :125 min() returns the first minimum
+            best = d;
+            kbest = k;
+            vmd = dadd((double)t1[2 * fs + o], -(double)t0[2 * fs + o]);            // :123, :126
+        }
+    }
+    if (P.hmd_ft) P.hmd_ft[s] = kbest < 0 ? 0.0 : best;
+    if (P.vmd_ft) P.vmd_ft[s] = vmd;
+    if (P.tcpa) {
+        P.tcpa[s] = (int16_t)(kbest < 0 ? 0 : kbest - P.tmax);                      // :127
+        P.tcpa[N + s] = (int16_t)(kbest < 0 ? 0 : kbest - lo[0] + 1);               // :128
+        P.tcpa[2 * N + s] = (int16_t)(kbest < 0 ? 0 : kbest - lo[1] + 1);           // :129
+    }
+    if (P.enc_time_s) P.enc_time_s[s] = (int16_t)(chi >= clo ? chi - clo + 1 : 0);  // track.m:88
+    if (P.runway) {                                                                 // CorTerminalModel.m:187-210
+        uint32_t bits = 0;
+        for (int a = 0; a < 2; ++a) {
+            const float* t = a ? t1 : t0;
+            bool close = false, low = false;
+            for (int k = lo[a]; k <= hi[a]; ++k) {
+                const int64_t o = (int64_t)k * N;
+                const double x = (double)t[o], y = (double)t[fs + o];
+                const double d_ft = dmul(::hypot(x, y), 1.68781);                   // :196-197 (the reference's own constant)
+                if (d_ft <= P.thres_dist_ft) {
+                    close = true;
+                    low = low || (double)t[2 * fs + o] <= P.thres_altlow_ft;        // :203-205
+                }
+            }
+            bits |= (close ? 1u : 0u) << (2 * a) | (low ? 1u : 0u) << (2 * a + 1);
+        }
+        P.runway[s] = (uint8_t)bits;
+    }
+}
+
 }  // namespace emb

@@ -236,7 +236,7 @@ class EncounterModel:
         if like is None:
             return np.zeros(shape, dtype=dtype)
         import torch
-        tdt = {np.int8: torch.int8, np.float32: torch.float32, np.float64: torch.float64, np.uint16: torch.int16, np.int16: torch.int16,
+        tdt = {np.int8: torch.int8, np.float32: torch.float32, np.float64: torch.float64, np.uint16: torch.int16, np.int16: torch.int16, np.uint8: torch.uint8,
                np.uint64: torch.int64}[dtype]
         return torch.zeros(shape, dtype=tdt, device=like)
 
@@ -618,6 +618,27 @@ class CorTerminalModel(EncounterModel):
         L.check(lib.emb_terminal_propagate(C.byref(tm), C.byref(rng), n, _ptr(geo), int(geo.shape[1]), rows, float(tmax_s),
                                            lim, C.byref(o), C.byref(to)))
         return out
+
+    def screen_encounters(self, res: "TrajectoryResult", thresDist_ft: float = 0.0, thresAltLow_ft: float = 0.0, device=None):
+        """Batch form of getGeneratedMissDistance (CorTerminalModel.m:117-133), the overlap length of track.m:88 and
+        CheckRunwayProximity (CorTerminalModel.m:187-210) on the trajectories of `create_encounters`.
+        -> dict(hmd_ft, vmd_ft (n,) float64; tcpa_s, tcpa_index_own, tcpa_index_int, enc_time_s (n,) int16;
+                is_close1, is_low1, is_close2, is_low2 (n,) bool)"""
+        n = res.n
+        o = self._opts()
+        if device is not None:
+            import torch
+            dev = torch.device(device)
+            o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+            o.stream = torch.cuda.current_stream(dev).cuda_stream
+        hmd, vmd = self._alloc((n,), np.float64, device), self._alloc((n,), np.float64, device)
+        tcpa, enc = self._alloc((3, n), np.int16, device), self._alloc((n,), np.int16, device)
+        rw = self._alloc((n,), np.uint8, device)
+        so = L.ScreenOut(_ptr(hmd), _ptr(vmd), _ptr(tcpa), _ptr(enc), _ptr(rw))
+        L.check(L.lib().emb_terminal_screen(_ptr(res.traj), _ptr(res.len), n, float(res.tmax), float(thresDist_ft),
+                                            float(thresAltLow_ft), C.byref(o), C.byref(so)))
+        return dict(hmd_ft=hmd, vmd_ft=vmd, tcpa_s=tcpa[0], tcpa_index_own=tcpa[1], tcpa_index_int=tcpa[2], enc_time_s=enc,
+                    is_close1=(rw & 1) != 0, is_low1=(rw & 2) != 0, is_close2=(rw & 4) != 0, is_low2=(rw & 8) != 0)
 
     def createEncounter(self, sample_geo: dict, tmax_s: float = 120, seed: int = 0, sample_index: int = 0):
         """createEncounter.m:1 for one `sample_geo` struct (a dict as returned in outSamples) -> traj(1:2)."""

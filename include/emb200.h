@@ -219,6 +219,20 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
                            const emb_sample_opts* opts, const emb_traj_out* out);
 int64_t emb_terminal_traj_len(int64_t n, double tmax_s); /* elements of emb_traj_out.traj */
 
+/* ---- encounter screening on the output of emb_terminal_propagate: getGeneratedMissDistance
+ *      (@CorTerminalModel/CorTerminalModel.m:117-133), the overlap length of @CorTerminalModel/track.m:88 and
+ *      CheckRunwayProximity (CorTerminalModel.m:187-210).  traj / len as in emb_traj_out (same memory kind as the outputs). */
+typedef struct emb_screen_out {
+    double* hmd_ft;       /* [n]                                                                       nullable */
+    double* vmd_ft;       /* [n]  z_int - z_own at the CPA                                             nullable */
+    int16_t* tcpa;        /* [3][n]: tcpa_s, tcpa_index_own, tcpa_index_int (1-based, MATLAB indices)  nullable */
+    int16_t* enc_time_s;  /* [n]  numel(intersect(traj(1).t_s, traj(2).t_s))                           nullable */
+    uint8_t* runway;      /* [n]  bit0 is_close1, bit1 is_low1, bit2 is_close2, bit3 is_low2           nullable */
+} emb_screen_out;
+int emb_terminal_screen(const float* traj, const int16_t* len, int64_t n, double tmax_s, double thres_dist_ft,
+                        double thres_altlow_ft, const emb_sample_opts* opts /* mem, device, stream */,
+                        const emb_screen_out* out);
+
 /* ---- first-order track integration: replaces the per-track loop of sample2track.m:188-244 (Euler update :199-218,
  *      CFIT and speed rejection :234-244) on the dense compact output of emb_sample_tracks ------------------------------ */
 typedef struct emb_integrate_opts {

@@ -16,6 +16,12 @@
 //          [own_intent own_distance own_bearing own_alt own_heading own_speed int_...]; limits: 5 x 2 double
 //          [minVel; maxVel; maxTurnRate; maxAltitude; maxVertRate] per aircraft;
 //          traj: n x (2*tmax+1) x 2 x 5 single (NaN = no state), len: n x 4 int16
+//   s = emb_mex('terminal_screen', traj, len, tmax_s, thresDist_ft, thresAltLow_ft)   % traj/len as returned above
+//          struct: hmd_ft, vmd_ft (n x 1 double), tcpa (n x 3 int16: tcpa_s, index_own, index_int), enc_time_s, runway (bits)
+//   [xyz, is_good] = emb_mex('tracks_integrate', h, out_inits, values, T, iopts)    % sample2track.m:188-244
+//          out_inits n x n_initial double and values 4 x n x ceil(T/4) x n_tv single as returned by 'sample_tracks';
+//          iopts: struct idx_altitude, idx_speed, idx_acceleration, idx_vertrate, idx_turnrate, ur_speed, ur_vertrate,
+//          ur_heading, min_speed, max_speed;  xyz: n x (T+1) x 3 single, is_good: n x 1 uint8
 //          emb_mex('free', h)
 // opts: struct with optional fields start (1 x n_initial, 0/NaN = free), reject_mode, idx_v, idx_dh,
 // idx_L, is_quantize500, layers (r_L x 2), box_lo, box_hi, max_attempts, device.
@@ -129,6 +135,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (nlhs > 1) plhs[1] = len; else mxDestroyArray(len);
         return;
     }
+    if (c == "terminal_screen") {                                 // CorTerminalModel.m:117-133, :187-210, track.m:88
+        const int64_t n = (int64_t)mxGetM(prhs[2]);
+        const char* names[] = {"hmd_ft", "vmd_ft", "tcpa", "enc_time_s", "runway"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 5, names);
+        mxArray* hmd = mxCreateDoubleMatrix(n, 1, mxREAL);
+        mxArray* vmd = mxCreateDoubleMatrix(n, 1, mxREAL);
+        mxArray* tcpa = mxCreateNumericMatrix(n, 3, mxINT16_CLASS, mxREAL);
+        mxArray* enc = mxCreateNumericMatrix(n, 1, mxINT16_CLASS, mxREAL);
+        mxArray* rw = mxCreateNumericMatrix(n, 1, mxUINT8_CLASS, mxREAL);
+        emb_sample_opts o;
+        emb_sample_opts_init(&o);
+        emb_screen_out so{mxGetPr(hmd), mxGetPr(vmd), (int16_t*)mxGetData(tcpa), (int16_t*)mxGetData(enc), (uint8_t*)mxGetData(rw)};
+        CHECK(emb_terminal_screen((const float*)mxGetData(prhs[1]), (const int16_t*)mxGetData(prhs[2]), n, mxGetScalar(prhs[3]),
+                                  mxGetScalar(prhs[4]), mxGetScalar(prhs[5]), &o, &so));
+        mxSetField(plhs[0], 0, "hmd_ft", hmd); mxSetField(plhs[0], 0, "vmd_ft", vmd); mxSetField(plhs[0], 0, "tcpa", tcpa);
+        mxSetField(plhs[0], 0, "enc_time_s", enc); mxSetField(plhs[0], 0, "runway", rw);
+        return;
+    }
     emb_model* m = handle(prhs[1]);
     emb_model_info info;
     CHECK(emb_model_get_info(m, &info));
@@ -193,6 +217,25 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (nlhs > 1) plhs[1] = bins; else mxDestroyArray(bins);
         if (nlhs > 2) plhs[2] = vals; else mxDestroyArray(vals);
         if (nlhs > 3) plhs[3] = att; else mxDestroyArray(att);
+    } else if (c == "tracks_integrate") {                         // sample2track.m:188-244
+        const int64_t n = (int64_t)mxGetM(prhs[2]);
+        const int32_t T = (int32_t)mxGetScalar(prhs[4]);
+        const mxArray* io = prhs[5];
+        emb_integrate_opts o;
+        std::memset(&o, 0, sizeof(o));
+        o.idx_altitude = (int)field_or(io, "idx_altitude", 0); o.idx_speed = (int)field_or(io, "idx_speed", 0);
+        o.idx_acceleration = (int)field_or(io, "idx_acceleration", 0); o.idx_vertrate = (int)field_or(io, "idx_vertrate", 0);
+        o.idx_turnrate = (int)field_or(io, "idx_turnrate", 0);
+        o.ur_speed = field_or(io, "ur_speed", 6076.1154855643 / 3600); o.ur_vertrate = field_or(io, "ur_vertrate", 1.0 / 60);
+        o.ur_heading = field_or(io, "ur_heading", 1.0);
+        o.min_speed = field_or(io, "min_speed", 0); o.max_speed = field_or(io, "max_speed", 1e300);
+        o.mem = EMB_MEM_HOST; o.device = -1;
+        const mwSize dx[3] = {(mwSize)n, (mwSize)(T + 1), 3};      // [3][T+1][n] == n x (T+1) x 3 column-major
+        plhs[0] = mxCreateNumericArray(3, dx, mxSINGLE_CLASS, mxREAL);
+        mxArray* good = mxCreateNumericMatrix(n, 1, mxUINT8_CLASS, mxREAL);
+        CHECK(emb_tracks_integrate(m, n, T, mxGetPr(prhs[2]), (const float*)mxGetData(prhs[3]), &o, (float*)mxGetData(plhs[0]),
+                                   (uint8_t*)mxGetData(good)));
+        if (nlhs > 1) plhs[1] = good; else mxDestroyArray(good);
     } else if (c == "sample_events") {                            // out_events of UncorEncounterModel.m:253-300
         emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
         const int64_t n = (int64_t)mxGetScalar(prhs[4]);

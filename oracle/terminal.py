@@ -257,3 +257,23 @@ def create_encounters(model_set, geo, seed, first_sample=0, tmax_s=120, dyn=("GE
             for f, name in enumerate(("x_nm", "y_nm", "z_ft", "heading_deg", "v_ft_s")):
                 traj[f, ac, slots, s] = m[name]
     return traj, length
+
+
+def get_generated_miss_distance(traj):
+    """@CorTerminalModel/CorTerminalModel.m:117-133 for traj = [own, intruder] dicts of arrays (t_s, x_nm, y_nm, z_ft)."""
+    t1, t2 = np.asarray(traj[0]["t_s"]), np.asarray(traj[1]["t_s"])
+    _, ia, ib = np.intersect1d(t1, t2, return_indices=True)                                     # :119
+    dx = np.asarray(traj[0]["x_nm"], dtype=np.float64)[ia] - np.asarray(traj[1]["x_nm"], dtype=np.float64)[ib]
+    dy = np.asarray(traj[0]["y_nm"], dtype=np.float64)[ia] - np.asarray(traj[1]["y_nm"], dtype=np.float64)[ib]
+    dxy_ft = np.sqrt(dx * dx + dy * dy) * FT_PER_NM                                             # :122
+    dz_ft = np.asarray(traj[1]["z_ft"], dtype=np.float64)[ib] - np.asarray(traj[0]["z_ft"], dtype=np.float64)[ia]
+    idx = int(np.argmin(dxy_ft))                                                                # :125 first minimum
+    return float(dxy_ft[idx]), float(dz_ft[idx]), float(t1[ia[idx]]), int(ia[idx]) + 1, int(ib[idx]) + 1, int(ia.size)
+
+
+def check_runway_proximity(tr, thres_dist_ft, thres_altlow_ft):
+    """CorTerminalModel.m:187-210 (1.68781 is the reference's own constant)."""
+    d_ft = np.hypot(np.asarray(tr["x_nm"], dtype=np.float64), np.asarray(tr["y_nm"], dtype=np.float64)) * 1.68781
+    close = d_ft <= thres_dist_ft
+    low = np.asarray(tr["z_ft"], dtype=np.float64)[close] <= thres_altlow_ft if close.any() else np.zeros(0, dtype=bool)
+    return bool(close.any()), bool(np.any(low))

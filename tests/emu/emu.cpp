@@ -268,4 +268,15 @@ int emu_tracks_integrate(int64_t n, int32_t T, int32_t i_alt, int32_t i_speed, i
     return 0;
 }
 
+// host emulation of emb_terminal_screen (same per-encounter code as k_terminal_screen)
+int emu_terminal_screen(const float* traj, const int16_t* len, int64_t n, double tmax_s, double thres_dist_ft,
+                        double thres_altlow_ft, double* hmd, double* vmd, int16_t* tcpa, int16_t* enc_time, uint8_t* runway) {
+    ScreenParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = n; P.tmax = (int32_t)tmax_s; P.thres_dist_ft = thres_dist_ft; P.thres_altlow_ft = thres_altlow_ft;
+    P.traj = traj; P.len = len; P.hmd_ft = hmd; P.vmd_ft = vmd; P.tcpa = tcpa; P.enc_time_s = enc_time; P.runway = runway;
+    for (int64_t s = 0; s < n; ++s) screen_encounter(P, s);
+    return 0;
+}
+
 }  // extern "C"

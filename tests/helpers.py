@@ -66,6 +66,7 @@ def emu_lib():
     lib.emu_sample_track_events.argtypes = [vp, u64, u64, i64, i32, C.POINTER(L.SampleOpts), i64, vp, vp, C.POINTER(i64)]
     lib.emu_terminal_propagate.argtypes = [C.POINTER(vp), u64, u64, i64, vp, i64, C.POINTER(i32), C.c_double,
                                            C.POINTER(L.DynLimits), i32, vp, vp]
+    lib.emu_terminal_screen.argtypes = [vp, vp, i64, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     lib.emu_tracks_integrate.argtypes = [i64, i32, i32, i32, i32, i32, i32] + [C.c_double] * 5 + [vp, vp, vp, vp]
     lib.emu_use_fast.argtypes = [C.c_int]
     lib.emu_last_fast.restype = C.c_int

@@ -2,7 +2,7 @@
 #include <cstddef>
 #include <cstdint>
 typedef struct mxArray_tag mxArray; typedef size_t mwSize;
-enum mxClassID { mxUINT64_CLASS, mxINT8_CLASS, mxUINT16_CLASS, mxINT16_CLASS, mxSINGLE_CLASS, mxDOUBLE_CLASS }; enum mxComplexity { mxREAL };
+enum mxClassID { mxUINT8_CLASS, mxUINT64_CLASS, mxINT8_CLASS, mxUINT16_CLASS, mxINT16_CLASS, mxSINGLE_CLASS, mxDOUBLE_CLASS }; enum mxComplexity { mxREAL };
 bool mxIsUint64(const mxArray*); size_t mxGetNumberOfElements(const mxArray*); void* mxGetData(const mxArray*); bool mxIsStruct(const mxArray*);
 mxArray* mxGetField(const mxArray*, int, const char*); bool mxIsEmpty(const mxArray*); double mxGetScalar(const mxArray*); double* mxGetPr(const mxArray*);
 size_t mxGetM(const mxArray*); bool mxIsChar(const mxArray*); int mxGetString(const mxArray*, char*, size_t);

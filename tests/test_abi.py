@@ -65,7 +65,7 @@ def test_mex_gateway_source_matches_the_header():
     assert r.returncode == 0, r.stderr
     src = open(os.path.join(ROOT, "matlab", "emb_mex.cpp")).read()
     for fn in ("emb_model_load", "emb_set_prior", "emb_sample_initial", "emb_sample_tracks", "emb_sample_track_events",
-               "emb_terminal_propagate"):
+               "emb_terminal_propagate", "emb_terminal_screen", "emb_tracks_integrate"):
         assert fn + "(" in src, fn
 
 

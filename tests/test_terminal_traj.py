@@ -132,6 +132,42 @@ def test_emu_chains_match_golden(traj_paths, golden):
     check_traj(traj, ln, g["traj"], g["len"])
 
 
+def _oracle_screen(traj32, ln, tmax, thres_dist, thres_low):
+    """Oracle screening of the fp32 trajectories the product wrote (a pure function of traj)."""
+    from oracle import terminal as T
+    n = traj32.shape[3]
+    out = dict(hmd=[], vmd=[], tcpa=[], io=[], ii=[], enc=[], rw=[])
+    for s in range(n):
+        pair = []
+        for ac in range(2):
+            lo, hi = tmax - (int(ln[2 * ac + 1, s]) - 1), tmax + int(ln[2 * ac, s]) - 1
+            pair.append(dict(t_s=np.arange(lo - tmax, hi - tmax + 1, dtype=np.float64), x_nm=traj32[0, ac, lo:hi + 1, s],
+                             y_nm=traj32[1, ac, lo:hi + 1, s], z_ft=traj32[2, ac, lo:hi + 1, s]))
+        h, v, t, io, ii, enc = T.get_generated_miss_distance(pair)
+        c1, l1 = T.check_runway_proximity(pair[0], thres_dist, thres_low)
+        c2, l2 = T.check_runway_proximity(pair[1], thres_dist, thres_low)
+        for k, x in zip(("hmd", "vmd", "tcpa", "io", "ii", "enc", "rw"), (h, v, t, io, ii, enc, c1 + 2 * l1 + 4 * c2 + 8 * l2)):
+            out[k].append(x)
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
+def test_emu_screening_matches_oracle(traj_paths, golden):
+    g = golden["terminal_traj_n16_T120_seed31"]
+    rc, traj, ln = emu_propagate(traj_paths, np.ascontiguousarray(g["geo"]), 31, int(g["first"]), 120)
+    assert rc == 0
+    n = traj.shape[3]
+    hmd, vmd = np.zeros(n), np.zeros(n)
+    tcpa, enc, rw = np.zeros((3, n), dtype=np.int16), np.zeros(n, dtype=np.int16), np.zeros(n, dtype=np.uint8)
+    thres_dist, thres_low = 3.0, 1500.0          # in the reference's own d_nm * 1.68781 "feet" (CorTerminalModel.m:197)
+    H.emu_lib().emu_terminal_screen(traj.ctypes.data, ln.ctypes.data, n, 120.0, thres_dist, thres_low, hmd.ctypes.data,
+                                    vmd.ctypes.data, tcpa.ctypes.data, enc.ctypes.data, rw.ctypes.data)
+    want = _oracle_screen(traj, ln, 120, thres_dist, thres_low)
+    assert np.array_equal(hmd, want["hmd"]) and np.array_equal(vmd, want["vmd"])          # fp64 on the same fp32 inputs
+    assert np.array_equal(tcpa[0], want["tcpa"]) and np.array_equal(tcpa[1], want["io"]) and np.array_equal(tcpa[2], want["ii"])
+    assert np.array_equal(enc, want["enc"]) and np.array_equal(rw, want["rw"])
+    assert 0 < rw.astype(int).sum() and len(set(rw.tolist())) > 1                          # thresholds exercise both outcomes
+
+
 def test_emu_unknown_intent_is_an_error(traj_paths, golden):
     geo = geo_from_golden(golden, 4)
     geo[0, 2] = 3.0                                   # own_intent = 3 has no ownship model (createEncounter.m:21-22)
@@ -235,6 +271,39 @@ def test_gpu_pipeline_properties_and_shard_invariance(model_paths, traj_paths):
     host = m.create_encounters(geo[:, :300].cpu().numpy(), tmax, seed=6)
     assert np.array_equal(np.asarray(host.len), ln[:, :300])
     assert np.array_equal(np.nan_to_num(np.asarray(host.traj), nan=-1.0), np.nan_to_num(traj[:, :, :, :300], nan=-1.0))
+
+
+@pytest.mark.gpu
+def test_gpu_screening_matches_oracle(model_paths, traj_paths, golden):
+    import torch
+    m = _product_model(model_paths, traj_paths)
+    n, tmax = 3000, 120
+    vals, _, _ = m.sample_raw(n, seed=15, device="cuda:0")
+    res = m.create_encounters(vals.T.contiguous(), tmax, seed=16, device="cuda:0")
+    sc = m.screen_encounters(res, thresDist_ft=3.0, thresAltLow_ft=1500.0, device="cuda:0")
+    torch.cuda.synchronize()
+    traj, ln = res.traj.cpu().numpy(), res.len.cpu().numpy()
+    k = 400                                                   # oracle on the first 400 encounters
+    want = _oracle_screen(traj[:, :, :, :k], ln[:, :k], tmax, 3.0, 1500.0)
+    assert np.array_equal(sc["hmd_ft"].cpu().numpy()[:k], want["hmd"]) and np.array_equal(sc["vmd_ft"].cpu().numpy()[:k], want["vmd"])
+    assert np.array_equal(sc["tcpa_s"].cpu().numpy()[:k], want["tcpa"])
+    assert np.array_equal(sc["tcpa_index_own"].cpu().numpy()[:k], want["io"]) and np.array_equal(sc["tcpa_index_int"].cpu().numpy()[:k], want["ii"])
+    assert np.array_equal(sc["enc_time_s"].cpu().numpy()[:k], want["enc"])
+    rw = (sc["is_close1"].to(torch.uint8) + 2 * sc["is_low1"].to(torch.uint8) + 4 * sc["is_close2"].to(torch.uint8)
+          + 8 * sc["is_low2"].to(torch.uint8)).cpu().numpy()
+    assert np.array_equal(rw[:k], want["rw"])
+    # size-independent properties on all encounters: the CPA is a common time, hmd is the minimum over them
+    t = sc["tcpa_s"].cpu().numpy().astype(int)
+    own_lo, own_hi = -(ln[1].astype(int) - 1), ln[0].astype(int) - 1
+    int_lo, int_hi = -(ln[3].astype(int) - 1), ln[2].astype(int) - 1
+    assert np.all(t >= np.maximum(own_lo, int_lo)) and np.all(t <= np.minimum(own_hi, int_hi))
+    assert np.array_equal(sc["enc_time_s"].cpu().numpy(), np.minimum(own_hi, int_hi) - np.maximum(own_lo, int_lo) + 1)
+    d0 = np.hypot(traj[0, 0, tmax] - traj[0, 1, tmax], traj[1, 0, tmax] - traj[1, 1, tmax]).astype(np.float64) * 6076.1154855643
+    assert np.all(sc["hmd_ft"].cpu().numpy() <= d0 * (1 + 1e-6) + 1e-3)
+    # host-memory call == device-memory call
+    host = type(res)(n=64, tmax=tmax, traj=np.ascontiguousarray(traj[:, :, :, :64]), len=np.ascontiguousarray(ln[:, :64]))
+    sh = m.screen_encounters(host, thresDist_ft=3.0, thresAltLow_ft=1500.0)
+    assert np.array_equal(sh["hmd_ft"], sc["hmd_ft"].cpu().numpy()[:64]) and np.array_equal(sh["tcpa_s"], t[:64])
 
 
 @pytest.mark.gpu
