@@ -435,6 +435,74 @@ class UncorEncounterModel(EncounterModel):
         return self.sample_events(n_samples, sample_time, seed=seed, first_sample=first_sample,
                                   opts=self.uncor_opts(isQuantize500, layers), device=device, **kw)
 
+    def getDynamicLimits(self, initial, results=None, idx_G=None, idx_A=None, idx_L=None, idx_V=None, idx_DH=None,
+                         is_discretized=None):
+        """@UncorEncounterModel/getDynamicLimits.m:1-129: speed and vertical-rate limits from the 1st/99th percentiles of
+        the count tables, conditioned on (G, A, L, v) when the model has them in positions 1, 2, 3, 4, 6 (:16).
+        `initial`: 1 x n_initial values (bins where is_discretized[i], continuous otherwise); `results`: dict with
+        `up_ft` and `speed_ftps` (only read for non-discretised L / v, :35-56).  Host-side table arithmetic."""
+        def disc(x, cut):                                    # discretize_bayes.m:14-22
+            x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+            cut = np.asarray(cut, dtype=np.float64)
+            return np.array([cut.size + 1 if v >= cut[-1] else int(np.nonzero(v < cut)[0][0]) + 1 for v in x])
+
+        lab = self.labels_initial
+        idx_G = _find(lab, '"G"') if idx_G is None else idx_G
+        idx_A = _find(lab, '"A"') if idx_A is None else idx_A
+        idx_L = self.idxL if idx_L is None else idx_L
+        idx_V = self.idxV if idx_V is None else idx_V
+        idx_DH = self.idxDH if idx_DH is None else idx_DH
+        if is_discretized is None:
+            is_discretized = [len(b) == 0 for b in self.boundaries]
+        N, r = self.N_initial, self.r_initial
+        if all((idx_G, idx_A, idx_L, idx_V, idx_DH)) and (idx_G, idx_A, idx_L, idx_V, idx_DH) == (1, 2, 3, 4, 6):   # :16
+            initial = np.asarray(initial, dtype=np.float64)
+            one = lambda i: int(initial[i - 1]) if is_discretized[i - 1] else int(disc(initial[i - 1], self.cutpoints_initial[i - 1])[0])
+            dG, dA = one(idx_G), one(idx_A)                                                            # :19-30
+            if is_discretized[idx_L - 1]:
+                dL = [int(initial[idx_L - 1])]
+            else:                                                                                      # :35-38
+                d = disc([np.min(results["up_ft"]), np.max(results["up_ft"])], self.cutpoints_initial[idx_L - 1])
+                dL = list(range(int(d.min()), int(d.max()) + 1))
+            if is_discretized[idx_V - 1]:
+                dV = [int(initial[idx_V - 1])]
+            else:                                                                                      # :46-50
+                kts = np.asarray(results["speed_ftps"], dtype=np.float64) * 0.592484
+                d = disc([kts.min(), kts.max()], self.cutpoints_initial[idx_V - 1])
+                dV = list(range(int(d.min()), int(d.max()) + 1))
+            rG, rA, rL, rV = int(r[idx_G - 1]), int(r[idx_A - 1]), int(r[idx_L - 1]), int(r[idx_V - 1])
+            v_G = N[idx_V - 1][:, dG - 1::rG]                                                          # :57-58
+            dh_G = N[idx_DH - 1][:, dG - 1::rG]
+            v_GA = v_G[:, dA - 1::rA]                                                                  # :61-62
+            dh_GA = dh_G[:, dA - 1::rA]
+            uL = sorted(set(dL))
+            v_GAL = v_GA[:, [k - 1 for k in uL]]                                                       # :66
+            dh_GAL = sum(dh_GA[:, k - 1::rL] for k in uL)                                              # :69-72
+            dh_GALV = sum(dh_GAL[:, k - 1::rV] for k in sorted(set(dV)))                               # :75-78
+            v_initial = v_GAL.sum(axis=1)
+            dh_initial = dh_GALV.sum(axis=1)
+        else:                                                                                          # :85-86
+            v_initial = N[idx_V - 1].sum(axis=1)
+            dh_initial = N[idx_DH - 1].sum(axis=1)
+
+        def pct(w):                                                                                    # :93-96, :115-118
+            cs = np.cumsum(100.0 * w / w.sum())
+            return int(np.nonzero(cs >= 1)[0][0]) + 1, int(np.nonzero(cs >= 99)[0][0]) + 1
+
+        k_lo, k_hi = pct(v_initial)
+        bV = self.boundaries[idx_V - 1]
+        min_speed, max_speed = bV[k_lo] * 1.68780972222222, bV[k_hi] * 1.68780972222222               # :99-100 (edge k+1, 1-based)
+        if self.isRotorcraft and max_speed > 304:                                                      # :104-109
+            max_speed = 304.0
+        if (not self.isRotorcraft) and min_speed < 30:
+            min_speed = 30.0
+        k_lo, k_hi = pct(dh_initial)
+        bH = self.boundaries[idx_DH - 1]
+        vr = float(np.max(np.abs(np.array([bH[k_lo], bH[k_hi]]) / 60.0)))                              # :120
+        if math.isnan(vr):
+            vr = 0.0
+        return dict(minVel_ft_s=float(min_speed), maxVel_ft_s=float(max_speed), maxVertRate_ft_s=vr)
+
     def sample(self, n_samples: int, sample_time: int, seed=float("nan"), isQuantize500=False, layers=None):
         """UncorEncounterModel.m:192-313 -> (out_inits n x n_initial, out_events list of k x 3 [dt var value],
         out_samples list of n_initial x T, out_EME list of controls [t, dh ft/s, dpsi rad/s, dv ft/s^2]).

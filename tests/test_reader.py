@@ -141,3 +141,40 @@ def test_crlf_and_blank_lines(tmp_path, model_paths):
     f.write_bytes(src.replace("\n", "\r\n\r\n").encode())
     a, b = EncounterModel(str(f)), EncounterModel(model_paths["balloon_v1"])
     assert np.array_equal(a.packed(0), b.packed(0)) and np.array_equal(a.packed(1), b.packed(1))
+
+
+def test_uncor_get_dynamic_limits_matches_direct_conditioning(model_paths):
+    """@UncorEncounterModel/getDynamicLimits.m: the strided-column arithmetic of :57-78 against the same
+    conditional distributions taken from the count tables reshaped to their parent axes."""
+    from em_model_manned_bayes_b200.model import UncorEncounterModel
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    N, r = m.N_initial, [int(x) for x in m.r_initial]
+    Nv = N[3].reshape((r[3], r[0], r[1], r[2]), order="F")                       # v | G, A, L
+    Ndh = N[5].reshape((r[5], r[0], r[1], r[2], r[3], r[4]), order="F")          # \dot h | G, A, L, v, \dot v
+    combos = [(g, a, l, v) for g in range(1, r[0] + 1) for a in range(1, r[1] + 1) for l in range(1, r[2] + 1)
+              for v in range(1, r[3] + 1) if Ndh[:, g - 1, a - 1, l - 1, v - 1, :].sum() > 0]
+    assert (1, 4, 2, 4) in combos
+    for (dG, dA, dL, dV) in [(1, 4, 2, 4), combos[0], combos[len(combos) // 2], combos[-1]]:
+        init = [dG, dA, dL, dV, 1, 1, 1]
+        got = m.getDynamicLimits(init, is_discretized=[True] * 7)
+        v = Nv[:, dG - 1, dA - 1, dL - 1]
+        dh = Ndh[:, dG - 1, dA - 1, dL - 1, dV - 1, :].sum(axis=1)
+
+        def pct(w):
+            cs = np.cumsum(100.0 * w / w.sum())
+            return int(np.argmax(cs >= 1)) + 1, int(np.argmax(cs >= 99)) + 1
+        klo, khi = pct(v)
+        bV, bH = m.boundaries[3], m.boundaries[5]
+        assert got["minVel_ft_s"] == max(bV[klo] * 1.68780972222222, 30.0)
+        assert got["maxVel_ft_s"] == bV[khi] * 1.68780972222222
+        klo, khi = pct(dh)
+        assert got["maxVertRate_ft_s"] == max(abs(bH[klo]), abs(bH[khi])) / 60.0
+    # continuous inputs: L and v come from the simulated track (results), G and A are bins already
+    got = m.getDynamicLimits([1, 4, 1650.0, 120.0, 0, 0, 0], results=dict(up_ft=[1300.0, 2900.0], speed_ftps=[150.0, 260.0]))
+    want = m.getDynamicLimits([1, 4, 2, 0, 0, 0, 0], is_discretized=[True, True, True, False, True, True, True],
+                              results=dict(up_ft=[0.0], speed_ftps=[150.0, 260.0]))
+    assert got == want and got["maxVel_ft_s"] > got["minVel_ft_s"] >= 30.0
+    # a model without G/A in positions 1-2 falls back to the marginal tables (:85-86)
+    g = UncorEncounterModel(model_paths["glider_v1"])
+    lim = g.getDynamicLimits([1, 1, 1, 1, 1])
+    assert lim["maxVel_ft_s"] > lim["minVel_ft_s"] and lim["maxVertRate_ft_s"] > 0
