@@ -27,7 +27,9 @@ def time_tracks(name, n, T, reps=3):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    print("%s n=%d T=%d: %.3f ms  %.3e track-timesteps/s" % (name, n, T, best, n * T / best * 1e3), flush=True)
+    # checksum of the last pass (same seed for every library variant): variants must agree bit for bit
+    cs = (int(res.bins_tiled.view(torch.int32).sum(dtype=torch.int64)), int(res.values_tiled.view(torch.int32).sum(dtype=torch.int64)))
+    print("%s n=%d T=%d: %.3f ms  %.3e track-timesteps/s  checksum %x %x" % (name, n, T, best, n * T / best * 1e3, cs[0] & (2**64 - 1), cs[1] & (2**64 - 1)), flush=True)
 
 
 def time_events(name, n, T, reps=3):
