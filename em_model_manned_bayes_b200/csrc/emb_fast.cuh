@@ -78,6 +78,16 @@ EMB_HD uint32_t add_gt(uint32_t acc, uint32_t k, uint32_t nt) {
 #endif
 }
 
+// acc - [k > t] for a threshold that is not complemented: k > t  <=>  t - k borrows
+EMB_HD uint32_t sub_gt(uint32_t acc, uint32_t k, uint32_t t) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .u32 d;\n\tsub.cc.u32 d, %2, %1;\n\tsubc.u32 %0, %0, 0;\n\t}" : "+r"(acc) : "r"(k), "r"(t));
+    return acc;
+#else
+    return acc - (k > t ? 1u : 0u);
+#endif
+}
+
 // The same count on the otherwise idle fp64 pipe: with kb = 2^52 + k and td = 2^52 + t (both exact: the word sits in
 // the low half of the mantissa under the high word 0x43300000) the double compare kb > td *is* the integer compare
 // k > t.  SASS: one DSETP (fp64 pipe) + one predicated add that ptxas places on whichever integer pipe is free.
@@ -129,7 +139,9 @@ EMB_HD float fmaf_rn(float a, float b, float c) {
 }
 
 // EV: 0 = dense outputs only, 1 = also count the rows of the event list, 2 = also write them (see emb200.h: emb_event)
-template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, class HistInc>
+// ORD (slow branch only): the order in which dbn_sample.m:66-79 samples the dynamic variables, two bits per position
+// (order_code below); a compile-time order keeps the per-second code straight-line (no jump table, a third of the code)
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD, class HistInc>
 struct FastTrack {
     using SH = DynShape<RS>;
     static constexpr int ND = SH::ND;
@@ -145,10 +157,12 @@ struct FastTrack {
     uint32_t bin[ND];         // current bins of the dynamic variables as entry-table indices: ebase + 0-based bin
     float val[NG];            // current continuous values of the gated variables
     DdEntry sent[NS > 0 ? NS : 1];   // entries of the static gated variables
-    uint32_t thr[ND][RPM];    // fast branch: frozen thresholds, complemented (~t); [RP-1] = lead
+    uint32_t thr[ND][RPM];    // fast branch: frozen thresholds, complemented (~t); [RP-1] = lead + ebase
+                              // slow branch: the column at coff[d] exactly as stored
     double thrd[ND][RPM];     // fast branch, F64(d): 2^52 + t (see add_gtd); the lead stays in thr[d][RP-1]
     double leadd[ND];         // EMB_F64ACC: 2^52 + thr[d][RP-1]
     uint32_t cbase[ND];       // slow branch: column offset from the parents that never change
+    uint32_t coff[ND];        // slow branch: offset of the column held in thr[d][] (0xFFFFFFFF: none yet)
     uint32_t ct[ND][ND], c1[ND][ND];   // slow branch: strides of the dynamic parents (uniform)
     int ebase[NG];            // entry-table bases (uniform)
     uint32_t G[NG];           // gate thresholds (uniform)
@@ -230,28 +244,35 @@ struct FastTrack {
                 for (int d = 0; d < ND; ++d) nb[d] = 0;
 #pragma unroll
                 for (int od = 0; od < ND; ++od) {
-                    const int dsel = M.order_dyn[od];   // uniform: which variable is sampled od-th
+                    const int dsel = (int)((ORD >> (2 * od)) & 3u);   // which variable is sampled od-th
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
                         if (dsel == d) {
                             uint32_t o = cbase[d];
 #pragma unroll
                             for (int e2 = 0; e2 < ND; ++e2) o += ct[d][e2] * bin[e2] + c1[d][e2] * nb[e2];   // cbase absorbs ebase
-                            const uint32_t* col = M.thr_trans + o;
-                            uint32_t t[RPM];
+                            // the column of the previous second stays in registers; a lane gathers only when its parent
+                            // configuration changed (a few percent of the track-seconds), so a warp touches a handful of
+                            // L1 lines per second instead of 32 per load
+                            if (__builtin_expect(o != coff[d], 0)) {
+                                coff[d] = o;
+                                const uint32_t* col = M.thr_trans + o;
 #pragma unroll
-                            for (int q = 0; q < SH::RP(d); q += 4) {
+                                for (int q = 0; q < SH::RP(d); q += 4) {
 #if defined(__CUDA_ARCH__)
-                                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(col + q));
-                                t[q] = v4.x; t[q + 1] = v4.y; t[q + 2] = v4.z; t[q + 3] = v4.w;
+                                    const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(col + q));
+                                    thr[d][q] = v4.x; thr[d][q + 1] = v4.y; thr[d][q + 2] = v4.z; thr[d][q + 3] = v4.w;
 #else
-                                t[q] = col[q]; t[q + 1] = col[q + 1]; t[q + 2] = col[q + 2]; t[q + 3] = col[q + 3];
+                                    thr[d][q] = col[q]; thr[d][q + 1] = col[q + 1]; thr[d][q + 2] = col[q + 2]; thr[d][q + 3] = col[q + 3];
 #endif
+                                }
                             }
+                            // thresholds as stored (not complemented): the borrow chain counts downwards; last slot = lead
                             const uint32_t k = W[j * NW + NS + d];
-                            uint32_t b = t[SH::RP(d) - 1] + (uint32_t)ebase[NS + d];
+                            uint32_t c = 0;
 #pragma unroll
-                            for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gt(b, k, ~t[m]);
+                            for (int m = 0; m < SH::R(d) - 1; ++m) c = sub_gt(c, k, thr[d][m]);
+                            const uint32_t b = thr[d][SH::RP(d) - 1] + (uint32_t)ebase[NS + d] - c;
                             nb[d] = b;
                         }
                     }
@@ -310,10 +331,10 @@ struct FastTrack {
     }
 };
 
-template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, class HistInc>
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD, class HistInc>
 EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut& O, int64_t s, const FastShared& S,
                        HistInc hist_inc) {
-    using FT = FastTrack<RS, NG, FAST, HIST, EV, HistInc>;
+    using FT = FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>;
     using SH = DynShape<RS>;
     constexpr int ND = FT::ND, NS = FT::NS;
     const uint64_t sample = P.first_sample + (uint64_t)s;
@@ -382,6 +403,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                     if (!isdyn) o += nd.stride_rp[p] * (uint32_t)x[nd.par[p]];
                 }
                 ft.cbase[d] = o;
+                ft.coff[d] = 0xFFFFFFFFu;
             }
         }
     }
@@ -467,13 +489,24 @@ inline uint32_t fast_shape_of(const DevModel& M) {
     return rs;
 }
 
-// Shapes compiled into libemb200.so: X(RS, NG, FAST).  Anything else runs on k_tracks_generic.
-//   0x070705 = bins (5,7,7): all 7-variable uncor models, uncor v1, littoral, glider/paraglider/fai/paramotor/
-//              skydiving/blimp;  0x070905: dueregard;  0x050707: haa;  0x09090909: cor_v1 / littoral_cor;  0x07: balloons
+// order_transition restricted to the dynamic variables, two bits per position (fast-branch models: 0, never read)
+inline uint32_t order_code(const DevModel& M) {
+    uint32_t c = 0;
+    if (!M.fast)
+        for (int od = 0; od < M.n_dyn && od < 4; ++od) c |= ((uint32_t)M.order_dyn[od] & 3u) << (2 * od);
+    return c;
+}
+constexpr uint32_t order_code_of(int a, int b, int c, int d) { return (uint32_t)(a | (b << 2) | (c << 4) | (d << 6)); }
+
+// Shapes compiled into libemb200.so: X(RS, NG, FAST, ORD).  Anything else runs on k_tracks_generic.
+//   0x070705 = bins (5,7,7): all 7-variable uncor models, blimp (fast branch); glider/paraglider/paramotor/skydiving/
+//              littoral_uncor/uncor_1200code_v1 (slow branch, order dh', dpsi', dv') and fai1/fai5 (dh', dv', dpsi');
+//   0x070905: dueregard;  0x050707: haa;  0x09090909: cor_v1 (slow, file order) / littoral_cor;  0x07: balloons
 #define EMB_FAST_SHAPES(X)                                                                         \
-    X(0x070705u, 3, true) X(0x070705u, 4, true) X(0x070705u, 5, true)                              \
-    X(0x070705u, 3, false) X(0x070705u, 4, false) X(0x070705u, 5, false)                           \
-    X(0x070905u, 5, true) X(0x050707u, 7, true) X(0x09090909u, 4, false) X(0x09090909u, 4, true)   \
-    X(0x07u, 1, true)
+    X(0x070705u, 3, true, 0u) X(0x070705u, 4, true, 0u) X(0x070705u, 5, true, 0u)                   \
+    X(0x070705u, 3, false, order_code_of(1, 2, 0, 0)) X(0x070705u, 3, false, order_code_of(1, 0, 2, 0)) \
+    X(0x070905u, 5, true, 0u) X(0x050707u, 7, true, 0u)                                             \
+    X(0x09090909u, 4, false, order_code_of(0, 1, 2, 3)) X(0x09090909u, 4, true, 0u)                 \
+    X(0x07u, 1, true, 0u)
 
 }  // namespace emb

@@ -27,6 +27,9 @@ namespace {
 #ifndef EMB_MINBLOCKS
 #define EMB_MINBLOCKS 4
 #endif
+#ifndef EMB_MINBLOCKS_SLOW      // slow branch (per-second column gathers): latency-bound, more resident warps help
+#define EMB_MINBLOCKS_SLOW 5
+#endif
 constexpr int BLOCK = EMB_BLOCK;
 
 struct SmemHist {
@@ -113,8 +116,8 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
 }
 
 // ---- tracks, register-resident specialisation (emb_fast.cuh) --------------------------------------
-template <uint32_t RS, int NG, bool FAST, bool HIST, int EV>
-__global__ void __launch_bounds__(BLOCK, EMB_MINBLOCKS)
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD>
+__global__ void __launch_bounds__(BLOCK, FAST ? EMB_MINBLOCKS : EMB_MINBLOCKS_SLOW)
 k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
               const __grid_constant__ TrackOut O) {
     __shared__ FastShared S;
@@ -124,7 +127,7 @@ k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sample
         for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) track_fast<RS, NG, FAST, HIST, EV>(M, P, O, s, S, SmemHist{sh});
+    if (s < P.n) track_fast<RS, NG, FAST, HIST, EV, ORD>(M, P, O, s, S, SmemHist{sh});
     if (HIST) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
@@ -277,15 +280,16 @@ int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, v
     const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
     const uint32_t rs = g_force_generic ? 0u : fast_shape_of(M);
     const bool fast = M.fast != 0;
+    const uint32_t ord = order_code(M);
     const bool hist = O.hist_initial || O.hist_transition;
     const int ev = O.ev_counts ? 1 : O.events ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
     bool done = false;
-#define EMB_X(RS_, NG_, FAST_)                                                                          \
-    if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_)) {                                \
-        if (ev == 1) k_tracks_fast<RS_, NG_, FAST_, false, 1><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);      \
-        else if (ev == 2) k_tracks_fast<RS_, NG_, FAST_, false, 2><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
-        else if (hist) k_tracks_fast<RS_, NG_, FAST_, true, 0><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);     \
-        else k_tracks_fast<RS_, NG_, FAST_, false, 0><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);              \
+#define EMB_X(RS_, NG_, FAST_, ORD_)                                                                    \
+    if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_) && ord == (ORD_)) {               \
+        if (ev == 1) k_tracks_fast<RS_, NG_, FAST_, false, 1, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);      \
+        else if (ev == 2) k_tracks_fast<RS_, NG_, FAST_, false, 2, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
+        else if (hist) k_tracks_fast<RS_, NG_, FAST_, true, 0, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);     \
+        else k_tracks_fast<RS_, NG_, FAST_, false, 0, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);              \
         done = true;                                                                                    \
     }
     EMB_FAST_SHAPES(EMB_X)

@@ -145,9 +145,9 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
         const bool fast = D.fast != 0;
         static FastShared S;
         fast_fill_shared(D, S, 0, 1);
-#define EMB_X(RS_, NG_, FAST_)                                                         \
-    if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_)) {               \
-        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_, true, 0>(D, P, O, s, S, hh); \
+#define EMB_X(RS_, NG_, FAST_, ORD_)                                                   \
+    if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_) && order_code(D) == (ORD_)) { \
+        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_, true, 0, ORD_>(D, P, O, s, S, hh); \
         done = true;                                                                   \
     }
         EMB_FAST_SHAPES(EMB_X)
@@ -188,11 +188,11 @@ int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, i
             O.events = reinterpret_cast<uint2*>(events);
         }
         bool done = false;
-#define EMB_X(RS_, NG_, FAST_)                                                                          \
-    if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_)) {                                \
+#define EMB_X(RS_, NG_, FAST_, ORD_)                                                                    \
+    if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_) && order_code(D) == (ORD_)) {     \
         for (int64_t s = 0; s < n; ++s) {                                                               \
-            if (pass == 1) track_fast<RS_, NG_, FAST_, false, 1>(D, P, O, s, S, hh);                    \
-            else track_fast<RS_, NG_, FAST_, false, 2>(D, P, O, s, S, hh);                              \
+            if (pass == 1) track_fast<RS_, NG_, FAST_, false, 1, ORD_>(D, P, O, s, S, hh);              \
+            else track_fast<RS_, NG_, FAST_, false, 2, ORD_>(D, P, O, s, S, hh);                        \
         }                                                                                               \
         done = true;                                                                                    \
     }
