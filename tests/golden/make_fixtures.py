@@ -39,6 +39,14 @@ MODELS = {
     "uncor_allcode_fwsingle_v1": "uncor_allcode_fwsingle_v1.txt",
     "uncor_1200only_fwse_v1p2": "uncor_1200only_fwse_v1p2.txt",
     "terminal_v3_radar_encounter_model": "correlated_terminal/terminalradar/terminal_v3_radar_encounter_model.txt",
+    # one model per remaining compiled kernel shape (GPU tests compare them with the C oracle; no golden vectors)
+    "fai1_v1": "fai1_v1.txt",                      # slow branch, order dh', dv', dpsi'
+    "uncor_1200code_v1": "uncor_1200code_v1.txt",  # slow branch, 6 initial variables
+    "blimp_v1": "blimp_v1.txt",                    # fast branch, 3 gated variables
+    "dueregard_v1": "dueregard_v1.txt",            # bins (5,9,7)
+    "haa_v1": "haa_v1.txt",                        # bins (7,7,5), 9 initial variables, 7 gated
+    "littoral_cor_v1": "littoral_cor_v1.txt",      # 4 dynamic variables, fast branch
+    "weatherballoon_v1": "weatherballoon_v1.txt",  # 1 dynamic variable
 }
 
 
@@ -84,6 +92,9 @@ def main():
         for k, v in pack_model(p).items():
             models[name + "/" + k] = v
     np.savez_compressed(os.path.join(HERE, "models.npz"), **models)
+    if "--models-only" in sys.argv:
+        print("models.npz", os.path.getsize(os.path.join(HERE, "models.npz")))
+        return
 
     vec = {}
 

@@ -161,7 +161,11 @@ def test_preset_dependent_variable_is_rejected(model_paths):
 
 
 @pytest.mark.parametrize("model,uncor,n,T", [("uncor_allcode_fwsingle_v1", True, 300, 600), ("glider_v1", True, 400, 150),
-                                             ("cor_v1", False, 300, 60), ("uncor_1200only_fwse_v1p2", True, 300, 100)])
+                                             ("cor_v1", False, 300, 60), ("uncor_1200only_fwse_v1p2", True, 300, 100),
+                                             ("fai1_v1", True, 300, 100), ("uncor_1200code_v1", True, 200, 100),
+                                             ("blimp_v1", True, 300, 100), ("dueregard_v1", True, 200, 100),
+                                             ("haa_v1", True, 200, 100), ("littoral_cor_v1", False, 200, 60),
+                                             ("weatherballoon_v1", False, 300, 60)])
 @pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
 def test_tracks_match_c_oracle(model_paths, model, uncor, n, T, fast):
     """Host emulation of the device code against the plain-C restatement at a few 10^4..10^5 track-seconds."""
@@ -183,6 +187,7 @@ def test_tracks_match_c_oracle(model_paths, model, uncor, n, T, fast):
     rates = np.asarray(p.resample_rates)
     tv = sorted(set(dyn) | {i for i in range(p.n_initial) if rates[i] > 0})
     got = m.sample_tracks(p.n_initial, len(dyn), len(tv), n, T, 92, 7 * 10 ** 10, H.EmuModel.opts(p.n_initial, **kw))
+    assert lib.emu_last_fast() == fast, "every shipped model shape has a specialised kernel (EMB_FAST_SHAPES)"
     lib.emu_use_fast(0)
     assert np.array_equal(got["init_bins"], ref["init_bins"]) and np.array_equal(got["init_values"], ref["init_values"])
     assert np.array_equal(got["attempts"].astype(np.int64), ref["attempts"].astype(np.int64))

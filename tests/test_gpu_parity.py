@@ -205,7 +205,11 @@ def test_tracks_match_live_oracle(model_paths, model, n, T, seed):
 
 SWEEP = [("uncor_1200code_v2p1", True, 4000, 300), ("uncor_allcode_fwsingle_v1", True, 2000, 600),
          ("uncor_1200only_fwse_v1p2", True, 3000, 200), ("glider_v1", True, 3000, 200), ("paramotor_v1", True, 3000, 150),
-         ("littoral_uncor_v1", True, 3000, 120), ("cor_v1", False, 3000, 60), ("balloon_v1", False, 5000, 100)]
+         ("littoral_uncor_v1", True, 3000, 120), ("cor_v1", False, 3000, 60), ("balloon_v1", False, 5000, 100),
+         # one model per remaining compiled shape of k_tracks_fast (emb_fast.cuh: EMB_FAST_SHAPES)
+         ("fai1_v1", True, 3000, 150), ("uncor_1200code_v1", True, 2000, 200), ("blimp_v1", True, 3000, 150),
+         ("dueregard_v1", True, 2000, 200), ("haa_v1", True, 2000, 200), ("littoral_cor_v1", False, 2000, 120),
+         ("weatherballoon_v1", False, 4000, 100)]
 
 
 @pytest.mark.parametrize("model,uncor,n,T", SWEEP)
@@ -218,6 +222,7 @@ def test_tracks_match_c_oracle_mid_scale(model_paths, model, uncor, n, T):
     assert ref["rc"] == 0
     m = (UncorEncounterModel if uncor else EncounterModel)(model_paths[model])
     got = m.sample_compact(n, T, seed=91, first_sample=10 ** 12) if uncor else m.sample_tracks(n, T, seed=91, first_sample=10 ** 12)
+    assert L.lib().emb_debug_last_kernel_fast() == 1, "no specialised kernel for this model shape"
     dyn = [int(v) - 1 for v in np.asarray(p.temporal_map)[:, 0]]
     tv = [v - 1 for v in got.tv_vars]
     assert np.array_equal(np.asarray(got.init_bins).T, ref["init_bins"])
