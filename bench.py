@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tracks", type=int, default=TRACKS_PER_GPU, help="tracks per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,10 +264,14 @@ def main():
         L.check(lib.emb_sample_track_events(m._h, C.byref(rng), n, T, C.byref(o), cap, h_ev.data_ptr(), h_off.data_ptr(),
                                             C.byref(init_only), C.byref(tot)))
     events_call(7)
+    events_call(8)      # two warm-up calls: the first one also fills the library's device memory pool
     barrier()
+    ev_steps = []
     t0 = time.perf_counter()
     for k in range(args.e2e_steps):
+        t1 = time.perf_counter()
         events_call(3000 + k)
+        ev_steps.append((time.perf_counter() - t1) * 1e3)
     barrier()
     ev_s = time.perf_counter() - t0
     t = torch.tensor([ev_s], dtype=torch.float64, device=dev)
@@ -294,6 +298,18 @@ def main():
         torch.cuda.synchronize()
         other["configs[1] glider_v1 initial network only, 100M samples, int8 bins"] = {
             "value": 3 * n2 / (e0.elapsed_time(e1) * 1e-3), "unit": "samples/s"}
+        # the same with the de-discretised values (bn_sample + dediscretize): SURVEY 8d counts 5*(1+4) = 25 B per sample
+        g.sample_initial(n2, seed=1, device=dev, want_values=True, want_attempts=False)
+        torch.cuda.synchronize()
+        e0.record()
+        for k in range(3):
+            g.sample_initial(n2, seed=2 + k, device=dev, want_values=True, want_attempts=False)
+        e1.record()
+        torch.cuda.synchronize()
+        v2 = 3 * n2 / (e0.elapsed_time(e1) * 1e-3)
+        other["configs[1] glider_v1 initial network only, 100M samples, int8 bins + fp64 values"] = {
+            "value": v2, "unit": "samples/s", "algorithmic_bytes_per_unit": 25.0, "written_bytes_per_unit": 45.0,
+            "roofline_frac": v2 * 25.0 / 1e9 / peaks()[0]}
         del g
         torch.cuda.empty_cache()
 
@@ -316,7 +332,10 @@ def main():
         r4 = cm.sample_tracks(n4, T4, seed=1, device=dev)
         dt = timed(lambda k: cm.sample_tracks(n4, T4, seed=10 + k, device=dev, out=r4))
         other["configs[3] cor_v1 (stand-in for the missing cor_v2p1), 10M encounters x 60 s, dense compact outputs"] = {
-            "value": n4 * T4 / dt, "unit": "track-timesteps/s", "ms": dt * 1e3}
+            "value": n4 * T4 / dt, "unit": "track-timesteps/s", "ms": dt * 1e3,
+            # 4*(1+4) B per step + (16*(1+4) + 4*(99+36)) B per track
+            "algorithmic_bytes_per_unit": 20.0 + (80.0 + 540.0) / T4,
+            "roofline_frac": n4 * T4 / dt * (20.0 + 620.0 / T4) / 1e9 / peaks()[0]}
         del r4, cm
         torch.cuda.empty_cache()
 
@@ -337,7 +356,10 @@ def main():
         other["configs[4] CorTerminalModel 1M encounters: sample (geometry) + createEncounter chains, tmax 120 s, synthetic "
               "trajectory DBNs"] = {"value": states / dt_traj, "unit": "trajectory states/s", "ms_chains": dt_traj * 1e3,
                                     "ms_geometry": dt_geo * 1e3, "encounters_per_s": n5 / (dt_traj + dt_geo),
-                                    "states_per_encounter": states / n5}
+                                    "states_per_encounter": states / n5,
+                                    # 5 fp32 fields per state written; the chains are fp64-trigonometry bound, not HBM bound
+                                    "algorithmic_bytes_per_unit": 20.0,
+                                    "roofline_frac": states / dt_traj * 20.0 / 1e9 / peaks()[0]}
         del r5, geo, vals, tm
         torch.cuda.empty_cache()
 
@@ -369,6 +391,7 @@ def main():
         # reference itself returns, UncorEncounterModel.m:253-300) through emb_sample_track_events with pinned HOST buffers
         "e2e": {"value": e2e_events_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400,
                 "d2h_bytes_per_step": ev_d2h, "steps": args.e2e_steps,
+                "ms_per_step": [round(x, 2) for x in ev_steps],
                 "contract": "UncorEncounterModel.sample outputs: sparse out_events rows (8 B) + offsets + out_inits in host memory, "
                             "emb_sample_track_events (count pass, prefix sum, write pass, D2H inside the timed region)"},
         "e2e_dense": {"value": e2e_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400, "d2h_bytes_per_step": d2h,

@@ -3,7 +3,9 @@
 #include <cuda_runtime_api.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -94,6 +96,28 @@ int pick_device(const emb_sample_opts* o, int& device) {
 }
 
 // Device-side staging for host-memory callers.
+// Per-call temporaries (staging buffers, counts, event rows) come from the device's stream-ordered memory pool with an
+// unlimited release threshold: repeated calls reuse the same memory instead of paying cudaMalloc/cudaFree (several ms per GB,
+// and an implicit device synchronisation) inside every call.  Model tables stay plain cudaMalloc.
+cudaError_t tmp_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static thread_local int configured_for = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_for != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured_for = dev;
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+void tmp_free(void* p) {
+    if (p) cudaFreeAsync(p, 0);   // every entry point has synchronised its streams before temporaries die
+}
+
 struct Staged {
     void* host = nullptr;
     void* dev = nullptr;
@@ -106,7 +130,7 @@ struct Stager {
     std::vector<Staged> items;
     ~Stager() {
         for (auto& s : items)
-            if (s.owned && s.dev) cudaFree(s.dev);
+            if (s.owned && s.dev) tmp_free(s.dev);
     }
     // returns the device pointer to use for a caller buffer (nullptr stays nullptr)
     int out(void* user, size_t bytes, bool zero, void** dev) {
@@ -120,14 +144,19 @@ struct Stager {
         s.host = user;
         s.bytes = bytes;
         s.owned = true;
-        CU(cudaMalloc(&s.dev, bytes));
+        CU(tmp_alloc(&s.dev, bytes, stream));
         if (zero) CU(cudaMemcpyAsync(s.dev, user, bytes, cudaMemcpyHostToDevice, stream));  // accumulate (+=) semantics
         items.push_back(s);
         *dev = s.dev;
         return 0;
     }
+    void already_copied(void* user) {   // the caller's buffer was filled early (event offsets): finish() skips it
+        for (auto& s : items)
+            if (s.host == user) s.host = nullptr;
+    }
     int finish() {
-        for (auto& s : items) CU(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, stream));
+        for (auto& s : items)
+            if (s.host) CU(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         return 0;
     }
@@ -402,17 +431,17 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     if ((rc = sg.out(values, (size_t)n * H.n_initial * 8, false, (void**)&d_vals))) return rc;
     if ((rc = sg.out(attempts, (size_t)n * 2, false, (void**)&d_att))) return rc;
     int32_t* d_status = nullptr;
-    CU(cudaMalloc((void**)&d_status, 4));
+    CU(tmp_alloc((void**)&d_status, 4, st));
     CU(cudaMemsetAsync(d_status, 0, 4, st));
     cudaError_t e = (cudaError_t)emb::launch_initial(D, P, (int)H.thr_initial.size(), d_bins, d_vals, d_att, nullptr, d_status, st);
     if (e != cudaSuccess) {
-        cudaFree(d_status);
+        tmp_free(d_status);
         return cuda_fail(e, "launch k_initial");
     }
     int32_t status = 0;
     e = cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_status);
+    tmp_free(d_status);
     if (e != cudaSuccess) return cuda_fail(e, "k_initial");
     if ((rc = sg.finish())) return rc;
     if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
@@ -461,22 +490,35 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     if ((rc = sg.out(out->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
     if ((rc = sg.out(out->hist_initial, ni * 64 * 8, true, (void**)&O.hist_initial))) return rc;
     if ((rc = sg.out(out->hist_transition, H.temporal_map.size() * 64 * 8, true, (void**)&O.hist_transition))) return rc;
-    CU(cudaMalloc((void**)&O.status, 4));
+    CU(tmp_alloc((void**)&O.status, 4, st));
     CU(cudaMemsetAsync(O.status, 0, 4, st));
     cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);
     if (e != cudaSuccess) {
-        cudaFree(O.status);
+        tmp_free(O.status);
         return cuda_fail(e, "launch k_tracks");
     }
     int32_t status = 0;
     e = cudaMemcpyAsync(&status, O.status, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(O.status);
+    tmp_free(O.status);
     if (e != cudaSuccess) return cuda_fail(e, "k_tracks");
     if ((rc = sg.finish())) return rc;
     if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
     return 0;
 }
+
+// EMB200_TRACE=1: host-side phase times of emb_sample_track_events on stderr (diagnostics for the e2e number)
+struct PhaseTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTrace() : on(std::getenv("EMB200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[emb200] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
                             int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
@@ -508,6 +550,7 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         else offsets[0] = 0;
         return 0;
     }
+    PhaseTrace tr;
     Stager sg{opts->mem, st, {}};
     const size_t ni = (size_t)H.n_initial;
     emb::TrackOut O{};
@@ -520,11 +563,11 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     }
     struct Scratch {
         void* p = nullptr;
-        ~Scratch() { if (p) cudaFree(p); }
+        ~Scratch() { tmp_free(p); }
     } counts, status, tiles;
-    CU(cudaMalloc(&counts.p, (size_t)n * 4));
-    CU(cudaMalloc(&tiles.p, (size_t)emb::scan_scratch_len(n) * 8));
-    CU(cudaMalloc(&status.p, 4));
+    CU(tmp_alloc(&counts.p, (size_t)n * 4, st));
+    CU(tmp_alloc(&tiles.p, (size_t)emb::scan_scratch_len(n) * 8, st));
+    CU(tmp_alloc(&status.p, 4, st));
     CU(cudaMemsetAsync(status.p, 0, 4, st));
     O.status = (int32_t*)status.p;
     // pass 1: rows per track (also writes the per-track initial outputs), then the prefix sum
@@ -538,6 +581,7 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     CU(cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&flag, status.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    tr.mark("alloc + count pass + scan");
     if (total_rows) *total_rows = total;
     if (flag) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
     if (total > capacity) {
@@ -568,14 +612,18 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         ~Guard() {
             for (auto& d : done) if (d) cudaEventDestroy(d);
             if (copy) cudaStreamDestroy(copy);
-            if (dev) cudaFree(dev);
+            tmp_free(dev);
         }
     } g;
-    CU(cudaMalloc(&g.dev, (size_t)total * 8));
+    CU(tmp_alloc(&g.dev, (size_t)total * 8, st));
     CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-    std::vector<long long> h_off((size_t)n + 1);
-    CU(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    tr.mark("cudaMalloc rows");
+    // the offsets go straight into the caller's buffer (they also say which rows each chunk produced)
+    const int64_t* h_off = offsets;
+    CU(cudaMemcpyAsync(offsets, d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    sg.already_copied(offsets);
+    tr.mark("offsets to host");
     const int chunks = 8;
     for (int c = 0; c < chunks; ++c) {
         const int64_t a = n * c / chunks, b = n * (c + 1) / chunks;
@@ -591,12 +639,15 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         CU(cudaEventCreateWithFlags(&g.done[c], cudaEventDisableTiming));
         CU(cudaEventRecord(g.done[c], st));
         CU(cudaStreamWaitEvent(g.copy, g.done[c], 0));
-        const long long r0 = h_off[(size_t)a], r1 = h_off[(size_t)b];
+        const long long r0 = (long long)h_off[(size_t)a], r1 = (long long)h_off[(size_t)b];
         if (r1 > r0)
             CU(cudaMemcpyAsync(events + r0, (const char*)g.dev + (size_t)r0 * 8, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, g.copy));
     }
+    tr.mark("enqueue write chunks");
     if ((rc = sg.finish())) return rc;          // offsets and per-track outputs, on the caller's stream
+    tr.mark("finish (offsets, inits D2H)");
     CU(cudaStreamSynchronize(g.copy));
+    tr.mark("rows D2H drained");
     return 0;
 }
 
@@ -661,20 +712,20 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
     Stager sg{opts->mem, st, {}};
     struct Scratch {
         void* p = nullptr;
-        ~Scratch() { if (p) cudaFree(p); }
+        ~Scratch() { tmp_free(p); }
     } d_geo, d_status;
     if (opts->mem == EMB_MEM_DEVICE) {
         P.geo = geo;
     } else {   // stage the rows that are read
         const size_t bytes = (size_t)(max_row + 1) * (size_t)geo_stride * 8;
-        CU(cudaMalloc(&d_geo.p, bytes));
+        CU(tmp_alloc(&d_geo.p, bytes, st));
         CU(cudaMemcpyAsync(d_geo.p, geo, bytes, cudaMemcpyHostToDevice, st));
         P.geo = (const double*)d_geo.p;
     }
     emb::TermOut O{};
     if ((rc = sg.out(out->traj, (size_t)emb_terminal_traj_len(n, tmax_s) * 4, false, (void**)&O.traj))) return rc;
     if ((rc = sg.out(out->len, (size_t)n * 4 * 2, false, (void**)&O.len))) return rc;
-    CU(cudaMalloc(&d_status.p, 4));
+    CU(tmp_alloc(&d_status.p, 4, st));
     CU(cudaMemsetAsync(d_status.p, 0, 4, st));
     O.status = (int32_t*)d_status.p;
     cudaError_t e = (cudaError_t)emb::launch_terminal(P, O, st);
@@ -726,7 +777,7 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
     Stager sg{opts->mem, st, {}};
     struct Scratch {
         void* p = nullptr;
-        ~Scratch() { if (p) cudaFree(p); }
+        ~Scratch() { tmp_free(p); }
     } d_init, d_vals;
     const size_t init_bytes = (size_t)H.n_initial * (size_t)n * 8;
     const size_t val_bytes = (size_t)emb_tracks_values_len(m, n, T) * 4;
@@ -734,8 +785,8 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
         P.init_values = init_values;
         P.values = values;
     } else {
-        CU(cudaMalloc(&d_init.p, init_bytes));
-        CU(cudaMalloc(&d_vals.p, val_bytes));
+        CU(tmp_alloc(&d_init.p, init_bytes, st));
+        CU(tmp_alloc(&d_vals.p, val_bytes, st));
         CU(cudaMemcpyAsync(d_init.p, init_values, init_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_vals.p, values, val_bytes, cudaMemcpyHostToDevice, st));
         P.init_values = (const double*)d_init.p;
@@ -765,15 +816,15 @@ int emb_terminal_screen(const float* traj, const int16_t* len, int64_t n, double
     P.thres_altlow_ft = thres_altlow_ft;
     struct Scratch {
         void* p = nullptr;
-        ~Scratch() { if (p) cudaFree(p); }
+        ~Scratch() { tmp_free(p); }
     } d_traj, d_len;
     const size_t tb = (size_t)emb_terminal_traj_len(n, tmax_s) * 4, lb = (size_t)n * 4 * 2;
     if (opts->mem == EMB_MEM_DEVICE) {
         P.traj = traj;
         P.len = len;
     } else {
-        CU(cudaMalloc(&d_traj.p, tb));
-        CU(cudaMalloc(&d_len.p, lb));
+        CU(tmp_alloc(&d_traj.p, tb, st));
+        CU(tmp_alloc(&d_len.p, lb, st));
         CU(cudaMemcpyAsync(d_traj.p, traj, tb, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_len.p, len, lb, cudaMemcpyHostToDevice, st));
         P.traj = (const float*)d_traj.p;
