@@ -263,8 +263,8 @@ def main():
         rng = L.Rng(seed, rank * n)
         L.check(lib.emb_sample_track_events(m._h, C.byref(rng), n, T, C.byref(o), cap, h_ev.data_ptr(), h_off.data_ptr(),
                                             C.byref(init_only), C.byref(tot)))
-    events_call(7)
-    events_call(8)      # two warm-up calls: the first one also fills the library's device memory pool
+    for k in range(max(3, args.warmup)):      # warm-up calls: the first one also fills the library's device memory pool
+        events_call(7 + k)
     barrier()
     ev_steps = []
     t0 = time.perf_counter()
