@@ -107,27 +107,12 @@ EMB_HD uint32_t add_gtd(uint32_t acc, double kb, double td) {
 #endif
 }
 
-// carry-free variant without any integer instruction: s = (2^52 + k) + (~t - 2^52) = k + ~t exactly, and
-// fma_rz(s, 2^-32, acc) adds floor(s / 2^32) = [k > t] to an accumulator that carries 2^52 (its low word is the count)
-EMB_HD double acc_gtd(double acc, double kb, double ntd) {
-#if defined(__CUDA_ARCH__)
-    return __fma_rz(__dadd_rn(kb, ntd), 2.3283064365386963e-10, acc);
-#else
-    return acc + (double)(uint64_t)((kb + ntd) * 2.3283064365386963e-10);
-#endif
-}
-
-// bit d set: the thresholds of dynamic variable d are compared on the fp64 pipe (fast branch only);
-// EMB_F64N: only the first EMB_F64N thresholds of such a variable (the rest stay on the carry chain);
-// EMB_F64ACC: use acc_gtd instead of add_gtd
+// bit d set: the thresholds of dynamic variable d are compared on the fp64 pipe (fast branch only).  6 = the two 7-bin
+// variables of the (5,7,7) shapes; the 5-bin variable stays on the carry chain, which balances the alu, fma and fp64 pipes
+// (tools/ubench/ubench3.cu and profiles/r1_ubench_fp64_compare.txt hold the measurements, including an all-fp64
+// DADD + DFMA.RZ accumulator that needs no integer instruction but was slower)
 #ifndef EMB_F64CMP
 #define EMB_F64CMP 6
-#endif
-#ifndef EMB_F64N
-#define EMB_F64N 99
-#endif
-#ifndef EMB_F64ACC
-#define EMB_F64ACC 0
 #endif
 
 EMB_HD float fmaf_rn(float a, float b, float c) {
@@ -148,7 +133,7 @@ struct FastTrack {
     static constexpr int NS = NG - ND;   // gated variables that are not dynamic (their bin never changes)
     static constexpr int NW = NG;        // stream spec v3: one word per (second, gated variable)
     static constexpr int RPM = SH::RPMAX;
-    static constexpr bool F64(int d, int m = 0) { return FAST && ((EMB_F64CMP >> d) & 1) != 0 && m < EMB_F64N; }
+    static constexpr bool F64(int d) { return FAST && ((EMB_F64CMP >> d) & 1) != 0; }
 
     const DevModel& M;
     const SampleParams& P;
@@ -160,7 +145,6 @@ struct FastTrack {
     uint32_t thr[ND][RPM];    // fast branch: frozen thresholds, complemented (~t); [RP-1] = lead + ebase
                               // slow branch: the column at coff[d] exactly as stored
     double thrd[ND][RPM];     // fast branch, F64(d): 2^52 + t (see add_gtd); the lead stays in thr[d][RP-1]
-    double leadd[ND];         // EMB_F64ACC: 2^52 + thr[d][RP-1]
     uint32_t cbase[ND];       // slow branch: column offset from the parents that never change
     uint32_t coff[ND];        // slow branch: offset of the column held in thr[d][] (0xFFFFFFFF: none yet)
     uint32_t ct[ND][ND], c1[ND][ND];   // slow branch: strides of the dynamic parents (uniform)
@@ -218,25 +202,12 @@ struct FastTrack {
                     uint32_t b = thr[d][SH::RP(d) - 1];
                     if (F64(d)) {
                         const double kb = biased_double(k);
-                        if (EMB_F64ACC) {
-                            double a = leadd[d];
 #pragma unroll
-                            for (int m = 0; m < SH::R(d) - 1; ++m)
-                                if (F64(d, m)) a = acc_gtd(a, kb, thrd[d][m]);
-#if defined(__CUDA_ARCH__)
-                            b = (uint32_t)__double2loint(a);
-#else
-                            b = (uint32_t)(uint64_t)(a - 4503599627370496.0);
-#endif
-                        } else {
+                        for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gtd(b, kb, thrd[d][m]);
+                    } else {
 #pragma unroll
-                            for (int m = 0; m < SH::R(d) - 1; ++m)
-                                if (F64(d, m)) b = add_gtd(b, kb, thrd[d][m]);
-                        }
+                        for (int m = 0; m < SH::R(d) - 1; ++m) b = add_gt(b, k, thr[d][m]);
                     }
-#pragma unroll
-                    for (int m = 0; m < SH::R(d) - 1; ++m)
-                        if (!F64(d, m)) b = add_gt(b, k, thr[d][m]);
                     nb[d] = act ? b : bin[d];
                 }
             } else if (act) {
@@ -388,9 +359,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                 const uint32_t* col = node_column(M.dyn[d], M.thr_trans, x);
 #pragma unroll
                 for (int m = 0; m < SH::RP(d); ++m) {
-                    if (m == SH::RP(d) - 1) ft.leadd[d] = biased_double(ldg32(col + m) + (uint32_t)ft.ebase[NS + d]);
-                    if (FT::F64(d, m) && m < SH::RP(d) - 1)
-                        ft.thrd[d][m] = EMB_F64ACC ? (double)(~ldg32(col + m)) - 4503599627370496.0 : biased_double(ldg32(col + m));
+                    if (FT::F64(d) && m < SH::RP(d) - 1) ft.thrd[d][m] = biased_double(ldg32(col + m));
                     else ft.thr[d][m] = m < SH::RP(d) - 1 ? ~ldg32(col + m) : ldg32(col + m) + (uint32_t)ft.ebase[NS + d];
                 }
             } else {
