@@ -226,9 +226,19 @@ EMB_HD double ldg64(const double* p) {
 #endif
 }
 
+// acc - [k > t] for a threshold as stored: k > t  <=>  t - k borrows (sub.cc / subc: two instructions, no compare+select)
+EMB_HD uint32_t sub_gt(uint32_t acc, uint32_t k, uint32_t t) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .u32 d;\n\tsub.cc.u32 d, %2, %1;\n\tsubc.u32 %0, %0, 0;\n\t}" : "+r"(acc) : "r"(k), "r"(t));
+    return acc;
+#else
+    return acc - (k > t ? 1u : 0u);
+#endif
+}
+
 // 0-based bin of word k in a packed column (rp slots, 16-byte aligned).
 EMB_HD int select_bin(const uint32_t* col, int rp, uint32_t k) {
-    int bin = 0;
+    uint32_t neg = 0, lead = 0;   // neg = minus the number of thresholds below k
     for (int q = 0; q < rp; q += 4) {
 #if defined(__CUDA_ARCH__)
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(col + q));
@@ -236,10 +246,10 @@ EMB_HD int select_bin(const uint32_t* col, int rp, uint32_t k) {
 #else
         const uint32_t a = col[q], b = col[q + 1], c = col[q + 2], d = col[q + 3];
 #endif
-        bin += (k > a) + (k > b) + (k > c);
-        if (q + 4 < rp) bin += (k > d); else bin += (int)d;   // last slot holds `lead`
+        neg = sub_gt(sub_gt(sub_gt(neg, k, a), k, b), k, c);
+        if (q + 4 < rp) neg = sub_gt(neg, k, d); else lead = d;   // last slot holds `lead`
     }
-    return bin;
+    return (int)(lead - neg);
 }
 
 // column address of a node given the state vector

@@ -78,16 +78,6 @@ EMB_HD uint32_t add_gt(uint32_t acc, uint32_t k, uint32_t nt) {
 #endif
 }
 
-// acc - [k > t] for a threshold that is not complemented: k > t  <=>  t - k borrows
-EMB_HD uint32_t sub_gt(uint32_t acc, uint32_t k, uint32_t t) {
-#if defined(__CUDA_ARCH__)
-    asm("{\n\t.reg .u32 d;\n\tsub.cc.u32 d, %2, %1;\n\tsubc.u32 %0, %0, 0;\n\t}" : "+r"(acc) : "r"(k), "r"(t));
-    return acc;
-#else
-    return acc - (k > t ? 1u : 0u);
-#endif
-}
-
 // The same count on the otherwise idle fp64 pipe: with kb = 2^52 + k and td = 2^52 + t (both exact: the word sits in
 // the low half of the mantissa under the high word 0x43300000) the double compare kb > td *is* the integer compare
 // k > t.  SASS: one DSETP (fp64 pipe) + one predicated add that ptxas places on whichever integer pipe is free.

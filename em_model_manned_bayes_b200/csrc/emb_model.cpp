@@ -617,6 +617,25 @@ void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M) {
         M.spd_hi = e1;
     }
     M.dist_max = H.bounds_initial[M.i_dist].second;
+    // pseudo-angles of the bearing cutpoints (emb_terminal.cuh: term_bearing_bin); bearings live in [0, 360)
+    const auto& eb = H.boundaries[M.i_bear];
+    const int rb = H.r_initial[M.i_bear];
+    M.n_bear_pc = -1;
+    if (!eb.empty() && rb - 1 <= TERM_PC_MAX) {
+        M.n_bear_pc = rb - 1;
+        for (int j = 1; j < rb; ++j) {
+            const double c = eb[(size_t)j];
+            double pc;
+            if (c <= 0.0) pc = -1.0;                                            // every bearing is >= this cutpoint
+            else if (c >= 360.0) pc = std::numeric_limits<double>::infinity();  // none is
+            else {
+                double sn, cs;
+                sincosd(c, sn, cs);
+                pc = pseudo_angle(cs, sn);
+            }
+            M.bear_pc[j - 1] = pc;
+        }
+    }
 }
 
 }  // namespace emb

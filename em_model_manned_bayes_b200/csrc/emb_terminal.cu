@@ -17,10 +17,22 @@ namespace {
 
 constexpr int TERM_BLOCK = 128;
 
-__global__ void __launch_bounds__(TERM_BLOCK, 6)
+#ifndef EMB_TERM_MINBLOCKS
+#define EMB_TERM_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(TERM_BLOCK, EMB_TERM_MINBLOCKS)
 k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ TermOut O) {
+    // the bearing cutpoints of the (up to three) models this block's chain can use: the binary search of every lane reads them
+    // at its own index, which shared memory serves and the constant bank would serialise
+    __shared__ double pc[3 * TERM_PC_MAX];
+    const int chain = (int)blockIdx.y, ac = chain >> 1, dir = chain & 1;
+    for (int q = threadIdx.x; q < 3 * TERM_PC_MAX; q += blockDim.x) {
+        const int it = q / TERM_PC_MAX, j = q % TERM_PC_MAX;
+        pc[q] = it < (ac ? 3 : 2) ? P.m[(ac ? 4 : 0) + it * 2 + dir].bear_pc[j] : 0.0;
+    }
+    __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) terminal_chain(P, O, s, (int)blockIdx.y);
+    if (s < P.n) terminal_chain(P, O, s, chain, pc);
 }
 
 // first-order track integration (emb_integrate.cuh): thread = track, HBM-bound (12 B read + 12 B written per track-second)

@@ -21,6 +21,7 @@ constexpr uint32_t P_TERM_SEL = 5, P_TERM_DD = 6;
 constexpr int TERM_NMODELS = 10;   // own {landing, takeoff} x {fwd, bck}, intruder {landing, takeoff, transit} x {fwd, bck}
 constexpr int TERM_FIELDS = 5;     // x_nm, y_nm, z_ft, heading_deg, v_ft_s  (t_s is the slot index)
 constexpr double TERM_FT_PER_NM = 6076.1154855643;   // createEncounter.m:172
+constexpr int TERM_PC_MAX = 48;    // bearing cutpoints held as pseudo-angles (r - 1 <= 47)
 
 // what a chain needs from one trajectory model (built on the host from HostModel::dev)
 struct TermModel {
@@ -38,6 +39,13 @@ struct TermModel {
     int32_t spd_lo, spd_hi;   // discreteValidV   = spd_lo..spd_hi   (:123-125), lo > hi = empty
     int32_t pad_;
     double dist_max;          // bounds_initial(idx.dist, 2)         (:263, :310)
+    // Bearing cell without atan2 (CreateStartDistribution :277/:293 only needs the *bin* of wrapTo360(atan2d(y, x))): the
+    // pseudo-angle p(x, y) = y >= 0 ? 1 - x/(|x|+|y|) : 3 + x/(|x|+|y|) is strictly increasing in the bearing over [0, 360),
+    // so #{j : bearing >= cut_j} = #{j : p(x, y) >= p(cosd cut_j, sind cut_j)}.  n_bear_pc = r - 1 cutpoints, or -1 when the
+    // variable has no boundaries or too many bins (then the bin comes from atan2d as in the reference).
+    int32_t n_bear_pc;
+    int32_t pad2_;
+    double bear_pc[TERM_PC_MAX];
 };
 
 struct TermLimits {           // @CorTerminalModel/getDynamicLimits.m:14-62
@@ -65,7 +73,8 @@ struct TermOut {
 
 // ---- MATLAB built-ins as restated by the oracle (oracle/terminal.py) --------------------------------
 EMB_HD void sincosd(double x, double& s, double& c) {
-    const double r = ::fmod(x, 360.0);
+    // fmod(x, 360) is x itself for |x| < 360 (every angle this path produces); fmod proper is a long software loop on the GPU
+    const double r = ::fabs(x) < 360.0 ? x : ::fmod(x, 360.0);
     const double a = dmul(r, 0.017453292519943295);     // pi/180
 #if defined(__CUDA_ARCH__)
     ::sincos(a, &s, &c);
@@ -73,7 +82,9 @@ EMB_HD void sincosd(double x, double& s, double& c) {
     s = ::sin(a);
     c = ::cos(a);
 #endif
-    if (::fmod(r, 90.0) == 0.0) {                       // exact at multiples of 90 degrees (cosd/sind); selects, no branch
+    // exact at multiples of 90 degrees (cosd/sind): |r| < 360, so fmod(r, 90) == 0 means r is one of 0, +-90, +-180, +-270
+    const double ar = ::fabs(r);
+    if (ar == 0.0 || ar == 90.0 || ar == 180.0 || ar == 270.0) {
         const int q = ((int)(r / 90.0)) & 3;            // two's complement: -1 -> 3, -2 -> 2, -3 -> 1
         c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
         s = q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
@@ -85,6 +96,18 @@ EMB_HD double atan2d(double y, double x) { return dmul(::atan2(y, x), 57.2957795
 EMB_HD double heading_of(double y, double x) {
     const double a = atan2d(y, x);
     return a < 0.0 ? dadd(a, 360.0) : a;
+}
+EMB_HD double wrap360(double a) {                       // wrapTo360 of any finite angle, result in [0, 360]
+    if (a >= 0.0 && a < 360.0) return a;
+    if (a >= 360.0 && a < 720.0) return dadd(a, -360.0);              // exact (Sterbenz), equal to fmod(a, 360)
+    const double r = (a < 0.0 && a > -360.0) ? a : ::fmod(a, 360.0);  // fmod(a, 360) = a for |a| < 360
+    return r < 0.0 ? dadd(r, 360.0) : r;
+}
+EMB_HD double pseudo_angle(double x, double y) {        // [0, 4), increasing with wrapTo360(atan2d(y, x)); (0, 0) -> 0 like atan2
+    const double d = dadd(::fabs(x), ::fabs(y));
+    if (!(d > 0.0)) return 0.0;
+    const double q = x / d;
+    return y >= 0.0 ? dadd(1.0, -q) : dadd(3.0, q);
 }
 EMB_HD double round2(double x) {                        // round(x, 2), half away from zero
     const double y = dmul(x, 100.0);
@@ -109,6 +132,16 @@ EMB_HD int term_discretize(const TermModel& M, int i, double x) {
     }
     return lo;
 }
+// bin of the bearing of (x, y) from the pseudo-angle cutpoints `pc` (TermModel::bear_pc, or its shared-memory copy)
+EMB_HD int term_bearing_bin(const double* pc, int n, double x, double y) {
+    const double p = pseudo_angle(x, y);
+    int lo = 0, hi = n;                                 // result = #{j in 0..n-1 : p >= pc[j]}
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p >= pc[mid - 1]) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
 EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // dediscretize.m:39, two-argument call
     if (M.edge_off[i] < 0) return (double)(b + 1);
     const double* e = M.edges + M.edge_off[i] + 2 * b;
@@ -124,7 +157,8 @@ EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // d
 #endif
 
 // One chain.  `s` = encounter index within this call, chain = 2*aircraft + direction.
-EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain) {
+// pc_rows: per-intent copies of TermModel::bear_pc in shared memory ([3][TERM_PC_MAX], device) or nullptr (host emulation)
+EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain, const double* pc_rows = nullptr) {
     const int ac = chain >> 1, dir = chain & 1;
     const double dt_s = dir ? -1.0 : 1.0;
     const int64_t N = P.n;
@@ -151,6 +185,7 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     const bool bad_intent = intent < 1 || intent > (ac ? 3 : 2);                 // createEncounter.m:14-38
     if (bad_intent && O.status) EMB_FLAG_OR(O.status, 2);
     const TermModel& M = P.m[(ac ? 4 : 0) + ((bad_intent ? 1 : intent) - 1) * 2 + dir];
+    const double* bear_pc = pc_rows ? pc_rows + ((bad_intent ? 1 : intent) - 1) * TERM_PC_MAX : M.bear_pc;
 
     double sb, cb, sh, ch;
     sincosd(bearing, sb, cb);
@@ -160,6 +195,19 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     double t_s = 0.0, z_prev = 0.0;
     bool go = !bad_intent;
     int len = 0;
+    // Three quantities the reference re-derives every second are carried instead, because they only change at events:
+    //  * curr_hdg = wrapTo360(atan2d(vy, vx)) (:176): (vx, vy) is only ever set to v*(cosd h, sind h) (:150, :228-229) or rotated by
+    //    delta (:252-255), so its direction is h resp. the previous direction + delta (equal to the atan2d value to ~1e-14 deg);
+    //  * speed = norm(v) (:168, :290): rotations keep it to an ulp; re-taken after a speed event;
+    //  * the cells of heading_deg, z_ft and speed (:278-293): re-discretised when an event changed the value.
+    double curr_hdg = (vx == 0.0 && vy == 0.0) ? 0.0 : wrap360(heading_deg);
+    double speed = norm2(vx, vy);
+    uint32_t b_hdg = 0, b_alt = 0, b_spd = 0;
+    if (go) {
+        b_hdg = (uint32_t)term_discretize(M, 3, heading_deg);
+        b_alt = (uint32_t)term_discretize(M, 4, z_ft);
+        b_spd = (uint32_t)term_discretize(M, 5, speed);
+    }
 
     for (int ii = 1; ii <= K; ++ii) {
         const bool store = O.traj && !(dir && ii == 1);                          // [fwd, bck(2:end)] (:77)
@@ -170,8 +218,6 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         }
         ++len;
         // state ii (:163-184)
-        const double curr_hdg = heading_of(vy, vx);                               // :176
-        const double speed = norm2(vx, vy);                                       // :168 and :290 (v does not change in between)
         double z_rec = z_ft;
         if (ii > 1) {                                                             // :180-184
             const double diff = dadd(z_ft, -z_prev);
@@ -190,13 +236,15 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         y = dadd(y, dmul(vy, dt_s) / TERM_FT_PER_NM);
 
         // CreateStartDistribution (:268-294), 0-based bins
+        const double d_nm = norm2(x, y);
         uint32_t st[6];
         st[0] = (uint32_t)(intent - 1);
-        st[1] = (uint32_t)term_discretize(M, M.i_dist, norm2(x, y));              // positional cell, cutpoints by label (:277,:293)
-        st[2] = (uint32_t)term_discretize(M, M.i_bear, heading_of(y, x));
-        st[3] = (uint32_t)term_discretize(M, 3, heading_deg);
-        st[4] = (uint32_t)term_discretize(M, 4, z_ft);
-        st[5] = (uint32_t)term_discretize(M, 5, speed);
+        st[1] = (uint32_t)term_discretize(M, M.i_dist, d_nm);                     // positional cell, cutpoints by label (:277,:293)
+        st[2] = M.n_bear_pc >= 0 ? (uint32_t)term_bearing_bin(bear_pc, M.n_bear_pc, x, y)
+                                 : (uint32_t)term_discretize(M, M.i_bear, heading_of(y, x));
+        st[3] = b_hdg;
+        st[4] = b_alt;
+        st[5] = b_spd;
         const uint32_t* col[3];                                                   // frozen parents (dbn_sample.m:110-135)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -206,6 +254,7 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
             col[d] = M.thr + o;
         }
 
+        bool ev_any = false, ev_v = false;
         for (uint32_t attempt = 0;; ++attempt) {                                  // while is_resample (:192-243)
             uint32_t w0, w1, w2, w3;
             philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
@@ -215,7 +264,8 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
             const int na = select_bin(col[1], (int)M.rp[1], w1);
             const int nv = select_bin(col[2], (int)M.rp[2], w2);
             bool redo = false;
-            if (nh != (int)st[3] || na != (int)st[4] || nv != (int)st[5]) {                      // events in variable order 4, 5, 6
+            if (nh != (int)st[3] || na != (int)st[4] || nv != (int)st[5]) {
+                ev_any = true;                      // events in variable order 4, 5, 6
                 uint32_t d0, d1, d2, d3;
                 philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
                               (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain, (uint32_t)P.seed,
@@ -233,6 +283,7 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
                         sincosd(heading_deg, sh, ch);
                         vx = dadd(dmul(ch, v1), -dmul(sh, 0.0));                  // :228-229
                         vy = dadd(dmul(sh, v1), dmul(ch, 0.0));
+                        ev_v = true;
                     } else {
                         redo = true;
                     }
@@ -244,20 +295,30 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
                 break;
             }
         }
-        // turn to the desired heading at the maximum rate (:246-256)
+        // turn to the desired heading at the maximum rate (:246-256); curr_hdg is still the heading at the top of this state
         const double turn1 = round2(dadd(heading_deg, -curr_hdg));
         const double mag = ::fmin(::fabs(turn1), L.maxTurn);
         const double delta = turn1 > 0.0 ? mag : turn1 < 0.0 ? -mag : dmul(mag, 0.0);
+        if (ev_v) {                                                               // v was re-pointed along heading_deg (:228-229)
+            curr_hdg = wrap360(heading_deg);
+            speed = norm2(vx, vy);
+        }
         if (delta != 0.0) {                                                       // rotation by 0 degrees is the identity
             double sd, cd;
             sincosd(delta, sd, cd);
             const double nvx = dadd(dmul(cd, vx), -dmul(sd, vy)), nvy = dadd(dmul(sd, vx), dmul(cd, vy));
             vx = nvx;
             vy = nvy;
+            curr_hdg = wrap360(dadd(curr_hdg, delta));
+        }
+        if (vx == 0.0 && vy == 0.0) curr_hdg = 0.0;                               // atan2d(0, 0) = 0
+        if (ev_any) {                                                             // cells of the values the events changed
+            b_hdg = (uint32_t)term_discretize(M, 3, heading_deg);
+            b_alt = (uint32_t)term_discretize(M, 4, z_ft);
+            if (ev_v) b_spd = (uint32_t)term_discretize(M, 5, speed);
         }
         t_s = dadd(t_s, dt_s);
         // CheckTrajectoryConditions (:296-329)
-        const double d_nm = norm2(x, y);
         const bool violate = ::fabs(t_s) > P.tmax_s || d_nm > M.dist_max || ((intent == 1 || intent == 2) && d_nm <= 0.25) ||
                              (ac == 0 && y > 0.25);
         go = !violate;
