@@ -254,6 +254,26 @@ int emu_terminal_propagate(void** models, uint64_t seed, uint64_t first, int64_t
     return (status & 1) ? EMB_E_REJECT : 0;
 }
 
+// bearing cells of n points: cells_pc = term_bearing_bin on the pseudo-angle cutpoints the chain kernel uses, cells_ref = the
+// reference's own route, discretize_bayes(wrapTo360(atan2d(y, x))) (createEncounter.m:277, :293)
+int emu_bearing_cells(void* model, int64_t n, const double* x, const double* y, int32_t* cells_pc, int32_t* cells_ref) {
+    const HostModel& H = *static_cast<HostModel*>(model);
+    TermModel M;
+    try {
+        make_term_model(H, TermLimits{0.0, 1e9, 3.0, 1e9, 1e9}, M);
+    } catch (const Error& e) {
+        g_err = e.msg;
+        return e.code;
+    }
+    M.edges = H.edges.data();
+    if (M.n_bear_pc < 0) return EMB_E_MODEL;
+    for (int64_t i = 0; i < n; ++i) {
+        cells_pc[i] = term_bearing_bin(M.bear_pc, M.n_bear_pc, x[i], y[i]);
+        cells_ref[i] = term_discretize(M, M.i_bear, heading_of(y[i], x[i]));
+    }
+    return 0;
+}
+
 // host emulation of emb_tracks_integrate (same per-track code as k_tracks_integrate); g_* = tile ordinals
 int emu_tracks_integrate(int64_t n, int32_t T, int32_t i_alt, int32_t i_speed, int32_t g_acc, int32_t g_vr, int32_t g_turn,
                          double ur_speed, double ur_vertrate, double ur_heading, double min_speed, double max_speed,

@@ -175,6 +175,42 @@ def test_emu_unknown_intent_is_an_error(traj_paths, golden):
     assert rc == L.EMB_E_ARG
 
 
+def test_bearing_cell_from_pseudo_angle_equals_atan2_route(traj_paths):
+    """The chain kernel takes the bearing cell from a pseudo-angle instead of wrapTo360(atan2d(y, x)) (createEncounter.m:277,
+    :293).  Both routes must give the same cell: 2e6 random points at all scales, the axes and diagonals, and points a hair to
+    either side of every cutpoint direction; points closer than 1e-9 deg to a cutpoint are where last-bit rounding of either
+    route decides, so only there may the cells differ (by one)."""
+    lib = H.emu_lib()
+    stem = SLOTS[0][0]
+    m = H.EmuModel(traj_paths[stem])
+    m.set_prior(1, L.EMB_PRIOR_STAY, 1.0)
+    from oracle.em_read import em_read
+    p = em_read(traj_paths[stem])
+    ib = [k for k, lab in enumerate(p.labels_initial) if lab == '"bearing"'][0]
+    cuts = np.asarray(p.boundaries[ib], dtype=np.float64)[1:-1]
+    rng = np.random.default_rng(5)
+    n = 2_000_000
+    r = 10.0 ** rng.uniform(-6, 3, n)
+    th = rng.uniform(0.0, 360.0, n)
+    x, y = r * np.cos(np.radians(th)), r * np.sin(np.radians(th))
+    ax = np.array([[1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [-1, -1], [1, -1], [0, 0], [1, -0.0], [-1, -0.0],
+                   [1e-300, -1e-320], [3, -1e-17]], dtype=np.float64)
+    eps = np.concatenate([cuts - 1e-7, cuts + 1e-7, cuts - 1e-11, cuts + 1e-11])
+    xe, ye = 2.5 * np.cos(np.radians(eps)), 2.5 * np.sin(np.radians(eps))
+    x = np.ascontiguousarray(np.concatenate([x, ax[:, 0], xe]))
+    y = np.ascontiguousarray(np.concatenate([y, ax[:, 1], ye]))
+    got = np.zeros(x.size, dtype=np.int32)
+    ref = np.zeros(x.size, dtype=np.int32)
+    assert lib.emu_bearing_cells(m.h, x.size, x.ctypes.data, y.ctypes.data, got.ctypes.data, ref.ctypes.data) == 0
+    bearing = np.mod(np.degrees(np.arctan2(y, x)), 360.0)
+    near = np.min(np.abs(bearing[:, None] - cuts[None, :]), axis=1) < 1e-9
+    assert np.array_equal(got[~near], ref[~near])
+    assert np.all(np.abs(got[near] - ref[near]) <= 1)
+    assert near.sum() < 200 and len(np.unique(got)) == len(cuts) + 1
+    # and the reference route agrees with NumPy's own digitize on the same angles
+    assert np.array_equal(ref[~near], np.searchsorted(cuts, bearing[~near], side="right"))
+
+
 def test_stay_prior_is_required(traj_paths):
     lib = H.emu_lib()
     models = [H.EmuModel(traj_paths[stem]) for stem, _, _ in SLOTS]
