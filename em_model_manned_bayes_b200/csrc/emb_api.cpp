@@ -189,6 +189,15 @@ int emb_host_alloc(void** p, int64_t bytes) {
     CU(cudaMallocHost(p, (size_t)bytes));
     return 0;
 }
+int emb_trim_device_memory(int device) {
+    int dev = device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return 0;
+}
 int emb_host_free(void* p) {
     CU(cudaFreeHost(p));
     return 0;

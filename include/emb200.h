@@ -252,6 +252,9 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
 int emb_host_alloc(void** p, int64_t bytes); /* pinned host memory */
 int emb_host_free(void* p);
 int emb_device_count(void);
+/* Per-call temporaries (staging buffers, event rows) are kept in the device's stream-ordered memory pool between calls so that
+ * repeated calls do not pay cudaMalloc/cudaFree; this returns that memory to the driver (device < 0: the current device). */
+int emb_trim_device_memory(int device);
 const char* emb_last_error(void);
 int emb_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */

@@ -410,3 +410,18 @@ def test_kernels_actually_launched(model_paths):
     before = lib.emb_launch_count()
     UncorEncounterModel(model_paths["uncor_1200code_v2p1"]).sample_compact(8, 8, seed=1)
     assert lib.emb_launch_count() == before + 1
+
+
+def test_temporaries_are_pooled_and_can_be_trimmed(model_paths):
+    """Host-buffer calls stage through the device memory pool (emb_api.cpp: tmp_alloc): results do not depend on whether the
+    pool is warm, and emb_trim_device_memory gives the memory back."""
+    import torch
+    lib = L.lib()
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    a = m.sample_events(3000, 120, seed=5, opts=m.uncor_opts())
+    free_warm = torch.cuda.mem_get_info()[0]
+    assert lib.emb_trim_device_memory(-1) == 0
+    assert torch.cuda.mem_get_info()[0] >= free_warm
+    b = m.sample_events(3000, 120, seed=5, opts=m.uncor_opts())
+    assert np.array_equal(np.asarray(a.offsets), np.asarray(b.offsets))
+    assert np.array_equal(np.asarray(a.events).view(np.uint8), np.asarray(b.events).view(np.uint8))
