@@ -285,6 +285,33 @@ def main():
     if rank == 0:
         from em_model_manned_bayes_b200.model import EncounterModel
         from em_model_manned_bayes_b200.model_archive import materialize
+        # configs[0]: the reference's own CPU-sized case, 1,000 tracks x 300 s on uncor_1200code_v2p1, through the reference-facing
+        # call with host buffers (launch- and latency-bound: three small kernels, two syncs and the D2H of ~100 rows per track)
+        p0 = materialize(os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid()),
+                         names=["uncor_1200code_v2p1"])["uncor_1200code_v2p1"]
+        m0 = UncorEncounterModel(p0)
+        o0 = m0.uncor_opts()
+        o0.mem, o0.device = L.EMB_MEM_HOST, local
+        n0, T0 = 1000, 300
+        ev0 = torch.empty(400 * n0, dtype=torch.int64).pin_memory()
+        off0 = torch.empty(n0 + 1, dtype=torch.int64).pin_memory()
+        iv0 = torch.empty((m0.n_initial, n0), dtype=torch.float64).pin_memory()
+        init0 = L.TrackOut(None, None, None, iv0.data_ptr(), None, None, None)
+        tot0 = C.c_int64(0)
+
+        def call0(seed):
+            rng = L.Rng(seed, 0)
+            L.check(lib.emb_sample_track_events(m0._h, C.byref(rng), n0, T0, C.byref(o0), ev0.numel(), ev0.data_ptr(),
+                                                off0.data_ptr(), C.byref(init0), C.byref(tot0)))
+        for k in range(5):
+            call0(k)
+        t0 = time.perf_counter()
+        for k in range(50):
+            call0(10 + k)
+        dt0 = (time.perf_counter() - t0) / 50
+        other["configs[0] uncor_1200code_v2p1, 1,000 tracks x 300 s, UncorEncounterModel.sample outputs in host memory"] = {
+            "value": n0 * T0 / dt0, "unit": "track-timesteps/s", "ms_per_call": dt0 * 1e3}
+        del m0
         gp = materialize(os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid()), names=["glider_v1"])["glider_v1"]
         g = EncounterModel(gp)
         n2 = 100_000_000

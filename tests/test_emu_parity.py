@@ -194,3 +194,37 @@ def test_tracks_match_c_oracle(model_paths, model, uncor, n, T, fast):
     assert np.array_equal(got["bins"], ref["sample_bins"][:, dyn, :])
     want = ref["samples"][:, tv, :]
     assert np.all(np.abs(got["values"].astype(np.float64) - want) <= 1e-6 * np.abs(want))
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="needs the reference checkout's model/*.txt (build container only)")
+def test_every_shipped_dbn_model_runs_specialised_and_matches_the_c_oracle():
+    """All model/*.txt files with a transition network (not just the archived ones): the specialised code path
+    (EMB_FAST_SHAPES covers every shipped shape and sampling order) against the plain-C restatement."""
+    import glob
+    import os
+    from oracle.c_oracle import COracle
+    lib = H.emu_lib()
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(H.REF_MODEL_DIR, "*.txt"))):
+        p = em_read(path)
+        if not p.n_transition:
+            continue
+        n, T = 60, 80
+        ref = COracle(p).sample_tracks(n, T, seed=93, first_sample=3 * 10 ** 9, threads=0)
+        assert ref["rc"] == 0
+        tm = np.asarray(p.temporal_map)
+        dyn = [int(v) - 1 for v in tm[:, 0]]
+        rates = np.asarray(p.resample_rates)
+        tv = sorted(set(dyn) | {i for i in range(p.n_initial) if rates[i] > 0})
+        lib.emu_use_fast(1)
+        try:
+            got = H.EmuModel(path).sample_tracks(p.n_initial, len(dyn), len(tv), n, T, 93, 3 * 10 ** 9, H.EmuModel.opts(p.n_initial))
+            assert lib.emu_last_fast() == 1, "no specialised kernel for " + os.path.basename(path)
+        finally:
+            lib.emu_use_fast(0)
+        assert np.array_equal(got["init_bins"], ref["init_bins"]), path
+        assert np.array_equal(got["bins"], ref["sample_bins"][:, dyn, :]), path
+        want = ref["samples"][:, tv, :]
+        assert np.all(np.abs(got["values"].astype(np.float64) - want) <= 1e-6 * np.abs(want)), path
+        seen += 1
+    assert seen >= 20
