@@ -8,8 +8,6 @@
 // tables (a few MB each) are gathered from L2.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "emb_launch.h"
 #include "emb_integrate.cuh"
 #include "emb_terminal.cuh"
@@ -68,8 +66,6 @@ int launch_integrate(const IntegrateParams& P, void* stream) {
 int launch_terminal(const TermParams& P, const TermOut& O, void* stream) {
     if (P.n <= 0) return 0;
     const dim3 grid((unsigned)((P.n + TERM_BLOCK - 1) / TERM_BLOCK), 4, 1);
-    if (std::getenv("EMB_TERM_MAXL1"))
-        cudaFuncSetAttribute(k_terminal_chains, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     k_terminal_chains<<<grid, TERM_BLOCK, 0, (cudaStream_t)stream>>>(P, O);
     g_launch_count.fetch_add(1);
     return (int)cudaGetLastError();
