@@ -121,7 +121,15 @@ EMB_HD double dadd(double a, double b) {
     return r;
 #endif
 }
-EMB_HD double u01(uint32_t k) { return dmul(dadd((double)k, 0.5), 2.3283064365386963e-10); }
+// u = (k + 0.5) * 2^-32, exact.  On the device k + 0.5 comes from the 2^52 trick (the word placed under the high word of 2^52,
+// minus 2^52 - 0.5: one exact DADD) instead of the quarter-rate I2F.F64.U32 conversion; the value is the same double.
+EMB_HD double u01(uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    return dmul(dadd(__hiloint2double(0x43300000, (int)k), -4503599627370495.5), 2.3283064365386963e-10);
+#else
+    return dmul(dadd((double)k, 0.5), 2.3283064365386963e-10);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11)
@@ -226,6 +234,18 @@ EMB_HD double ldg64(const double* p) {
 #endif
 }
 
+// one {a, b - a} edge pair (DevModel::edges holds pairs, 16-byte aligned: cudaMalloc base + even offsets) as one 16-byte load
+EMB_HD void ldg_pair(const double* e, double& a, double& w) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldg(reinterpret_cast<const double2*>(e));
+    a = v.x;
+    w = v.y;
+#else
+    a = e[0];
+    w = e[1];
+#endif
+}
+
 // acc - [k > t] for a threshold as stored: k > t  <=>  t - k borrows (sub.cc / subc: two instructions, no compare+select)
 EMB_HD uint32_t sub_gt(uint32_t acc, uint32_t k, uint32_t t) {
 #if defined(__CUDA_ARCH__)
@@ -266,8 +286,9 @@ EMB_HD bool needs_uniform(const DevModel& M, int i, int b) {
 EMB_HD double dedisc(const DevModel& M, int i, int b, double u) {
     if (M.edge_off[i] < 0) return (double)(b + 1);          // dediscretize.m:7-10: return the bin
     if (M.zero_bin[i] == b + 1) return 0.0;                 // :24-25
-    const double* e = M.edges + M.edge_off[i] + 2 * b;
-    return dadd(ldg64(e), dmul(ldg64(e + 1), u));           // :39  a + (b-a)*rand
+    double a, w;
+    ldg_pair(M.edges + M.edge_off[i] + 2 * b, a, w);
+    return dadd(a, dmul(w, u));                             // :39  a + (b-a)*rand
 }
 
 EMB_HD double round500(double num) {                        // UncorEncounterModel.m:196

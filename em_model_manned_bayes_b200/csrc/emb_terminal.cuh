@@ -144,8 +144,9 @@ EMB_HD int term_bearing_bin(const double* pc, int n, double x, double y) {
 }
 EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // dediscretize.m:39, two-argument call
     if (M.edge_off[i] < 0) return (double)(b + 1);
-    const double* e = M.edges + M.edge_off[i] + 2 * b;
-    return dadd(ldg64(e), dmul(ldg64(e + 1), u01(k)));
+    double a, w;
+    ldg_pair(M.edges + M.edge_off[i] + 2 * b, a, w);
+    return dadd(a, dmul(w, u01(k)));
 }
 
 #if defined(__CUDA_ARCH__)
