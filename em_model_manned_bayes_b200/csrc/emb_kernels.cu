@@ -82,8 +82,11 @@ k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SamplePara
 // SMEM: the whole threshold table (glider family 42 KB, balloons, HAA transition-free models ...) is
 // staged in shared memory once per persistent block, so the per-lane column gathers are LDS.128
 // instead of 32-sector L1 lookups; larger tables (7-variable uncor: 0.6-1.1 MB) are gathered from L1/L2.
+#ifndef EMB_INIT_MINBLOCKS_V    // resident blocks asked of the values variant (its fp64 tail otherwise takes 102 registers)
+#define EMB_INIT_MINBLOCKS_V 3
+#endif
 template <int NV, bool VALUES, bool SMEM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VALUES ? EMB_INIT_MINBLOCKS_V : 1)
 k_initial_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
                const __grid_constant__ InitStrides ST, int table_words, int8_t* __restrict__ bins,
                double* __restrict__ values, uint16_t* __restrict__ attempts) {
