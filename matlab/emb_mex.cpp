@@ -96,6 +96,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     mxGetString(prhs[0], cmd, sizeof(cmd));
     const std::string c(cmd);
 
+    if (c == "trim") {                                            // return the pooled per-call temporaries to the driver
+        CHECK(emb_trim_device_memory(nrhs > 1 ? (int)mxGetScalar(prhs[1]) : -1));
+        return;
+    }
     if (c == "load") {                                            // replaces em_read.m:1-141
         char path[4096];
         mxGetString(prhs[1], path, sizeof(path));
