@@ -15,6 +15,7 @@ EMB_MAX_GATED = 16
 
 EMB_MEM_HOST = 0
 EMB_MEM_DEVICE = 1
+EMB_MEM_ASYNC = 0x100
 EMB_PRIOR_CONSTANT, EMB_PRIOR_DBE, EMB_PRIOR_STAY = 0, 1, 2
 EMB_REJECT_NONE, EMB_REJECT_UNCOR, EMB_REJECT_BOX = 0, 1, 2
 
@@ -124,6 +125,7 @@ def lib():
         "emb_host_alloc": (C.c_int, [P(vp), i64]),
         "emb_host_free": (C.c_int, [vp]),
         "emb_trim_device_memory": (C.c_int, [C.c_int]),
+        "emb_async_status": (C.c_int, [C.c_int]),
         "emb_rng_word": (u32, [u64, u64, u32, u32, u32, u32, u32]),
         "emb_model_load": (C.c_int, [C.c_char_p, C.c_int, P(i32), i32, P(vp)]),
         "emb_model_from_arrays": (C.c_int, [i32, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp, i32, vp, vp, vp, P(vp)]),
@@ -157,7 +159,7 @@ def lib():
 
 
 EXPORTED = [
-    "emb_abi_version", "emb_last_error", "emb_launch_count", "emb_debug_force_generic", "emb_debug_last_kernel_fast", "emb_device_count", "emb_host_alloc", "emb_host_free", "emb_trim_device_memory",
+    "emb_abi_version", "emb_last_error", "emb_launch_count", "emb_debug_force_generic", "emb_debug_last_kernel_fast", "emb_device_count", "emb_host_alloc", "emb_host_free", "emb_trim_device_memory", "emb_async_status",
     "emb_rng_word", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",

@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -82,7 +84,9 @@ int ensure_device(const HostModel& H, int device, DevModel& D) {
     return 0;
 }
 
-int pick_device(const emb_sample_opts* o, int& device) {
+int pick_device(const emb_sample_opts* o, int& device, bool allow_async = false) {
+    if ((o->mem & ~0xFF) && !(allow_async && (o->mem & ~0xFF) == EMB_MEM_ASYNC && (o->mem & 0xFF) == EMB_MEM_DEVICE))
+        return set_err(EMB_E_ARG, "emb_sample_opts.mem: EMB_MEM_ASYNC goes with EMB_MEM_DEVICE and emb_sample_tracks only");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0)
@@ -92,6 +96,22 @@ int pick_device(const emb_sample_opts* o, int& device) {
     if (device < 0) CU(cudaGetDevice(&device));
     if (device >= count) return set_err(EMB_E_ARG, "device ordinal out of range");
     CU(cudaSetDevice(device));
+    return 0;
+}
+
+// EMB_MEM_ASYNC launches report an exhausted rejection loop through one persistent word per device (read by emb_async_status)
+std::mutex g_async_mu;
+std::map<int, int32_t*> g_async_status;
+int async_status_word(int device, int32_t** out) {
+    std::lock_guard<std::mutex> lk(g_async_mu);
+    auto it = g_async_status.find(device);
+    if (it == g_async_status.end()) {
+        int32_t* p = nullptr;
+        CU(cudaMalloc((void**)&p, 4));
+        CU(cudaMemset(p, 0, 4));
+        it = g_async_status.emplace(device, p).first;
+    }
+    *out = it->second;
     return 0;
 }
 
@@ -187,6 +207,22 @@ int emb_device_count(void) {
 
 int emb_host_alloc(void** p, int64_t bytes) {
     CU(cudaMallocHost(p, (size_t)bytes));
+    return 0;
+}
+int emb_async_status(int device) {
+    int dev = device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    CU(cudaSetDevice(dev));
+    CU(cudaDeviceSynchronize());
+    int32_t* word = nullptr;
+    int rc = async_status_word(dev, &word);
+    if (rc) return rc;
+    int32_t flag = 0;
+    CU(cudaMemcpy(&flag, word, 4, cudaMemcpyDeviceToHost));
+    if (flag) {
+        CU(cudaMemset(word, 0, 4));
+        return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop (asynchronous pass)");
+    }
     return 0;
 }
 int emb_trim_device_memory(int device) {
@@ -485,11 +521,12 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     }
     if (n == 0) return 0;
     int device;
-    if ((rc = pick_device(opts, device))) return rc;
+    if ((rc = pick_device(opts, device, true))) return rc;
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
-    Stager sg{opts->mem, st, {}};
+    const bool async = (opts->mem & EMB_MEM_ASYNC) != 0;
+    Stager sg{opts->mem & 0xFF, st, {}};
     emb::TrackOut O{};
     const size_t ni = (size_t)H.n_initial;
     if ((rc = sg.out(out->bins, (size_t)emb_tracks_bins_len(m, n, T), false, (void**)&O.bins))) return rc;
@@ -499,6 +536,11 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     if ((rc = sg.out(out->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
     if ((rc = sg.out(out->hist_initial, ni * 64 * 8, true, (void**)&O.hist_initial))) return rc;
     if ((rc = sg.out(out->hist_transition, H.temporal_map.size() * 64 * 8, true, (void**)&O.hist_transition))) return rc;
+    if (async) {   // enqueue only: no host round trip between consecutive passes; emb_async_status collects the flag
+        if ((rc = async_status_word(device, &O.status))) return rc;
+        const cudaError_t ea = (cudaError_t)emb::launch_tracks(D, P, O, st);
+        return ea == cudaSuccess ? 0 : cuda_fail(ea, "launch k_tracks");
+    }
     CU(tmp_alloc((void**)&O.status, 4, st));
     CU(cudaMemsetAsync(O.status, 0, 4, st));
     cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);

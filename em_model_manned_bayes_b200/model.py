@@ -264,15 +264,20 @@ class EncounterModel:
 
     def sample_tracks(self, n: int, T: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
                       want_bins=True, want_values=True, want_init=True, hist_initial=None, hist_transition=None,
-                      out: Optional[TrackResult] = None) -> TrackResult:
-        """Dense compact tracks (emb200.h: emb_sample_tracks)."""
+                      out: Optional[TrackResult] = None, enqueue_only: bool = False) -> TrackResult:
+        """Dense compact tracks (emb200.h: emb_sample_tracks).  `enqueue_only` (device outputs only): EMB_MEM_ASYNC, the pass
+        is queued on the current stream and the call returns at once; `async_status()` later reports rejection exhaustion."""
         lib = L.lib()
         o = opts if opts is not None else self._opts(start=start)
+        if enqueue_only and device is None:
+            raise L.EmbError(L.EMB_E_ARG, "enqueue_only needs device outputs")
         if device is not None:
             import torch
             dev = torch.device(device)
             o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
             o.stream = torch.cuda.current_stream(dev).cuda_stream
+            if enqueue_only:
+                o.mem |= L.EMB_MEM_ASYNC
         ni = self.n_initial
         if out is None:
             nb = int(lib.emb_tracks_bins_len(self._h, n, T))
@@ -289,6 +294,11 @@ class EncounterModel:
         rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
         L.check(lib.emb_sample_tracks(self._h, C.byref(rng), n, T, C.byref(o), C.byref(to)))
         return out
+
+
+def async_status(device: int = -1) -> None:
+    """Synchronise `device` and raise if an enqueue_only pass exhausted its rejection loop (emb_async_status)."""
+    L.check(L.lib().emb_async_status(int(device)))
 
 
 @dataclass

@@ -48,6 +48,9 @@ extern "C" {
 /* memory kind of caller buffers */
 #define EMB_MEM_HOST 0
 #define EMB_MEM_DEVICE 1
+/* or-ed with EMB_MEM_DEVICE, emb_sample_tracks only: enqueue the pass on opts.stream and return without waiting for it, so
+ * consecutive passes run back to back; emb_async_status(device) later synchronises and reports an exhausted rejection loop */
+#define EMB_MEM_ASYNC 0x100
 
 /* prior kinds: bn_dirichlet_prior.m:17-38 and setTransitionPriors.m:12-33 */
 #define EMB_PRIOR_CONSTANT 0 /* alpha = value everywhere (EncounterModel.m:45 default 0) */
@@ -255,6 +258,8 @@ int emb_device_count(void);
 /* Per-call temporaries (staging buffers, event rows) are kept in the device's stream-ordered memory pool between calls so that
  * repeated calls do not pay cudaMalloc/cudaFree; this returns that memory to the driver (device < 0: the current device). */
 int emb_trim_device_memory(int device);
+/* waits for the device and returns EMB_E_REJECT if an EMB_MEM_ASYNC pass since the last call exhausted max_attempts, else 0 */
+int emb_async_status(int device);
 const char* emb_last_error(void);
 int emb_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */

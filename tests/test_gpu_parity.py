@@ -425,3 +425,34 @@ def test_temporaries_are_pooled_and_can_be_trimmed(model_paths):
     b = m.sample_events(3000, 120, seed=5, opts=m.uncor_opts())
     assert np.array_equal(np.asarray(a.offsets), np.asarray(b.offsets))
     assert np.array_equal(np.asarray(a.events).view(np.uint8), np.asarray(b.events).view(np.uint8))
+
+
+def test_enqueue_only_passes_equal_synchronous_passes(model_paths):
+    """EMB_MEM_ASYNC: emb_sample_tracks only enqueues; the outputs equal those of the synchronous call, emb_async_status
+    reports nothing for a healthy pass and EMB_E_REJECT after a pass whose rejection loop was cut to one attempt."""
+    import torch
+    from em_model_manned_bayes_b200.model import async_status
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    a = m.sample_compact(5000, 90, seed=77, device="cuda:0")
+    b = m.sample_compact(5000, 90, seed=78, device="cuda:0")
+    m.sample_compact(5000, 90, seed=77, device="cuda:0", out=b, enqueue_only=True)
+    async_status(0)
+    assert torch.equal(a.bins_tiled, b.bins_tiled) and torch.equal(a.values_tiled, b.values_tiled)
+    assert torch.equal(a.init_values, b.init_values)
+    # a rejection loop that may not retry: some of 200 000 samples are rejected by v*1.68781 > |dh|/60 on their first attempt
+    o = m.uncor_opts(max_attempts=1)
+    o.max_attempts = 1
+    big = m.sample_tracks(200_000, 8, seed=3, opts=m.uncor_opts(), device="cuda:0")
+    if int((big.attempts.to(torch.int32) > 2).sum()) > 0:
+        m.sample_tracks(200_000, 8, seed=3, opts=o, device="cuda:0", out=big, enqueue_only=True)
+        with pytest.raises(L.EmbError):
+            async_status(0)
+        async_status(0)      # the flag is cleared by the report
+    with pytest.raises(L.EmbError):
+        m.sample_events(10, 10, seed=1, opts=_async_host_opts(m))
+
+
+def _async_host_opts(m):
+    o = m.uncor_opts()
+    o.mem = L.EMB_MEM_HOST | L.EMB_MEM_ASYNC
+    return o
