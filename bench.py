@@ -265,7 +265,7 @@ def main():
         rng = L.Rng(seed, rank * n)
         L.check(lib.emb_sample_track_events(m._h, C.byref(rng), n, T, C.byref(o), cap, h_ev.data_ptr(), h_off.data_ptr(),
                                             C.byref(init_only), C.byref(tot)))
-    for k in range(max(3, args.warmup)):      # warm-up calls: the first one also fills the library's device memory pool
+    for k in range(max(6, args.warmup)):      # warm-up calls: the first one also fills the library's device memory pool
         events_call(7 + k)
     barrier()
     ev_steps = []
@@ -317,24 +317,28 @@ def main():
         gp = materialize(os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid()), names=["glider_v1"])["glider_v1"]
         g = EncounterModel(gp)
         n2 = 100_000_000
-        g.sample_initial(n2, seed=1, device=dev, want_values=False, want_attempts=False)
+        buf = g.sample_initial(n2, seed=1, device=dev, want_values=False, want_attempts=False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for k in range(3):
-            g.sample_initial(n2, seed=2 + k, device=dev, want_values=False, want_attempts=False)
+            g.sample_initial(n2, seed=2 + k, device=dev, want_values=False, want_attempts=False, out=buf, enqueue_only=True)
         e1.record()
         torch.cuda.synchronize()
+        async_status(local)
+        del buf
         other["configs[1] glider_v1 initial network only, 100M samples, int8 bins"] = {
             "value": 3 * n2 / (e0.elapsed_time(e1) * 1e-3), "unit": "samples/s"}
         # the same with the de-discretised values (bn_sample + dediscretize): SURVEY 8d counts 5*(1+4) = 25 B per sample
-        g.sample_initial(n2, seed=1, device=dev, want_values=True, want_attempts=False)
+        buf = g.sample_initial(n2, seed=1, device=dev, want_values=True, want_attempts=False)
         torch.cuda.synchronize()
         e0.record()
         for k in range(3):
-            g.sample_initial(n2, seed=2 + k, device=dev, want_values=True, want_attempts=False)
+            g.sample_initial(n2, seed=2 + k, device=dev, want_values=True, want_attempts=False, out=buf, enqueue_only=True)
         e1.record()
         torch.cuda.synchronize()
+        async_status(local)
+        del buf
         v2 = 3 * n2 / (e0.elapsed_time(e1) * 1e-3)
         other["configs[1] glider_v1 initial network only, 100M samples, int8 bins + fp64 values"] = {
             "value": v2, "unit": "samples/s", "algorithmic_bytes_per_unit": 25.0, "written_bytes_per_unit": 45.0,
@@ -359,7 +363,8 @@ def main():
         cm = EncounterModel(cp)
         n4, T4 = 10_000_000, 60
         r4 = cm.sample_tracks(n4, T4, seed=1, device=dev)
-        dt = timed(lambda k: cm.sample_tracks(n4, T4, seed=10 + k, device=dev, out=r4))
+        dt = timed(lambda k: cm.sample_tracks(n4, T4, seed=10 + k, device=dev, out=r4, enqueue_only=True))
+        async_status(local)
         other["configs[3] cor_v1 (stand-in for the missing cor_v2p1), 10M encounters x 60 s, dense compact outputs"] = {
             "value": n4 * T4 / dt, "unit": "track-timesteps/s", "ms": dt * 1e3,
             # 4*(1+4) B per step + (16*(1+4) + 4*(99+36)) B per track

@@ -86,7 +86,7 @@ int ensure_device(const HostModel& H, int device, DevModel& D) {
 
 int pick_device(const emb_sample_opts* o, int& device, bool allow_async = false) {
     if ((o->mem & ~0xFF) && !(allow_async && (o->mem & ~0xFF) == EMB_MEM_ASYNC && (o->mem & 0xFF) == EMB_MEM_DEVICE))
-        return set_err(EMB_E_ARG, "emb_sample_opts.mem: EMB_MEM_ASYNC goes with EMB_MEM_DEVICE and emb_sample_tracks only");
+        return set_err(EMB_E_ARG, "emb_sample_opts.mem: EMB_MEM_ASYNC goes with EMB_MEM_DEVICE, in emb_sample_tracks and emb_sample_initial only");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0)
@@ -464,10 +464,16 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     }
     if (n == 0) return 0;
     int device;
-    if ((rc = pick_device(opts, device))) return rc;
+    if ((rc = pick_device(opts, device, true))) return rc;
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    if (opts->mem & EMB_MEM_ASYNC) {   // enqueue only (device buffers): see emb_sample_tracks
+        int32_t* word = nullptr;
+        if ((rc = async_status_word(device, &word))) return rc;
+        const cudaError_t ea = (cudaError_t)emb::launch_initial(D, P, (int)H.thr_initial.size(), bins, values, attempts, nullptr, word, st);
+        return ea == cudaSuccess ? 0 : cuda_fail(ea, "launch k_initial");
+    }
     Stager sg{opts->mem, st, {}};
     int8_t* d_bins;
     double* d_vals;

@@ -242,7 +242,7 @@ class EncounterModel:
 
     # -- sampling ----------------------------------------------------------------------------------
     def sample_initial(self, n: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
-                       want_values=True, want_attempts=True):
+                       want_values=True, want_attempts=True, out=None, enqueue_only: bool = False):
         """bn_sample.m:25-58 over n samples + de-discretisation.  Returns (bins (n, n_initial) int8,
         values (n, n_initial) float64 or None, attempts (n,) or None).  `device`: torch device string
         to keep the outputs in HBM; default host numpy."""
@@ -254,10 +254,17 @@ class EncounterModel:
             o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
             stream = torch.cuda.current_stream(dev).cuda_stream
             o.stream = stream
+            if enqueue_only:      # EMB_MEM_ASYNC: queue the pass and return; async_status() collects the rejection flag
+                o.mem |= L.EMB_MEM_ASYNC
+        elif enqueue_only:
+            raise L.EmbError(L.EMB_E_ARG, "enqueue_only needs device outputs")
         ni = self.n_initial
-        bins = self._alloc((ni, n), np.int8, device)
-        vals = self._alloc((ni, n), np.float64, device) if want_values else None
-        att = self._alloc((n,), np.uint16, device) if want_attempts else None
+        if out is not None:       # reuse the buffers of a previous call: (bins.T, values.T, attempts) as returned
+            bins, vals, att = out[0].T, (out[1].T if out[1] is not None else None), out[2]
+        else:
+            bins = self._alloc((ni, n), np.int8, device)
+            vals = self._alloc((ni, n), np.float64, device) if want_values else None
+            att = self._alloc((n,), np.uint16, device) if want_attempts else None
         rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
         L.check(L.lib().emb_sample_initial(self._h, C.byref(rng), n, C.byref(o), _ptr(bins), _ptr(vals), _ptr(att)))
         return bins.T, (vals.T if vals is not None else None), att

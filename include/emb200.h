@@ -48,7 +48,7 @@ extern "C" {
 /* memory kind of caller buffers */
 #define EMB_MEM_HOST 0
 #define EMB_MEM_DEVICE 1
-/* or-ed with EMB_MEM_DEVICE, emb_sample_tracks only: enqueue the pass on opts.stream and return without waiting for it, so
+/* or-ed with EMB_MEM_DEVICE, emb_sample_tracks / emb_sample_initial only: enqueue the pass on opts.stream and return without waiting for it, so
  * consecutive passes run back to back; emb_async_status(device) later synchronises and reports an exhausted rejection loop */
 #define EMB_MEM_ASYNC 0x100
 

@@ -456,3 +456,14 @@ def _async_host_opts(m):
     o = m.uncor_opts()
     o.mem = L.EMB_MEM_HOST | L.EMB_MEM_ASYNC
     return o
+
+
+def test_enqueue_only_initial_equals_synchronous(model_paths):
+    import torch
+    from em_model_manned_bayes_b200.model import async_status
+    g = EncounterModel(model_paths["glider_v1"])
+    a = g.sample_initial(100_003, seed=9, device="cuda:0")
+    b = g.sample_initial(100_003, seed=10, device="cuda:0")
+    g.sample_initial(100_003, seed=9, device="cuda:0", out=b, enqueue_only=True)
+    async_status(0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
