@@ -89,6 +89,14 @@ def materialise_model():
     return materialize(d, names=[MODEL])[MODEL]
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm is about)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port(path, n_tracks, threads):
     """Time oracle/oracle_c.c on `threads` host threads over n_tracks x T; returns track-timesteps/s."""
     import ctypes as C
@@ -111,8 +119,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.c_oracle import lib
-    threads = lib().oc_num_threads()
+    threads = host_threads()
     path = materialise_model()
     per_thread = 30000
     n = per_thread * threads
@@ -439,8 +446,7 @@ def main():
         "clocks": clk,
     }
     if world == 1 and not args.no_cpu:
-        from oracle.c_oracle import lib as olib
-        threads = olib().oc_num_threads()
+        threads = host_threads()
         ntr = 80000 * threads
         v, dt = cpu_port(path, ntr, threads)
         out["cpu_baseline"] = {"value": v, "unit": "track-timesteps/s", "cores": threads, "kind": "port",
