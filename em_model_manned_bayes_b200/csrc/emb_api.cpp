@@ -627,30 +627,31 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     CU(tmp_alloc(&status.p, 4, st));
     CU(cudaMemsetAsync(status.p, 0, 4, st));
     O.status = (int32_t*)status.p;
-    // pass 1: rows per track (also writes the per-track initial outputs), then the prefix sum
-    O.ev_counts = (uint32_t*)counts.p;
-    cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);
-    if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event count)");
-    e = (cudaError_t)emb::launch_scan_counts((const uint32_t*)counts.p, d_off, n, (long long*)tiles.p, st);
-    if (e != cudaSuccess) return cuda_fail(e, "launch k_scan_counts");
-    long long total = 0;
-    int32_t flag = 0;
-    CU(cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&flag, status.p, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    tr.mark("alloc + count pass + scan");
-    if (total_rows) *total_rows = total;
-    if (flag) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
-    if (total > capacity) {
-        if ((rc = sg.finish())) return rc;   // offsets and the initial outputs are valid
-        return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
-    }
-    // pass 2: write the rows (the keyed stream reproduces pass 1 exactly)
-    O.ev_counts = nullptr;
-    O.init_bins = nullptr;
-    O.init_values = nullptr;
-    O.attempts = nullptr;
-    if (opts->mem == EMB_MEM_DEVICE || total == 0 || n < 8192) {
+    const bool pipelined = (opts->mem & 0xFF) == EMB_MEM_HOST && n >= 8192;
+    if (!pipelined) {
+        // pass 1: rows per track (also writes the per-track initial outputs), then the prefix sum
+        O.ev_counts = (uint32_t*)counts.p;
+        cudaError_t e = (cudaError_t)emb::launch_tracks(D, P, O, st);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event count)");
+        e = (cudaError_t)emb::launch_scan_counts((const uint32_t*)counts.p, d_off, n, (long long*)tiles.p, st);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_scan_counts");
+        long long total = 0;
+        int32_t flag = 0;
+        CU(cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&flag, status.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        tr.mark("alloc + count pass + scan");
+        if (total_rows) *total_rows = total;
+        if (flag) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+        if (total > capacity) {
+            if ((rc = sg.finish())) return rc;   // offsets and the initial outputs are valid
+            return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
+        }
+        // pass 2: write the rows (the keyed stream reproduces pass 1 exactly)
+        O.ev_counts = nullptr;
+        O.init_bins = nullptr;
+        O.init_values = nullptr;
+        O.attempts = nullptr;
         uint2* d_ev = nullptr;
         if ((rc = sg.out(events, (size_t)total * 8, false, (void**)&d_ev))) return rc;
         O.ev_offsets = d_off;
@@ -660,8 +661,10 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         CU(cudaStreamSynchronize(st));
         return sg.finish();
     }
-    // host-memory caller: the write pass runs in chunks of tracks on the caller's stream while a second stream copies
-    // the rows of the previous chunk to the host (rows of a track range are contiguous: [offsets[a], offsets[b]))
+    // Host-memory caller, large batch: the tracks go through in chunks, each chunk = count pass -> prefix sum (carrying the
+    // rows of the chunks before it) -> write pass on the caller's stream, while a second stream copies the rows of the
+    // finished chunks to the host (rows of a track range are contiguous: [offsets[a], offsets[b])).  Only the first chunk's
+    // count pass is not hidden behind a copy.
     struct Guard {
         void* dev = nullptr;
         cudaStream_t copy = nullptr;
@@ -672,39 +675,63 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
             tmp_free(dev);
         }
     } g;
-    CU(tmp_alloc(&g.dev, (size_t)total * 8, st));
+    if (capacity > 0) CU(tmp_alloc(&g.dev, (size_t)capacity * 8, st));
     CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-    tr.mark("cudaMalloc rows");
-    // the offsets go straight into the caller's buffer (they also say which rows each chunk produced)
-    const int64_t* h_off = offsets;
-    CU(cudaMemcpyAsync(offsets, d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    sg.already_copied(offsets);
-    tr.mark("offsets to host");
+    CU(cudaMemsetAsync(d_off, 0, 8, st));                 // carry of the first chunk
     const int chunks = 8;
+    long long total = 0;
+    bool overflow = false;
+    static thread_local long long* pub = nullptr;         // mapped pinned host memory, 2 words per chunk, kept for the thread
+    if (!pub) CU(cudaHostAlloc((void**)&pub, sizeof(long long) * 2 * 16, cudaHostAllocMapped | cudaHostAllocPortable));
     for (int c = 0; c < chunks; ++c) {
         const int64_t a = n * c / chunks, b = n * (c + 1) / chunks;
         if (b <= a) continue;
         emb::SampleParams Pc = P;
         Pc.first_sample = P.first_sample + (uint64_t)a;
         Pc.n = b - a;
-        emb::TrackOut Oc = O;
-        Oc.ev_offsets = d_off + a;
-        Oc.events = (uint2*)g.dev;
-        e = (cudaError_t)emb::launch_tracks(D, Pc, Oc, st);
+        emb::TrackOut Oc = O;                             // count pass of the chunk: also its per-track initial outputs
+        Oc.init_stride = n;
+        if (O.init_bins) Oc.init_bins = O.init_bins + a;
+        if (O.init_values) Oc.init_values = O.init_values + a;
+        if (O.attempts) Oc.attempts = O.attempts + a;
+        Oc.ev_counts = (uint32_t*)counts.p + a;
+        cudaError_t e = (cudaError_t)emb::launch_tracks(D, Pc, Oc, st);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event count)");
+        e = (cudaError_t)emb::launch_scan_counts((const uint32_t*)counts.p + a, d_off + a, b - a, (long long*)tiles.p, st, d_off + a);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_scan_counts");
+        // the chunk's running total and the rejection flag reach the host through mapped memory (an SM store): a cudaMemcpy
+        // would queue on the copy engine behind the previous chunk's rows and serialise the pipeline
+        e = (cudaError_t)emb::launch_publish(d_off + b, (const int32_t*)status.p, pub + 2 * c, st);
+        if (e != cudaSuccess) return cuda_fail(e, "launch k_publish");
+        CU(cudaStreamSynchronize(st));
+        const long long r0 = total, r1 = pub[2 * c];
+        const int32_t flag = (int32_t)pub[2 * c + 1];
+        if (c == 0) tr.mark("first chunk: count + scan");
+        if (flag) {
+            CU(cudaStreamSynchronize(g.copy));
+            return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+        }
+        total = r1;
+        if (total > capacity) overflow = true;            // keep counting: the caller learns how many rows are needed
+        if (overflow || r1 == r0) continue;
+        emb::TrackOut Ow{};                               // write pass of the chunk (the keyed stream reproduces the count pass)
+        Ow.status = O.status;
+        Ow.ev_offsets = d_off + a;
+        Ow.events = (uint2*)g.dev;
+        e = (cudaError_t)emb::launch_tracks(D, Pc, Ow, st);
         if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
         CU(cudaEventCreateWithFlags(&g.done[c], cudaEventDisableTiming));
         CU(cudaEventRecord(g.done[c], st));
         CU(cudaStreamWaitEvent(g.copy, g.done[c], 0));
-        const long long r0 = (long long)h_off[(size_t)a], r1 = (long long)h_off[(size_t)b];
-        if (r1 > r0)
-            CU(cudaMemcpyAsync(events + r0, (const char*)g.dev + (size_t)r0 * 8, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, g.copy));
+        CU(cudaMemcpyAsync(events + r0, (const char*)g.dev + (size_t)r0 * 8, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, g.copy));
     }
-    tr.mark("enqueue write chunks");
+    tr.mark("chunks enqueued");
+    if (total_rows) *total_rows = total;
     if ((rc = sg.finish())) return rc;          // offsets and per-track outputs, on the caller's stream
     tr.mark("finish (offsets, inits D2H)");
     CU(cudaStreamSynchronize(g.copy));
     tr.mark("rows D2H drained");
+    if (overflow) return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
     return 0;
 }
 

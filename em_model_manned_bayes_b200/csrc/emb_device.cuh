@@ -101,6 +101,8 @@ struct TrackOut {
     uint32_t* ev_counts;           // pass 1: [n] rows of each track (including the closing row)
     const long long* ev_offsets;   // pass 2: [n] first row of each track
     uint2* events;                 // pass 2: rows
+    int64_t init_stride;           // samples between consecutive variables of init_bins / init_values; 0 = P.n (a chunk of
+                                   // a larger call writes into the whole call's [n_initial][n] arrays)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -366,8 +368,8 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     }
     if (O.attempts) O.attempts[s] = (uint16_t)(attempt + 1);
     for (int i = 0; i < n; ++i) {
-        if (O.init_bins) O.init_bins[(int64_t)i * N + s] = (int8_t)(x[i] + 1);
-        if (O.init_values) O.init_values[(int64_t)i * N + s] = vals[i];
+        if (O.init_bins) O.init_bins[(int64_t)i * (O.init_stride ? O.init_stride : N) + s] = (int8_t)(x[i] + 1);
+        if (O.init_values) O.init_values[(int64_t)i * (O.init_stride ? O.init_stride : N) + s] = vals[i];
         if (O.hist_initial) hist_inc(0, i, x[i]);
     }
     if (T <= 0 || (!O.bins && !O.values && !O.hist_transition && !O.ev_counts && !O.events)) return;

@@ -316,8 +316,8 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
         }
         if (O.attempts) O.attempts[s] = (uint16_t)(attempt + 1);
         for (int i = 0; i < M.n_initial; ++i) {
-            if (O.init_bins) O.init_bins[(int64_t)i * N + s] = (int8_t)(x[i] + 1);
-            if (O.init_values) O.init_values[(int64_t)i * N + s] = vals[i];
+            if (O.init_bins) O.init_bins[(int64_t)i * (O.init_stride ? O.init_stride : N) + s] = (int8_t)(x[i] + 1);
+            if (O.init_values) O.init_values[(int64_t)i * (O.init_stride ? O.init_stride : N) + s] = vals[i];
             if (O.hist_initial) hist_inc(0, i, x[i]);
         }
         if (T <= 0 || (!EV && !O.bins && !O.values && !O.hist_transition)) return;

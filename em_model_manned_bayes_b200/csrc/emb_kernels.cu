@@ -177,10 +177,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t*
 }
 
 // one block: tile_sum[0..m) -> exclusive prefixes in place, grand total to *total_out
-__global__ void __launch_bounds__(1024) k_scan_tile_prefix(long long* __restrict__ tile_sum, long long m, long long* __restrict__ total_out) {
+// carry_in (nullable): value the prefixes start from (the total of the tracks before this range)
+__global__ void __launch_bounds__(1024) k_scan_tile_prefix(long long* __restrict__ tile_sum, long long m, long long* __restrict__ total_out,
+                                                           const long long* __restrict__ carry_in) {
     __shared__ long long warp_sum[32];
     __shared__ long long carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = carry_in ? *carry_in : 0;
     __syncthreads();
     for (long long base = 0; base < m; base += 1024) {
         const long long i = base + threadIdx.x;
@@ -214,15 +216,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
     }
 }
 
+// {*total, *flag} -> dst (mapped host memory): a store from an SM does not queue behind the row copies on the copy engine,
+// which a cudaMemcpy of the same eight bytes would
+__global__ void k_publish(const long long* __restrict__ total, const int32_t* __restrict__ flag, volatile long long* dst) {
+    dst[0] = *total;
+    dst[1] = (long long)*flag;
+}
+
 }  // namespace
+
+int launch_publish(const long long* total, const int32_t* flag, long long* mapped_dst, void* stream) {
+    k_publish<<<1, 1, 0, (cudaStream_t)stream>>>(total, flag, mapped_dst);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 
 long long scan_scratch_len(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
 
-int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream) {
+int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream,
+                       const long long* carry_in) {
     const long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     cudaStream_t st = (cudaStream_t)stream;
     k_scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, scratch, n);
-    k_scan_tile_prefix<<<1, 1024, 0, st>>>(scratch, tiles, offsets + n);
+    k_scan_tile_prefix<<<1, 1024, 0, st>>>(scratch, tiles, offsets + n, carry_in);
     k_scan_apply<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, scratch, offsets, n);
     g_launch_count.fetch_add(3);
     return (int)cudaGetLastError();

@@ -16,9 +16,14 @@ extern int g_last_kernel_fast;
 int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
                    uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream);
 int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream);
-// offsets[0..n] = exclusive prefix sums of counts[0..n), offsets[n] = total; scratch: scan_scratch_len(n) long longs
+// offsets[0..n] = carry + exclusive prefix sums of counts[0..n), offsets[n] = carry + total; carry = *carry_in (device pointer,
+// may alias offsets) or 0; scratch: scan_scratch_len(n) long longs
 long long scan_scratch_len(long long n);
-int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream);
+int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream,
+                       const long long* carry_in = nullptr);
+
+// {*total, *flag} written by an SM into mapped pinned host memory (two long longs)
+int launch_publish(const long long* total, const int32_t* flag, long long* mapped_dst, void* stream);
 
 // terminal trajectory chains (emb_terminal.cu): 4 chains per encounter
 struct TermParams;
