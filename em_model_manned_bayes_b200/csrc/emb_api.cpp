@@ -170,10 +170,6 @@ struct Stager {
         *dev = s.dev;
         return 0;
     }
-    void already_copied(void* user) {   // the caller's buffer was filled early (event offsets): finish() skips it
-        for (auto& s : items)
-            if (s.host == user) s.host = nullptr;
-    }
     int finish() {
         for (auto& s : items)
             if (s.host) CU(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, stream));
