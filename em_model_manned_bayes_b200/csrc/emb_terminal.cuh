@@ -75,7 +75,7 @@ struct TermOut {
 // Not inlined on the device: three call sites of a ~300-instruction body made the chain kernel 60 KB of code and
 // `no_instruction` its third stall reason; as a call the kernel is 15 % smaller and 3 % faster.
 #if defined(__CUDACC__)
-__host__ __device__ __noinline__ void sincosd(double x, double& s, double& c) {
+inline __host__ __device__ __noinline__ void sincosd(double x, double& s, double& c) {
 #else
 EMB_HD void sincosd(double x, double& s, double& c) {
 #endif
