@@ -498,12 +498,12 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
 int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T) {
     if (!m || n < 0 || T < 0) return 0;
     const int64_t nch4 = (T + 3) / 4;
-    return (int64_t)m->h->temporal_map.size() * nch4 * n * 4;
+    return (int64_t)m->h->temporal_map.size() * nch4 * emb::num_tiles(n) * emb::TRACK_TILE * 4;
 }
 int64_t emb_tracks_values_len(const emb_model* m, int64_t n, int32_t T) {
     if (!m || n < 0 || T < 0) return 0;
     const int64_t nch4 = (T + 3) / 4;
-    return (int64_t)m->h->timevarying.size() * nch4 * n * 4;
+    return (int64_t)m->h->timevarying.size() * nch4 * emb::num_tiles(n) * emb::TRACK_TILE * 4;
 }
 
 int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
@@ -840,6 +840,7 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
     P.g_acc = tv_of(opts->idx_acceleration);
     P.g_vr = tv_of(opts->idx_vertrate);
     P.g_turn = tv_of(opts->idx_turnrate);
+    P.n_tv = (int32_t)H.timevarying.size();
     if (P.g_acc < 0 || P.g_vr < 0 || P.g_turn < 0)
         return set_err(EMB_E_ARG, "sample2track: acceleration, vertical rate and turn rate must be time-varying variables of the model");
     P.ur_speed = opts->ur_speed;

@@ -33,9 +33,13 @@ constexpr int MAXG = 16;  // EMB_MAX_GATED
 constexpr int MAXX = MAXV + MAXD;
 constexpr int HIST_STRIDE = 64;
 
-// stream spec v3 purposes (oracle/philox.py)
+// stream spec v4 (oracle/philox.py): counter = (sample >> 32, sample & 0xffffffff, attempt << 16 | purpose << 8 | sub, index);
+// the step stream (P_STEP) carries no attempt: the rejection test only reads the initial draw (UncorEncounterModel.m:275),
+// so the seconds of the accepted attempt are the same words whichever attempt was accepted.
 constexpr uint32_t P_INIT = 1, P_STEP = 2, P_LAYER = 4;
-// one word k per (second, gated variable): select on k, gate on k*GATE_MULT, de-discretisation on k*DD_MULT (spec v3)
+// one word k per (second, gated variable): select on k, gate on k*GATE_MULT; the de-discretisation word of the variable is
+// k*DD_MULT + k', k' = the word of the next gated variable of the same second (cyclic; 0 when there is only one), which makes
+// the value independent of the variable's own select and gate decisions
 constexpr uint32_t GATE_MULT = 0x9E3779B1u;
 constexpr uint32_t DD_MULT = 0x85EBCA6Bu;
 
@@ -76,6 +80,9 @@ struct SampleParams {
     uint64_t seed;
     uint64_t first_sample;
     int64_t n;
+    int64_t s_begin, s_end;        // tracks [s_begin, s_end) of [0, n) handled by this launch (track kernels): a launch never
+                                   // straddles a multiple of 2^32 of the global sample index, so that counter word 0 of the
+                                   // step stream is the same for all its tracks (spec v4; next_segment below)
     int32_t T;
     int32_t reject_mode;           // EMB_REJECT_*
     int32_t idx_v, idx_dh, idx_L;  // 0-based, -1 if unused
@@ -87,6 +94,40 @@ struct SampleParams {
     double layers[8][2];
     double box_lo[MAXV], box_hi[MAXV];
 };
+
+// Dense output layout (emb200.h: emb_track_out): tiles of TRACK_TILE tracks x four seconds, all variables of a tile together:
+//     [ceil(T/4)][ceil(n/128)][var][128][4]
+// so that one thread's stores of a four-second group sit at compile-time offsets (var * 128 * 4 elements) from a single running
+// pointer, a warp still writes 128 (int8) or 512 (fp32) contiguous bytes per variable, and the pointer advances by one uniform
+// stride per group.  (The former [var][ceil(T/4)][n][4] layout cost two 64-bit adds per store.)
+constexpr int TRACK_TILE = 128;
+EMB_HD int64_t num_tiles(int64_t n) { return (n + TRACK_TILE - 1) / TRACK_TILE; }
+// element offset of (variable var of nvar, group grp, track s, second 0 of the group)
+EMB_HD int64_t tile_offset(int nvar, int64_t ntile, int var, int64_t grp, int64_t s) {
+    return (((grp * ntile + s / TRACK_TILE) * nvar + var) * TRACK_TILE + s % TRACK_TILE) * 4;
+}
+
+// zeros for padding track s (n <= s < 128 * ceil(n/128)) of the dense outputs, so that the buffers are fully defined
+template <class TO>
+EMB_HD void zero_padding_track(const TO& O, int nd, int ng, int T, int64_t N, int64_t s) {
+    const int64_t ntile = num_tiles(N);
+    if (s < N || s >= ntile * TRACK_TILE) return;
+    for (int grp = 0; grp < (T + 3) >> 2; ++grp) {
+        if (O.values)
+            for (int g = 0; g < ng; ++g)
+                for (int j = 0; j < 4; ++j) O.values[tile_offset(ng, ntile, g, grp, s) + j] = 0.0f;
+        if (O.bins)
+            for (int d = 0; d < nd; ++d)
+                for (int j = 0; j < 4; ++j) O.bins[tile_offset(nd, ntile, d, grp, s) + j] = 0;
+    }
+}
+
+// end of the segment that starts at track s0: the largest s1 <= n with (first_sample + s) >> 32 constant on [s0, s1)
+inline int64_t next_segment(uint64_t first_sample, int64_t s0, int64_t n) {
+    const uint64_t a = first_sample + (uint64_t)s0;
+    const uint64_t room = 0x100000000ull - (a & 0xFFFFFFFFull);   // samples left before the next multiple of 2^32
+    return (uint64_t)(n - s0) <= room ? n : s0 + (int64_t)room;
+}
 
 struct TrackOut {
     int8_t* bins;
@@ -186,6 +227,60 @@ EMB_HD void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
+// ---- the same function split by what its first three rounds depend on ------------------------------------------------
+// With the spec-v4 counter (c0, c1, c2, c3) = (sample_hi, sample_lo, purpose word, index) and c0, c2 the same for every track
+// of a launch, round 0 multiplies constants, round 1 multiplies one track-invariant word (M0 * a0, a0 from sample_lo) and one
+// word that only depends on the index (M1 * a2), and so does round 2 -- only from round 3 on do the products depend on both.
+// A track therefore keeps three words (PhiloxTrack), every call index has three words that all tracks share (philox_call:
+// computed once per block into shared memory), and a call costs 7 rounds = 14 IMAD.WIDE instead of 20.  The result is
+// bit-for-bit philox4x32_10(c0, c1, c2, c3) (tests/test_oracle_kat.py checks the split against the plain function).
+struct PhiloxTrack {
+    uint32_t r1h, r1l, q0l;
+};
+EMB_HD PhiloxTrack philox_track(uint32_t c0, uint32_t c1, uint32_t c2, const uint32_t (&rk)[20]) {
+    uint32_t p0h, p0l, p1h, p1l, q0h, q0l;
+    mulhilo(PHILOX_M0, c0, p0h, p0l);
+    mulhilo(PHILOX_M1, c2, p1h, p1l);
+    const uint32_t a0 = p1h ^ c1 ^ rk[0];
+    mulhilo(PHILOX_M0, a0, q0h, q0l);
+    const uint32_t b2 = q0h ^ p0l ^ rk[3];
+    PhiloxTrack t;
+    mulhilo(PHILOX_M1, b2, t.r1h, t.r1l);
+    t.q0l = q0l;
+    return t;
+}
+// x = q1l ^ rk4, y = r0h ^ rk5, z = r0l (w unused)
+EMB_HD uint4 philox_call(uint32_t c0, uint32_t c2, uint32_t index, const uint32_t (&rk)[20]) {
+    uint32_t p0h, p0l, p1h, p1l, q1h, q1l, r0h, r0l;
+    mulhilo(PHILOX_M0, c0, p0h, p0l);
+    mulhilo(PHILOX_M1, c2, p1h, p1l);
+    const uint32_t a2 = p0h ^ index ^ rk[1];
+    mulhilo(PHILOX_M1, a2, q1h, q1l);
+    const uint32_t b0 = q1h ^ p1l ^ rk[2];
+    mulhilo(PHILOX_M0, b0, r0h, r0l);
+    uint4 e;
+    e.x = q1l ^ rk[4];
+    e.y = r0h ^ rk[5];
+    e.z = r0l;
+    e.w = 0;
+    return e;
+}
+EMB_HD void philox_finish(const PhiloxTrack& t, const uint4& e, const uint32_t (&rk)[20],
+                          uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+    uint32_t c0 = t.r1h ^ e.x, c1 = t.r1l, c2 = e.y ^ t.q0l, c3 = e.z;
+#pragma unroll
+    for (int i = 3; i < 10; ++i) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(PHILOX_M0, c0, h0, l0);
+        mulhilo(PHILOX_M1, c2, h1, l1);
+        c0 = h1 ^ c1 ^ rk[2 * i];
+        c2 = h0 ^ c3 ^ rk[2 * i + 1];
+        c1 = l1;
+        c3 = l0;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
 // Sequential reader of one (sample, attempt, purpose) word stream: position p -> block p/4, lane p%4.
 // Caches the last block, so monotone access costs one Philox call per 4 words.
 struct WordStream {
@@ -194,7 +289,7 @@ struct WordStream {
     uint32_t w[4];
     EMB_HD void init(uint64_t seed, uint64_t sample, uint32_t attempt, uint32_t purpose) {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        c0 = (uint32_t)sample; c1 = (uint32_t)(sample >> 32);
+        c0 = (uint32_t)(sample >> 32); c1 = (uint32_t)sample;
         w3 = (attempt << 16) | (purpose << 8);
         blk = 0xFFFFFFFFu;
     }
@@ -202,7 +297,7 @@ struct WordStream {
         const uint32_t b = p >> 2;
         if (b != blk) {
             blk = b;
-            philox4x32_10(c0, c1, b, w3, k0, k1, w[0], w[1], w[2], w[3]);
+            philox4x32_10(c0, c1, w3, b, k0, k1, w[0], w[1], w[2], w[3]);
         }
         const uint32_t l = p & 3u;
         return l == 0 ? w[0] : l == 1 ? w[1] : l == 2 ? w[2] : w[3];
@@ -212,14 +307,16 @@ struct WordStream {
 EMB_HD uint32_t keyed_word(uint64_t seed, uint64_t sample, uint32_t attempt, uint32_t purpose, uint32_t index,
                            uint32_t sub, uint32_t lane) {
     uint32_t o0, o1, o2, o3;
-    philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), index, (attempt << 16) | (purpose << 8) | sub,
+    philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (purpose << 8) | sub, index,
                   (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
     return lane == 0 ? o0 : lane == 1 ? o1 : lane == 2 ? o2 : o3;
 }
 
 // ---------------------------------------------------------------------------------------------
-// stream spec v3: de-discretisation uniform of a step word, (((k*B) mod 2^32 >> 9) + 0.5) 2^-23
-EMB_HD double u_dd(uint32_t k) { return dmul(dadd((double)((k * DD_MULT) >> 9), 0.5), 1.1920928955078125e-07); }
+// stream spec v4: de-discretisation uniform of a step word k with partner word kn, (((k*B + kn) mod 2^32 >> 9) + 0.5) 2^-23
+EMB_HD double u_dd(uint32_t k, uint32_t kn) { return dmul(dadd((double)((k * DD_MULT + kn) >> 9), 0.5), 1.1920928955078125e-07); }
+// partner word of gated ordinal g among the nw words of one second
+EMB_HD uint32_t dd_partner(const uint32_t* wstep, int g, int nw) { return nw > 1 ? wstep[g + 1 < nw ? g + 1 : 0] : 0u; }
 
 EMB_HD uint32_t ldg32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
@@ -402,7 +499,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     };
 
     WordStream ws;
-    ws.init(P.seed, sample, (uint32_t)attempt, P_STEP);
+    ws.init(P.seed, sample, 0u, P_STEP);
     const int nch4 = (T + 3) >> 2;
     uint32_t bpack[MAXD];
     float vbuf[MAXV][4];
@@ -419,7 +516,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 const uint32_t k = wstep[g];
                 if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                     const int v = M.gated_var[g];
-                    vals[v] = dedisc(M, v, x[v], u_dd(k));
+                    vals[v] = dedisc(M, v, x[v], u_dd(k, dd_partner(wstep, g, nw)));
                     if (ev) emit((uint32_t)c, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, vals[v]);
                 }
             }
@@ -436,7 +533,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 const uint8_t nb = x[M.dyn_t1[d]];
                 if (nb != x[vt]) {
                     x[vt] = nb;
-                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[M.gate_of_dyn[d]]));
+                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[M.gate_of_dyn[d]], dd_partner(wstep, M.gate_of_dyn[d], nw)));
                     if (ev) emit((uint32_t)c, (uint32_t)vt + 1u, (uint32_t)nb + 1u, vals[vt]);
                 }
             }
@@ -451,7 +548,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
         if ((c & 3) == 3) {
             if (O.values) {
                 for (int g = 0; g < ng; ++g) {
-                    float* dst = O.values + (((int64_t)g * nch4 + (c >> 2)) * N + s) * 4;
+                    float* dst = O.values + tile_offset(ng, num_tiles(N), g, c >> 2, s);
 #if defined(__CUDA_ARCH__)
                     *reinterpret_cast<float4*>(dst) = make_float4(vbuf[g][0], vbuf[g][1], vbuf[g][2], vbuf[g][3]);
 #else
@@ -461,7 +558,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
             }
             if (O.bins) {
                 for (int d = 0; d < nd; ++d) {
-                    int8_t* dst = O.bins + (((int64_t)d * nch4 + (c >> 2)) * N + s) * 4;
+                    int8_t* dst = O.bins + tile_offset(nd, num_tiles(N), d, c >> 2, s);
 #if defined(__CUDA_ARCH__)
                     *reinterpret_cast<uint32_t*>(dst) = bpack[d];
 #else
@@ -474,11 +571,13 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     }
     if (ev) {
         // gates of the last held second T (resample_events.m:23-29), then the closing row (dbn_hierarchical_sample.m:15-19)
+        uint32_t wlast[MAXG];
+        for (int q = 0; q < nw; ++q) wlast[q] = ws.at((uint32_t)T * (uint32_t)nw + (uint32_t)q);
         for (int g = 0; g < ng; ++g) {
-            const uint32_t k = ws.at((uint32_t)T * (uint32_t)nw + (uint32_t)g);
+            const uint32_t k = wlast[g];
             if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                 const int v = M.gated_var[g];
-                emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k)));
+                emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k, dd_partner(wlast, g, nw))));
             }
         }
         emit((uint32_t)T, 0u, 0u, 0.0);

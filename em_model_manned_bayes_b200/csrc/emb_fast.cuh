@@ -12,7 +12,8 @@
 //     from a 16-byte shared-memory entry indexed by the bin (no fp64, no int->float conversion: the
 //     23-bit value-word fraction is placed in the mantissa of f in [1,2)),
 //   * bins and values leave as 4-second tiles: one 4-byte store per dynamic variable and one 16-byte
-//     store per gated variable per thread, contiguous across the warp.
+//     store per gated variable per thread, contiguous across the warp, at compile-time offsets from one
+//     running pointer (layout [grp][tile of 128 tracks][var][128][4], emb_device.cuh: tile_offset).
 // Requirements checked on the host (fast_shape_of): the gated list ends with the dynamic variables in
 // temporal_map order (true for every shipped model); all gate thresholds G < 2^32; no gated bin
 // straddles zero without being the zero bin (DevModel::fast32_ok).
@@ -37,10 +38,28 @@ struct DdEntry {
     float slope, base, s, c;
 };
 
+// groups of four seconds whose shared Philox words (philox_call) sit in shared memory at a time
+constexpr int UT_GROUPS = 160;
+
 // per-block constants of the fast kernel (shared memory on the device)
 struct alignas(16) FastShared {
     DdEntry ent[FAST_MAX_EDGES];  // per (gated ordinal, bin), DevModel::dd32
 };
+// the index-only part of the Philox calls of UT_GROUPS consecutive groups (NW calls per group)
+template <int NW>
+struct alignas(16) CallTable {
+    uint4 e[UT_GROUPS * NW];
+};
+template <int NW>
+EMB_HD void fill_call_table(CallTable<NW>& U, const SampleParams& P, uint32_t c0, uint32_t c2, int grp0, int ngroups, int tid,
+                            int nthreads) {
+    for (int q = tid; q < ngroups * NW; q += nthreads) U.e[q] = philox_call(c0, c2, (uint32_t)(grp0 * NW + q), P.rk);
+}
+EMB_HD void block_sync() {
+#if defined(__CUDA_ARCH__)
+    __syncthreads();
+#endif
+}
 
 // fill FastShared (called by all threads of a block with their index, or by the host with tid=0,nthreads=1)
 EMB_HD void fast_fill_shared(const DevModel& M, FastShared& S, int tid, int nthreads) {
@@ -50,10 +69,10 @@ EMB_HD void fast_fill_shared(const DevModel& M, FastShared& S, int tid, int nthr
     for (int q = tid; q < 4 * total; q += nthreads) dst[q] = M.dd32[q];
 }
 
-// the 23 fraction bits of a step word as a float in [1,2)   (stream spec v3: u_dd = (f - 1) + 2^-24):
-// one IMAD (hash) + one funnel shift that drops the exponent of 1.0f on top of the fraction
-EMB_HD float dd_fraction(uint32_t k) {
-    const uint32_t h = k * DD_MULT;
+// the 23 fraction bits of the value word of a step word k (partner kn) as a float in [1,2)
+// (stream spec v4: u_dd = (f - 1) + 2^-24): one IMAD (hash) + one funnel shift that drops the exponent of 1.0f on top
+EMB_HD float dd_fraction(uint32_t k, uint32_t kn) {
+    const uint32_t h = k * DD_MULT + kn;
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(__funnelshift_r(h, 0x7Fu, 9));
 #else
@@ -140,7 +159,7 @@ struct FastTrack {
     uint32_t ct[ND][ND], c1[ND][ND];   // slow branch: strides of the dynamic parents (uniform)
     int ebase[NG];            // entry-table bases (uniform)
     uint32_t G[NG];           // gate thresholds (uniform)
-    uint32_t c0, c1w, w3;
+    PhiloxTrack pt;           // track-invariant part of the step stream's Philox calls
     uint32_t sbin1[NS > 0 ? NS : 1];   // EV: 1-based bins of the static gated variables
     uint32_t ev_last, ev_n;            // EV: second of the last row, rows so far
     uint2* ev_ptr;                     // EV == 2: next row of this track
@@ -168,11 +187,11 @@ struct FastTrack {
 
     // one group of four seconds e = 4*grp .. 4*grp+3; CHECK = the group may contain e == 0 or e >= T
     template <bool CHECK>
-    EMB_HD void group(int grp, int T, uint32_t (&bout)[ND], float (&vout)[NG][4]) {
+    EMB_HD void group(int grp, int T, uint32_t (&bout)[ND], float (&vout)[NG][4], const uint4* ut) {
         uint32_t W[4 * NW];
 #pragma unroll
         for (int c = 0; c < NW; ++c)
-            philox4x32_10_rk(c0, c1w, (uint32_t)(grp * NW + c), w3, P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
+            philox_finish(pt, ut[c], P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
 #pragma unroll
         for (int d = 0; d < ND; ++d) bout[d] = 0;
 #pragma unroll
@@ -246,11 +265,12 @@ struct FastTrack {
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const uint32_t k = W[j * NW + g];
+                const uint32_t kn = NW > 1 ? W[j * NW + (g + 1) % NW] : 0u;   // partner word of the value (spec v4)
                 const int d = g - NS;
                 DdEntry en;
                 if (g >= NS) en = S.ent[nb[d >= 0 ? d : 0]];
                 else en = sent[g < NS ? g : 0];
-                const float gp = fmaf_rn(dd_fraction(k), en.s, en.c);
+                const float gp = fmaf_rn(dd_fraction(k, kn), en.s, en.c);
                 const float cand = fmaf_rn(en.slope, gp, en.base);
                 const bool fired = (k * GATE_MULT) < G[g];
                 const bool changed = g >= NS && nb[d >= 0 ? d : 0] != bin[d >= 0 ? d : 0];
@@ -262,7 +282,7 @@ struct FastTrack {
                     uint32_t b1 = g >= NS ? bin[d >= 0 ? d : 0] - (uint32_t)ebase[g] + 1u : sbin1[g < NS ? g : 0];
                     if (g >= NS && fired && changed) {
                         const DdEntry eo = S.ent[bin[d >= 0 ? d : 0]];
-                        gv = fmaf_rn(eo.slope, fmaf_rn(dd_fraction(k), eo.s, eo.c), eo.base);
+                        gv = fmaf_rn(eo.slope, fmaf_rn(dd_fraction(k, kn), eo.s, eo.c), eo.base);
                     }
                     emit(fired && act_gate, (uint32_t)e, (uint32_t)M.gated_var[g] + 1u, b1, gv);
                     if (g >= NS) {
@@ -292,9 +312,11 @@ struct FastTrack {
     }
 };
 
+// `valid` = this thread owns track s (s < P.n); the other threads of a block only help filling the call table U.
+// (tid, nthreads) = the caller's index among the threads that share U (the host emulation calls with 0, 1).
 template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD, class HistInc>
-EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut& O, int64_t s, const FastShared& S,
-                       HistInc hist_inc) {
+EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut& O, int64_t s, bool valid, const FastShared& S,
+                       CallTable<NG>& U, int tid, int nthreads, HistInc hist_inc) {
     using FT = FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>;
     using SH = DynShape<RS>;
     constexpr int ND = FT::ND, NS = FT::NS;
@@ -302,14 +324,20 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     const int T = P.T;
     const int64_t N = P.n;
     FT ft(M, P, S, hist_inc);
+    // step stream (spec v4): every track of a launch shares c0 = first_sample >> 32 (the host splits a launch at multiples
+    // of 2^32: SampleParams::s_begin) and c2 = P_STEP << 8
+    const uint32_t c0 = (uint32_t)((P.first_sample + (uint64_t)P.s_begin) >> 32), c2 = P_STEP << 8;
+    const int nch4 = (T + 3) >> 2;
+    const int nfull = T >> 2;       // groups 1 .. nfull-1 contain only seconds 1 <= e < T
+    const int ngrp = EV ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
+    const bool steps = T > 0 && (EV || O.bins || O.values || O.hist_transition);   // uniform
 
     // ---- initial network (once per track; generic code, cost amortised over T seconds) -----------
-    int attempt;
-    {
+    if (valid) {
         uint8_t x[MAXX];
         double vals[MAXV];
         for (int i = 0; i < MAXX; ++i) x[i] = 0;
-        attempt = sample_initial(M, P, sample, x, vals);
+        int attempt = sample_initial(M, P, sample, x, vals);
         if (attempt < 0) {
             if (O.status) *O.status = 1;
             attempt = P.max_attempts;
@@ -320,8 +348,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
             if (O.init_values) O.init_values[(int64_t)i * (O.init_stride ? O.init_stride : N) + s] = vals[i];
             if (O.hist_initial) hist_inc(0, i, x[i]);
         }
-        if (T <= 0 || (!EV && !O.bins && !O.values && !O.hist_transition)) return;
-        {
+        if (steps) {
             int b = 0;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -334,96 +361,103 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                     ft.sbin1[g] = (uint32_t)x[M.gated_var[g]] + 1u;
                 }
             }
-        }
-        ft.ev_last = 0;
-        ft.ev_n = 0;
-        ft.ev_ptr = EV == 2 ? O.events + O.ev_offsets[s] : nullptr;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            ft.bin[d] = (uint32_t)ft.ebase[NS + d] + x[M.dyn_t[d]];
-            x[M.dyn_t1[d]] = x[M.dyn_t[d]];
-        }
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            if (FAST) {
-                const uint32_t* col = node_column(M.dyn[d], M.thr_trans, x);
-#pragma unroll
-                for (int m = 0; m < SH::RP(d); ++m) {
-                    if (FT::F64(d) && m < SH::RP(d) - 1) ft.thrd[d][m] = biased_double(ldg32(col + m));
-                    else ft.thr[d][m] = m < SH::RP(d) - 1 ? ~ldg32(col + m) : ldg32(col + m) + (uint32_t)ft.ebase[NS + d];
-                }
-            } else {
-                // column offset contributed by parents that are neither X(t) nor X(t+1) of a dynamic variable
-                const Node& nd = M.dyn[d];
-                uint32_t o = nd.off;
-                for (int p = 0; p < nd.np; ++p) {
-                    bool isdyn = false;
-                    for (int e = 0; e < ND; ++e) isdyn = isdyn || nd.par[p] == M.dyn_t[e] || nd.par[p] == M.dyn_t1[e];
-                    if (!isdyn) o += nd.stride_rp[p] * (uint32_t)x[nd.par[p]];
-                }
-                ft.cbase[d] = o;
-                ft.coff[d] = 0xFFFFFFFFu;
-            }
-        }
-    }
-    if (!FAST) {   // strides of the dynamic parents (uniform across threads)
-#pragma unroll
-        for (int d = 0; d < ND; ++d)
-#pragma unroll
-            for (int e = 0; e < ND; ++e) {
-                ft.ct[d][e] = 0;
-                ft.c1[d][e] = 0;
-                for (int p = 0; p < M.dyn[d].np; ++p) {
-                    if (M.dyn[d].par[p] == M.dyn_t[e]) ft.ct[d][e] = M.dyn[d].stride_rp[p];
-                    if (M.dyn[d].par[p] == M.dyn_t1[e]) ft.c1[d][e] = M.dyn[d].stride_rp[p];
-                }
-                // bin[] / nb[] carry ebase: take it out of the column offset once
-                ft.cbase[d] -= (ft.ct[d][e] + ft.c1[d][e]) * (uint32_t)ft.ebase[NS + e];
-            }
-    }
-    ft.c0 = (uint32_t)sample;
-    ft.c1w = (uint32_t)(sample >> 32);
-    ft.w3 = ((uint32_t)attempt << 16) | (P_STEP << 8);
-
-    const int nch4 = (T + 3) >> 2;
-    const int nfull = T >> 2;       // groups 1 .. nfull-1 contain only seconds 1 <= e < T
-    // [var][grp][n][4]: per-thread running pointers, one uniform stride per variable
-    int8_t* pb = O.bins ? O.bins + s * 4 : nullptr;
-    float* pv = O.values ? O.values + s * 4 : nullptr;
-    const int64_t var_stride = (int64_t)nch4 * N * 4;   // elements between consecutive variables
-    const int ngrp = EV ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
-    for (int grp = 0; grp < ngrp; ++grp) {
-        uint32_t bout[ND];
-        float vout[NG][4];
-        if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout);
-        else ft.template group<true>(grp, T, bout, vout);
-        if (EV && grp >= nch4) break;
-        if (O.values) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                float* dst = pv + g * var_stride;
-#if defined(__CUDA_ARCH__)
-                __stcs(reinterpret_cast<float4*>(dst), make_float4(vout[g][0], vout[g][1], vout[g][2], vout[g][3]));
-#else
-                dst[0] = vout[g][0]; dst[1] = vout[g][1]; dst[2] = vout[g][2]; dst[3] = vout[g][3];
-#endif
-            }
-            pv += N * 4;
-        }
-        if (O.bins) {
+            ft.ev_last = 0;
+            ft.ev_n = 0;
+            ft.ev_ptr = EV == 2 ? O.events + O.ev_offsets[s] : nullptr;
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                int8_t* dst = pb + d * var_stride;
-#if defined(__CUDA_ARCH__)
-                __stcs(reinterpret_cast<uint32_t*>(dst), bout[d]);
-#else
-                for (int b = 0; b < 4; ++b) dst[b] = (int8_t)((bout[d] >> (8 * b)) & 0xFF);
-#endif
+                ft.bin[d] = (uint32_t)ft.ebase[NS + d] + x[M.dyn_t[d]];
+                x[M.dyn_t1[d]] = x[M.dyn_t[d]];
             }
-            pb += N * 4;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                if (FAST) {
+                    const uint32_t* col = node_column(M.dyn[d], M.thr_trans, x);
+#pragma unroll
+                    for (int m = 0; m < SH::RP(d); ++m) {
+                        if (FT::F64(d) && m < SH::RP(d) - 1) ft.thrd[d][m] = biased_double(ldg32(col + m));
+                        else ft.thr[d][m] = m < SH::RP(d) - 1 ? ~ldg32(col + m) : ldg32(col + m) + (uint32_t)ft.ebase[NS + d];
+                    }
+                } else {
+                    // column offset contributed by parents that are neither X(t) nor X(t+1) of a dynamic variable
+                    const Node& nd = M.dyn[d];
+                    uint32_t o = nd.off;
+                    for (int p = 0; p < nd.np; ++p) {
+                        bool isdyn = false;
+                        for (int e = 0; e < ND; ++e) isdyn = isdyn || nd.par[p] == M.dyn_t[e] || nd.par[p] == M.dyn_t1[e];
+                        if (!isdyn) o += nd.stride_rp[p] * (uint32_t)x[nd.par[p]];
+                    }
+                    ft.cbase[d] = o;
+                    ft.coff[d] = 0xFFFFFFFFu;
+                }
+            }
+            if (!FAST) {   // strides of the dynamic parents (uniform across threads)
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+#pragma unroll
+                    for (int e = 0; e < ND; ++e) {
+                        ft.ct[d][e] = 0;
+                        ft.c1[d][e] = 0;
+                        for (int p = 0; p < M.dyn[d].np; ++p) {
+                            if (M.dyn[d].par[p] == M.dyn_t[e]) ft.ct[d][e] = M.dyn[d].stride_rp[p];
+                            if (M.dyn[d].par[p] == M.dyn_t1[e]) ft.c1[d][e] = M.dyn[d].stride_rp[p];
+                        }
+                        // bin[] / nb[] carry ebase: take it out of the column offset once
+                        ft.cbase[d] -= (ft.ct[d][e] + ft.c1[d][e]) * (uint32_t)ft.ebase[NS + e];
+                    }
+            }
+            ft.pt = philox_track(c0, (uint32_t)sample, c2, P.rk);
         }
     }
-    if (EV) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
+    if (!steps) return;
+
+    // [grp][tile][var][128][4]: one running pointer per output, variables at compile-time offsets, one uniform stride per group
+    const int64_t ntile = num_tiles(N);
+    // (a null output only predicates the stores off: its pointer is advanced but never dereferenced)
+    const bool wb = O.bins != nullptr, wv = O.values != nullptr;
+    int8_t* pb = O.bins + tile_offset(ND, ntile, 0, 0, s);
+    float* pv = O.values + tile_offset(NG, ntile, 0, 0, s);
+    const int64_t bstep = ntile * (ND * TRACK_TILE * 4), vstep = ntile * (NG * TRACK_TILE * 4);
+    for (int grp0 = 0; grp0 < ngrp; grp0 += UT_GROUPS) {
+        const int gcount = ngrp - grp0 < UT_GROUPS ? ngrp - grp0 : UT_GROUPS;
+        if (grp0 > 0) block_sync();
+        fill_call_table<NG>(U, P, c0, c2, grp0, gcount, tid, nthreads);
+        block_sync();
+        if (!valid) continue;
+        for (int grp = grp0; grp < grp0 + gcount; ++grp) {
+            uint32_t bout[ND];
+            float vout[NG][4];
+            const uint4* ut = U.e + (grp - grp0) * NG;
+            if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout, ut);
+            else ft.template group<true>(grp, T, bout, vout, ut);
+            if (EV && grp >= nch4) break;
+            if (wv) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float* dst = pv + g * (TRACK_TILE * 4);
+#if defined(__CUDA_ARCH__)
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(vout[g][0], vout[g][1], vout[g][2], vout[g][3]));
+#else
+                    dst[0] = vout[g][0]; dst[1] = vout[g][1]; dst[2] = vout[g][2]; dst[3] = vout[g][3];
+#endif
+                }
+            }
+            pv += vstep;
+            if (wb) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    int8_t* dst = pb + d * (TRACK_TILE * 4);
+#if defined(__CUDA_ARCH__)
+                    __stcs(reinterpret_cast<uint32_t*>(dst), bout[d]);
+#else
+                    for (int b = 0; b < 4; ++b) dst[b] = (int8_t)((bout[d] >> (8 * b)) & 0xFF);
+#endif
+                }
+            }
+            pb += bstep;
+        }
+    }
+    if (EV && valid) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
         ft.emit(true, (uint32_t)T, 0u, 0u, 0.0f);
         if (EV == 1) O.ev_counts[s] = ft.ev_n;
     }

@@ -78,7 +78,7 @@ EMB_HD void initial_fast4(const DevModel& M, const SampleParams& P, const InitSt
         const uint64_t sample = P.first_sample + (uint64_t)(s0 + j);
 #pragma unroll
         for (int c = 0; c < NCALL; ++c)
-            philox4x32_10_rk((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)c, P_INIT << 8, P.rk, W[j][4 * c],
+            philox4x32_10_rk((uint32_t)(sample >> 32), (uint32_t)sample, P_INIT << 8, (uint32_t)c, P.rk, W[j][4 * c],
                              W[j][4 * c + 1], W[j][4 * c + 2], W[j][4 * c + 3]);
     }
     uint32_t x[INIT_SPT][NV];

@@ -3,7 +3,7 @@
 // emb_sample_tracks while it is still in HBM.
 //
 // One call of integrate_track = one track: reads the fp32 tiles of the three dynamic variables
-// ([var][ceil(T/4)][n][4]: a warp reads 512 contiguous bytes per variable per tile), accumulates in fp64 like the
+// ([ceil(T/4)][ceil(n/128)][var][128][4]: a warp reads 512 contiguous bytes per variable per tile), accumulates in fp64 like the
 // reference, writes T+1 points [3][T+1][n] fp32 (a warp writes 128 contiguous bytes per field per second).
 #pragma once
 #include "emb_terminal.cuh"   // sincosd
@@ -15,10 +15,11 @@ struct IntegrateParams {
     int32_t T;
     int32_t i_alt, i_speed;        // 0-based initial variables: altitude layer value 'L', airspeed 'v'
     int32_t g_acc, g_vr, g_turn;   // ordinals of \dot v, \dot h, \dot\psi among the time-varying variables (tile index)
+    int32_t n_tv;                  // number of time-varying variables (variables per tile)
     double ur_speed, ur_vertrate, ur_heading;   // sample2track.m:108-125
     double min_speed, max_speed;   // boundaries{v}([1 end]) * ur_speed (:98-99, :140-141)
     const double* init_values;     // [n_initial][n]
-    const float* values;           // [n_tv][ceil(T/4)][n][4]
+    const float* values;           // [ceil(T/4)][ceil(n/128)][n_tv][128][4]
     float* xyz;                    // [3][T+1][n]   x_ft, y_ft, z_ft at time_s = 0..T
     uint8_t* is_good;              // [n]  ~is_cfit & ~is_reject_speed (:241)
 };
@@ -38,9 +39,10 @@ EMB_HD void integrate_track(const IntegrateParams& P, int64_t s) {
         EMB_STREAM_F32(out + fs, 0.0f);
         EMB_STREAM_F32(out + 2 * fs, (float)z);
     }
-    const float* pa = P.values + ((int64_t)P.g_acc * nch4 * N + s) * 4;
-    const float* pv = P.values + ((int64_t)P.g_vr * nch4 * N + s) * 4;
-    const float* pt = P.values + ((int64_t)P.g_turn * nch4 * N + s) * 4;
+    const int64_t ntile = num_tiles(N), gstep = ntile * ((int64_t)P.n_tv * TRACK_TILE * 4);
+    const float* pa = P.values + tile_offset(P.n_tv, ntile, P.g_acc, 0, s);
+    const float* pv = P.values + tile_offset(P.n_tv, ntile, P.g_vr, 0, s);
+    const float* pt = P.values + tile_offset(P.n_tv, ntile, P.g_turn, 0, s);
     for (int grp = 0; grp < nch4; ++grp) {
         float a4[4], v4[4], t4[4];
 #if defined(__CUDA_ARCH__)
@@ -52,7 +54,7 @@ EMB_HD void integrate_track(const IntegrateParams& P, int64_t s) {
 #else
         for (int j = 0; j < 4; ++j) { a4[j] = pa[j]; v4[j] = pv[j]; t4[j] = pt[j]; }
 #endif
-        pa += N * 4; pv += N * 4; pt += N * 4;
+        pa += gstep; pv += gstep; pt += gstep;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = 4 * grp + j;               // updates of row pInd = c+1, i.e. dense column c (:203-205)

@@ -113,8 +113,9 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
         for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
         __syncthreads();
     }
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) track_generic(M, P, O, s, SmemHist{sh});
+    const int64_t s = P.s_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.s_end) track_generic(M, P, O, s, SmemHist{sh});
+    else if (P.s_end == P.n) zero_padding_track(O, M.n_dyn, M.n_gated, P.T, P.n, s);
     if (want_hist) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
@@ -124,13 +125,15 @@ __global__ void __launch_bounds__(BLOCK, FAST ? EMB_MINBLOCKS : EMB_MINBLOCKS_SL
 k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
               const __grid_constant__ TrackOut O) {
     __shared__ FastShared S;
+    __shared__ CallTable<NG> U;
     __shared__ uint32_t sh[HIST ? (MAXV + MAXD) * HIST_STRIDE : 1];
     fast_fill_shared(M, S, threadIdx.x, blockDim.x);
     if (HIST)
         for (int q = threadIdx.x; q < (MAXV + MAXD) * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
     __syncthreads();
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) track_fast<RS, NG, FAST, HIST, EV, ORD>(M, P, O, s, S, SmemHist{sh});
+    const int64_t s = P.s_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    track_fast<RS, NG, FAST, HIST, EV, ORD>(M, P, O, s, s < P.s_end, S, U, (int)threadIdx.x, (int)blockDim.x, SmemHist{sh});
+    if (!EV && s >= P.s_end && P.s_end == P.n) zero_padding_track(O, M.n_dyn, NG, P.T, P.n, s);
     if (HIST) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
@@ -294,15 +297,21 @@ int launch_initial(const DevModel& M, const SampleParams& P, int table_words, in
     return (int)cudaGetLastError();
 }
 
-int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream) {
-    if (P.n <= 0) return 0;
-    const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
+int launch_tracks(const DevModel& M, const SampleParams& P0, const TrackOut& O, void* stream) {
+    if (P0.n <= 0) return 0;
     const uint32_t rs = g_force_generic ? 0u : fast_shape_of(M);
     const bool fast = M.fast != 0;
     const uint32_t ord = order_code(M);
     const bool hist = O.hist_initial || O.hist_transition;
     const int ev = O.ev_counts ? 1 : O.events ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
     bool done = false;
+    // one launch per run of tracks whose global sample index shares its high word (spec v4: counter word 0 is launch-uniform)
+    SampleParams P = P0;
+    for (int64_t s0 = 0; s0 < P0.n; s0 = P.s_end) {
+        P.s_begin = s0;
+        P.s_end = next_segment(P0.first_sample, s0, P0.n);
+        const unsigned grid = (unsigned)((P.s_end - P.s_begin + BLOCK - 1) / BLOCK);
+        done = false;
 #define EMB_X(RS_, NG_, FAST_, ORD_)                                                                    \
     if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_) && ord == (ORD_)) {               \
         if (ev == 1) k_tracks_fast<RS_, NG_, FAST_, false, 1, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);      \
@@ -311,11 +320,12 @@ int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, v
         else k_tracks_fast<RS_, NG_, FAST_, false, 0, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);              \
         done = true;                                                                                    \
     }
-    EMB_FAST_SHAPES(EMB_X)
+        EMB_FAST_SHAPES(EMB_X)
 #undef EMB_X
-    if (!done) k_tracks_generic<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);
+        if (!done) k_tracks_generic<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);
+        g_launch_count.fetch_add(1);
+    }
     g_last_kernel_fast = done ? 1 : 0;
-    g_launch_count.fetch_add(1);
     return (int)cudaGetLastError();
 }
 

@@ -496,6 +496,8 @@ void fill_params(const HostModel& H, uint64_t seed, uint64_t first_sample, int64
     }
     P.first_sample = first_sample;
     P.n = n;
+    P.s_begin = 0;
+    P.s_end = n;
     P.T = T;
     P.reject_mode = o->reject_mode;
     P.idx_v = o->idx_v - 1;

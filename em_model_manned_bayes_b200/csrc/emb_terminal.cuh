@@ -264,8 +264,8 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         bool ev_any = false, ev_v = false;
         for (uint32_t attempt = 0;; ++attempt) {                                  // while is_resample (:192-243)
             uint32_t w0, w1, w2, w3;
-            philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
-                          (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain, (uint32_t)P.seed,
+            philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample,
+                          (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain, (uint32_t)ii, (uint32_t)P.seed,
                           (uint32_t)(P.seed >> 32), w0, w1, w2, w3);
             const int nh = select_bin(col[0], (int)M.rp[0], w0);
             const int na = select_bin(col[1], (int)M.rp[1], w1);
@@ -274,8 +274,8 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
             if (nh != (int)st[3] || na != (int)st[4] || nv != (int)st[5]) {
                 ev_any = true;                      // events in variable order 4, 5, 6
                 uint32_t d0, d1, d2, d3;
-                philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)ii,
-                              (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain, (uint32_t)P.seed,
+                philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample,
+                              (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain, (uint32_t)ii, (uint32_t)P.seed,
                               (uint32_t)(P.seed >> 32), d0, d1, d2, d3);
                 if (nh != (int)st[3]) heading_deg = term_dedisc(M, 3, nh, d0);         // :200-205
                 if (na != (int)st[4]) {                                                // :206-212

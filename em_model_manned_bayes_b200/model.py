@@ -33,20 +33,32 @@ def _ptr(a):
     return a.data_ptr()  # torch tensor
 
 
+TRACK_TILE = 128   # tracks per tile of the dense layout (emb200.h: emb_track_out)
+
+
+def untile(buf, nvar: int, n: int, T: int):
+    """[ceil(T/4)][ceil(n/128)][nvar][128][4] -> (n, nvar, T).  Works on numpy arrays and torch tensors."""
+    nch, ntile = (T + 3) // 4, (n + TRACK_TILE - 1) // TRACK_TILE
+    a = buf.reshape(nch, ntile, nvar, TRACK_TILE, 4)
+    a = a.transpose(1, 3, 2, 0, 4) if isinstance(a, np.ndarray) else a.permute(1, 3, 2, 0, 4)
+    return a.reshape(ntile * TRACK_TILE, nvar, nch * 4)[:n, :, :T]
+
+
+def tile(vals: np.ndarray) -> np.ndarray:
+    """(n, nvar, T) -> the dense layout as a flat array (the inverse of `untile`; padding tracks and seconds are 0)."""
+    n, nvar, T = vals.shape
+    nch, ntile = (T + 3) // 4, (n + TRACK_TILE - 1) // TRACK_TILE
+    pad = np.zeros((ntile * TRACK_TILE, nvar, nch * 4), dtype=vals.dtype)
+    pad[:n, :, :T] = vals
+    return np.ascontiguousarray(pad.reshape(ntile, TRACK_TILE, nvar, nch, 4).transpose(3, 0, 2, 1, 4)).ravel()
+
+
 def untile_bins(buf, n_dyn: int, n: int, T: int):
-    """[n_dyn][ceil(T/4)][n][4] -> (n, n_dyn, T).  Works on numpy arrays and torch tensors."""
-    nch = (T + 3) // 4
-    a = buf.reshape(n_dyn, nch, n, 4)
-    a = a.transpose(2, 0, 1, 3) if isinstance(a, np.ndarray) else a.permute(2, 0, 1, 3)
-    return a.reshape(n, n_dyn, nch * 4)[:, :, :T]
+    return untile(buf, n_dyn, n, T)
 
 
 def untile_values(buf, n_tv: int, n: int, T: int):
-    """[n_tv][ceil(T/4)][n][4] -> (n, n_tv, T)."""
-    nch = (T + 3) // 4
-    a = buf.reshape(n_tv, nch, n, 4)
-    a = a.transpose(2, 0, 1, 3) if isinstance(a, np.ndarray) else a.permute(2, 0, 1, 3)
-    return a.reshape(n, n_tv, nch * 4)[:, :, :T]
+    return untile(buf, n_tv, n, T)
 
 
 @dataclass

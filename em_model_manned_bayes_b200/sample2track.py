@@ -20,7 +20,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib as L
-from .model import EncounterModel, TrackResult, _ptr
+from .model import EncounterModel, TrackResult, _ptr, tile
 
 FT_PER_NM = 1852.0 / 0.3048           # unitsratio('ft', 'nm')
 
@@ -111,13 +111,10 @@ def sample2track(parameters_filename: str, initial_filename: str, transition_fil
     rows = (first[:, None] + np.arange(T)[None, :]).ravel()
     upd = Tt[rows, 2:].reshape(n, T, len(dyn_t))                          # (n, T, n_dyn)
     tv = list(model.timevarying_vars)
-    nch = (T + 3) // 4
-    tiles = np.zeros((len(tv), nch, n, 4), dtype=np.float32)
+    dense = np.zeros((n, len(tv), T), dtype=np.float32)
     for k, v in enumerate(dyn_t):
-        pad = np.zeros((n, nch * 4), dtype=np.float32)
-        pad[:, :T] = upd[:, :, k]
-        tiles[tv.index(v)] = pad.reshape(n, nch, 4).transpose(1, 0, 2)
-    res = TrackResult(n=n, T=T, dyn_vars=dyn_t, tv_vars=tv, bins_tiled=None, values_tiled=tiles.ravel(), init_bins=None,
+        dense[:, tv.index(v), :] = upd[:, :, k]
+    res = TrackResult(n=n, T=T, dyn_vars=dyn_t, tv_vars=tv, bins_tiled=None, values_tiled=tile(dense), init_bins=None,
                       init_values=np.ascontiguousarray(Ti[:, 1:].T), attempts=None)
     xyz, good = integrate_tracks(model, res, opts=o)
     is_good = good.astype(bool)

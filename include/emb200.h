@@ -143,11 +143,14 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
 /* ---- tracks: replaces UncorEncounterModel.m:244-307 loop around dbn_hierarchical_sample.m:9-37
  *      (dbn_sample.m both branches, resample_events.m, dediscretize.m, events2samples.m) ---------- */
 typedef struct emb_track_out {
-    /* dense, in tiles of four seconds so that a warp stores contiguous memory; column c (0-based)
-     * is the state during second c+1, i.e. out_samples{ii}(:, c+1) (events2samples.m:9-27); the
-     * padding seconds of the last tile are 0 */
-    int8_t* bins;        /* [n_dyn][ceil(T/4)][n][4]  1-based bins of the dynamic variables  nullable */
-    float* values;       /* [n_timevarying][ceil(T/4)][n][4] continuous values               nullable */
+    /* dense, in tiles of 128 tracks x four seconds, all variables of a tile together, so that a warp stores
+     * contiguous memory and a thread's stores sit at fixed offsets from one pointer:
+     *     element (variable g, track s, second c) = [c/4][s/128][g][s%128][c%4]
+     * column c (0-based) is the state during second c+1, i.e. out_samples{ii}(:, c+1) (events2samples.m:9-27);
+     * padding seconds of the last group are 0, padding tracks of the last tile are never written.  Buffer
+     * lengths (elements): emb_tracks_bins_len / emb_tracks_values_len */
+    int8_t* bins;        /* [ceil(T/4)][ceil(n/128)][n_dyn][128][4]  1-based bins of the dynamic variables  nullable */
+    float* values;       /* [ceil(T/4)][ceil(n/128)][n_timevarying][128][4] continuous values               nullable */
     /* per track */
     int8_t* init_bins;   /* [n_initial][n]                                                   nullable */
     double* init_values; /* [n_initial][n]  out_inits (after layers/quantize500)             nullable */
@@ -246,7 +249,7 @@ typedef struct emb_integrate_opts {
     int32_t mem, device;                                  /* EMB_MEM_*, CUDA ordinal (-1 = current) */
     void* stream;
 } emb_integrate_opts;
-/* init_values: double [n_initial][n] and values: float [n_timevarying][ceil(T/4)][n][4] as written by emb_sample_tracks;
+/* init_values: double [n_initial][n] and values: float [ceil(T/4)][ceil(n/128)][n_timevarying][128][4] as written by emb_sample_tracks;
  * xyz: float [3][T+1][n] = x_ft, y_ft, z_ft at time_s = 0..T (nullable); is_good: uint8 [n] (nullable). */
 int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double* init_values, const float* values,
                          const emb_integrate_opts* opts, float* xyz, uint8_t* is_good);

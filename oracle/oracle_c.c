@@ -56,7 +56,7 @@ typedef struct {
     int32_t max_attempts;
 } oc_model;
 
-/* ---- keyed Philox4x32-10 (stream spec v3) ----------------------------------------------------- */
+/* ---- keyed Philox4x32-10 (stream spec v4: counter = (sample_hi, sample_lo, attempt<<16 | purpose<<8 | sub, index); the step stream, purpose 2, carries no attempt) ----------------------------------------------------- */
 static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* o) {
     for (int i = 0; i < 10; ++i) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -71,10 +71,10 @@ static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t 
 typedef struct { uint64_t seed, sample; uint32_t attempt; int nd, nw, n_initial;
                  uint32_t c_idx[8], c_w3[8], c_o[8][4]; int c_ok[8]; } ukey;
 static uint32_t word(ukey* k, uint32_t purpose, uint32_t index, uint32_t sub, uint32_t lane) {
-    const uint32_t w3 = (k->attempt << 16) | (purpose << 8) | sub;
+    const uint32_t w3 = ((purpose == 2 ? 0u : k->attempt) << 16) | (purpose << 8) | sub;
     const int q = (int)(purpose & 7);
     if (!k->c_ok[q] || k->c_idx[q] != index || k->c_w3[q] != w3) {
-        philox((uint32_t)k->sample, (uint32_t)(k->sample >> 32), index, w3, (uint32_t)k->seed, (uint32_t)(k->seed >> 32), k->c_o[q]);
+        philox((uint32_t)(k->sample >> 32), (uint32_t)k->sample, w3, index, (uint32_t)k->seed, (uint32_t)(k->seed >> 32), k->c_o[q]);
         k->c_idx[q] = index; k->c_w3[q] = w3; k->c_ok[q] = 1;
     }
     return k->c_o[q][lane];
@@ -235,11 +235,13 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
             int var = (int)ev2[e].var;
             double rnd = 0.5;
             if (dd_needs_u(M, var, ev2[e].val)) {
-                /* stream spec v3: fired-gate and transition values both read the variable's word of that second */
+                /* stream spec v4: fired-gate and transition values both read the variable's word of that second and, as an
+                 * independent partner, the word of the next gated variable (cyclic; none when there is only one) */
                 int g = 0;
                 while (M->gated[g] != var) ++g;
                 uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + g);
-                uint32_t h = k * 0x85EBCA6Bu;
+                uint32_t kn = K.nw > 1 ? word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + (g + 1) % K.nw) : 0u;
+                uint32_t h = k * 0x85EBCA6Bu + kn;
                 rnd = ((double)(h >> 9) + 0.5) * 1.1920928955078125e-07; /* 2^-23 */
             }
             /* keep the bin for the dense bin expansion in .second's place holder */

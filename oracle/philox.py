@@ -2,7 +2,7 @@
 
 Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy
 as 1, 2, 3", SC'11; the Random123 `philox4x32_R(10, ctr, key)` function) and the keyed
-stream layout ("stream spec v3") shared by the oracle and the CUDA sampler.
+stream layout ("stream spec v4") shared by the oracle and the CUDA sampler.
 
 The reference (`/root/reference/code/matlab/select_random.m:14`, `dbn_sample.m:133`,
 `resample_events.m:24`, `dediscretize.m:39`) draws from MATLAB's global `rand`.  The B200
@@ -10,11 +10,15 @@ sampler replaces *when* a uniform is consumed by *what it is for*: every uniform
 function of (seed, sample, attempt, purpose, index, lane).  The oracle is fed exactly these
 uniforms (uniform-injection), so bin indices must be bit-identical.
 
-Stream spec v3
+Stream spec v4
 --------------
 key     = (seed & 0xffffffff, seed >> 32)
-counter = (sample & 0xffffffff, sample >> 32, index, (attempt << 16) | (purpose << 8) | sub)
-A call returns four 32-bit words; `lane` picks one.
+counter = (sample >> 32, sample & 0xffffffff, (attempt << 16) | (purpose << 8) | sub, index)
+A call returns four 32-bit words; `lane` picks one.  (With the sample in counter word 1 and the index in word 3,
+and words 0 and 2 the same for every track of a launch, the first three Philox rounds factor into a part that only
+depends on the track and a part that only depends on the index -- the CUDA kernel computes each once and runs 7 of
+the 10 rounds per call, csrc/emb_device.cuh: philox_track / philox_call / philox_finish.  The words are the plain
+Philox4x32-10 words of that counter.)
 
 purpose INIT (1):    word position p;  p = i            -> select word of initial variable i (0-based)
                                       p = n_initial + i -> dediscretize word of initial variable i
@@ -23,14 +27,18 @@ purpose STEP (2):    ONE word per (second, variable): word position p = e * nw +
                      g the ordinal of the variable among the *gated* variables -- in increasing id, the
                      initial variables that have a resample rate > 0 or are dynamic (temporal_map column
                      1); nw = their number.  (The nw positions of e = 0 are unused, which keeps groups of
-                     four seconds aligned to nw Philox calls.)   index = p // 4, lane = p % 4
+                     four seconds aligned to nw Philox calls.)   index = p // 4, lane = p % 4.
+                     attempt = 0 ALWAYS: the driver's rejection test (UncorEncounterModel.m:275) reads only the
+                     initial draw, so the seconds of the accepted attempt are the same words whichever attempt
+                     was accepted (the seconds of a rejected attempt are discarded by the reference anyway).
 purpose LAYER (4):   index = 0, lane = 0 -> altitude-layer draw (UncorEncounterModel.m:260)
 purpose TERM_* (5+): terminal trajectory chains, see oracle/terminal.py
 
 word -> uniform: u = (k + 0.5) * 2**-32  (strictly inside (0,1), exact in fp64).
 
-Everything random that happens to variable v in second e comes from its one word k, through three
-different bijections of the 32-bit words (A = 0x9E3779B1, B = 0x85EBCA6B, both odd):
+What happens to variable v (gated ordinal g) in second e comes from its word k = W[e*nw + g] and, for the value, the
+word of the next gated variable of the same second, k' = W[e*nw + (g+1) % nw] (k' = 0 when nw == 1), with
+A = 0x9E3779B1, B = 0x85EBCA6B, both odd:
   * transition select of a dynamic variable, loop index t = e + 1 (dbn_sample.m:77 / :133,144):
         u_sel  = (k + 0.5) 2**-32
   * resample gate `rand < rate` (resample_events.m:24):
@@ -38,13 +46,15 @@ different bijections of the 32-bit words (A = 0x9E3779B1, B = 0x85EBCA6B, both o
         G = #{h : (h + 0.5) 2**-32 < rate}  (G = 0 for rate 0)
   * every de-discretisation of v that takes effect in second e -- the re-emitted bin of a fired gate
     and/or the new bin of a transition event (dbn_hierarchical_sample.m:35):
-        u_dd   = ((((k * B) mod 2**32) >> 9) + 0.5) 2**-23
-An odd multiplier is a bijection that spreads any interval of k evenly over the top bits of the
-product (a Kronecker/golden-ratio lattice), so each of the three uniforms is uniform given the
-outcome of the other two decisions up to O(2**-32) in probability; the 23-bit resolution of u_dd
-makes the word -> float conversion exact in fp32 arithmetic on the GPU.
-(spec v1 spent separate Philox calls on event values; spec v2 still drew a separate select word per
-dynamic variable, 7 words per second for the 7-variable uncorrelated models instead of 4.)
+        u_dd   = ((((k * B + k') mod 2**32) >> 9) + 0.5) 2**-23
+The reference draws these three uniforms independently.  Here u_dd is exactly uniform and independent of v's own
+select and gate (k' is an independent full-entropy word), and pairwise independent of every other decision of the
+second; what remains coupled is (i) select and gate of the same variable, through the odd multiplier A that
+spreads any interval of k evenly over the gate word (a Kronecker lattice: given a transition of probability p the
+gate frequency is off by O(1/(p 2**32))), and (ii) three-way: u_dd of v given *both* v's and the next variable's
+decisions.  (spec v3 took u_dd from k alone, so after a rare transition the value could only take p 2**32 distinct
+values; spec v1/v2 spent separate Philox calls: 7 words per second for the 7-variable models instead of 4.)
+The 23-bit resolution of u_dd makes the word -> float conversion exact in fp32 arithmetic on the GPU.
 """
 from __future__ import annotations
 
@@ -97,10 +107,10 @@ def make_counter(sample, index, attempt, purpose, sub=0):
     w3 = (attempt << np.uint64(16)) | np.uint64(purpose << 8) | sub
     sample, index, w3 = np.broadcast_arrays(sample, index, w3)
     ctr = np.empty(sample.shape + (4,), dtype=np.uint32)
-    ctr[..., 0] = (sample & MASK32).astype(np.uint32)
-    ctr[..., 1] = (sample >> np.uint64(32)).astype(np.uint32)
-    ctr[..., 2] = (index & MASK32).astype(np.uint32)
-    ctr[..., 3] = (w3 & MASK32).astype(np.uint32)
+    ctr[..., 0] = (sample >> np.uint64(32)).astype(np.uint32)
+    ctr[..., 1] = (sample & MASK32).astype(np.uint32)
+    ctr[..., 2] = (w3 & MASK32).astype(np.uint32)
+    ctr[..., 3] = (index & MASK32).astype(np.uint32)
     return ctr
 
 
@@ -134,13 +144,14 @@ DD_MULT = 0x85EBCA6B
 
 
 def gate_word(k):
-    """step word -> the 32-bit word the resample gate compares (stream spec v3)."""
+    """step word -> the 32-bit word the resample gate compares (stream spec v4)."""
     return (int(k) * GATE_MULT) & 0xFFFFFFFF
 
 
-def dd_uniform(k):
-    """step word -> de-discretisation uniform (stream spec v3), exact in fp64."""
-    h = (int(k) * DD_MULT) & 0xFFFFFFFF
+def dd_uniform(k, k_next=0):
+    """step word k and partner word k_next (the next gated variable's word of the same second, 0 when nw == 1)
+    -> de-discretisation uniform (stream spec v4), exact in fp64."""
+    h = (int(k) * DD_MULT + int(k_next)) & 0xFFFFFFFF
     return (float(h >> 9) + 0.5) * 2.0 ** -23
 
 

@@ -4,7 +4,7 @@ Uniform providers for the restated reference sampler.  The restatement (oracle/s
 provider for a uniform at every place the reference calls `rand`, passing the *context* of the
 draw.  Two providers:
 
-* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v3"): the uniform is a pure
+* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v4"): the uniform is a pure
   function of the context.  This is the uniform-injection hook of BASELINE.json's north star: the
   reference algorithm, fed these uniforms, must give bit-identical bins to the CUDA sampler.
 * MTStream     -- MATLAB's `rng(seed,'twister'); rand` emulation (MT19937 `genrand_res53`, which
@@ -36,7 +36,7 @@ class _Base:
 
 class KeyedPhilox(_Base):
     """Context-keyed uniforms.  `bind(parms)` must be called once per model so that the dynamic and
-    gated ordinals (stream spec v3) are known."""
+    gated ordinals (stream spec v4) are known."""
 
     def __init__(self, seed: int, record: bool = False):
         super().__init__()
@@ -64,7 +64,8 @@ class KeyedPhilox(_Base):
         self.attempt = int(attempt)
 
     def _w(self, purpose, position):
-        return int(px.word_at(self.seed, self.sample, self.attempt, purpose, position))
+        attempt = 0 if purpose == px.P_STEP else self.attempt      # spec v4: the step stream carries no attempt
+        return int(px.word_at(self.seed, self.sample, attempt, purpose, position))
 
     # -- draws ---------------------------------------------------------------------------------
     def select_init(self, var):                      # bn_sample.m:55 -> select_random.m:14
@@ -102,9 +103,10 @@ class KeyedPhilox(_Base):
         # both kinds (re-emitted bin of a fired gate, new bin of a transition) read the variable's word of that second
         g = self.gated.index(int(var))
         k = self._w(px.P_STEP, second * self.nw + g)
+        kn = self._w(px.P_STEP, second * self.nw + (g + 1) % self.nw) if self.nw > 1 else 0
         if kind == "gate":
             assert px.gate_word(k) < self.G[int(var)]
-        return self._rec(("event_dd", kind, second, var), px.dd_uniform(k))
+        return self._rec(("event_dd", kind, second, var), px.dd_uniform(k, kn))
 
     def layer(self):                                 # UncorEncounterModel.m:260
         return self._rec(("layer",), px.u01(self._w(px.P_LAYER, 0)))

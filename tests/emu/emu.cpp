@@ -147,7 +147,11 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
         fast_fill_shared(D, S, 0, 1);
 #define EMB_X(RS_, NG_, FAST_, ORD_)                                                   \
     if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_) && order_code(D) == (ORD_)) { \
-        for (int64_t s = 0; s < n; ++s) track_fast<RS_, NG_, FAST_, true, 0, ORD_>(D, P, O, s, S, hh); \
+        static CallTable<NG_> U;                                                      \
+        for (int64_t s = 0; s < n; ++s) {                                             \
+            if (s == P.s_end || s == 0) { P.s_begin = s; P.s_end = next_segment(P.first_sample, s, n); } \
+            track_fast<RS_, NG_, FAST_, true, 0, ORD_>(D, P, O, s, true, S, U, 0, 1, hh); \
+        }                                                                             \
         done = true;                                                                   \
     }
         EMB_FAST_SHAPES(EMB_X)
@@ -190,9 +194,11 @@ int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, i
         bool done = false;
 #define EMB_X(RS_, NG_, FAST_, ORD_)                                                                    \
     if (!done && rs == (RS_) && D.n_gated == (NG_) && fast == (FAST_) && order_code(D) == (ORD_)) {     \
+        static CallTable<NG_> U;                                                                        \
         for (int64_t s = 0; s < n; ++s) {                                                               \
-            if (pass == 1) track_fast<RS_, NG_, FAST_, false, 1, ORD_>(D, P, O, s, S, hh);              \
-            else track_fast<RS_, NG_, FAST_, false, 2, ORD_>(D, P, O, s, S, hh);                        \
+            if (s == P.s_end || s == 0) { P.s_begin = s; P.s_end = next_segment(P.first_sample, s, n); } \
+            if (pass == 1) track_fast<RS_, NG_, FAST_, false, 1, ORD_>(D, P, O, s, true, S, U, 0, 1, hh); \
+            else track_fast<RS_, NG_, FAST_, false, 2, ORD_>(D, P, O, s, true, S, U, 0, 1, hh);           \
         }                                                                                               \
         done = true;                                                                                    \
     }
@@ -275,12 +281,12 @@ int emu_bearing_cells(void* model, int64_t n, const double* x, const double* y, 
 }
 
 // host emulation of emb_tracks_integrate (same per-track code as k_tracks_integrate); g_* = tile ordinals
-int emu_tracks_integrate(int64_t n, int32_t T, int32_t i_alt, int32_t i_speed, int32_t g_acc, int32_t g_vr, int32_t g_turn,
+int emu_tracks_integrate(int64_t n, int32_t T, int32_t i_alt, int32_t i_speed, int32_t g_acc, int32_t g_vr, int32_t g_turn, int32_t n_tv,
                          double ur_speed, double ur_vertrate, double ur_heading, double min_speed, double max_speed,
                          const double* init_values, const float* values, float* xyz, uint8_t* is_good) {
     IntegrateParams P;
     std::memset(&P, 0, sizeof(P));
-    P.n = n; P.T = T; P.i_alt = i_alt; P.i_speed = i_speed; P.g_acc = g_acc; P.g_vr = g_vr; P.g_turn = g_turn;
+    P.n = n; P.T = T; P.i_alt = i_alt; P.i_speed = i_speed; P.g_acc = g_acc; P.g_vr = g_vr; P.g_turn = g_turn; P.n_tv = n_tv;
     P.ur_speed = ur_speed; P.ur_vertrate = ur_vertrate; P.ur_heading = ur_heading;
     P.min_speed = min_speed; P.max_speed = max_speed;
     P.init_values = init_values; P.values = values; P.xyz = xyz; P.is_good = is_good;

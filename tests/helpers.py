@@ -67,7 +67,7 @@ def emu_lib():
     lib.emu_terminal_propagate.argtypes = [C.POINTER(vp), u64, u64, i64, vp, i64, C.POINTER(i32), C.c_double,
                                            C.POINTER(L.DynLimits), i32, vp, vp]
     lib.emu_terminal_screen.argtypes = [vp, vp, i64, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp]
-    lib.emu_tracks_integrate.argtypes = [i64, i32, i32, i32, i32, i32, i32] + [C.c_double] * 5 + [vp, vp, vp, vp]
+    lib.emu_tracks_integrate.argtypes = [i64, i32, i32, i32, i32, i32, i32, i32] + [C.c_double] * 5 + [vp, vp, vp, vp]
     lib.emu_bearing_cells.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.emu_use_fast.argtypes = [C.c_int]
     lib.emu_last_fast.restype = C.c_int
@@ -144,9 +144,9 @@ class EmuModel:
         return ev[:total.value], off
 
     def sample_tracks(self, n_initial, n_dyn, n_tv, n, T, seed, first, opts, hist=False):
-        nch = (T + 3) // 4
-        bins = np.zeros(n_dyn * nch * n * 4, dtype=np.int8)
-        vals = np.zeros(n_tv * nch * n * 4, dtype=np.float32)
+        nch, npad = (T + 3) // 4, (n + 127) // 128 * 128
+        bins = np.zeros(n_dyn * nch * npad * 4, dtype=np.int8)
+        vals = np.zeros(n_tv * nch * npad * 4, dtype=np.float32)
         ib = np.zeros((n_initial, n), dtype=np.int8)
         iv = np.zeros((n_initial, n), dtype=np.float64)
         att = np.zeros(n, dtype=np.uint16)

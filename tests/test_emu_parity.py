@@ -196,6 +196,35 @@ def test_tracks_match_c_oracle(model_paths, model, uncor, n, T, fast):
     assert np.all(np.abs(got["values"].astype(np.float64) - want) <= 1e-6 * np.abs(want))
 
 
+@pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
+def test_tracks_across_a_2_32_sample_boundary(model_paths, fast):
+    """Stream spec v4 puts sample >> 32 into counter word 0, which the specialised kernel treats as launch-uniform
+    (philox_track / philox_call): a call whose global sample indices straddle a multiple of 2^32 is split into two
+    launches (next_segment).  Tracks on both sides of the boundary must match the C restatement."""
+    from oracle.c_oracle import COracle
+    from oracle.em_read import em_read
+    p = em_read(model_paths["uncor_1200code_v2p1"])
+    n, T, first = 90, 40, 3 * 2 ** 32 - 37
+    ref = COracle(p, uncor=True).sample_tracks(n, T, seed=5, first_sample=first, threads=0)
+    lib = H.emu_lib()
+    lib.emu_use_fast(fast)
+    m = H.EmuModel(model_paths["uncor_1200code_v2p1"])
+    lab = p.labels_initial
+    kw = dict(reject_mode=L.EMB_REJECT_UNCOR, idx_v=cases.label_index(lab, '"v"'), idx_dh=cases.label_index(lab, '"\\dot h"'),
+              idx_L=cases.label_index(lab, '"L"'))
+    tm = np.asarray(p.temporal_map)
+    dyn = [int(v) - 1 for v in tm[:, 0]]
+    rates = np.asarray(p.resample_rates)
+    tv = sorted(set(dyn) | {i for i in range(p.n_initial) if rates[i] > 0})
+    got = m.sample_tracks(p.n_initial, len(dyn), len(tv), n, T, 5, first, H.EmuModel.opts(p.n_initial, **kw))
+    assert lib.emu_last_fast() == fast
+    lib.emu_use_fast(0)
+    assert np.array_equal(got["init_bins"], ref["init_bins"])
+    assert np.array_equal(got["bins"], ref["sample_bins"][:, dyn, :])
+    want = ref["samples"][:, tv, :]
+    assert np.all(np.abs(got["values"].astype(np.float64) - want) <= 1e-6 * np.abs(want))
+
+
 @pytest.mark.skipif(not H.have_reference(), reason="needs the reference checkout's model/*.txt (build container only)")
 def test_every_shipped_dbn_model_runs_specialised_and_matches_the_c_oracle():
     """All model/*.txt files with a transition network (not just the archived ones): the specialised code path

@@ -20,12 +20,16 @@ from oracle.uniforms import KeyedPhilox
 
 
 def tiles_from_samples(vals):
-    """(n, n_tv, T) -> [n_tv][ceil(T/4)][n][4] float32 (the dense layout of emb_sample_tracks)."""
+    """(n, n_tv, T) -> [ceil(T/4)][ceil(n/128)][n_tv][128][4] float32 (the dense layout of emb_sample_tracks), written
+    element by element from the layout's definition (emb200.h: emb_track_out)."""
     n, ntv, T = vals.shape
-    nch = (T + 3) // 4
-    pad = np.zeros((n, ntv, nch * 4), dtype=np.float32)
-    pad[:, :, :T] = vals
-    return np.ascontiguousarray(pad.reshape(n, ntv, nch, 4).transpose(1, 2, 0, 3)).ravel()
+    nch, ntile = (T + 3) // 4, (n + 127) // 128
+    out = np.zeros((nch, ntile, ntv, 128, 4), dtype=np.float32)
+    s = np.arange(n)
+    for g in range(ntv):
+        for t in range(T):
+            out[t // 4, s // 128, g, s % 128, t % 4] = vals[:, g, t]
+    return out.ravel()
 
 
 def oracle_tracks(p, out, T, from_fp32=True):
@@ -81,7 +85,7 @@ def test_emu_integration_matches_oracle(model_paths, model, n, T):
     good = np.zeros(n, dtype=np.uint8)
     b = p.boundaries[iv]
     ur = FT_PER_NM / 3600.0
-    rc = H.emu_lib().emu_tracks_integrate(n, T, iL, iv, tv.index(ia + 1), tv.index(ih + 1), tv.index(it + 1), ur, 1.0 / 60.0, 1.0,
+    rc = H.emu_lib().emu_tracks_integrate(n, T, iL, iv, tv.index(ia + 1), tv.index(ih + 1), tv.index(it + 1), len(tv), ur, 1.0 / 60.0, 1.0,
                                           float(b[0]) * ur, float(b[-1]) * ur, init.ctypes.data, tiles.ctypes.data,
                                           xyz.ctypes.data, good.ctypes.data)
     assert rc == 0
