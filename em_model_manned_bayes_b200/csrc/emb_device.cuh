@@ -33,13 +33,14 @@ constexpr int MAXG = 16;  // EMB_MAX_GATED
 constexpr int MAXX = MAXV + MAXD;
 constexpr int HIST_STRIDE = 64;
 
-// stream spec v4 (oracle/philox.py): counter = (sample >> 32, sample & 0xffffffff, attempt << 16 | purpose << 8 | sub, index);
+// stream spec v5 (oracle/philox.py): counter = (sample >> 32, sample & 0xffffffff, attempt << 16 | purpose << 8 | sub, index);
 // the step stream (P_STEP) carries no attempt: the rejection test only reads the initial draw (UncorEncounterModel.m:275),
 // so the seconds of the accepted attempt are the same words whichever attempt was accepted.
 constexpr uint32_t P_INIT = 1, P_STEP = 2, P_LAYER = 4;
-// one word k per (second, gated variable): select on k, gate on k*GATE_MULT; the de-discretisation word of the variable is
-// k*DD_MULT + k', k' = the word of the next gated variable of the same second (cyclic; 0 when there is only one), which makes
-// the value independent of the variable's own select and gate decisions
+// one word k(e, g) per (second e, gated variable g); one Philox call = four consecutive seconds of ONE variable
+// (index (e >> 2) * nw + g, lane e & 3).  Select on k, gate on k*GATE_MULT; the de-discretisation word is k*DD_MULT + k',
+// k' = the same variable's word of the cyclically next second of the call, which makes the value independent of the
+// variable's own select and gate decisions of that second
 constexpr uint32_t GATE_MULT = 0x9E3779B1u;
 constexpr uint32_t DD_MULT = 0x85EBCA6Bu;
 
@@ -60,7 +61,7 @@ struct DevModel {
     Node dyn[MAXD];
     int32_t dyn_t[MAXD];           // x index of the variable at time t
     int32_t dyn_t1[MAXD];          // x index of its (t+1)/(t-1) counterpart
-    int32_t gated_var[MAXG];       // variables with a word per second: rate > 0 or dynamic, ascending (spec v3)
+    int32_t gated_var[MAXG];       // variables with a word per second: rate > 0 or dynamic, ascending (spec v5)
     uint64_t gate_G[MAXG];         // fires iff k*GATE_MULT mod 2^32 < G (0 for rate 0)
     int32_t gate_of_dyn[MAXD];     // gated ordinal of the d-th dynamic variable
     int32_t dd_off[MAXG];          // first entry of gated ordinal g in dd32
@@ -82,7 +83,7 @@ struct SampleParams {
     int64_t n;
     int64_t s_begin, s_end;        // tracks [s_begin, s_end) of [0, n) handled by this launch (track kernels): a launch never
                                    // straddles a multiple of 2^32 of the global sample index, so that counter word 0 of the
-                                   // step stream is the same for all its tracks (spec v4; next_segment below)
+                                   // step stream is the same for all its tracks (spec v5; next_segment below)
     int32_t T;
     int32_t reject_mode;           // EMB_REJECT_*
     int32_t idx_v, idx_dh, idx_L;  // 0-based, -1 if unused
@@ -313,10 +314,12 @@ EMB_HD uint32_t keyed_word(uint64_t seed, uint64_t sample, uint32_t attempt, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// stream spec v4: de-discretisation uniform of a step word k with partner word kn, (((k*B + kn) mod 2^32 >> 9) + 0.5) 2^-23
+// stream spec v5: de-discretisation uniform of a step word k with partner word kn, (((k*B + kn) mod 2^32 >> 9) + 0.5) 2^-23
 EMB_HD double u_dd(uint32_t k, uint32_t kn) { return dmul(dadd((double)((k * DD_MULT + kn) >> 9), 0.5), 1.1920928955078125e-07); }
-// partner word of gated ordinal g among the nw words of one second
-EMB_HD uint32_t dd_partner(const uint32_t* wstep, int g, int nw) { return nw > 1 ? wstep[g + 1 < nw ? g + 1 : 0] : 0u; }
+// position of the step word of second e, gated ordinal g in the (sample, P_STEP) word stream (call index * 4 + lane)
+EMB_HD uint32_t step_pos(uint32_t e, uint32_t g, uint32_t nw) { return (((e >> 2) * nw + g) << 2) | (e & 3u); }
+// second whose word is the partner of second e
+EMB_HD uint32_t partner_second(uint32_t e) { return (e & ~3u) | ((e + 1u) & 3u); }
 
 EMB_HD uint32_t ldg32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
@@ -508,15 +511,17 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     const int Tpad = nch4 * 4;
     for (int c = 0; c < Tpad; ++c) {          // column c = state during second c+1; step e = c
         if (c > 0 && c < T) {
-            const uint32_t base = (uint32_t)c * (uint32_t)nw;   // stream spec v3: p = e*nw + g
-            uint32_t wstep[MAXG];
-            for (int q = 0; q < nw; ++q) wstep[q] = ws.at(base + (uint32_t)q);
+            uint32_t wstep[MAXG], wpart[MAXG];                  // stream spec v5: k(e, g) and its value partner k(e', g)
+            for (int q = 0; q < nw; ++q) {
+                wstep[q] = ws.at(step_pos((uint32_t)c, (uint32_t)q, (uint32_t)nw));
+                wpart[q] = ws.at(step_pos(partner_second((uint32_t)c), (uint32_t)q, (uint32_t)nw));
+            }
             // resample gates on the pre-transition bins (resample_events.m:23-29)
             for (int g = 0; g < ng; ++g) {
                 const uint32_t k = wstep[g];
                 if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                     const int v = M.gated_var[g];
-                    vals[v] = dedisc(M, v, x[v], u_dd(k, dd_partner(wstep, g, nw)));
+                    vals[v] = dedisc(M, v, x[v], u_dd(k, wpart[g]));
                     if (ev) emit((uint32_t)c, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, vals[v]);
                 }
             }
@@ -533,7 +538,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 const uint8_t nb = x[M.dyn_t1[d]];
                 if (nb != x[vt]) {
                     x[vt] = nb;
-                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[M.gate_of_dyn[d]], dd_partner(wstep, M.gate_of_dyn[d], nw)));
+                    vals[vt] = dedisc(M, vt, nb, u_dd(wstep[M.gate_of_dyn[d]], wpart[M.gate_of_dyn[d]]));
                     if (ev) emit((uint32_t)c, (uint32_t)vt + 1u, (uint32_t)nb + 1u, vals[vt]);
                 }
             }
@@ -571,13 +576,12 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     }
     if (ev) {
         // gates of the last held second T (resample_events.m:23-29), then the closing row (dbn_hierarchical_sample.m:15-19)
-        uint32_t wlast[MAXG];
-        for (int q = 0; q < nw; ++q) wlast[q] = ws.at((uint32_t)T * (uint32_t)nw + (uint32_t)q);
         for (int g = 0; g < ng; ++g) {
-            const uint32_t k = wlast[g];
+            const uint32_t k = ws.at(step_pos((uint32_t)T, (uint32_t)g, (uint32_t)nw));
             if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                 const int v = M.gated_var[g];
-                emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k, dd_partner(wlast, g, nw))));
+                const uint32_t kn = ws.at(step_pos(partner_second((uint32_t)T), (uint32_t)g, (uint32_t)nw));
+                emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k, kn)));
             }
         }
         emit((uint32_t)T, 0u, 0u, 0.0);

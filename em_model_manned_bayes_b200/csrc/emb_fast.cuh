@@ -1,6 +1,6 @@
 // emb_fast.cuh -- register-resident, branch-free track sampler for the common model shapes.
 //
-// Same semantics and same keyed stream (spec v3, oracle/philox.py) as track_generic (emb_device.cuh);
+// Same semantics and same keyed stream (spec v5, oracle/philox.py) as track_generic (emb_device.cuh);
 // what changes is where the state lives and that nothing in the per-second loop diverges.  Template
 // parameters fix the number of bins of every dynamic variable (RS packs up to four of them, one per
 // byte, in temporal_map order) and the number of gated variables NG, so that
@@ -70,7 +70,7 @@ EMB_HD void fast_fill_shared(const DevModel& M, FastShared& S, int tid, int nthr
 }
 
 // the 23 fraction bits of the value word of a step word k (partner kn) as a float in [1,2)
-// (stream spec v4: u_dd = (f - 1) + 2^-24): one IMAD (hash) + one funnel shift that drops the exponent of 1.0f on top
+// (stream spec v5: u_dd = (f - 1) + 2^-24): one IMAD (hash) + one funnel shift that drops the exponent of 1.0f on top
 EMB_HD float dd_fraction(uint32_t k, uint32_t kn) {
     const uint32_t h = k * DD_MULT + kn;
 #if defined(__CUDA_ARCH__)
@@ -140,7 +140,7 @@ struct FastTrack {
     using SH = DynShape<RS>;
     static constexpr int ND = SH::ND;
     static constexpr int NS = NG - ND;   // gated variables that are not dynamic (their bin never changes)
-    static constexpr int NW = NG;        // stream spec v3: one word per (second, gated variable)
+    static constexpr int NW = NG;        // stream spec v5: one word per (second, gated variable)
     static constexpr int RPM = SH::RPMAX;
     static constexpr bool F64(int d) { return FAST && ((EMB_F64CMP >> d) & 1) != 0; }
 
@@ -207,7 +207,7 @@ struct FastTrack {
             if (FAST) {
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    const uint32_t k = W[j * NW + NS + d];
+                    const uint32_t k = W[4 * (NS + d) + j];
                     uint32_t b = thr[d][SH::RP(d) - 1];
                     if (F64(d)) {
                         const double kb = biased_double(k);
@@ -248,7 +248,7 @@ struct FastTrack {
                                 }
                             }
                             // thresholds as stored (not complemented): the borrow chain counts downwards; last slot = lead
-                            const uint32_t k = W[j * NW + NS + d];
+                            const uint32_t k = W[4 * (NS + d) + j];
                             uint32_t c = 0;
 #pragma unroll
                             for (int m = 0; m < SH::R(d) - 1; ++m) c = sub_gt(c, k, thr[d][m]);
@@ -264,8 +264,8 @@ struct FastTrack {
             float ev_val[ND];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                const uint32_t k = W[j * NW + g];
-                const uint32_t kn = NW > 1 ? W[j * NW + (g + 1) % NW] : 0u;   // partner word of the value (spec v4)
+                const uint32_t k = W[4 * g + j];
+                const uint32_t kn = W[4 * g + ((j + 1) & 3)];   // partner word of the value (spec v5)
                 const int d = g - NS;
                 DdEntry en;
                 if (g >= NS) en = S.ent[nb[d >= 0 ? d : 0]];
@@ -324,7 +324,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     const int T = P.T;
     const int64_t N = P.n;
     FT ft(M, P, S, hist_inc);
-    // step stream (spec v4): every track of a launch shares c0 = first_sample >> 32 (the host splits a launch at multiples
+    // step stream (spec v5): every track of a launch shares c0 = first_sample >> 32 (the host splits a launch at multiples
     // of 2^32: SampleParams::s_begin) and c2 = P_STEP << 8
     const uint32_t c0 = (uint32_t)((P.first_sample + (uint64_t)P.s_begin) >> 32), c2 = P_STEP << 8;
     const int nch4 = (T + 3) >> 2;

@@ -305,7 +305,7 @@ int launch_tracks(const DevModel& M, const SampleParams& P0, const TrackOut& O, 
     const bool hist = O.hist_initial || O.hist_transition;
     const int ev = O.ev_counts ? 1 : O.events ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
     bool done = false;
-    // one launch per run of tracks whose global sample index shares its high word (spec v4: counter word 0 is launch-uniform)
+    // one launch per run of tracks whose global sample index shares its high word (spec v5: counter word 0 is launch-uniform)
     SampleParams P = P0;
     for (int64_t s0 = 0; s0 < P0.n; s0 = P.s_end) {
         P.s_begin = s0;

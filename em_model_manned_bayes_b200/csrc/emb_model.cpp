@@ -308,7 +308,7 @@ void HostModel::derive() {
         for (int i = 0; i < n; ++i)
             if (r_transition[i] != r_initial[i]) fail(EMB_E_MODEL, "r_transition(1:n_initial) differs from r_initial");
     }
-    // stream spec v3: a variable owns one word per second iff its value can change (rate > 0 or dynamic)
+    // stream spec v5: a variable owns one word per second iff its value can change (rate > 0 or dynamic)
     gated.clear();
     for (int i = 0; i < n; ++i) {
         bool g = resample_rates[i] > 0.0;
@@ -381,7 +381,7 @@ void HostModel::pack() {
     D.n_dyn = (int32_t)temporal_map.size();
     D.n_gated = (int32_t)gated.size();
     D.n_tv = (int32_t)timevarying.size();
-    D.nw = D.n_gated;   // stream spec v3: one word per (second, gated variable)
+    D.nw = D.n_gated;   // stream spec v5: one word per (second, gated variable)
     D.fast = is_dynvar_depend ? 0 : 1;
     D.two23 = 1 << 23;
     for (int i = 0; i < n; ++i) D.order_initial[i] = order_initial[i];

@@ -8,8 +8,8 @@
 // branch: three selects from columns addressed by the re-discretised state), the dynamic-limit
 // rejection loop of createEncounter.m:192-243 and the kinematic update of :171-184 / :246-256 in fp64.
 //
-// Uniforms (stream spec v3, terminal part -- oracle/terminal.py): Philox counter
-//   (encounter_lo, encounter_hi, step ii, attempt << 16 | purpose << 8 | chain), chain = 2*aircraft + (0 fwd, 1 bck);
+// Uniforms (stream spec v5, terminal part -- oracle/terminal.py): Philox counter
+//   (encounter_hi, encounter_lo, attempt << 16 | purpose << 8 | chain, step ii), chain = 2*aircraft + (0 fwd, 1 bck);
 //   purpose TERM_SEL: lane d = row 2 of the rand(2,1) of the d-th dynamic variable (dbn_sample.m:133,144);
 //   purpose TERM_DD : lane d = the rand of dediscretize for its event (createEncounter.m:203,208,216).
 #pragma once

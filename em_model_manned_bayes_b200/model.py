@@ -107,6 +107,48 @@ class EncounterModel:
         if prior != 0:
             self.prior = prior
 
+    @classmethod
+    def from_arrays(cls, G_initial, r_initial, N_initial, G_transition=None, r_transition=None, N_transition=None,
+                    temporal_map=None, boundaries=None, resample_rates=None, dirichlet_initial=None,
+                    dirichlet_transition=None):
+        """The array form of the constructor (@EncounterModel/EncounterModel.m:106-114) over emb_model_from_arrays -- the
+        call sequence of matlab/emb_handle.m: the tables handed over are the weights select_random.m:17 sums,
+        N{i} + alpha{i}, so any prior (constant, 'dbe', stay, hand-made dirichlet cells) is reproduced exactly.
+        N_* / dirichlet_*: one r_i x q_i array per variable (None for the first n_initial entries of the transition
+        lists, like the reference's cells); G: [parent, child]."""
+        def weights(N, alpha):
+            out = []
+            for i, t in enumerate(N or []):
+                if t is None or np.size(t) == 0:
+                    continue
+                w = np.asarray(t, dtype=np.float64)
+                if alpha is not None and alpha[i] is not None and np.size(alpha[i]):
+                    w = w + np.asarray(alpha[i], dtype=np.float64)
+                out.append(w.ravel(order="F"))
+            return np.ascontiguousarray(np.concatenate(out)) if out else np.zeros(0)
+
+        Gi = np.ascontiguousarray(np.asarray(G_initial, dtype=np.uint8))
+        ri = np.ascontiguousarray(np.asarray(r_initial, dtype=np.int32).ravel())
+        n = int(ri.size)
+        wi = weights(N_initial, dirichlet_initial)
+        nt = 0 if r_transition is None else int(np.size(r_transition))
+        Gt = np.ascontiguousarray(np.asarray(G_transition, dtype=np.uint8)) if nt else None
+        rt = np.ascontiguousarray(np.asarray(r_transition, dtype=np.int32).ravel()) if nt else None
+        wt = weights(N_transition, dirichlet_transition) if nt else np.zeros(0)
+        tm = np.ascontiguousarray(np.asarray(temporal_map if temporal_map is not None else np.zeros((0, 2)), dtype=np.int32).reshape(-1, 2))
+        bl = [np.asarray(b, dtype=np.float64).ravel() for b in (boundaries if boundaries is not None else [[]] * n)]
+        blen = np.ascontiguousarray(np.array([b.size for b in bl], dtype=np.int32))
+        bflat = np.ascontiguousarray(np.concatenate(bl)) if sum(b.size for b in bl) else np.zeros(1)
+        rates = np.ascontiguousarray(np.asarray(resample_rates if resample_rates is not None else np.zeros(n), dtype=np.float64).ravel())
+        h = C.c_void_p()
+        L.check(L.lib().emb_model_from_arrays(n, Gi.ctypes.data, ri.ctypes.data, wi.ctypes.data, wi.size, nt,
+                                              Gt.ctypes.data if nt else None, rt.ctypes.data if nt else None,
+                                              wt.ctypes.data if nt else None, wt.size, tm.ctypes.data, tm.shape[0],
+                                              bflat.ctypes.data, blen.ctypes.data, rates.ctypes.data, C.byref(h)))
+        self = cls.__new__(cls)
+        EncounterModel.__init__(self, _handle=h)
+        return self
+
     # -- lifetime ----------------------------------------------------------------------------------
     def __del__(self):
         try:
@@ -339,39 +381,99 @@ class EventResult:
         return np.stack([e["dt"].astype(np.float64), e["var"].astype(np.float64), e["value"].astype(np.float64)], axis=1)
 
 
+def _row_times(dt: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """Seconds elapsed at the END of every row's hold (dt summed from the first row of the row's own track)."""
+    cum = np.cumsum(dt, dtype=np.int64)
+    first = np.asarray(offsets[:-1], dtype=np.int64)
+    before = np.where(first > 0, cum[np.maximum(first, 1) - 1], 0)          # total of the tracks before each track
+    return cum - np.repeat(before, np.diff(np.asarray(offsets, dtype=np.int64)))
+
+
+def expand_events(initial: np.ndarray, dt, var, value, offsets, T: int) -> np.ndarray:
+    """Batch form of events2samples.m:9-27 for the rows of many tracks at once.
+
+    initial (n, n_initial); dt / var / value: the rows of all tracks back to back; offsets int64 [n+1].
+    -> (n, n_initial, T): column c is the state during second c+1.  A row [dt, var, value] lets the current state
+    hold for dt more seconds and then sets `var`, so its value is visible from column sum(dt up to and including the
+    row) on; of several rows that set the same variable in the same second the last one is the visible one.  Built
+    without a per-row loop: the row that owns each (track, variable, column) is found by sorting, then carried forward
+    in time with a running maximum of row ids."""
+    initial = np.asarray(initial, dtype=np.float64)
+    n, ni = initial.shape
+    dt = np.asarray(dt, dtype=np.int64)
+    var = np.asarray(var, dtype=np.int64)
+    value = np.asarray(value, dtype=np.float64)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    col = _row_times(dt, offsets)
+    trk = np.repeat(np.arange(n, dtype=np.int64), np.diff(offsets))
+    rows = np.nonzero((var > 0) & (col < T))[0]
+    owner = np.full(n * ni * T, -1, dtype=np.int64)
+    if rows.size:
+        key = (trk[rows] * ni + (var[rows] - 1)) * T + col[rows]
+        uniq, first_rev = np.unique(key[::-1], return_index=True)              # first in reversed order = last row of the key
+        owner[uniq] = rows[::-1][first_rev]
+    owner = np.maximum.accumulate(owner.reshape(n, ni, T), axis=2)
+    return np.where(owner >= 0, value[np.maximum(owner, 0)], initial[:, :, None])
+
+
+def controls_of(dense: np.ndarray, dt, offsets, var_cols: Sequence[int]) -> List[np.ndarray]:
+    """Batch form of events2controls.m:9-31: for every row with dt > 0, [t, x(var_cols)] with t the second the hold starts
+    and x the state during the hold -- read from the expanded matrix instead of replaying the list.
+    -> one (k_i, 1 + len(var_cols)) matrix per track."""
+    dt = np.asarray(dt, dtype=np.int64)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = dense.shape[0]
+    t0 = _row_times(dt, offsets) - dt
+    trk = np.repeat(np.arange(n, dtype=np.int64), np.diff(offsets))
+    keep = np.nonzero(dt > 0)[0]
+    x = dense[trk[keep][:, None], np.asarray(var_cols, dtype=np.int64)[None, :], t0[keep][:, None]]
+    ctl = np.concatenate([t0[keep][:, None].astype(np.float64), x], axis=1)
+    cuts = np.searchsorted(keep, offsets[1:-1])
+    return np.split(ctl, cuts)
+
+
 def events2samples(initial, events) -> np.ndarray:
-    """events2samples.m:9-27 (host-side expansion of one track's event list to n_initial x T)."""
-    n = len(initial)
-    T = int(sum(e[0] for e in events))
-    d = np.zeros((n, T))
-    x = np.array(initial, dtype=np.float64)
-    t = 0
-    for (delta_t, var, val) in events:
-        delta_t = int(delta_t)
-        if var == 0:
-            t = t + 1
-            d[:, t - 1: t - 1 + delta_t] = x[:, None]
-        else:
-            if delta_t > 0:
-                d[:, t: t + delta_t] = x[:, None]
-                t = t + delta_t
-            x[int(var) - 1] = val
-    return d
+    """events2samples.m:9-27 for one track: (n_initial,) initial vector and k x 3 [dt var value] rows -> n_initial x T."""
+    ev = np.asarray(events, dtype=np.float64).reshape(-1, 3)
+    T = int(ev[:, 0].sum())
+    return expand_events(np.asarray(initial, dtype=np.float64)[None, :], ev[:, 0], ev[:, 1], ev[:, 2],
+                         np.array([0, ev.shape[0]]), T)[0]
 
 
 def events2controls(initial, events, temporal_map) -> np.ndarray:
-    """events2controls.m:9-31: one row [t, x(temporal_map(:,1))] per event with dt > 0, before applying it."""
-    vars_ = np.asarray(temporal_map)[:, 0] - 1
-    x = np.array(initial, dtype=np.float64)
-    rows = []
-    t = 0
-    for (delta_t, var, val) in events:
-        if delta_t > 0:
-            rows.append(np.concatenate(([t], x[vars_])))
-            t = t + delta_t
-        if var > 0:
-            x[int(var) - 1] = val
-    return np.asarray(rows).reshape(-1, 1 + len(vars_))
+    """events2controls.m:9-31 for one track: one row [t, x(temporal_map(:,1))] per event with dt > 0."""
+    ev = np.asarray(events, dtype=np.float64).reshape(-1, 3)
+    off = np.array([0, ev.shape[0]])
+    T = int(ev[:, 0].sum())
+    dense = expand_events(np.asarray(initial, dtype=np.float64)[None, :], ev[:, 0], ev[:, 1], ev[:, 2], off, T)
+    return controls_of(dense, ev[:, 0], off, np.asarray(temporal_map)[:, 0] - 1)[0]
+
+
+class EncounterModelEvents:
+    """@EncounterModelEvents/EncounterModelEvents.m:18-49: times at which the aircraft dynamics change.
+    `event` is the k x 4 matrix [time_s, verticalRate_fps, turnRate_radps, longitudeAccel_ftpss] (at least one row)."""
+
+    def __init__(self, event=None, time_s=0.0, verticalRate_fps=0.0, turnRate_radps=0.0, longitudeAccel_ftpss=0.0):
+        if event is not None:
+            self.event = event
+        else:
+            cols = [np.atleast_1d(np.asarray(c, dtype=np.float64)).ravel()
+                    for c in (time_s, verticalRate_fps, turnRate_radps, longitudeAccel_ftpss)]
+            if len({c.size for c in cols}) != 1:                                   # EncounterModelEvents.m:77
+                raise L.EmbError(L.EMB_E_ARG, "Sizes of time_s, verticalRate_fps, turnRate_radps, longitudeAccel_ftpss are not equal")
+            self.time_s, self.verticalRate_fps, self.turnRate_radps, self.longitudeAccel_ftpss = cols
+
+    @property
+    def event(self) -> np.ndarray:
+        m = np.stack([self.time_s, self.verticalRate_fps, self.turnRate_radps, self.longitudeAccel_ftpss], axis=1)
+        return m if m.shape[0] else np.zeros((1, 4))                              # :44-47
+
+    @event.setter
+    def event(self, m):
+        m = np.asarray(m, dtype=np.float64)
+        if m.ndim != 2 or m.shape[1] != 4:                                        # :35
+            raise L.EmbError(L.EMB_E_ARG, "event matrix must have 4 columns")
+        self.time_s, self.verticalRate_fps, self.turnRate_radps, self.longitudeAccel_ftpss = (m[:, k].copy() for k in range(4))
 
 
 def _find(labels, name):
@@ -534,26 +636,25 @@ class UncorEncounterModel(EncounterModel):
 
     def sample(self, n_samples: int, sample_time: int, seed=float("nan"), isQuantize500=False, layers=None):
         """UncorEncounterModel.m:192-313 -> (out_inits n x n_initial, out_events list of k x 3 [dt var value],
-        out_samples list of n_initial x T, out_EME list of controls [t, dh ft/s, dpsi rad/s, dv ft/s^2]).
+        out_samples list of n_initial x T, out_EME list of EncounterModelEvents whose `event` is [t, dh ft/s, dpsi rad/s, dv ft/s^2]).
         `seed` NaN draws a fresh 64-bit seed (the reference keeps the global stream; here streams are keyed).
-        out_samples is expanded on the host from the event lists exactly as events2samples.m does."""
+        out_samples and the controls are expanded on the host from the event lists (expand_events / controls_of)."""
         if isinstance(seed, float) and math.isnan(seed):
             seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
         res = self.sample_events_uncor(n_samples, sample_time, seed=int(seed), isQuantize500=isQuantize500, layers=layers)
         out_inits = np.ascontiguousarray(res.init_values.T)
-        out_events, out_samples, out_EME = [], [], []
-        order = [self.idxDH, self.idxDPsi, self.idxDV]                       # UncorEncounterModel.m:291-292
-        cols = [1 + list(self.temporal_map[:, 0]).index(v) for v in order]
-        for k in range(n_samples):
-            ev = res.track(k)
-            out_events.append(ev)
-            out_samples.append(events2samples(out_inits[k], ev))
-            c = events2controls(out_inits[k], ev, self.temporal_map)
-            c = c[:, [0] + cols]
-            c[:, 1] = c[:, 1] / 60.0                                          # :295 ft/min -> ft/s
-            c[:, 2] = np.deg2rad(c[:, 2])                                     # :296
-            c[:, 3] = c[:, 3] * 1.68780972222222                              # :297 kt/s -> ft/s^2
-            out_EME.append(c)
+        ev, off = np.asarray(res.events), np.asarray(res.offsets, dtype=np.int64)
+        dense = expand_events(out_inits, ev["dt"], ev["var"], ev["value"], off, sample_time)          # :283
+        dyn = list(self.temporal_map[:, 0])
+        ctl = controls_of(dense, ev["dt"], off, [v - 1 for v in (self.idxDH, self.idxDPsi, self.idxDV)])   # :286-292
+        assert all(v in dyn for v in (self.idxDH, self.idxDPsi, self.idxDV))
+        for c in ctl:
+            c[:, 1] /= 60.0                       # :295 dh: ft/min -> ft/s
+            c[:, 2] *= math.pi / 180.0            # :296 dpsi: deg2rad
+            c[:, 3] *= 1.68780972222222           # :297 dv: kt/s -> ft/s^2
+        out_events = [res.track(k) for k in range(n_samples)]
+        out_samples = [dense[k] for k in range(n_samples)]
+        out_EME = [EncounterModelEvents(event=c) for c in ctl]                                # :300
         return out_inits, out_events, out_samples, out_EME
 
 

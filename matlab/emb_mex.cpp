@@ -5,6 +5,11 @@
 //     mex -R2018a matlab/emb_mex.cpp -Iinclude -Lem_model_manned_bayes_b200 -lemb200
 //
 //   h    = emb_mex('load', parameters_filename, isOverwriteZeroBoundaries, idxZeroBoundaries)
+//   h    = emb_mex('from_arrays', G_initial, r_initial, w_initial, G_transition, r_transition, w_transition, ...
+//                  temporal_map, boundaries, resample_rates)
+//          the object form (EncounterModel.m:5-70 properties; matlab/emb_handle.m): G_* logical n x n (G(parent, child)),
+//          r_* n x 1, w_* the weight tables N{i} + alpha{i} of all variables back to back (each r_i x q_i, column-major,
+//          variable order: em_read.m:191-198), temporal_map k x 2, boundaries 1 x n_initial cell, resample_rates n_initial x 1
 //   s    = emb_mex('info', h)                       % struct mirroring emb_model_info (1-based ids)
 //          emb_mex('set_prior', h, which, kind, value)
 //   [bins, values, attempts] = emb_mex('sample_initial', h, seed, first, n, opts)
@@ -19,7 +24,7 @@
 //   s = emb_mex('terminal_screen', traj, len, tmax_s, thresDist_ft, thresAltLow_ft)   % traj/len as returned above
 //          struct: hmd_ft, vmd_ft (n x 1 double), tcpa (n x 3 int16: tcpa_s, index_own, index_int), enc_time_s, runway (bits)
 //   [xyz, is_good] = emb_mex('tracks_integrate', h, out_inits, values, T, iopts)    % sample2track.m:188-244
-//          out_inits n x n_initial double and values 4 x n x ceil(T/4) x n_tv single as returned by 'sample_tracks';
+//          out_inits n x n_initial double and values 4 x 128 x n_tv x ceil(n/128) x ceil(T/4) single as returned by 'sample_tracks';
 //          iopts: struct idx_altitude, idx_speed, idx_acceleration, idx_vertrate, idx_turnrate, ur_speed, ur_vertrate,
 //          ur_heading, min_speed, max_speed;  xyz: n x (T+1) x 3 single, is_good: n x 1 uint8
 //          emb_mex('free', h)
@@ -109,6 +114,50 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             for (size_t i = 0; i < mxGetNumberOfElements(prhs[3]); ++i) idx.push_back((int32_t)mxGetPr(prhs[3])[i]);
         emb_model* m = nullptr;
         CHECK(emb_model_load(path, overwrite, idx.data(), (int32_t)idx.size(), &m));
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *static_cast<uint64_t*>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(m);
+        return;
+    }
+    if (c == "from_arrays") {                                     // EncounterModel objects built without a file (EncounterModel.m:106-114)
+        if (nrhs < 10) mexErrMsgIdAndTxt("emb200:arg", "from_arrays needs 9 arguments");
+        auto as_i32 = [](const mxArray* a) {
+            std::vector<int32_t> v(mxGetNumberOfElements(a));
+            for (size_t i = 0; i < v.size(); ++i) v[i] = (int32_t)mxGetPr(a)[i];
+            return v;
+        };
+        auto graph = [](const mxArray* a) {                       // MATLAB G(parent, child), column-major -> ABI G[parent * n + child]
+            const size_t n = mxGetM(a);
+            std::vector<uint8_t> g(n * n);
+            const mxLogical* src = mxIsLogical(a) ? mxGetLogicals(a) : nullptr;
+            for (size_t pa = 0; pa < n; ++pa)
+                for (size_t ch = 0; ch < n; ++ch)
+                    g[pa * n + ch] = (uint8_t)(src ? src[ch * n + pa] : mxGetPr(a)[ch * n + pa] != 0.0);
+            return g;
+        };
+        const std::vector<uint8_t> Gi = graph(prhs[1]), Gt = graph(prhs[4]);
+        const std::vector<int32_t> ri = as_i32(prhs[2]), rt = as_i32(prhs[5]);
+        const int32_t n_initial = (int32_t)ri.size(), n_transition = (int32_t)rt.size();
+        std::vector<int32_t> tmap(mxGetNumberOfElements(prhs[7]));
+        const size_t k = mxGetM(prhs[7]);
+        for (size_t r = 0; r < k; ++r) {                          // k x 2 column-major -> row-major pairs
+            tmap[2 * r] = (int32_t)mxGetPr(prhs[7])[r];
+            tmap[2 * r + 1] = (int32_t)mxGetPr(prhs[7])[k + r];
+        }
+        std::vector<double> bnd;
+        std::vector<int32_t> bnd_len((size_t)n_initial, 0);
+        for (int32_t i = 0; i < n_initial && (size_t)i < mxGetNumberOfElements(prhs[8]); ++i) {
+            const mxArray* b = mxGetCell(prhs[8], i);
+            const size_t m = b ? mxGetNumberOfElements(b) : 0;
+            bnd_len[(size_t)i] = (int32_t)m;
+            for (size_t q = 0; q < m; ++q) bnd.push_back(mxGetPr(b)[q]);
+        }
+        std::vector<double> rates((size_t)n_initial, 0.0);
+        for (size_t i = 0; i < rates.size() && i < mxGetNumberOfElements(prhs[9]); ++i) rates[i] = mxGetPr(prhs[9])[i];
+        emb_model* m = nullptr;
+        CHECK(emb_model_from_arrays(n_initial, Gi.data(), ri.data(), mxGetPr(prhs[3]), (int64_t)mxGetNumberOfElements(prhs[3]),
+                                    n_transition, n_transition ? Gt.data() : nullptr, n_transition ? rt.data() : nullptr,
+                                    n_transition ? mxGetPr(prhs[6]) : nullptr, (int64_t)mxGetNumberOfElements(prhs[6]),
+                                    tmap.data(), (int32_t)k, bnd.data(), bnd_len.data(), rates.data(), &m));
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
         *static_cast<uint64_t*>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(m);
         return;
@@ -204,13 +253,14 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         const int32_t T = (int32_t)mxGetScalar(prhs[5]);
         emb_sample_opts o;
         fill_opts(nrhs > 6 ? prhs[6] : nullptr, ni, &o);
-        const mwSize nch = (mwSize)((T + 3) / 4);
-        // tiles [var][ceil(T/4)][n][4] == column-major MATLAB arrays of size 4 x n x nch x var
-        const mwSize db[4] = {4, (mwSize)n, nch, (mwSize)info.n_dyn};
-        const mwSize dv[4] = {4, (mwSize)n, nch, (mwSize)info.n_timevarying};
+        const mwSize nch = (mwSize)((T + 3) / 4), ntile = (mwSize)((n + 127) / 128);
+        // tiles [ceil(T/4)][ceil(n/128)][var][128][4] == column-major MATLAB arrays of size 4 x 128 x var x ntile x nch:
+        // element (second c, track s, variable g) is A(mod(c,4)+1, mod(s,128)+1, g, floor(s/128)+1, floor(c/4)+1), 0-based c, s
+        const mwSize db[5] = {4, 128, (mwSize)info.n_dyn, ntile, nch};
+        const mwSize dv[5] = {4, 128, (mwSize)info.n_timevarying, ntile, nch};
         plhs[0] = mxCreateDoubleMatrix(n, ni, mxREAL);            // out_inits
-        mxArray* bins = mxCreateNumericArray(4, db, mxINT8_CLASS, mxREAL);
-        mxArray* vals = mxCreateNumericArray(4, dv, mxSINGLE_CLASS, mxREAL);
+        mxArray* bins = mxCreateNumericArray(5, db, mxINT8_CLASS, mxREAL);
+        mxArray* vals = mxCreateNumericArray(5, dv, mxSINGLE_CLASS, mxREAL);
         mxArray* att = mxCreateNumericMatrix(n, 1, mxUINT16_CLASS, mxREAL);
         emb_track_out out{};
         out.bins = (int8_t*)mxGetData(bins);

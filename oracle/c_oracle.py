@@ -115,7 +115,7 @@ class COracle:
         rates = np.asarray(parms.resample_rates, dtype=np.float64)
         m.rates = arr(rates, np.float64)
         dynt = {int(v) for v in tm[:, 0]} if nt else set()
-        gated = [i + 1 for i in range(n) if rates[i] > 0 or (i + 1) in dynt] if nt else []   # stream spec v3
+        gated = [i + 1 for i in range(n) if rates[i] > 0 or (i + 1) in dynt] if nt else []   # stream spec v5
         m.n_gated = len(gated)
         m.gated = arr(gated + [0], np.int32)
         m.gate_G = arr([px.gate_threshold(rates[g - 1]) for g in gated] + [0], np.uint64)

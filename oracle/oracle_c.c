@@ -12,7 +12,7 @@
  * reference's data flow -- event lists, resample pass, de-discretisation pass, dense expansion --
  * and uses none of the product's tricks (no word-space thresholds: every draw is a cumsum + fp64
  * compare exactly like select_random.m).  The model arrays come from the oracle's own reader
- * (oracle/em_read.py); nothing is shared with libemb200.so.  Uniforms: keyed Philox, stream spec v3
+ * (oracle/em_read.py); nothing is shared with libemb200.so.  Uniforms: keyed Philox, stream spec v5
  * (oracle/philox.py).
  *
  * PARITY UNPINNED: validated only against the Python oracle (tests/test_oracle_c.py), which in turn
@@ -56,7 +56,7 @@ typedef struct {
     int32_t max_attempts;
 } oc_model;
 
-/* ---- keyed Philox4x32-10 (stream spec v4: counter = (sample_hi, sample_lo, attempt<<16 | purpose<<8 | sub, index); the step stream, purpose 2, carries no attempt) ----------------------------------------------------- */
+/* ---- keyed Philox4x32-10 (stream spec v5: counter = (sample_hi, sample_lo, attempt<<16 | purpose<<8 | sub, index); the step stream, purpose 2, carries no attempt) ----------------------------------------------------- */
 static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* o) {
     for (int i = 0; i < 10; ++i) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -80,6 +80,8 @@ static uint32_t word(ukey* k, uint32_t purpose, uint32_t index, uint32_t sub, ui
     return k->c_o[q][lane];
 }
 static uint32_t word_at(ukey* k, uint32_t purpose, uint64_t p) { return word(k, purpose, (uint32_t)(p >> 2), 0, (uint32_t)(p & 3)); }
+/* step word of second e, gated ordinal g (stream spec v5): one call = four consecutive seconds of one variable */
+static uint32_t step_word(ukey* k, int e, int g) { return word(k, 2, (uint32_t)((e >> 2) * k->nw + g), 0, (uint32_t)(e & 3)); }
 static double u01(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
 
 /* ---- select_random.m:17-20 --------------------------------------------------------------------- */
@@ -129,7 +131,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
     int gate_of_var[MAXV + 1];
     for (int i = 0; i <= n; ++i) gate_of_var[i] = -1;
     for (int g = 0; g < M->n_gated; ++g) gate_of_var[M->gated[g]] = g;
-    int gate_of_dyn[8];   /* stream spec v3: the word of (second, variable) also selects the variable's transition */
+    int gate_of_dyn[8];   /* stream spec v5: the word of (second, variable) also selects the variable's transition */
     for (int d = 0; d < nd; ++d) gate_of_dyn[d] = gate_of_var[M->temporal_map[2 * d]];
     for (int attempt = 0; attempt <= M->max_attempts; ++attempt) {
         K.attempt = (uint32_t)attempt;
@@ -172,14 +174,14 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                         for (int d = 0; d < nd; ++d) if (M->temporal_map[2 * d + 1] == i) {
                             int64_t j = parent_index(M->G_transition, nt, i - 1, M->r, x);
                             const double* w = M->W_transition + M->off_transition[i - 1] + (j - 1) * M->r[i - 1];
-                            double rnd = u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + gate_of_dyn[d]));
+                            double rnd = u01(step_word(&K, t - 1, gate_of_dyn[d]));
                             x[i - 1] = (double)select_random(w, M->r[i - 1], rnd);
                         }
                     }
                 } else { /* :143-146 */
                     for (int d = 0; d < nd; ++d) {
                         int ii = M->temporal_map[2 * d + 1];
-                        volatile double sthres = s[d][rdyn[d] - 1] * u01(word_at(&K, 2, (uint64_t)(t - 1) * K.nw + gate_of_dyn[d]));
+                        volatile double sthres = s[d][rdyn[d] - 1] * u01(step_word(&K, t - 1, gate_of_dyn[d]));
                         int m = 0;
                         while (!(s[d][m] >= sthres)) ++m;
                         x[ii - 1] = (double)(m + 1);
@@ -212,7 +214,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
                     delta_t += 1;
                     for (int i = 1; i <= n; ++i) { /* changes = find(rand(size(rates)) < rates) */
                         double u = 0.5;
-                        if (gate_of_var[i] >= 0) u = u01(word_at(&K, 2, (uint64_t)second * K.nw + gate_of_var[i]) * 0x9E3779B1u);
+                        if (gate_of_var[i] >= 0) u = u01(step_word(&K, second, gate_of_var[i]) * 0x9E3779B1u);
                         if (u < M->rates[i - 1]) {
                             ev2[n2].dt = first ? delta_t : 0; ev2[n2].var = i; ev2[n2].val = xr[i - 1];
                             ev2[n2].kind = 1; ev2[n2].second = second; ++n2;
@@ -235,12 +237,13 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
             int var = (int)ev2[e].var;
             double rnd = 0.5;
             if (dd_needs_u(M, var, ev2[e].val)) {
-                /* stream spec v4: fired-gate and transition values both read the variable's word of that second and, as an
-                 * independent partner, the word of the next gated variable (cyclic; none when there is only one) */
+                /* stream spec v5: fired-gate and transition values both read the variable's word of that second and, as an
+                 * independent partner, the same variable's word of the cyclically next second of the same call */
                 int g = 0;
                 while (M->gated[g] != var) ++g;
-                uint32_t k = word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + g);
-                uint32_t kn = K.nw > 1 ? word_at(&K, 2, (uint64_t)ev2[e].second * K.nw + (g + 1) % K.nw) : 0u;
+                const int sec = ev2[e].second;
+                uint32_t k = step_word(&K, sec, g);
+                uint32_t kn = step_word(&K, (sec & ~3) | ((sec + 1) & 3), g);
                 uint32_t h = k * 0x85EBCA6Bu + kn;
                 rnd = ((double)(h >> 9) + 0.5) * 1.1920928955078125e-07; /* 2^-23 */
             }

@@ -2,7 +2,7 @@
 
 Philox4x32-10 counter-based generator (Salmon et al., "Parallel random numbers: as easy
 as 1, 2, 3", SC'11; the Random123 `philox4x32_R(10, ctr, key)` function) and the keyed
-stream layout ("stream spec v4") shared by the oracle and the CUDA sampler.
+stream layout ("stream spec v5") shared by the oracle and the CUDA sampler.
 
 The reference (`/root/reference/code/matlab/select_random.m:14`, `dbn_sample.m:133`,
 `resample_events.m:24`, `dediscretize.m:39`) draws from MATLAB's global `rand`.  The B200
@@ -10,7 +10,7 @@ sampler replaces *when* a uniform is consumed by *what it is for*: every uniform
 function of (seed, sample, attempt, purpose, index, lane).  The oracle is fed exactly these
 uniforms (uniform-injection), so bin indices must be bit-identical.
 
-Stream spec v4
+Stream spec v5
 --------------
 key     = (seed & 0xffffffff, seed >> 32)
 counter = (sample >> 32, sample & 0xffffffff, (attempt << 16) | (purpose << 8) | sub, index)
@@ -23,11 +23,12 @@ Philox4x32-10 words of that counter.)
 purpose INIT (1):    word position p;  p = i            -> select word of initial variable i (0-based)
                                       p = n_initial + i -> dediscretize word of initial variable i
                      index = p // 4, lane = p % 4
-purpose STEP (2):    ONE word per (second, variable): word position p = e * nw + g, e = 1..T the second,
-                     g the ordinal of the variable among the *gated* variables -- in increasing id, the
-                     initial variables that have a resample rate > 0 or are dynamic (temporal_map column
-                     1); nw = their number.  (The nw positions of e = 0 are unused, which keeps groups of
-                     four seconds aligned to nw Philox calls.)   index = p // 4, lane = p % 4.
+purpose STEP (2):    ONE word per (second, variable): k(e, g), e = 1..T the second, g the ordinal of the variable
+                     among the *gated* variables -- in increasing id, the initial variables that have a resample
+                     rate > 0 or are dynamic (temporal_map column 1); nw = their number.  One Philox call holds four
+                     consecutive seconds of ONE variable:  index = (e >> 2) * nw + g,  lane = e & 3
+                     (so a thread that owns one variable of one track consumes whole calls, and a thread that owns
+                     the whole track consumes nw calls per four seconds; the lane of e = 0 is unused).
                      attempt = 0 ALWAYS: the driver's rejection test (UncorEncounterModel.m:275) reads only the
                      initial draw, so the seconds of the accepted attempt are the same words whichever attempt
                      was accepted (the seconds of a rejected attempt are discarded by the reference anyway).
@@ -36,8 +37,8 @@ purpose TERM_* (5+): terminal trajectory chains, see oracle/terminal.py
 
 word -> uniform: u = (k + 0.5) * 2**-32  (strictly inside (0,1), exact in fp64).
 
-What happens to variable v (gated ordinal g) in second e comes from its word k = W[e*nw + g] and, for the value, the
-word of the next gated variable of the same second, k' = W[e*nw + (g+1) % nw] (k' = 0 when nw == 1), with
+What happens to variable v (gated ordinal g) in second e comes from its word k = k(e, g) and, for the value, the word
+of the same variable in the cyclically next second of the same call, k' = k(e', g), e' = (e & ~3) | ((e + 1) & 3), with
 A = 0x9E3779B1, B = 0x85EBCA6B, both odd:
   * transition select of a dynamic variable, loop index t = e + 1 (dbn_sample.m:77 / :133,144):
         u_sel  = (k + 0.5) 2**-32
@@ -48,12 +49,13 @@ A = 0x9E3779B1, B = 0x85EBCA6B, both odd:
     and/or the new bin of a transition event (dbn_hierarchical_sample.m:35):
         u_dd   = ((((k * B + k') mod 2**32) >> 9) + 0.5) 2**-23
 The reference draws these three uniforms independently.  Here u_dd is exactly uniform and independent of v's own
-select and gate (k' is an independent full-entropy word), and pairwise independent of every other decision of the
-second; what remains coupled is (i) select and gate of the same variable, through the odd multiplier A that
-spreads any interval of k evenly over the gate word (a Kronecker lattice: given a transition of probability p the
-gate frequency is off by O(1/(p 2**32))), and (ii) three-way: u_dd of v given *both* v's and the next variable's
-decisions.  (spec v3 took u_dd from k alone, so after a rare transition the value could only take p 2**32 distinct
-values; spec v1/v2 spent separate Philox calls: 7 words per second for the 7-variable models instead of 4.)
+select and gate in that second (k' is an independent full-entropy word), and pairwise independent of every other
+decision; what remains coupled is (i) select and gate of the same variable in the same second, through the odd
+multiplier A that spreads any interval of k evenly over the gate word (a Kronecker lattice: given a transition of
+probability p the gate frequency is off by O(1/(p 2**32))), and (ii) three-way: u_dd of v in second e given *both* v's
+decisions in e and in e'.  (spec v3 took u_dd from k alone, so after a rare transition the value could only take
+p 2**32 distinct values; spec v4 used the next *variable's* word as partner, which ties the four variables of a track to
+one thread; spec v1/v2 spent separate Philox calls: 7 words per second for the 7-variable models instead of 4.)
 The 23-bit resolution of u_dd makes the word -> float conversion exact in fp32 arithmetic on the GPU.
 """
 from __future__ import annotations
@@ -144,13 +146,23 @@ DD_MULT = 0x85EBCA6B
 
 
 def gate_word(k):
-    """step word -> the 32-bit word the resample gate compares (stream spec v4)."""
+    """step word -> the 32-bit word the resample gate compares (stream spec v5)."""
     return (int(k) * GATE_MULT) & 0xFFFFFFFF
 
 
+def step_position(e, g, nw):
+    """(index, lane) of the step word of second e, gated ordinal g (stream spec v5)."""
+    return (int(e) >> 2) * int(nw) + int(g), int(e) & 3
+
+
+def partner_second(e):
+    """second whose word (same variable) is mixed into the de-discretisation word of second e (stream spec v5)."""
+    return (int(e) & ~3) | ((int(e) + 1) & 3)
+
+
 def dd_uniform(k, k_next=0):
-    """step word k and partner word k_next (the next gated variable's word of the same second, 0 when nw == 1)
-    -> de-discretisation uniform (stream spec v4), exact in fp64."""
+    """step word k and partner word k_next (same variable, second partner_second(e))
+    -> de-discretisation uniform (stream spec v5), exact in fp64."""
     h = (int(k) * DD_MULT + int(k_next)) & 0xFFFFFFFF
     return (float(h >> 9) + 0.5) * 2.0 ** -23
 

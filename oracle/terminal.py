@@ -17,7 +17,7 @@ MATLAB built-ins are restated as: cosd/sind(x) = cos/sin(x*pi/180) with the exac
 90 degrees; atan2d = atan2*180/pi; wrapTo360 (Mapping Toolbox): mod(x,360) with positive multiples of 360
 mapped to 360; round(x,2) = round(100x)/100 half away from zero; norm([a;b]) = sqrt(a^2+b^2).
 
-Uniforms ("stream spec v3", terminal part): Philox counter (sample_lo, sample_hi, index, attempt<<16 | purpose<<8 | chain)
+Uniforms ("stream spec v5", terminal part): Philox counter (sample_hi, sample_lo, attempt<<16 | purpose<<8 | chain, index)
 with sample = global encounter index, chain = 2*aircraft + (0 forward, 1 reverse), index = step ii (1-based),
 attempt = the inner `while is_resample` repetition; purpose TERM_SEL (5): lane d = the rand(2,1) row 2 of the d-th
 dynamic variable (dbn_sample.m:133,144); purpose TERM_DD (6): lane d = the dediscretize draw of its event

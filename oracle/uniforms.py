@@ -4,7 +4,7 @@ Uniform providers for the restated reference sampler.  The restatement (oracle/s
 provider for a uniform at every place the reference calls `rand`, passing the *context* of the
 draw.  Two providers:
 
-* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v4"): the uniform is a pure
+* KeyedPhilox  -- the product stream (oracle/philox.py, "stream spec v5"): the uniform is a pure
   function of the context.  This is the uniform-injection hook of BASELINE.json's north star: the
   reference algorithm, fed these uniforms, must give bit-identical bins to the CUDA sampler.
 * MTStream     -- MATLAB's `rng(seed,'twister'); rand` emulation (MT19937 `genrand_res53`, which
@@ -36,7 +36,7 @@ class _Base:
 
 class KeyedPhilox(_Base):
     """Context-keyed uniforms.  `bind(parms)` must be called once per model so that the dynamic and
-    gated ordinals (stream spec v4) are known."""
+    gated ordinals (stream spec v5) are known."""
 
     def __init__(self, seed: int, record: bool = False):
         super().__init__()
@@ -64,8 +64,8 @@ class KeyedPhilox(_Base):
         self.attempt = int(attempt)
 
     def _w(self, purpose, position):
-        attempt = 0 if purpose == px.P_STEP else self.attempt      # spec v4: the step stream carries no attempt
-        return int(px.word_at(self.seed, self.sample, attempt, purpose, position))
+        assert purpose != px.P_STEP
+        return int(px.word_at(self.seed, self.sample, self.attempt, purpose, position))
 
     # -- draws ---------------------------------------------------------------------------------
     def select_init(self, var):                      # bn_sample.m:55 -> select_random.m:14
@@ -74,10 +74,14 @@ class KeyedPhilox(_Base):
     def dedisc_init(self, var):                      # dbn_hierarchical_sample.m:29 -> dediscretize.m:39
         return self._rec(("init_dd", var), px.u01(self._w(px.P_INIT, self.n_initial + var - 1)))
 
+    def _step(self, e, g):
+        """step word of second e, gated ordinal g (spec v5: no attempt in the step stream)"""
+        index, lane = px.step_position(e, g, self.nw)
+        return int(px.word(self.seed, self.sample, 0, px.P_STEP, index, lane))
+
     def _sel_word(self, t, var_t1):
         g = self.gated.index(self.dyn_vars_t[self.dyn_vars_t1.index(int(var_t1))])
-        e = t - 1
-        return self._w(px.P_STEP, e * self.nw + g)
+        return self._step(t - 1, g)
 
     def select_trans(self, t, var_t1):               # dbn_sample.m:77 (slow branch)
         return self._rec(("trans_sel", t, var_t1), px.u01(self._sel_word(t, var_t1)))
@@ -93,7 +97,7 @@ class KeyedPhilox(_Base):
     def gates(self, second):                         # resample_events.m:24  rand(size(rates))
         u = np.full(self.n_initial, 0.5)
         for g, v in enumerate(self.gated):
-            u[v - 1] = px.u01(px.gate_word(self._w(px.P_STEP, second * self.nw + g)))
+            u[v - 1] = px.u01(px.gate_word(self._step(second, g)))
         if self.record:
             for v in range(1, self.n_initial + 1):
                 self.tape.append((("gate", second, v), float(u[v - 1])))
@@ -102,8 +106,8 @@ class KeyedPhilox(_Base):
     def dedisc_event(self, kind, second, var):       # dbn_hierarchical_sample.m:35
         # both kinds (re-emitted bin of a fired gate, new bin of a transition) read the variable's word of that second
         g = self.gated.index(int(var))
-        k = self._w(px.P_STEP, second * self.nw + g)
-        kn = self._w(px.P_STEP, second * self.nw + (g + 1) % self.nw) if self.nw > 1 else 0
+        k = self._step(second, g)
+        kn = self._step(px.partner_second(second), g)
         if kind == "gate":
             assert px.gate_word(k) < self.G[int(var)]
         return self._rec(("event_dd", kind, second, var), px.dd_uniform(k, kn))

@@ -10,3 +10,4 @@ mxArray* mxCreateNumericMatrix(size_t, size_t, mxClassID, mxComplexity); mxArray
 void mxSetField(mxArray*, int, const char*, mxArray*); mxArray* mxCreateDoubleScalar(double); mxArray* mxCreateDoubleMatrix(size_t, size_t, mxComplexity);
 mxArray* mxCreateNumericArray(int, const mwSize*, mxClassID, mxComplexity); void mxDestroyArray(mxArray*);
 [[noreturn]] void mexErrMsgIdAndTxt(const char*, const char*, ...);
+typedef bool mxLogical; bool mxIsLogical(const mxArray*); mxLogical* mxGetLogicals(const mxArray*); mxArray* mxGetCell(const mxArray*, size_t);
