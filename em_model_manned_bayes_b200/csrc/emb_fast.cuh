@@ -55,6 +55,18 @@ EMB_HD void fill_call_table(CallTable<NW>& U, const SampleParams& P, uint32_t c0
                             int nthreads) {
     for (int q = tid; q < ngroups * NW; q += nthreads) U.e[q] = philox_call(c0, c2, (uint32_t)(grp0 * NW + q), P.rk);
 }
+// 16-byte load from the call table: on the device through its 32-bit shared-window address (one LDS with an immediate offset;
+// a generic pointer makes ptxas rebuild the shared window base in every group)
+EMB_HD uint4 lds_call(const uint4* base, uint32_t saddr, int c) {
+#if defined(__CUDA_ARCH__)
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr + 16u * (uint32_t)c));
+    return v;
+#else
+    (void)saddr;
+    return base[c];
+#endif
+}
 EMB_HD void block_sync() {
 #if defined(__CUDA_ARCH__)
     __syncthreads();
@@ -187,11 +199,11 @@ struct FastTrack {
 
     // one group of four seconds e = 4*grp .. 4*grp+3; CHECK = the group may contain e == 0 or e >= T
     template <bool CHECK>
-    EMB_HD void group(int grp, int T, uint32_t (&bout)[ND], float (&vout)[NG][4], const uint4* ut) {
+    EMB_HD void group(int grp, int T, uint32_t (&bout)[ND], float (&vout)[NG][4], const uint4* ut, uint32_t ut_s) {
         uint32_t W[4 * NW];
 #pragma unroll
         for (int c = 0; c < NW; ++c)
-            philox_finish(pt, ut[c], P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
+            philox_finish(pt, lds_call(ut, ut_s, c), P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
 #pragma unroll
         for (int d = 0; d < ND; ++d) bout[d] = 0;
 #pragma unroll
@@ -312,6 +324,68 @@ struct FastTrack {
     }
 };
 
+// the loop over the four-second groups of one track; BOTH = both dense outputs are present (no per-group pointer tests)
+template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD, class HistInc, bool BOTH>
+EMB_HD void fast_groups(FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>& ft, const SampleParams& P, const TrackOut& O,
+                        CallTable<NG>& U, int64_t s, bool valid, int tid, int nthreads, uint32_t c0, uint32_t c2) {
+    constexpr int ND = DynShape<RS>::ND;
+    const int T = P.T;
+    const int64_t N = P.n;
+    const int nch4 = (T + 3) >> 2;
+    const int nfull = T >> 2;       // groups 1 .. nfull-1 contain only seconds 1 <= e < T
+    const int ngrp = EV ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
+    const int64_t ntile = num_tiles(N);
+    // (a null output only predicates the stores off: its pointer is advanced but never dereferenced)
+    const bool wb = BOTH || O.bins != nullptr, wv = BOTH || O.values != nullptr;
+    int8_t* pb = O.bins + tile_offset(ND, ntile, 0, 0, s);
+    float* pv = O.values + tile_offset(NG, ntile, 0, 0, s);
+    const int64_t bstep = ntile * (ND * TRACK_TILE * 4), vstep = ntile * (NG * TRACK_TILE * 4);
+    for (int grp0 = 0; grp0 < ngrp; grp0 += UT_GROUPS) {
+        const int gcount = ngrp - grp0 < UT_GROUPS ? ngrp - grp0 : UT_GROUPS;
+        if (grp0 > 0) block_sync();
+        fill_call_table<NG>(U, P, c0, c2, grp0, gcount, tid, nthreads);
+        block_sync();
+        if (!valid) continue;
+#if defined(__CUDA_ARCH__)
+        uint32_t ut_s = (uint32_t)__cvta_generic_to_shared(U.e);
+#else
+        uint32_t ut_s = 0;
+#endif
+        const uint4* ut = U.e;
+        for (int grp = grp0; grp < grp0 + gcount; ++grp, ut += NG, ut_s += 16u * NG) {
+            uint32_t bout[ND];
+            float vout[NG][4];
+            if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout, ut, ut_s);
+            else ft.template group<true>(grp, T, bout, vout, ut, ut_s);
+            if (EV && grp >= nch4) break;
+            if (wv) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float* dst = pv + g * (TRACK_TILE * 4);
+#if defined(__CUDA_ARCH__)
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(vout[g][0], vout[g][1], vout[g][2], vout[g][3]));
+#else
+                    dst[0] = vout[g][0]; dst[1] = vout[g][1]; dst[2] = vout[g][2]; dst[3] = vout[g][3];
+#endif
+                }
+            }
+            pv += vstep;
+            if (wb) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    int8_t* dst = pb + d * (TRACK_TILE * 4);
+#if defined(__CUDA_ARCH__)
+                    __stcs(reinterpret_cast<uint32_t*>(dst), bout[d]);
+#else
+                    for (int b = 0; b < 4; ++b) dst[b] = (int8_t)((bout[d] >> (8 * b)) & 0xFF);
+#endif
+                }
+            }
+            pb += bstep;
+        }
+    }
+}
+
 // `valid` = this thread owns track s (s < P.n); the other threads of a block only help filling the call table U.
 // (tid, nthreads) = the caller's index among the threads that share U (the host emulation calls with 0, 1).
 template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD, class HistInc>
@@ -412,51 +486,9 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     if (!steps) return;
 
     // [grp][tile][var][128][4]: one running pointer per output, variables at compile-time offsets, one uniform stride per group
-    const int64_t ntile = num_tiles(N);
-    // (a null output only predicates the stores off: its pointer is advanced but never dereferenced)
-    const bool wb = O.bins != nullptr, wv = O.values != nullptr;
-    int8_t* pb = O.bins + tile_offset(ND, ntile, 0, 0, s);
-    float* pv = O.values + tile_offset(NG, ntile, 0, 0, s);
-    const int64_t bstep = ntile * (ND * TRACK_TILE * 4), vstep = ntile * (NG * TRACK_TILE * 4);
-    for (int grp0 = 0; grp0 < ngrp; grp0 += UT_GROUPS) {
-        const int gcount = ngrp - grp0 < UT_GROUPS ? ngrp - grp0 : UT_GROUPS;
-        if (grp0 > 0) block_sync();
-        fill_call_table<NG>(U, P, c0, c2, grp0, gcount, tid, nthreads);
-        block_sync();
-        if (!valid) continue;
-        for (int grp = grp0; grp < grp0 + gcount; ++grp) {
-            uint32_t bout[ND];
-            float vout[NG][4];
-            const uint4* ut = U.e + (grp - grp0) * NG;
-            if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout, ut);
-            else ft.template group<true>(grp, T, bout, vout, ut);
-            if (EV && grp >= nch4) break;
-            if (wv) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    float* dst = pv + g * (TRACK_TILE * 4);
-#if defined(__CUDA_ARCH__)
-                    __stcs(reinterpret_cast<float4*>(dst), make_float4(vout[g][0], vout[g][1], vout[g][2], vout[g][3]));
-#else
-                    dst[0] = vout[g][0]; dst[1] = vout[g][1]; dst[2] = vout[g][2]; dst[3] = vout[g][3];
-#endif
-                }
-            }
-            pv += vstep;
-            if (wb) {
-#pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    int8_t* dst = pb + d * (TRACK_TILE * 4);
-#if defined(__CUDA_ARCH__)
-                    __stcs(reinterpret_cast<uint32_t*>(dst), bout[d]);
-#else
-                    for (int b = 0; b < 4; ++b) dst[b] = (int8_t)((bout[d] >> (8 * b)) & 0xFF);
-#endif
-                }
-            }
-            pb += bstep;
-        }
-    }
+    // (the loop is instantiated for "both dense outputs present", the bench case, and for the general case)
+    if (O.bins && O.values) fast_groups<RS, NG, FAST, HIST, EV, ORD, HistInc, true>(ft, P, O, U, s, valid, tid, nthreads, c0, c2);
+    else fast_groups<RS, NG, FAST, HIST, EV, ORD, HistInc, false>(ft, P, O, U, s, valid, tid, nthreads, c0, c2);
     if (EV && valid) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
         ft.emit(true, (uint32_t)T, 0u, 0u, 0.0f);
         if (EV == 1) O.ev_counts[s] = ft.ev_n;

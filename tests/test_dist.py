@@ -60,3 +60,46 @@ def test_two_rank_gloo_sharding_and_histogram_reduce(model_paths, tmp_path):
     for q in parts:   # every rank holds the global histogram after the single all-reduce
         assert np.array_equal(q["hi"], whole["hist_initial"].astype(np.int64))
         assert np.array_equal(q["ht"], whole["hist_transition"].astype(np.int64))
+
+
+def _terminal_worker(rank, world, port, traj_dir, geo_path, tmp):
+    here = os.path.dirname(os.path.abspath(__file__))
+    for q in (os.path.dirname(here), here):
+        if q not in sys.path:
+            sys.path.insert(0, q)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import test_terminal_traj as TT
+    from em_model_manned_bayes_b200.synthetic import write_terminal_model_set
+    paths = write_terminal_model_set(traj_dir)
+    geo = np.load(geo_path)
+    first, cnt = shard_range(geo.shape[1], rank, world)
+    rc, traj, ln = TT.emu_propagate(paths, np.ascontiguousarray(geo[:, first:first + cnt]), 77, first, 60)
+    assert rc == 0
+    states = torch.tensor([int(ln.astype(np.int64).sum())])
+    dist.all_reduce(states, op=dist.ReduceOp.SUM)           # what bench.py reduces for configs[4]: total trajectory states
+    np.savez(os.path.join(tmp, "term%d.npz" % rank), traj=traj, len=ln, states=states.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_terminal_chains_are_shard_invariant(golden, tmp_path):
+    """configs[4] shards by encounter index like everything else: rank r propagates encounters [first, first+cnt) with
+    first_sample = first, and the union equals the single-rank result bit for bit (the chains are keyed by the global
+    encounter index, emb_terminal.cuh)."""
+    import test_terminal_traj as TT
+    from em_model_manned_bayes_b200.synthetic import write_terminal_model_set
+    traj_dir = str(tmp_path / "traj")
+    paths = write_terminal_model_set(traj_dir)
+    geo = TT.geo_from_golden(golden, 13)
+    geo_path = str(tmp_path / "geo.npy")
+    np.save(geo_path, geo)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_terminal_worker, args=(2, port, traj_dir, geo_path, str(tmp_path)), nprocs=2, join=True)
+    rc, traj, ln = TT.emu_propagate(paths, geo, 77, 0, 60)
+    assert rc == 0
+    parts = [np.load(os.path.join(str(tmp_path), "term%d.npz" % r)) for r in range(2)]
+    got = np.concatenate([q["traj"] for q in parts], axis=3)
+    assert np.array_equal(np.concatenate([q["len"] for q in parts], axis=1), ln)
+    assert np.array_equal(np.isnan(got), np.isnan(traj)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(traj))
+    assert all(int(q["states"][0]) == int(ln.astype(np.int64).sum()) for q in parts)
