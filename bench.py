@@ -381,42 +381,70 @@ def main():
         del r4, cm
         torch.cuda.empty_cache()
 
-        # configs[4]: CorTerminalModel, 1M encounters: geometry sampling (sample.m) + four trajectory chains per encounter
-        # (createEncounter.m) on synthetic trajectory DBNs of the documented layout (the 20 model files are missing upstream)
-        from em_model_manned_bayes_b200.model import CorTerminalModel
-        from em_model_manned_bayes_b200.synthetic import write_terminal_model_set
-        tp_ = materialize(mdir, names=["terminal_v3_radar_encounter_model"])["terminal_v3_radar_encounter_model"]
-        write_terminal_model_set(os.path.join(mdir, "traj"))
-        tm = CorTerminalModel(tp_, parameters_directory=os.path.join(mdir, "traj"))
-        n5, tmax5 = 1_000_000, 120
-        vals, _, _ = tm.sample_raw(n5, seed=1, device=dev)
-        geo = vals.T.contiguous()
-        r5 = tm.create_encounters(geo, tmax5, seed=2, device=dev)
-        dt_geo = timed(lambda k: tm.sample_raw(n5, seed=20 + k, device=dev))
-        dt_traj = timed(lambda k: tm.create_encounters(geo, tmax5, seed=30 + k, device=dev, out=r5))
-        states = int(r5.len.to(torch.int64).sum().item())
-        other["configs[4] CorTerminalModel 1M encounters: sample (geometry) + createEncounter chains, tmax 120 s, synthetic "
-              "trajectory DBNs"] = {"value": states / dt_traj, "unit": "trajectory states/s", "ms_chains": dt_traj * 1e3,
-                                    "ms_geometry": dt_geo * 1e3, "encounters_per_s": n5 / (dt_traj + dt_geo),
-                                    "states_per_encounter": states / n5,
-                                    # 5 fp32 fields per state written; the chains are fp64-trigonometry bound, not HBM bound
-                                    "algorithmic_bytes_per_unit": 20.0,
-                                    "roofline_frac": states / dt_traj * 20.0 / 1e9 / peaks()[0]}
-        del r5, geo, vals, tm
-        torch.cuda.empty_cache()
+    # ---- configs[4]: CorTerminalModel, 1M encounters PER GPU (weak scaling like the main workload), every rank -------------
+    # geometry sampling (sample.m) + four trajectory chains per encounter (createEncounter.m) on synthetic trajectory DBNs of
+    # the documented layout (the 20 model files are missing upstream); sharded by encounter index: rank r owns encounters
+    # [r*n5, (r+1)*n5), both kernels keyed by the global index (first_sample), no collective on the data path
+    from em_model_manned_bayes_b200.model import CorTerminalModel
+    from em_model_manned_bayes_b200.model_archive import materialize as _mat
+    from em_model_manned_bayes_b200.synthetic import write_terminal_model_set
+    mdir5 = os.path.join(tempfile.gettempdir(), "emb_bench_models_%d" % os.getuid())
+    tp_ = _mat(mdir5, names=["terminal_v3_radar_encounter_model"])["terminal_v3_radar_encounter_model"]
+    write_terminal_model_set(os.path.join(mdir5, "traj"))
+    tm = CorTerminalModel(tp_, parameters_directory=os.path.join(mdir5, "traj"))
+    n5, tmax5 = 1_000_000, 120
+    vals5, _, _ = tm.sample_raw(n5, seed=1, first_sample=rank * n5, device=dev)
+    geo = vals5.T.contiguous()
+    r5 = tm.create_encounters(geo, tmax5, seed=2, first_sample=rank * n5, device=dev)
+    e5 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps5 = 3
+    barrier()
+    e5[0].record()
+    for k in range(reps5):
+        tm.sample_raw(n5, seed=20 + k, first_sample=rank * n5, device=dev)
+    e5[1].record()
+    for k in range(reps5):
+        tm.create_encounters(geo, tmax5, seed=30 + k, first_sample=rank * n5, device=dev, out=r5)
+    e5[2].record()
+    barrier()
+    t5 = torch.tensor([e5[0].elapsed_time(e5[1]) / reps5, e5[1].elapsed_time(e5[2]) / reps5], dtype=torch.float64, device=dev)
+    st5 = r5.len.to(torch.int64).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)           # device time: max over ranks
+        dist.all_reduce(st5, op=dist.ReduceOp.SUM)          # trajectory states of the whole job
+    dt_geo, dt_traj, states = float(t5[0]) * 1e-3, float(t5[1]) * 1e-3, int(st5.item())
+    config4 = {"value": states / dt_traj, "unit": "trajectory states/s", "ms_chains": dt_traj * 1e3, "ms_geometry": dt_geo * 1e3,
+               "encounters_per_s": world * n5 / (dt_traj + dt_geo), "encounters": world * n5, "n_gpus": world, "scaling": "weak",
+               "states_per_encounter": states / (world * n5),
+               # 5 fp32 fields per state written; the chains are fp64-trigonometry bound, not HBM bound
+               "algorithmic_bytes_per_unit": 20.0, "roofline_frac": states / dt_traj * 20.0 / 1e9 / (peaks()[0] * world)}
+    del r5, geo, vals5, tm
+    torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    other["configs[4] CorTerminalModel 1M encounters per GPU: sample (geometry) + createEncounter chains, tmax 120 s, synthetic "
+          "trajectory DBNs, sharded by encounter index"] = config4
     peak, peak_src = peaks()
     k_ms = statistics.mean(kern_ms)
     achieved = ALGO_BYTES_PER_UNIT * n * T / (k_ms * 1e-3) / 1e9
     traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per unit from the committed ncu --set full capture
+    issue = None        # the limiter the ncu capture names: warp-instructions issued against the schedulers' peak
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("bytes_per_unit") * n * T
+            tj = json.load(open(tp))
+            traffic = tj.get("bytes_per_unit") * n * T
+            # smsp__inst_executed.sum / (units / 32) of the same capture; one warp-instruction per scheduler per clock is the
+            # issue peak: SMs x 4 schedulers x the SM clock sampled during the timed region
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
+            wi = float(tj["warp_inst_per_warp_unit"])
+            issue = {"warp_inst_per_32_units": wi, "issue_peak_per_s": sms * 4 * mhz * 1e6,
+                     "frac": (n * T / 32.0) * wi / (k_ms * 1e-3) / (sms * 4 * mhz * 1e6),
+                     "pipes_pct": tj.get("pipes_pct"), "source": tj.get("source")}
         except Exception:
             traffic = None
     out = {
@@ -443,9 +471,25 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": ALGO_BYTES_PER_UNIT,
-                     "written_bytes_per_unit": (nb + nv * 4) / (n * T), "kernel_ms": k_ms},
+                     "written_bytes_per_unit": (nb + nv * 4) / (n * T), "kernel_ms": k_ms,
+                     # the kernel is bound by instruction issue, not by HBM: issue slots used / peak
+                     "issue_frac": issue["frac"] if issue else None, "issue": issue},
         "clocks": clk,
     }
+    n1_file = os.path.join(tempfile.gettempdir(), "emb_bench_e2e_n1_%d.json" % os.getuid())
+    if world == 1:
+        try:
+            json.dump({"e2e": e2e_events_value, "value": value, "tracks": n}, open(n1_file, "w"))
+        except OSError:
+            pass
+        out["e2e"]["efficiency_vs_n1"] = 1.0
+    else:   # weak-scaling efficiency of the end-to-end number against the N=1 run of the same box (driver runs 1,2,4,8 in turn)
+        try:
+            n1 = json.load(open(n1_file))
+            out["e2e"]["efficiency_vs_n1"] = e2e_events_value / (world * n1["e2e"]) if n1.get("tracks") == n else None
+            out["efficiency_vs_n1"] = value / (world * n1["value"]) if n1.get("tracks") == n else None
+        except (OSError, ValueError, KeyError):
+            out["e2e"]["efficiency_vs_n1"] = None
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         ntr = 80000 * threads

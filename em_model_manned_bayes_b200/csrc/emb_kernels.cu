@@ -27,8 +27,8 @@ namespace {
 #ifndef EMB_MINBLOCKS
 #define EMB_MINBLOCKS 4
 #endif
-#ifndef EMB_MINBLOCKS_SLOW      // slow branch (per-second column gathers): latency-bound, more resident warps help
-#define EMB_MINBLOCKS_SLOW 5
+#ifndef EMB_MINBLOCKS_SLOW      // slow branch (per-second column gathers): latency-bound, more resident warps help -- as long as
+#define EMB_MINBLOCKS_SLOW 5    // the columns of all dynamic variables still fit in registers (four 9-bin variables need 128)
 #endif
 constexpr int BLOCK = EMB_BLOCK;
 
@@ -121,7 +121,7 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
 
 // ---- tracks, register-resident specialisation (emb_fast.cuh) --------------------------------------
 template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD>
-__global__ void __launch_bounds__(BLOCK, FAST ? EMB_MINBLOCKS : EMB_MINBLOCKS_SLOW)
+__global__ void __launch_bounds__(BLOCK, FAST ? EMB_MINBLOCKS : (DynShape<RS>::ND >= 4 ? EMB_MINBLOCKS : EMB_MINBLOCKS_SLOW))
 k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
               const __grid_constant__ TrackOut O) {
     __shared__ FastShared S;

@@ -322,8 +322,8 @@ def test_initial_full_size_chi_square_config2(model_paths):
         assert chi2 < 50.0, (i, chi2)
 
 
-def test_step_word_statistics_spec_v3(model_paths):
-    """Stream spec v3 derives the transition select, the resample gate and the de-discretisation of a variable in
+def test_step_word_statistics_spec_v5(model_paths):
+    """Stream spec v5 derives the transition select, the resample gate and the de-discretisation of a variable in
     a second from ONE Philox word.  With every initial variable preset the frozen-parent columns are known, so:
     transition bins ~ the normalised count column (chi-square), rows per variable = gates (rate) + changes
     (1 - stay probability) within 5 sigma, and the de-discretised values of the gate rows are uniform in their bin."""
@@ -371,6 +371,135 @@ def test_step_word_statistics_spec_v3(model_paths):
     h = np.histogram(u, bins=20, range=(0, 1))[0].astype(np.float64)
     chi2 = ((h - len(u) / 20) ** 2 / (len(u) / 20)).sum()
     assert chi2 < 60.0, chi2
+
+
+@pytest.mark.gpu
+def _row_table(ev, n, T):
+    """rows of an EventResult on the device -> numpy (track, second, var, bin, value) with the closing rows dropped"""
+    rows = ev.events.cpu().numpy().view(L.EVENT_DTYPE)
+    off = ev.offsets.cpu().numpy()
+    trk = np.repeat(np.arange(n), np.diff(off))
+    cum = np.cumsum(rows["dt"].astype(np.int64))
+    before = np.where(off[:-1] > 0, cum[np.maximum(off[:-1], 1) - 1], 0)
+    sec = cum - np.repeat(before, np.diff(off))
+    keep = rows["var"] > 0
+    return trk[keep], sec[keep], rows["var"][keep].astype(np.int64), rows["bin"][keep].astype(np.int64), rows["value"][keep].astype(np.float64)
+
+
+def _uniformity(u, cells=16):
+    assert u.min() >= 0.0 and u.max() <= 1.0
+    h = np.histogram(u, bins=cells, range=(0, 1))[0].astype(np.float64)
+    return float(((h - len(u) / cells) ** 2 / (len(u) / cells)).sum())
+
+
+def test_joint_law_of_select_gate_and_value_fast_branch(model_paths):
+    """The reference draws the transition select, the resample gate and the de-discretisation uniform of a variable
+    independently; stream spec v5 derives them from the variable's word of the second (select on k, gate on k*A, value on
+    k*B + k').  Joint check on the frozen-parent branch with every initial variable preset (the column of each dynamic
+    variable is then known exactly), 2e7 track-seconds:
+      * chi-square of the 2 x r table (gate fired) x (new bin) against  p(bin) * rate  -- including the bins of probability
+        < 1e-3 of columns 3918 / 1960 / 558;
+      * the value of every row is uniform inside its bin GIVEN the kind of row: gate only, transition only, gate and
+        transition in the same second, and transition into a bin of probability < 1e-2."""
+    import torch
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    start = [1, 4, 2, 4, 3, 4, 4]
+    n, T = 80_000, 250
+    dense = m.sample_tracks(n, T, seed=123, opts=m.uncor_opts(start=start), device="cuda:0", want_values=False, want_init=False)
+    ev = m.sample_events(n, T, seed=123, opts=m.uncor_opts(start=start), device="cuda:0", want_init=False)
+    torch.cuda.synchronize()
+    bins = dense.bins.cpu().numpy()                      # (n, n_dyn, T) 1-based; column c = second c + 1 (state after step e = c)
+    trk, sec, var, rbin, val = _row_table(ev, n, T)
+    G, r, Nt = m.G_transition, m.r_transition, m.N_transition
+    x = np.array(start) - 1
+    rare_seen = 0
+    for d, (vt, vt1) in enumerate(m.temporal_map):
+        par = np.nonzero(G[:, vt1 - 1])[0]
+        j, stride = 0, 1
+        for p_ in par:
+            j += stride * x[p_]
+            stride *= int(r[p_])
+        col = Nt[vt1 - 1][:, j]
+        pcol = col / col.sum()
+        rate = float(m.resample_rates[vt - 1])
+        b = bins[:, d, :].astype(np.int64)
+        prev, new = b[:, :-1], b[:, 1:]                  # seconds e = 1 .. T-1
+        sel = (var == vt) & (sec >= 1) & (sec <= T - 1)
+        t_, e_, rb_, v_ = trk[sel], sec[sel], rbin[sel], val[sel]
+        is_gate = rb_ == prev[t_, e_ - 1]                # a gate row re-emits the PRE-transition bin (resample_events.m:26-29)
+        fired = np.zeros((n, T - 1), dtype=bool)
+        fired[t_[is_gate], e_[is_gate] - 1] = True
+        changed = new != prev
+        # every transition row is there and carries the new bin
+        tr = ~is_gate
+        assert tr.sum() == changed.sum() and np.array_equal(rb_[tr], new[t_[tr], e_[tr] - 1])
+        steps = n * (T - 1)
+        obs = np.zeros((2, len(pcol)))
+        for f in (0, 1):
+            obs[f] = np.bincount(new[fired == bool(f)] - 1, minlength=len(pcol))
+        exp = np.outer([1 - rate, rate], pcol) * steps
+        keep = exp > 0
+        assert obs[~keep].sum() == 0
+        chi2 = float(((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum())
+        assert chi2 < 60.0, (vt, chi2, obs, exp)          # <= 2r - 1 = 13 degrees of freedom
+        rare_seen += int(obs[:, (pcol > 0) & (pcol < 1e-3)].sum())
+        # values: u = (value - a) / (b - a) inside the row's bin
+        edges = np.asarray(m.boundaries[vt - 1])
+        zb = m.zero_bins[vt - 1][0] if m.zero_bins[vt - 1] else 0
+        nz = rb_ != zb
+        u = (v_ - edges[rb_ - 1]) / (edges[rb_] - edges[rb_ - 1])
+        assert np.all(v_[~nz] == 0.0)
+        both = np.zeros(len(rb_), dtype=bool)
+        both[tr] = fired[t_[tr], e_[tr] - 1]              # transition rows of seconds in which the gate fired too
+        into_rare = tr & np.isin(rb_ - 1, np.nonzero(pcol < 1e-2)[0])
+        for name, pick in (("gate", is_gate), ("transition", tr), ("gate+transition", both), ("rare transition", into_rare)):
+            pick = pick & nz
+            if pick.sum() >= 800:
+                c2 = _uniformity(u[pick])
+                assert c2 < 55.0, (vt, name, int(pick.sum()), c2)
+    assert rare_seen > 1000      # the tables really contained bins of probability < 1e-3 (columns 3918 and 558)
+
+
+@pytest.mark.gpu
+def test_joint_law_of_gate_and_value_slow_branch(model_paths):
+    """The same on the slow branch (glider_v1: dynamic -> dynamic edges, parents re-evaluated every second), where the
+    transition columns vary along the track: the gate frequency GIVEN that the variable changes in that second equals its
+    resample rate, and the values of gate rows, transition rows and same-second rows are uniform inside their bins."""
+    import torch
+    m = UncorEncounterModel(model_paths["glider_v1"])
+    n, T = 60_000, 200
+    dense = m.sample_compact(n, T, seed=321, device="cuda:0", want_values=False, want_init=False)
+    ev = m.sample_events_uncor(n, T, seed=321, device="cuda:0", want_init=False)
+    torch.cuda.synchronize()
+    bins = dense.bins.cpu().numpy()
+    trk, sec, var, rbin, val = _row_table(ev, n, T)
+    for d, (vt, vt1) in enumerate(m.temporal_map):
+        rate = float(m.resample_rates[vt - 1])
+        b = bins[:, d, :].astype(np.int64)
+        prev, new = b[:, :-1], b[:, 1:]
+        sel = (var == vt) & (sec >= 1) & (sec <= T - 1)
+        t_, e_, rb_, v_ = trk[sel], sec[sel], rbin[sel], val[sel]
+        is_gate = rb_ == prev[t_, e_ - 1]
+        fired = np.zeros((n, T - 1), dtype=bool)
+        fired[t_[is_gate], e_[is_gate] - 1] = True
+        changed = new != prev
+        k, tot = int((fired & changed).sum()), int(changed.sum())
+        assert tot > 20_000
+        assert abs(k - tot * rate) < 5.0 * np.sqrt(tot * rate * (1 - rate)) + 1.0, (vt, k, tot, rate)
+        k0, tot0 = int((fired & ~changed).sum()), int((~changed).sum())
+        assert abs(k0 - tot0 * rate) < 5.0 * np.sqrt(tot0 * rate * (1 - rate)) + 1.0, (vt, k0, tot0, rate)
+        edges = np.asarray(m.boundaries[vt - 1])
+        zb = m.zero_bins[vt - 1][0] if m.zero_bins[vt - 1] else 0
+        nz = rb_ != zb
+        u = (v_ - edges[rb_ - 1]) / (edges[rb_] - edges[rb_ - 1])
+        tr = ~is_gate
+        both = np.zeros(len(rb_), dtype=bool)
+        both[tr] = fired[t_[tr], e_[tr] - 1]
+        for name, pick in (("gate", is_gate), ("transition", tr), ("gate+transition", both)):
+            pick = pick & nz
+            if pick.sum() >= 800:
+                c2 = _uniformity(u[pick])
+                assert c2 < 55.0, (vt, name, int(pick.sum()), c2)
 
 
 def test_em_sample_files_match_oracle(model_paths, tmp_path):
