@@ -262,7 +262,8 @@ def main():
     cap = int(probe.total * 1.03)
     del probe
     torch.cuda.empty_cache()
-    h_ev = torch.empty(cap, dtype=torch.int64).pin_memory()
+    h_words = torch.empty(cap, dtype=torch.int32).pin_memory()      # packed rows: 4 + 1 bytes (emb_sample_track_events_packed)
+    h_dts = torch.empty(cap, dtype=torch.uint8).pin_memory()
     h_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
     import ctypes as C
     tot = C.c_int64(0)
@@ -270,8 +271,8 @@ def main():
 
     def events_call(seed):
         rng = L.Rng(seed, rank * n)
-        L.check(lib.emb_sample_track_events(m._h, C.byref(rng), n, T, C.byref(o), cap, h_ev.data_ptr(), h_off.data_ptr(),
-                                            C.byref(init_only), C.byref(tot)))
+        L.check(lib.emb_sample_track_events_packed(m._h, C.byref(rng), n, T, C.byref(o), cap, h_words.data_ptr(), h_dts.data_ptr(),
+                                                   h_off.data_ptr(), C.byref(init_only), C.byref(tot)))
     for k in range(max(6, args.warmup)):      # warm-up calls: the first one also fills the library's device memory pool
         events_call(7 + k)
     barrier()
@@ -288,7 +289,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_events_value = units_per_step * ev_n / float(t.item())
-    ev_d2h = int(tot.value) * 8 + (n + 1) * 8 + h_iv.numel() * 8 + 12
+    ev_d2h = int(tot.value) * 5 + (n + 1) * 8 + h_iv.numel() * 8 + 12
 
     # ---- the other single-GPU configuration of BASELINE.json, for the record (rank 0, device-resident) -----
     other = {}
@@ -462,8 +463,10 @@ def main():
         "e2e": {"value": e2e_events_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400,
                 "d2h_bytes_per_step": ev_d2h, "steps": ev_n,
                 "ms_per_step": [round(x, 2) for x in ev_steps],
-                "contract": "UncorEncounterModel.sample outputs: sparse out_events rows (8 B) + offsets + out_inits in host memory, "
-                            "emb_sample_track_events (count pass, prefix sum, write pass, D2H inside the timed region)"},
+                "d2h_bytes_per_unit": ev_d2h / (n * T),
+                "contract": "UncorEncounterModel.sample outputs: sparse out_events rows (5-byte packed rows: dt, variable, bin and the "
+                            "23 value bits; the host evaluates dediscretize.m:39 in fp64) + offsets + out_inits in host memory, "
+                            "emb_sample_track_events_packed (count pass, prefix sum, write pass, D2H inside the timed region)"},
         "e2e_dense": {"value": e2e_value, "unit": "track-timesteps/s", "h2d_bytes_per_step": 3400, "d2h_bytes_per_step": d2h,
                       "steps": args.e2e_steps,
                       "contract": "dense compact tiles in host memory (the same emb_sample_tracks call as `value`); PCIe-bound at 19.0 B/unit"},

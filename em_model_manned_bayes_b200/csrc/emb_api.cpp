@@ -573,17 +573,27 @@ struct PhaseTrace {
     }
 };
 
-int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
-                            int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
-                            int64_t* total_rows) {
-    if (!m || !rng || !opts || !offsets || n < 0 || T < 1 || capacity < 0 || (capacity > 0 && !events))
+// Both event entry points.  The write pass always produces packed rows on the device (emb_device.cuh: pack_event_word);
+// `events` != nullptr: the 8-byte emb_event rows, expanded on the device before they leave it;
+// `words` / `dts` != nullptr: the packed rows themselves (5 bytes per row over PCIe instead of 8).
+static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                              int64_t capacity, emb_event* events, uint32_t* words, uint8_t* dts, int64_t* offsets,
+                              const emb_track_out* init, int64_t* total_rows) {
+    const bool packed = events == nullptr;
+    if (!m || !rng || !opts || !offsets || n < 0 || T < 1 || capacity < 0 || (capacity > 0 && packed && (!words || !dts)))
         return set_err(EMB_E_ARG, "null or out-of-range argument");
-    if (T > 65535) return set_err(EMB_E_LIMIT, "event rows store dt in 16 bits: T must be <= 65535");
     if (init && (init->bins || init->values || init->hist_initial || init->hist_transition))
         return set_err(EMB_E_ARG, "emb_sample_track_events: dense outputs and histograms belong to emb_sample_tracks");
     const HostModel& H = *m->h;
     if (!H.has_transition || H.temporal_map.empty())
         return set_err(EMB_E_ARG, "dynvar:empty: model has no transition network");
+    int max_bins = 0;
+    for (int v : H.gated) max_bins = std::max(max_bins, (int)H.r_initial[v]);
+    emb::EventFormat fm{};
+    if (!emb::event_format_for((int)H.gated.size(), max_bins, T, fm))
+        return set_err(EMB_E_LIMIT, "event rows need <= 15 time-varying variables with <= 16 bins each and T <= 65535");
+    if (packed && (fm.gord_bits != 3 || fm.dt_bytes != 1))
+        return set_err(EMB_E_LIMIT, "packed event rows need <= 7 time-varying variables and T <= 1023 (use emb_sample_track_events)");
     emb::SampleParams P;
     int rc = 0;
     try {
@@ -607,6 +617,8 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     Stager sg{opts->mem, st, {}};
     const size_t ni = (size_t)H.n_initial;
     emb::TrackOut O{};
+    O.ev_gord_bits = fm.gord_bits;
+    O.ev_dt_bytes = fm.dt_bytes;
     long long* d_off = nullptr;
     if ((rc = sg.out(offsets, (size_t)(n + 1) * 8, false, (void**)&d_off))) return rc;
     if (init) {
@@ -617,13 +629,14 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     struct Scratch {
         void* p = nullptr;
         ~Scratch() { tmp_free(p); }
-    } counts, status, tiles;
+    } counts, status, tiles, pw, pd;
     CU(tmp_alloc(&counts.p, (size_t)n * 4, st));
     CU(tmp_alloc(&tiles.p, (size_t)emb::scan_scratch_len(n) * 8, st));
     CU(tmp_alloc(&status.p, 4, st));
     CU(cudaMemsetAsync(status.p, 0, 4, st));
     O.status = (int32_t*)status.p;
-    const bool pipelined = (opts->mem & 0xFF) == EMB_MEM_HOST && n >= 8192;
+    const bool host = (opts->mem & 0xFF) == EMB_MEM_HOST;
+    const bool pipelined = host && n >= 8192;
     if (!pipelined) {
         // pass 1: rows per track (also writes the per-track initial outputs), then the prefix sum
         O.ev_counts = (uint32_t*)counts.p;
@@ -643,35 +656,58 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
             if ((rc = sg.finish())) return rc;   // offsets and the initial outputs are valid
             return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
         }
-        // pass 2: write the rows (the keyed stream reproduces pass 1 exactly)
+        // pass 2: write the packed rows (the keyed stream reproduces pass 1 exactly)
         O.ev_counts = nullptr;
         O.init_bins = nullptr;
         O.init_values = nullptr;
         O.attempts = nullptr;
-        uint2* d_ev = nullptr;
-        if ((rc = sg.out(events, (size_t)total * 8, false, (void**)&d_ev))) return rc;
+        uint32_t* d_words = nullptr;
+        uint8_t* d_dts = nullptr;
+        if (packed) {
+            if ((rc = sg.out(words, (size_t)total * 4, false, (void**)&d_words))) return rc;
+            if ((rc = sg.out(dts, (size_t)total, false, (void**)&d_dts))) return rc;
+        } else {
+            CU(tmp_alloc(&pw.p, (size_t)std::max<long long>(total, 1) * 4, st));
+            CU(tmp_alloc(&pd.p, (size_t)std::max<long long>(total, 1) * fm.dt_bytes, st));
+            d_words = (uint32_t*)pw.p;
+            d_dts = (uint8_t*)pd.p;
+        }
         O.ev_offsets = d_off;
-        O.events = d_ev;
+        O.ev_words = d_words;
+        O.ev_dts = d_dts;
         e = (cudaError_t)emb::launch_tracks(D, P, O, st);
         if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
+        if (!packed) {
+            uint2* d_ev = nullptr;
+            if ((rc = sg.out(events, (size_t)total * 8, false, (void**)&d_ev))) return rc;
+            e = (cudaError_t)emb::launch_expand_events(D, d_words, d_dts, d_ev, 0, total, fm, st);
+            if (e != cudaSuccess) return cuda_fail(e, "launch k_expand_events");
+        }
         CU(cudaStreamSynchronize(st));
         return sg.finish();
     }
     // Host-memory caller, large batch: the tracks go through in chunks, each chunk = count pass -> prefix sum (carrying the
-    // rows of the chunks before it) -> write pass on the caller's stream, while a second stream copies the rows of the
-    // finished chunks to the host (rows of a track range are contiguous: [offsets[a], offsets[b])).  Only the first chunk's
-    // count pass is not hidden behind a copy.
+    // rows of the chunks before it) -> write pass (-> expansion) on the caller's stream, while a second stream copies the rows
+    // of the finished chunks to the host (rows of a track range are contiguous: [offsets[a], offsets[b])).  Only the first
+    // chunk's count pass is not hidden behind a copy.
     struct Guard {
-        void* dev = nullptr;
+        void* rows = nullptr;       // 8-byte rows (legacy entry point only)
         cudaStream_t copy = nullptr;
         cudaEvent_t done[16] = {};
         ~Guard() {
             for (auto& d : done) if (d) cudaEventDestroy(d);
-            if (copy) cudaStreamDestroy(copy);
-            tmp_free(dev);
+            if (copy) {
+                cudaStreamSynchronize(copy);
+                cudaStreamDestroy(copy);
+            }
+            tmp_free(rows);
         }
     } g;
-    if (capacity > 0) CU(tmp_alloc(&g.dev, (size_t)capacity * 8, st));
+    if (capacity > 0) {
+        CU(tmp_alloc(&pw.p, (size_t)capacity * 4, st));
+        CU(tmp_alloc(&pd.p, (size_t)capacity * fm.dt_bytes, st));
+        if (!packed) CU(tmp_alloc(&g.rows, (size_t)capacity * 8, st));
+    }
     CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
     CU(cudaMemsetAsync(d_off, 0, 8, st));                 // carry of the first chunk
     const int chunks = 8;
@@ -685,6 +721,8 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         emb::SampleParams Pc = P;
         Pc.first_sample = P.first_sample + (uint64_t)a;
         Pc.n = b - a;
+        Pc.s_begin = 0;
+        Pc.s_end = b - a;
         emb::TrackOut Oc = O;                             // count pass of the chunk: also its per-track initial outputs
         Oc.init_stride = n;
         if (O.init_bins) Oc.init_bins = O.init_bins + a;
@@ -713,13 +751,25 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
         emb::TrackOut Ow{};                               // write pass of the chunk (the keyed stream reproduces the count pass)
         Ow.status = O.status;
         Ow.ev_offsets = d_off + a;
-        Ow.events = (uint2*)g.dev;
+        Ow.ev_words = (uint32_t*)pw.p;
+        Ow.ev_dts = (uint8_t*)pd.p;
+        Ow.ev_gord_bits = fm.gord_bits;
+        Ow.ev_dt_bytes = fm.dt_bytes;
         e = (cudaError_t)emb::launch_tracks(D, Pc, Ow, st);
         if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks (event write)");
+        if (!packed) {
+            e = (cudaError_t)emb::launch_expand_events(D, (const uint32_t*)pw.p, (const uint8_t*)pd.p, g.rows, r0, r1 - r0, fm, st);
+            if (e != cudaSuccess) return cuda_fail(e, "launch k_expand_events");
+        }
         CU(cudaEventCreateWithFlags(&g.done[c], cudaEventDisableTiming));
         CU(cudaEventRecord(g.done[c], st));
         CU(cudaStreamWaitEvent(g.copy, g.done[c], 0));
-        CU(cudaMemcpyAsync(events + r0, (const char*)g.dev + (size_t)r0 * 8, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, g.copy));
+        if (packed) {
+            CU(cudaMemcpyAsync(words + r0, (const uint32_t*)pw.p + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, g.copy));
+            CU(cudaMemcpyAsync(dts + r0, (const uint8_t*)pd.p + r0, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy));
+        } else {
+            CU(cudaMemcpyAsync(events + r0, (const char*)g.rows + (size_t)r0 * 8, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, g.copy));
+        }
     }
     tr.mark("chunks enqueued");
     if (total_rows) *total_rows = total;
@@ -729,6 +779,28 @@ int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, i
     tr.mark("rows D2H drained");
     if (overflow) return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
     return 0;
+}
+
+int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                            int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
+                            int64_t* total_rows) {
+    if (capacity > 0 && !events) return set_err(EMB_E_ARG, "null or out-of-range argument");
+    emb_event dummy;
+    return sample_events_impl(m, rng, n, T, opts, capacity, events ? events : &dummy, nullptr, nullptr, offsets, init, total_rows);
+}
+
+int emb_sample_track_events_packed(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                                   int64_t capacity, uint32_t* words, uint8_t* dts, int64_t* offsets, const emb_track_out* init,
+                                   int64_t* total_rows) {
+    return sample_events_impl(m, rng, n, T, opts, capacity, nullptr, words, dts, offsets, init, total_rows);
+}
+
+int64_t emb_model_get_gated(const emb_model* m, int32_t* buf, int64_t cap) {
+    if (!m) return 0;
+    const auto& g = m->h->gated;
+    if (buf)
+        for (size_t i = 0; i < g.size() && (int64_t)i < cap; ++i) buf[i] = g[i] + 1;
+    return (int64_t)g.size();
 }
 
 int emb_dyn_limits_named(const char* ac_type, emb_dyn_limits* out) {

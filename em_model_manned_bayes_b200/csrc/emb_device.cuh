@@ -142,10 +142,40 @@ struct TrackOut {
     // sparse event list (emb200.h: emb_event), two passes: count rows per track, then write them
     uint32_t* ev_counts;           // pass 1: [n] rows of each track (including the closing row)
     const long long* ev_offsets;   // pass 2: [n] first row of each track
-    uint2* events;                 // pass 2: rows
+    uint32_t* ev_words;            // pass 2: packed rows (pack_event_word below), one word and
+    uint8_t* ev_dts;               //         ev_fmt.dt_bytes bytes per row
+    int32_t ev_gord_bits, ev_dt_bytes;   // EventFormat of the write pass
     int64_t init_stride;           // samples between consecutive variables of init_bins / init_values; 0 = P.n (a chunk of
                                    // a larger call writes into the whole call's [n_initial][n] arrays)
 };
+
+// ---- packed event rows: what the write pass produces and emb_sample_track_events_packed returns --------------------------------
+// word = frac | (bin - 1) << 23 | gord << 27 | (dt >> 8*dt_bytes) << (27 + gord_bits);  dts = the low dt_bytes bytes of dt
+//   frac : the 23 bits of the de-discretisation word, u_dd = (frac + 0.5) 2^-23 (stream spec v5) -- the value is
+//          boundaries[bin] + (boundaries[bin+1] - boundaries[bin]) * u_dd, 0 in a zero bin, the bin itself for a '*' variable
+//   gord : 1-based ordinal of the variable among the gated variables, 0 in the closing row (then bin and frac are 0)
+//   dt   : seconds since the previous row
+// The public packed format is (gord_bits, dt_bytes) = (3, 1): 5 bytes per row, n_gated <= 7, T <= 1023 -- every shipped model.
+// The 8-byte emb_event rows of emb_sample_track_events are expanded from packed rows on the device (expand_event) and also
+// accept 4-bit ordinals and 2-byte dts (n_gated <= 15, T <= 65535); bins of gated variables must be <= 16.
+struct EventFormat {
+    int32_t gord_bits, dt_bytes;
+};
+inline bool event_format_for(int n_gated, int max_bins, int T, EventFormat& f) {
+    if (n_gated > 15 || max_bins > 16) return false;
+    f.gord_bits = n_gated <= 7 ? 3 : 4;
+    f.dt_bytes = T < (1 << (8 + 5 - f.gord_bits)) ? 1 : 2;
+    return T < (1 << (16 + 5 - f.gord_bits));
+}
+EMB_HD uint32_t pack_event_word(uint32_t dt, uint32_t gord, uint32_t bin1, uint32_t frac, const EventFormat& f) {
+    return frac | ((bin1 ? bin1 - 1u : 0u) << 23) | (gord << 27) | ((dt >> (8 * f.dt_bytes)) << (27 + f.gord_bits));
+}
+EMB_HD void store_event(uint32_t* words, uint8_t* dts, long long i, uint32_t dt, uint32_t gord, uint32_t bin1, uint32_t frac,
+                        const EventFormat& f) {
+    words[i] = pack_event_word(dt, gord, bin1, frac, f);
+    if (f.dt_bytes == 1) dts[i] = (uint8_t)(dt & 255u);
+    else reinterpret_cast<uint16_t*>(dts)[i] = (uint16_t)(dt & 65535u);
+}
 
 // ---------------------------------------------------------------------------------------------
 // exact fp64 helpers (no FMA contraction, round-to-nearest) so host emulation == device
@@ -393,6 +423,43 @@ EMB_HD double dedisc(const DevModel& M, int i, int b, double u) {
     return dadd(a, dmul(w, u));                             // :39  a + (b-a)*rand
 }
 
+// packed row -> emb_event fields {dt | var << 16 | bin << 24, value as fp32 bits}.  The value is computed exactly as the
+// kernel that wrote the dense output computes it: from the fp32 entry table when the model has one (emb_fast.cuh), else in
+// fp64 (dediscretize.m:22-41) and rounded to fp32.
+EMB_HD uint2 expand_event(const DevModel& M, uint32_t word, uint32_t dt_lo, const EventFormat& fm) {
+    const uint32_t gord = (word >> 27) & ((1u << fm.gord_bits) - 1u), dt = dt_lo | ((word >> (27 + fm.gord_bits)) << (8 * fm.dt_bytes));
+    uint2 row;
+    if (gord == 0) {
+        row.x = dt;
+        row.y = 0u;
+        return row;
+    }
+    const int g = (int)gord - 1, v = M.gated_var[g], b = (int)((word >> 23) & 15u);
+    const uint32_t frac = word & 0x7FFFFFu;
+    float value;
+    if (M.fast32_ok) {
+        const float* en = M.dd32 + 4 * (M.dd_off[g] + b);   // {slope, base, s, c}
+        const uint32_t fb = frac | 0x3F800000u;
+        float f;
+#if defined(__CUDA_ARCH__)
+        f = __uint_as_float(fb);
+        value = __fmaf_rn(en[0], __fmaf_rn(f, en[2], en[3]), en[1]);
+#else
+        __builtin_memcpy(&f, &fb, 4);
+        value = __builtin_fmaf(en[0], __builtin_fmaf(f, en[2], en[3]), en[1]);
+#endif
+    } else {
+        value = (float)dedisc(M, v, b, dmul(dadd((double)frac, 0.5), 1.1920928955078125e-07));
+    }
+    row.x = dt | ((uint32_t)(v + 1) << 16) | ((uint32_t)(b + 1) << 24);
+#if defined(__CUDA_ARCH__)
+    row.y = __float_as_uint(value);
+#else
+    __builtin_memcpy(&row.y, &value, 4);
+#endif
+    return row;
+}
+
 EMB_HD double round500(double num) {                        // UncorEncounterModel.m:196
     double m = ::fmod(num, 500.0);
     if (m < 0) m += 500.0;
@@ -472,7 +539,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
         if (O.init_values) O.init_values[(int64_t)i * (O.init_stride ? O.init_stride : N) + s] = vals[i];
         if (O.hist_initial) hist_inc(0, i, x[i]);
     }
-    if (T <= 0 || (!O.bins && !O.values && !O.hist_transition && !O.ev_counts && !O.events)) return;
+    if (T <= 0 || (!O.bins && !O.values && !O.hist_transition && !O.ev_counts && !O.ev_words)) return;
 
     // frozen columns of the fast branch (dbn_sample.m:110-135): parents evaluated once at t = 1
     const uint32_t* col[MAXD];
@@ -482,20 +549,14 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
     }
 
     // event list (emb200.h: emb_event): pass 1 counts rows, pass 2 writes them
-    const bool ev = O.ev_counts || O.events;
-    uint2* ev_ptr = O.events ? O.events + O.ev_offsets[s] : nullptr;
+    const bool ev = O.ev_counts || O.ev_words;
+    long long ev_i = O.ev_words ? O.ev_offsets[s] : 0;
     uint32_t ev_last = 0, ev_n = 0;
-    auto emit = [&](uint32_t e, uint32_t var1, uint32_t bin1, double value) {
-        if (ev_ptr) {
-            const float f = (float)value;
-            uint2 row;
-            row.x = (e - ev_last) | (var1 << 16) | (bin1 << 24);
-#if defined(__CUDA_ARCH__)
-            row.y = __float_as_uint(f);
-#else
-            __builtin_memcpy(&row.y, &f, 4);
-#endif
-            *ev_ptr++ = row;
+    // gord: 1-based gated ordinal (0 = closing row); frac: the 23 value bits of the row (see pack_event_word)
+    auto emit = [&](uint32_t e, uint32_t gord, uint32_t bin1, uint32_t frac) {
+        if (O.ev_words) {
+            store_event(O.ev_words, O.ev_dts, ev_i, e - ev_last, gord, bin1, frac, EventFormat{O.ev_gord_bits, O.ev_dt_bytes});
+            ++ev_i;
         }
         ev_last = e;
         ++ev_n;
@@ -522,7 +583,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                     const int v = M.gated_var[g];
                     vals[v] = dedisc(M, v, x[v], u_dd(k, wpart[g]));
-                    if (ev) emit((uint32_t)c, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, vals[v]);
+                    if (ev) emit((uint32_t)c, (uint32_t)g + 1u, (uint32_t)x[v] + 1u, (k * DD_MULT + wpart[g]) >> 9);
                 }
             }
             // transitions (dbn_sample.m:69-79 slow / :143-146 fast): the variable's own word selects
@@ -539,7 +600,8 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
                 if (nb != x[vt]) {
                     x[vt] = nb;
                     vals[vt] = dedisc(M, vt, nb, u_dd(wstep[M.gate_of_dyn[d]], wpart[M.gate_of_dyn[d]]));
-                    if (ev) emit((uint32_t)c, (uint32_t)vt + 1u, (uint32_t)nb + 1u, vals[vt]);
+                    if (ev) emit((uint32_t)c, (uint32_t)M.gate_of_dyn[d] + 1u, (uint32_t)nb + 1u,
+                                 (wstep[M.gate_of_dyn[d]] * DD_MULT + wpart[M.gate_of_dyn[d]]) >> 9);
                 }
             }
         }
@@ -581,10 +643,10 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
             if ((uint64_t)(k * GATE_MULT) < M.gate_G[g]) {
                 const int v = M.gated_var[g];
                 const uint32_t kn = ws.at(step_pos(partner_second((uint32_t)T), (uint32_t)g, (uint32_t)nw));
-                emit((uint32_t)T, (uint32_t)v + 1u, (uint32_t)x[v] + 1u, dedisc(M, v, x[v], u_dd(k, kn)));
+                emit((uint32_t)T, (uint32_t)g + 1u, (uint32_t)x[v] + 1u, (k * DD_MULT + kn) >> 9);
             }
         }
-        emit((uint32_t)T, 0u, 0u, 0.0);
+        emit((uint32_t)T, 0u, 0u, 0u);
         if (O.ev_counts) O.ev_counts[s] = ev_n;
     }
 }

@@ -136,6 +136,15 @@ EMB_HD uint32_t add_gtd(uint32_t acc, double kb, double td) {
 #define EMB_F64CMP 6
 #endif
 
+EMB_HD uint32_t f2u_(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    __builtin_memcpy(&u, &f, 4);
+    return u;
+#endif
+}
 EMB_HD float fmaf_rn(float a, float b, float c) {
 #if defined(__CUDA_ARCH__)
     return __fmaf_rn(a, b, c);
@@ -174,24 +183,22 @@ struct FastTrack {
     PhiloxTrack pt;           // track-invariant part of the step stream's Philox calls
     uint32_t sbin1[NS > 0 ? NS : 1];   // EV: 1-based bins of the static gated variables
     uint32_t ev_last, ev_n;            // EV: second of the last row, rows so far
-    uint2* ev_ptr;                     // EV == 2: next row of this track
+    long long ev_i;                    // EV == 2: next row of this track
+    uint32_t* O_words;                 // EV == 2: TrackOut::ev_words / ev_dts
+    uint8_t* O_dts;
+    EventFormat O_fmt;
 
     EMB_HD FastTrack(const DevModel& M_, const SampleParams& P_, const FastShared& S_, HistInc h)
         : M(M_), P(P_), S(S_), hist_inc(h) {}
 
     // one row [dt, var, value] of out_events (dbn_hierarchical_sample.m:9-37 after resample_events.m:11-37):
     // dt = seconds since the previous row, 0 for further rows of the same second
-    EMB_HD void emit(bool on, uint32_t e, uint32_t var1, uint32_t bin1, float value) {
+    // gord: 1-based gated ordinal, 0 in the closing row; frac: the 23 value bits (emb_device.cuh: pack_event_word)
+    EMB_HD void emit(bool on, uint32_t e, uint32_t gord, uint32_t bin1, uint32_t frac) {
         if (!on) return;
         if (EV == 2) {
-            uint2 row;
-            row.x = (e - ev_last) | (var1 << 16) | (bin1 << 24);
-#if defined(__CUDA_ARCH__)
-            row.y = __float_as_uint(value);
-#else
-            __builtin_memcpy(&row.y, &value, 4);
-#endif
-            *ev_ptr++ = row;
+            store_event(O_words, O_dts, ev_i, e - ev_last, gord, bin1, frac, O_fmt);
+            ++ev_i;
         }
         ev_last = e;
         ++ev_n;
@@ -273,7 +280,7 @@ struct FastTrack {
             // ---- values: gate (resample_events.m:23-29) and/or bin change (dbn_sample.m:82-92) ------
             // bin[] / nb[] hold entry-table indices (ebase + bin), see track_fast
             bool ev_chg[ND];
-            float ev_val[ND];
+            uint32_t ev_frac[ND];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const uint32_t k = W[4 * g + j];
@@ -289,17 +296,14 @@ struct FastTrack {
                 if ((fired || changed) && act) val[g] = cand;
                 if (EV) {
                     // gate row: the re-emitted *current* bin (resample_events.m:26-29); when the variable also changes
-                    // in this second the row is hidden in the dense output but present in the list
-                    float gv = cand;
+                    // in this second the row is hidden in the dense output but present in the list.  A row carries the 23
+                    // value bits, not the value (pack_event_word): gate and transition row of a second share them.
+                    const uint32_t fr = f2u_(dd_fraction(k, kn)) & 0x7FFFFFu;
                     uint32_t b1 = g >= NS ? bin[d >= 0 ? d : 0] - (uint32_t)ebase[g] + 1u : sbin1[g < NS ? g : 0];
-                    if (g >= NS && fired && changed) {
-                        const DdEntry eo = S.ent[bin[d >= 0 ? d : 0]];
-                        gv = fmaf_rn(eo.slope, fmaf_rn(dd_fraction(k, kn), eo.s, eo.c), eo.base);
-                    }
-                    emit(fired && act_gate, (uint32_t)e, (uint32_t)M.gated_var[g] + 1u, b1, gv);
+                    emit(fired && act_gate, (uint32_t)e, (uint32_t)g + 1u, b1, fr);
                     if (g >= NS) {
                         ev_chg[d >= 0 ? d : 0] = changed && act;
-                        ev_val[d >= 0 ? d : 0] = cand;
+                        ev_frac[d >= 0 ? d : 0] = fr;
                     }
                 }
                 if (g >= NS) bin[d >= 0 ? d : 0] = nb[d >= 0 ? d : 0];
@@ -308,7 +312,7 @@ struct FastTrack {
             if (EV) {   // transition rows follow the gate rows of the same second, variables ascending (dbn_sample.m:84-92)
 #pragma unroll
                 for (int d = 0; d < ND; ++d)
-                    emit(ev_chg[d], (uint32_t)e, (uint32_t)M.dyn_t[d] + 1u, bin[d] - (uint32_t)ebase[NS + d] + 1u, ev_val[d]);
+                    emit(ev_chg[d], (uint32_t)e, (uint32_t)(NS + d) + 1u, bin[d] - (uint32_t)ebase[NS + d] + 1u, ev_frac[d]);
             }
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
@@ -437,7 +441,10 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
             }
             ft.ev_last = 0;
             ft.ev_n = 0;
-            ft.ev_ptr = EV == 2 ? O.events + O.ev_offsets[s] : nullptr;
+            ft.ev_i = EV == 2 ? O.ev_offsets[s] : 0;
+            ft.O_words = O.ev_words;
+            ft.O_dts = O.ev_dts;
+            ft.O_fmt = EventFormat{O.ev_gord_bits, O.ev_dt_bytes};
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 ft.bin[d] = (uint32_t)ft.ebase[NS + d] + x[M.dyn_t[d]];
@@ -490,7 +497,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     if (O.bins && O.values) fast_groups<RS, NG, FAST, HIST, EV, ORD, HistInc, true>(ft, P, O, U, s, valid, tid, nthreads, c0, c2);
     else fast_groups<RS, NG, FAST, HIST, EV, ORD, HistInc, false>(ft, P, O, U, s, valid, tid, nthreads, c0, c2);
     if (EV && valid) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
-        ft.emit(true, (uint32_t)T, 0u, 0u, 0.0f);
+        ft.emit(true, (uint32_t)T, 0u, 0u, 0u);
         if (EV == 1) O.ev_counts[s] = ft.ev_n;
     }
 }

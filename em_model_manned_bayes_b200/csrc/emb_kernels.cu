@@ -219,6 +219,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
     }
 }
 
+// packed rows [first, first + count) -> 8-byte emb_event rows (emb_device.cuh: expand_event)
+__global__ void __launch_bounds__(256) k_expand_events(const __grid_constant__ DevModel M, const uint32_t* __restrict__ words,
+                                                       const uint8_t* __restrict__ dts, uint2* __restrict__ rows,
+                                                       long long first, long long count, EventFormat fm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t dt_lo = fm.dt_bytes == 1 ? (uint32_t)__ldg(dts + first + i)
+                                            : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(dts) + first + i);
+    rows[first + i] = expand_event(M, __ldg(words + first + i), dt_lo, fm);
+}
+
 // {*total, *flag} -> dst (mapped host memory): a store from an SM does not queue behind the row copies on the copy engine,
 // which a cudaMemcpy of the same eight bytes would
 __global__ void k_publish(const long long* __restrict__ total, const int32_t* __restrict__ flag, volatile long long* dst) {
@@ -230,6 +241,14 @@ __global__ void k_publish(const long long* __restrict__ total, const int32_t* __
 
 int launch_publish(const long long* total, const int32_t* flag, long long* mapped_dst, void* stream) {
     k_publish<<<1, 1, 0, (cudaStream_t)stream>>>(total, flag, mapped_dst);
+    g_launch_count.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int launch_expand_events(const DevModel& M, const uint32_t* words, const uint8_t* dts, void* rows, long long first, long long count,
+                         const EventFormat& fm, void* stream) {
+    if (count <= 0) return 0;
+    k_expand_events<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(M, words, dts, (uint2*)rows, first, count, fm);
     g_launch_count.fetch_add(1);
     return (int)cudaGetLastError();
 }
@@ -303,7 +322,7 @@ int launch_tracks(const DevModel& M, const SampleParams& P0, const TrackOut& O, 
     const bool fast = M.fast != 0;
     const uint32_t ord = order_code(M);
     const bool hist = O.hist_initial || O.hist_transition;
-    const int ev = O.ev_counts ? 1 : O.events ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
+    const int ev = O.ev_counts ? 1 : O.ev_words ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
     bool done = false;
     // one launch per run of tracks whose global sample index shares its high word (spec v5: counter word 0 is launch-uniform)
     SampleParams P = P0;

@@ -22,6 +22,10 @@ long long scan_scratch_len(long long n);
 int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, long long* scratch, void* stream,
                        const long long* carry_in = nullptr);
 
+// packed event rows [first, first + count) (emb_device.cuh: pack_event_word) -> 8-byte emb_event rows at the same indices
+int launch_expand_events(const DevModel& M, const uint32_t* words, const uint8_t* dts, void* rows, long long first, long long count,
+                         const EventFormat& fm, void* stream);
+
 // {*total, *flag} written by an SM into mapped pinned host memory (two long longs)
 int launch_publish(const long long* total, const int32_t* flag, long long* mapped_dst, void* stream);
 

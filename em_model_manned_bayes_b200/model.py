@@ -178,6 +178,9 @@ class EncounterModel:
         self.resample_rates = np.array(info.resample_rates[:n], dtype=np.float64)
         self.bounds_initial = np.array([[info.bounds_initial[i][0], info.bounds_initial[i][1]] for i in range(n)])
         self.timevarying_vars = list(info.timevarying_vars[:info.n_timevarying])
+        gv = (C.c_int32 * max(1, info.n_gated))()
+        lib.emb_model_get_gated(self._h, gv, info.n_gated)
+        self.gated_vars = list(gv[:info.n_gated])                # 1-based ids the packed event rows refer to by ordinal
         self.labels_initial = self._labels(0)
         self.labels_transition = self._labels(1) if nt else []
         G = np.zeros(n * n, dtype=np.uint8)
@@ -381,6 +384,59 @@ class EventResult:
         return np.stack([e["dt"].astype(np.float64), e["var"].astype(np.float64), e["value"].astype(np.float64)], axis=1)
 
 
+@dataclass
+class PackedEventResult:
+    """Result of `EncounterModel.sample_events_packed`: the 5-byte rows of emb_sample_track_events_packed.
+    Row k of track s is (words[offsets[s] + k], dts[offsets[s] + k]); `decode()` gives the reference's [dt, var, value]."""
+    n: int
+    T: int
+    words: object         # uint32 (host) / int32 tensor (device)
+    dts: object           # uint8
+    offsets: object       # int64 [n + 1]
+    init_bins: Optional[object]
+    init_values: Optional[object]
+    attempts: Optional[object]
+    total: int
+    gated_vars: List[int]
+    boundaries: List[np.ndarray]
+    zero_bins: List[List[int]]
+
+    def decode(self):
+        """-> (dt int64, var int64 (1-based, 0 = closing row), bin int64 (1-based), value float64) over all rows.
+        value = dediscretize.m:22-41 with u = (frac + 0.5) 2^-23, evaluated in fp64 on the host."""
+        w = np.asarray(self.words.cpu() if hasattr(self.words, "cpu") else self.words).view(np.uint32).astype(np.int64)
+        d = np.asarray(self.dts.cpu() if hasattr(self.dts, "cpu") else self.dts).astype(np.int64)
+        gord = (w >> 27) & 7
+        dt = d | ((w >> 30) << 8)
+        b = ((w >> 23) & 15) + 1
+        u = ((w & 0x7FFFFF).astype(np.float64) + 0.5) * 2.0 ** -23
+        var = np.zeros_like(gord)
+        val = np.zeros(len(w))
+        binv = np.where(gord > 0, b, 0)
+        for k, v in enumerate(self.gated_vars, start=1):
+            m = gord == k
+            if not m.any():
+                continue
+            var[m] = v
+            e = np.asarray(self.boundaries[v - 1], dtype=np.float64)
+            if e.size == 0:
+                val[m] = b[m]                                          # dediscretize.m:7-10
+                continue
+            bb = b[m]
+            x = e[bb - 1] + (e[bb] - e[bb - 1]) * u[m]                 # :39
+            if self.zero_bins[v - 1]:
+                x = np.where(bb == self.zero_bins[v - 1][0], 0.0, x)   # :24-25
+            val[m] = x
+        return dt, var, binv, val
+
+    def track(self, s: int) -> np.ndarray:
+        """out_events{s+1} as a k x 3 float64 matrix [dt, var, value]."""
+        dt, var, _, val = self.decode()
+        o = np.asarray(self.offsets.cpu() if hasattr(self.offsets, "cpu") else self.offsets)
+        a, b = int(o[s]), int(o[s + 1])
+        return np.stack([dt[a:b].astype(np.float64), var[a:b].astype(np.float64), val[a:b]], axis=1)
+
+
 def _row_times(dt: np.ndarray, offsets: np.ndarray) -> np.ndarray:
     """Seconds elapsed at the END of every row's hold (dt summed from the first row of the row's own track)."""
     cum = np.cumsum(dt, dtype=np.int64)
@@ -523,6 +579,50 @@ def _sample_events(self, n: int, T: int, seed: int = 0, first_sample: int = 0, s
 
 
 EncounterModel.sample_events = _sample_events
+
+
+def _sample_events_packed(self, n: int, T: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
+                          want_init=True, capacity: Optional[int] = None) -> PackedEventResult:
+    """Sparse tracks as 5-byte packed rows (emb200.h: emb_sample_track_events_packed): what crosses PCIe."""
+    lib = L.lib()
+    o = opts if opts is not None else self._opts(start=start)
+    if device is not None:
+        import torch
+        dev = torch.device(device)
+        o.mem, o.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+        o.stream = torch.cuda.current_stream(dev).cuda_stream
+    ni = self.n_initial
+    ib = self._alloc((ni, n), np.int8, device) if want_init else None
+    iv = self._alloc((ni, n), np.float64, device) if want_init else None
+    att = self._alloc((n,), np.uint16, device) if want_init else None
+    init = L.TrackOut(None, None, _ptr(ib), _ptr(iv), _ptr(att), None, None)
+    rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
+    total = C.c_int64(0)
+    if capacity is None:
+        capacity = int(n * (T * (float(np.sum(self.resample_rates)) + 0.15) + 8)) + 1024
+
+    def alloc(cap):
+        if device is None:
+            return np.zeros(max(cap, 1), dtype=np.uint32), np.zeros(max(cap, 1), dtype=np.uint8), np.zeros(n + 1, dtype=np.int64)
+        import torch
+        return (torch.zeros(max(cap, 1), dtype=torch.int32, device=device), torch.zeros(max(cap, 1), dtype=torch.uint8, device=device),
+                torch.zeros(n + 1, dtype=torch.int64, device=device))
+
+    w, d, off = alloc(capacity)
+    rc = lib.emb_sample_track_events_packed(self._h, C.byref(rng), n, T, C.byref(o), capacity, _ptr(w), _ptr(d), _ptr(off),
+                                            C.byref(init), C.byref(total))
+    if rc == L.EMB_E_LIMIT and total.value > capacity:
+        capacity = int(total.value)
+        w, d, off = alloc(capacity)
+        rc = lib.emb_sample_track_events_packed(self._h, C.byref(rng), n, T, C.byref(o), capacity, _ptr(w), _ptr(d), _ptr(off),
+                                                C.byref(init), C.byref(total))
+    L.check(rc)
+    return PackedEventResult(n=n, T=T, words=w[:total.value], dts=d[:total.value], offsets=off, init_bins=ib, init_values=iv,
+                             attempts=att, total=int(total.value), gated_vars=list(self.gated_vars),
+                             boundaries=self.boundaries, zero_bins=self.zero_bins)
+
+
+EncounterModel.sample_events_packed = _sample_events_packed
 
 
 class UncorEncounterModel(EncounterModel):

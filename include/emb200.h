@@ -178,10 +178,24 @@ typedef struct emb_event {
  * events: capacity rows.  *total_rows (host, nullable) always receives the number of rows; if it exceeds
  * `capacity` nothing is written to `events` and EMB_E_LIMIT is returned -- call again with a larger buffer
  * (the stream is keyed, the result is the same).  `init` (nullable) may carry init_bins / init_values /
- * attempts; its dense fields and histograms must be NULL.  Requires T <= 65535. */
+ * attempts; its dense fields and histograms must be NULL.  Requires T <= 65535, <= 15 time-varying variables, <= 16 bins. */
 int emb_sample_track_events(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
                             int64_t capacity, emb_event* events, int64_t* offsets, const emb_track_out* init,
                             int64_t* total_rows);
+
+/* The same lists as 5-byte packed rows -- what the device writes and what crosses PCIe (the 8-byte rows above are expanded
+ * from these on the device):   row k of track s is (words[offsets[s] + k], dts[offsets[s] + k]) with
+ *     word = frac | (bin - 1) << 23 | gord << 27 | (dt >> 8) << 30,    dts = dt & 255
+ *   gord : 1-based ordinal of the variable in emb_model_get_gated (the time-varying variables), 0 in the closing row
+ *   frac : 23 bits; the row's value is boundaries[bin] + (boundaries[bin+1] - boundaries[bin]) * (frac + 0.5) * 2^-23
+ *          (dediscretize.m:39 with the uniform of stream spec v5), 0 in a zero bin, the bin itself for a '*' variable
+ * Needs <= 7 time-varying variables with <= 16 bins and T <= 1023 (EMB_E_LIMIT otherwise); same two-pass protocol,
+ * `capacity` in rows for both arrays. */
+int emb_sample_track_events_packed(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                                   int64_t capacity, uint32_t* words, uint8_t* dts, int64_t* offsets,
+                                   const emb_track_out* init, int64_t* total_rows);
+/* 1-based ids of the time-varying ("gated") variables, ascending: resample rate > 0 or dynamic.  Returns their number. */
+int64_t emb_model_get_gated(const emb_model* m, int32_t* buf, int64_t cap);
 
 /* ---- terminal trajectory chains: replaces @CorTerminalModel/createEncounter.m:1-329 over a batch of encounters
  *      (PropagateTrajectory :93-265 = per state one dbn_sample.m:95-166 call with t_max = 2 and every initial

@@ -4,6 +4,7 @@
 // on the CPU (one loop iteration per CUDA thread) so the `-m "not gpu"` test-suite can check the
 // device logic against the oracle without a GPU.  It is NOT part of libemb200.so, is not reachable
 // from the C ABI, and is never used by bench.py or the product path.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -183,13 +184,24 @@ int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, i
     fast_fill_shared(D, S, 0, 1);
     const uint32_t rs = g_use_fast ? fast_shape_of(D) : 0;
     const bool fast = D.fast != 0;
+    int max_bins = 0;
+    for (int g = 0; g < D.n_gated; ++g) max_bins = std::max(max_bins, (int)D.init[D.gated_var[g]].r);
+    EventFormat fm{};
+    if (!event_format_for(D.n_gated, max_bins, T, fm)) return EMB_E_LIMIT;
+    std::vector<uint32_t> words;       // the write pass produces packed rows; they are expanded to emb_event rows below
+    std::vector<uint8_t> dts;
     for (int pass = 1; pass <= 2; ++pass) {
         TrackOut O{};
         O.status = &status;
+        O.ev_gord_bits = fm.gord_bits;
+        O.ev_dt_bytes = fm.dt_bytes;
         if (pass == 1) O.ev_counts = counts.data();
         else {
+            words.assign((size_t)off[(size_t)n] + 1, 0u);
+            dts.assign(((size_t)off[(size_t)n] + 1) * (size_t)fm.dt_bytes, 0);
             O.ev_offsets = off.data();
-            O.events = reinterpret_cast<uint2*>(events);
+            O.ev_words = words.data();
+            O.ev_dts = dts.data();
         }
         bool done = false;
 #define EMB_X(RS_, NG_, FAST_, ORD_)                                                                    \
@@ -218,6 +230,11 @@ int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, i
             *total_rows = acc;
             if (acc > capacity) return EMB_E_LIMIT;
         }
+    }
+    for (long long i = 0; i < off[(size_t)n]; ++i) {
+        const uint32_t dt_lo = fm.dt_bytes == 1 ? dts[(size_t)i] : reinterpret_cast<const uint16_t*>(dts.data())[i];
+        const uint2 row = expand_event(D, words[(size_t)i], dt_lo, fm);
+        std::memcpy(&events[i], &row, 8);
     }
     return status ? EMB_E_REJECT : 0;
 }

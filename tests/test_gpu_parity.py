@@ -78,6 +78,44 @@ def test_event_lists_match_golden(model_paths, golden, name, generic):
     assert np.array_equal(res.attempts.astype(np.int64), golden[name]["attempts"].astype(np.int64))
 
 
+@pytest.mark.parametrize("name", sorted(cases.TRACK_CASES))
+def test_packed_event_rows_match_golden(model_paths, golden, name):
+    """emb_sample_track_events_packed: the 5-byte rows (what crosses PCIe) decode to the oracle's out_events -- dt, variable
+    and bin identical, and the value, evaluated on the host in fp64 from (bin, 23-bit fraction) exactly as dediscretize.m:39
+    does, equal to the oracle's fp64 value to 1e-12 (the 8-byte rows carry it rounded to fp32)."""
+    c = cases.TRACK_CASES[name]
+    m = _model(model_paths, c)
+    res = m.sample_events_packed(c["n"], c["T"], seed=c["seed"], first_sample=c.get("first", 0), opts=_opts_of(m, c))
+    legacy = m.sample_events(c["n"], c["T"], seed=c["seed"], first_sample=c.get("first", 0), opts=_opts_of(m, c))
+    dt, var, b, val = res.decode()
+    rows = np.asarray(legacy.events)
+    assert np.array_equal(res.offsets, legacy.offsets) and res.total == legacy.total
+    assert np.array_equal(dt, rows["dt"]) and np.array_equal(var, rows["var"]) and np.array_equal(b, rows["bin"])
+    assert np.all(np.abs(val - rows["value"].astype(np.float64)) <= 1e-6 * np.abs(val))
+    g = golden[name]
+    want = g["events"] if "events" in g else None
+    if want is not None:          # golden rows: [dt, var, value] per track, concatenated
+        assert np.all(np.abs(val - want[:, 2]) <= 1e-12 * np.abs(want[:, 2]))
+    assert np.array_equal(res.init_values.T, g["init_values"])
+
+
+def test_packed_event_rows_on_device_and_limits(model_paths):
+    """Device buffers give the same packed rows as host buffers (pipelined path); T > 1023 is refused by the packed entry
+    point (10-bit dt) while the 8-byte entry point still works (it switches the device rows to 2-byte dts)."""
+    m = UncorEncounterModel(model_paths["uncor_allcode_fwsingle_v1"])
+    n, T = 20_000, 600
+    h = m.sample_events_packed(n, T, seed=41, first_sample=7, opts=m.uncor_opts())
+    d = m.sample_events_packed(n, T, seed=41, first_sample=7, opts=m.uncor_opts(), device="cuda:0")
+    assert h.total == d.total and np.array_equal(h.offsets, d.offsets.cpu().numpy())
+    assert np.array_equal(h.words, d.words.cpu().numpy().view(np.uint32)) and np.array_equal(h.dts, d.dts.cpu().numpy())
+    with pytest.raises(L.EmbError) as ei:
+        m.sample_events_packed(50, 1500, seed=1, opts=m.uncor_opts())
+    assert ei.value.code == L.EMB_E_LIMIT
+    long_ = m.sample_events(50, 1500, seed=1, opts=m.uncor_opts())
+    off = np.asarray(long_.offsets)
+    assert np.array_equal(np.add.reduceat(np.asarray(long_.events)["dt"].astype(np.int64), off[:-1]), np.full(50, 1500))
+
+
 def test_event_buffer_too_small_is_reported_and_retried(model_paths):
     c = cases.TRACK_CASES["uncor_v2p1_n24_T300_seed1"]
     m = _model(model_paths, c)
