@@ -64,6 +64,7 @@ class SampleOpts(C.Structure):
         ("mem", C.c_int32),
         ("device", C.c_int32),
         ("stream", C.c_void_p),
+        ("start_per_sample", C.c_void_p),
     ]
 
 

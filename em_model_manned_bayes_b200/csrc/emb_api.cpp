@@ -170,6 +170,23 @@ struct Stager {
         *dev = s.dev;
         return 0;
     }
+    // device copy of a caller INPUT buffer (not copied back)
+    int in(const void* user, size_t bytes, const void** dev) {
+        *dev = nullptr;
+        if (!user || !bytes) return 0;
+        if (mem == EMB_MEM_DEVICE) {
+            *dev = user;
+            return 0;
+        }
+        Staged s;
+        s.bytes = bytes;
+        s.owned = true;
+        CU(tmp_alloc(&s.dev, bytes, stream));
+        CU(cudaMemcpyAsync(s.dev, user, bytes, cudaMemcpyHostToDevice, stream));
+        items.push_back(s);
+        *dev = s.dev;
+        return 0;
+    }
     int finish() {
         for (auto& s : items)
             if (s.host) CU(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, stream));
@@ -177,6 +194,25 @@ struct Stager {
         return 0;
     }
 };
+
+// per-sample presets of emb_sample_opts -> SampleParams (device pointer, one row of n per initial variable)
+int stage_start(Stager& sg, const emb_sample_opts* opts, const HostModel& H, int64_t n, emb::SampleParams& P) {
+    P.start_ps = nullptr;
+    P.start_stride = n;
+    if (!opts->start_per_sample) return 0;
+    const void* d = nullptr;
+    int rc = sg.in(opts->start_per_sample, (size_t)n * (size_t)H.n_initial, &d);
+    if (rc) return rc;
+    P.start_ps = (const int8_t*)d;
+    return 0;
+}
+// the device status word of the sampling kernels: 1 = rejection loop exhausted, 2 = invalid per-sample preset
+int status_error(int32_t status) {
+    if (status == 2)
+        return set_err(EMB_E_ARG, "Attempt to preset a dependent variable (or a preset bin out of range) in start_per_sample");
+    if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+    return 0;
+}
 
 template <class T>
 int64_t copy_out(const std::vector<T>& v, T* buf, int64_t cap) {
@@ -217,7 +253,7 @@ int emb_async_status(int device) {
     CU(cudaMemcpy(&flag, word, 4, cudaMemcpyDeviceToHost));
     if (flag) {
         CU(cudaMemset(word, 0, 4));
-        return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop (asynchronous pass)");
+        return status_error(flag);
     }
     return 0;
 }
@@ -464,6 +500,8 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    P.start_ps = opts->start_per_sample;   // device pointer in the enqueue-only path; staged below otherwise
+    P.start_stride = n;
     if (opts->mem & EMB_MEM_ASYNC) {   // enqueue only (device buffers): see emb_sample_tracks
         int32_t* word = nullptr;
         if ((rc = async_status_word(device, &word))) return rc;
@@ -477,6 +515,7 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     if ((rc = sg.out(bins, (size_t)n * H.n_initial, false, (void**)&d_bins))) return rc;
     if ((rc = sg.out(values, (size_t)n * H.n_initial * 8, false, (void**)&d_vals))) return rc;
     if ((rc = sg.out(attempts, (size_t)n * 2, false, (void**)&d_att))) return rc;
+    if ((rc = stage_start(sg, opts, H, n, P))) return rc;
     int32_t* d_status = nullptr;
     CU(tmp_alloc((void**)&d_status, 4, st));
     CU(cudaMemsetAsync(d_status, 0, 4, st));
@@ -491,8 +530,7 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     tmp_free(d_status);
     if (e != cudaSuccess) return cuda_fail(e, "k_initial");
     if ((rc = sg.finish())) return rc;
-    if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
-    return 0;
+    return status_error(status);
 }
 
 int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T) {
@@ -538,6 +576,7 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     if ((rc = sg.out(out->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
     if ((rc = sg.out(out->hist_initial, ni * 64 * 8, true, (void**)&O.hist_initial))) return rc;
     if ((rc = sg.out(out->hist_transition, H.temporal_map.size() * 64 * 8, true, (void**)&O.hist_transition))) return rc;
+    if ((rc = stage_start(sg, opts, H, n, P))) return rc;
     if (async) {   // enqueue only: no host round trip between consecutive passes; emb_async_status collects the flag
         if ((rc = async_status_word(device, &O.status))) return rc;
         const cudaError_t ea = (cudaError_t)emb::launch_tracks(D, P, O, st);
@@ -556,8 +595,7 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     tmp_free(O.status);
     if (e != cudaSuccess) return cuda_fail(e, "k_tracks");
     if ((rc = sg.finish())) return rc;
-    if (status) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
-    return 0;
+    return status_error(status);
 }
 
 // EMB200_TRACE=1: host-side phase times of emb_sample_track_events on stderr (diagnostics for the e2e number)
@@ -626,6 +664,7 @@ static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n,
         if ((rc = sg.out(init->init_values, (size_t)n * ni * 8, false, (void**)&O.init_values))) return rc;
         if ((rc = sg.out(init->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
     }
+    if ((rc = stage_start(sg, opts, H, n, P))) return rc;
     struct Scratch {
         void* p = nullptr;
         ~Scratch() { tmp_free(p); }
@@ -651,7 +690,7 @@ static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n,
         CU(cudaStreamSynchronize(st));
         tr.mark("alloc + count pass + scan");
         if (total_rows) *total_rows = total;
-        if (flag) return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+        if (flag) return status_error(flag);
         if (total > capacity) {
             if ((rc = sg.finish())) return rc;   // offsets and the initial outputs are valid
             return set_err(EMB_E_LIMIT, "event buffer too small: " + std::to_string(total) + " rows needed");
@@ -723,6 +762,7 @@ static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n,
         Pc.n = b - a;
         Pc.s_begin = 0;
         Pc.s_end = b - a;
+        if (P.start_ps) Pc.start_ps = P.start_ps + a;     // rows stay n apart (start_stride)
         emb::TrackOut Oc = O;                             // count pass of the chunk: also its per-track initial outputs
         Oc.init_stride = n;
         if (O.init_bins) Oc.init_bins = O.init_bins + a;
@@ -743,7 +783,7 @@ static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n,
         if (c == 0) tr.mark("first chunk: count + scan");
         if (flag) {
             CU(cudaStreamSynchronize(g.copy));
-            return set_err(EMB_E_REJECT, "a sample exhausted max_attempts in the rejection loop");
+            return status_error(flag);
         }
         total = r1;
         if (total > capacity) overflow = true;            // keep counting: the caller learns how many rows are needed

@@ -92,6 +92,8 @@ struct SampleParams {
     int32_t max_attempts;
     uint32_t rk[20];               // Philox round keys (k0 + i*W0, k1 + i*W1), read from the constant bank
     uint8_t start[MAXV];           // preset 1-based bin, 0 = free
+    const int8_t* start_ps;        // per-sample presets [n_initial][start_stride] (device memory) or nullptr
+    int64_t start_stride;
     double layers[8][2];
     double box_lo[MAXV], box_hi[MAXV];
 };
@@ -471,16 +473,29 @@ EMB_HD double round500(double num) {                        // UncorEncounterMod
 // Initial network: bn_sample.m:39-58 + dbn_hierarchical_sample.m:25-31 (+ rejection of the driver:
 // UncorEncounterModel.m:248-280 / @CorTerminalModel/sample.m:32-72).
 // x: 0-based bins (size >= n_transition, dynamic slots untouched); vals: continuous values.
-// Returns the attempt index that was accepted, or -1 when max_attempts was exhausted.
+// Returns the attempt index that was accepted, -1 when max_attempts was exhausted, -2 when this sample's presets are invalid
+// (per-sample `start` rows only; the uniform `start` is validated on the host).
 EMB_HD int sample_initial(const DevModel& M, const SampleParams& P, uint64_t sample, uint8_t* x, double* vals) {
     const int n = M.n_initial;
+    uint8_t st[MAXV];                                                               // this sample's presets (bn_sample.m:45)
+    const int64_t sl = (int64_t)(sample - P.first_sample);
+    for (int i = 0; i < n; ++i) {
+        int v = P.start_ps ? (int)P.start_ps[(int64_t)i * P.start_stride + sl] : (int)P.start[i];
+        if (v < 0 || v > M.init[i].r) return -2;                                    // preset bin out of range
+        st[i] = (uint8_t)v;
+    }
+    if (P.start_ps)                                                                 // bn_sample.m:46-47, per sample
+        for (int i = 0; i < n; ++i)
+            if (st[i])
+                for (int q = 0; q < M.init[i].np; ++q)
+                    if (!st[M.init[i].par[q]]) return -2;
     for (int attempt = 0; attempt <= P.max_attempts; ++attempt) {
         WordStream ws;
         ws.init(P.seed, sample, (uint32_t)attempt, P_INIT);
         for (int oi = 0; oi < n; ++oi) {
             const int i = M.order_initial[oi];
-            if (P.start[i]) {
-                x[i] = (uint8_t)(P.start[i] - 1);                                   // bn_sample.m:49
+            if (st[i]) {
+                x[i] = (uint8_t)(st[i] - 1);                                        // bn_sample.m:49
             } else {
                 const Node& nd = M.init[i];
                 x[i] = (uint8_t)select_bin(node_column(nd, M.thr_init, x), nd.rp, ws.at((uint32_t)i));
@@ -530,7 +545,7 @@ EMB_HD void track_generic(const DevModel& M, const SampleParams& P, const TrackO
 
     int attempt = sample_initial(M, P, sample, x, vals);
     if (attempt < 0) {
-        if (O.status) *O.status = 1;
+        if (O.status) *O.status = attempt == -2 ? 2 : 1;
         attempt = P.max_attempts;  // keep the last attempt's state so the outputs are defined
     }
     if (O.attempts) O.attempts[s] = (uint16_t)(attempt + 1);

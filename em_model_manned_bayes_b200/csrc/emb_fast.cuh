@@ -417,7 +417,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
         for (int i = 0; i < MAXX; ++i) x[i] = 0;
         int attempt = sample_initial(M, P, sample, x, vals);
         if (attempt < 0) {
-            if (O.status) *O.status = 1;
+            if (O.status) *O.status = attempt == -2 ? 2 : 1;
             attempt = P.max_attempts;
         }
         if (O.attempts) O.attempts[s] = (uint16_t)(attempt + 1);

@@ -24,7 +24,7 @@ struct InitStrides {
 };
 
 inline bool initial_fast_ok(const DevModel& M, const SampleParams& P) {
-    if (P.reject_mode != 0) return false;
+    if (P.reject_mode != 0 || P.start_ps) return false;
     for (int i = 0; i < M.n_initial; ++i)
         if (M.order_initial[i] != i) return false;
     return true;

@@ -65,7 +65,7 @@ k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SamplePara
         double vals[MAXV];
         int attempt = sample_initial(M, P, P.first_sample + (uint64_t)s, x, vals);
         if (attempt < 0) {
-            *status = 1;
+            *status = attempt == -2 ? 2 : 1;
             attempt = P.max_attempts;
         }
         if (attempts) attempts[s] = (uint16_t)(attempt + 1);

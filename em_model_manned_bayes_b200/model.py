@@ -271,9 +271,22 @@ class EncounterModel:
         return buf[:int(n)]
 
     # -- option plumbing ---------------------------------------------------------------------------
-    def _opts(self, start=None, device=None, stream=None, mem=L.EMB_MEM_HOST, max_attempts=0):
+    def _opts(self, start=None, device=None, stream=None, mem=L.EMB_MEM_HOST, max_attempts=0, start_per_sample=None):
+        """`start`: one preset per variable (the `start` cell of bn_sample.m:45; None / [] / NaN = free).
+        `start_per_sample`: (n_samples, n_initial) presets, 0 / NaN = free -- the rows of
+        @CorTerminalModel/InitStartTerminal.m, one per sample; a numpy array (host calls) or an int8 torch tensor of shape
+        (n_initial, n_samples) already on the device the outputs live on."""
         o = L.SampleOpts()
         L.lib().emb_sample_opts_init(C.byref(o))
+        if start_per_sample is not None:
+            if isinstance(start_per_sample, np.ndarray) or isinstance(start_per_sample, (list, tuple)):
+                a = np.nan_to_num(np.asarray(start_per_sample, dtype=np.float64), nan=0.0)
+                if a.ndim != 2 or a.shape[1] != self.n_initial:
+                    raise L.EmbError(L.EMB_E_ARG, "start_per_sample must be n_samples x n_initial")
+                start_per_sample = np.ascontiguousarray(a.T.astype(np.int8))
+            o._keep = start_per_sample                            # keep the buffer alive as long as the options
+            o.start_per_sample = _ptr(start_per_sample)
+            start = [None] * self.n_initial if start is None else start
         start = self.start if start is None else start
         if len(start) != self.n_initial:
             raise L.EmbError(L.EMB_E_ARG, "start must have n_initial entries")
@@ -813,8 +826,34 @@ class CorTerminalModel(EncounterModel):
         if parameters_directory is not None:
             self.load_trajectory_models(parameters_directory)
 
-    def _terminal_opts(self, start=None, max_attempts=0):
-        o = self._opts(start=start, max_attempts=max_attempts)
+    def InitStartTerminal(self, nSamples: int = 1000000, airspace_class=(False, True, True, True), own_intent=(True, True),
+                          int_intent=(True, True, True), isVerbose: bool = False):
+        """@CorTerminalModel/InitStartTerminal.m:43-92: the `start` rows for every kept combination of airspace class x
+        ownship intent x intruder intent, ceil(nSamples / n_combs) rows each, class slowest and intruder intent fastest.
+        -> list of rows, each a list of n_initial entries (the preset bin for variables 1..3, None elsewhere); like the
+        reference's cell it has n_combs * ceil(nSamples / n_combs) rows (>= nSamples)."""
+        lab = self.labels_initial
+        if lab[:3] != ['"airspace_class"', '"own_intent"', '"int_intent"']:                          # :31-33
+            raise L.EmbError(L.EMB_E_ARG, "InitStartTerminal: the first three variables must be airspace_class, own_intent, int_intent")
+        keep = [np.nonzero(np.asarray(k, dtype=bool))[0] + 1 for k in (airspace_class, own_intent, int_intent)]
+        for k, sel in enumerate((airspace_class, own_intent, int_intent)):                           # :36-38
+            if len(sel) != int(self.r_initial[k]):
+                raise L.EmbError(L.EMB_E_ARG, "InitStartTerminal: one flag per bin of variable %d" % (k + 1))
+        n_combs = len(keep[0]) * len(keep[1]) * len(keep[2])                                          # :47
+        n_samples = max(int(nSamples), n_combs)                                                      # :50-53
+        per = -(-n_samples // n_combs)                                                               # :56
+        rows = []
+        for ii in keep[0]:                                                                           # :67-90
+            for jj in keep[1]:
+                for kk in keep[2]:
+                    if isVerbose:
+                        print("encounters %d-%d, airspace_class = %d, own_intent = %d, int_intent = %d"
+                              % (len(rows) + 1, len(rows) + per, ii, jj, kk))
+                    rows += [[int(ii), int(jj), int(kk)] + [None] * (self.n_initial - 3) for _ in range(per)]
+        return rows
+
+    def _terminal_opts(self, start=None, max_attempts=0, start_per_sample=None):
+        o = self._opts(start=start, max_attempts=max_attempts, start_per_sample=start_per_sample)
         o.reject_mode = L.EMB_REJECT_BOX
         lo, hi = self.bounds_sample[:, 0].copy(), self.bounds_sample[:, 1].copy()
         for idx, ac in ((self.idx_own_speed, self.acType1), (self.idx_int_speed, self.acType2)):   # sample.m:64-65
@@ -825,10 +864,20 @@ class CorTerminalModel(EncounterModel):
             o.box_lo[i], o.box_hi[i] = lo[i], hi[i]
         return o
 
-    def sample_raw(self, nSamples: int, seed: int = 0, first_sample: int = 0, device=None):
-        """-> (outInits (n, 15) float64, bins (n, 15) int8, attempts)."""
+    def sample_raw(self, nSamples: int, seed: int = 0, first_sample: int = 0, device=None, start_per_sample=None):
+        """-> (outInits (n, 15) float64, bins (n, 15) int8, attempts).  `start_per_sample`: one `start` row per sample
+        (e.g. the rows of InitStartTerminal; None entries = free) -- the whole batch in one call."""
+        sps = None
+        if start_per_sample is not None:
+            sps = np.array([[0 if (v is None or (isinstance(v, float) and math.isnan(v))) else int(v) for v in row]
+                            for row in start_per_sample], dtype=np.float64)
+            if sps.shape[0] != nSamples:
+                raise L.EmbError(L.EMB_E_ARG, "start_per_sample needs one row per sample")
+            if device is not None:
+                import torch
+                sps = torch.from_numpy(np.ascontiguousarray(sps.T.astype(np.int8))).to(device)
         bins, vals, att = self.sample_initial(nSamples, seed=seed, first_sample=first_sample,
-                                              opts=self._terminal_opts(), device=device)
+                                              opts=self._terminal_opts(start_per_sample=sps), device=device)
         return vals, bins, att
 
     def sample(self, nSamples: int, seed=float("nan")):

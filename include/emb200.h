@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EMB_ABI_VERSION 1
+#define EMB_ABI_VERSION 2
 
 /* status codes */
 #define EMB_OK 0
@@ -129,6 +129,10 @@ typedef struct emb_sample_opts {
     int32_t mem;                              /* EMB_MEM_HOST / EMB_MEM_DEVICE for all output buffers */
     int32_t device;                           /* CUDA device ordinal; -1 = current */
     void* stream;                             /* cudaStream_t or NULL */
+    /* per-sample presets (the n_samples x n_initial `start` cell of @CorTerminalModel/InitStartTerminal.m:43-92, one row per
+     * sample): int8 [n_initial][n], 1-based bins, 0 = free; NULL = use `start` for every sample.  Host or device memory
+     * like the outputs (`mem`).  A preset variable with a free parent is refused like bn_sample.m:46-47 does (EMB_E_ARG). */
+    const int8_t* start_per_sample;
 } emb_sample_opts;
 void emb_sample_opts_init(emb_sample_opts* o);
 

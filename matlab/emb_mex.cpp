@@ -29,7 +29,8 @@
 //          ur_heading, min_speed, max_speed;  xyz: n x (T+1) x 3 single, is_good: n x 1 uint8
 //          emb_mex('free', h)
 // opts: struct with optional fields start (1 x n_initial, 0/NaN = free), reject_mode, idx_v, idx_dh,
-// idx_L, is_quantize500, layers (r_L x 2), box_lo, box_hi, max_attempts, device.
+// idx_L, is_quantize500, layers (r_L x 2), box_lo, box_hi, max_attempts, device, start_per_sample (n x n_initial, 0/NaN = free:
+// one `start` row per sample, the cell of @CorTerminalModel/InitStartTerminal.m as a matrix).
 // Errors become mexErrMsgIdAndTxt with the reference's identifiers where the reference has one
 // ('dynvar:empty', UncorEncounterModel.m:231-234; 'prior:notdbe', EncounterModel.m:200).
 #include <cmath>
@@ -63,6 +64,9 @@ double field_or(const mxArray* s, const char* name, double dflt) {
     return f && !mxIsEmpty(f) ? mxGetScalar(f) : dflt;
 }
 
+// int8 [n_initial][n] copy of opts.start_per_sample (n x n_initial double, 0 / NaN = free), alive for the duration of the call
+std::vector<int8_t> g_start_rows;
+
 void fill_opts(const mxArray* s, int n_initial, emb_sample_opts* o) {
     emb_sample_opts_init(o);
     o->mem = EMB_MEM_HOST;
@@ -78,6 +82,15 @@ void fill_opts(const mxArray* s, int n_initial, emb_sample_opts* o) {
         const double* p = mxGetPr(st);
         for (size_t i = 0; i < mxGetNumberOfElements(st) && (int)i < n_initial; ++i)
             o->start[i] = std::isnan(p[i]) ? 0 : (int32_t)p[i];
+    }
+    if (const mxArray* sp = mxGetField(s, 0, "start_per_sample")) {   // rows of InitStartTerminal.m, one per sample
+        if (!mxIsEmpty(sp)) {
+            const size_t cnt = mxGetNumberOfElements(sp);             // column-major n x n_initial == [n_initial][n]
+            const double* p = mxGetPr(sp);
+            g_start_rows.resize(cnt);
+            for (size_t i = 0; i < cnt; ++i) g_start_rows[i] = std::isnan(p[i]) ? (int8_t)0 : (int8_t)p[i];
+            o->start_per_sample = g_start_rows.data();
+        }
     }
     if (const mxArray* ly = mxGetField(s, 0, "layers")) {         // UncorEncounterModel.m:259-263, r_L x 2 column-major
         const size_t r = mxGetM(ly);

@@ -2,10 +2,12 @@ function [outInits, outSamples] = sample_terminal_b200(self, nSamples, varargin)
 % SAMPLE_TERMINAL_B200  Drop-in body for @CorTerminalModel/sample.m:1-82 (encounter-geometry sampling with the bounds and
 % speed rejection of :45-70) that runs on a B200 through emb_mex('sample_initial', ...) with reject_mode = 2.
 % Same arguments ('seed'), same outputs: outInits nSamples x n_initial, outSamples cell of structs whose fields are the
-% unquoted labels (:58-61).  SOURCE ONLY (no MATLAB in the build image).
+% unquoted labels (:58-61).  Extra: 'starts', an nSamples x n_initial cell as returned by InitStartTerminal -- the whole set
+% of start rows in ONE call instead of the loop of RUN_terminal.m:35-44.  SOURCE ONLY (no MATLAB in the build image).
 p = inputParser;
 addRequired(p, 'nSamples', @isnumeric);
 addParameter(p, 'seed', nan, @isnumeric);
+addParameter(p, 'starts', {}, @iscell);
 parse(p, nSamples, varargin{:});
 seed = p.Results.seed;
 if ~isnan(seed) && ~isempty(seed)                                   % :19-22 (see sample_b200.m for the key convention)
@@ -31,6 +33,15 @@ for i = 1:n
     if ~isempty(self.start{i}), st(i) = self.start{i}; end
 end
 opts = struct('reject_mode', 2, 'box_lo', lo, 'box_hi', hi, 'start', st);
+if ~isempty(p.Results.starts)
+    rows = nan(nSamples, n);
+    for i = 1:nSamples
+        for k = 1:n
+            if ~isempty(p.Results.starts{i, k}), rows(i, k) = p.Results.starts{i, k}; end
+        end
+    end
+    opts.start_per_sample = rows;
+end
 [~, outInits] = emb_mex('sample_initial', h, key, 0, nSamples, opts);
 
 outSamples = cell(nSamples, 1);

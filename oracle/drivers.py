@@ -160,6 +160,39 @@ def terminal_sample(parms, n_samples, U, *, first_sample=0, prior=0, start=None,
     return out_inits, out_bins, attempts
 
 
+def init_start_terminal(parms, n_samples=1000000, airspace_class=(False, True, True, True), own_intent=(True, True),
+                        int_intent=(True, True, True)):
+    """@CorTerminalModel/InitStartTerminal.m:43-92 -> out_start as a list of rows (cells: [] = free).
+    The cell is preallocated with n_samples rows (:59) and filled in blocks of n_enc_per_comb rows (:75-80), so it ends up with
+    n_combs * ceil(n_samples / n_combs) rows."""
+    assert parms.labels_initial[0] == '"airspace_class"'                                             # :31
+    assert parms.labels_initial[1] == '"own_intent"'
+    assert parms.labels_initial[2] == '"int_intent"'
+    assert len(airspace_class) == parms.r_initial[0] and len(own_intent) == parms.r_initial[1]       # :36-38
+    assert len(int_intent) == parms.r_initial[2]
+    idx_class = [k + 1 for k, f in enumerate(airspace_class) if f]                                   # :42-44
+    idx_ownint = [k + 1 for k, f in enumerate(own_intent) if f]
+    idx_intint = [k + 1 for k, f in enumerate(int_intent) if f]
+    n_combs = len(idx_class) * len(idx_ownint) * len(idx_intint)                                     # :47
+    if n_combs > n_samples:                                                                          # :50-53
+        n_samples = n_combs
+    n_enc_per_comb = int(np.ceil(n_samples / n_combs))                                               # :56
+    out_start = [[[] for _ in range(parms.n_initial)] for _ in range(n_samples)]                     # :59
+    s = 1                                                                                            # :63
+    for ii in idx_class:                                                                             # :67
+        for jj in idx_ownint:
+            for kk in idx_intint:
+                e = s + n_enc_per_comb - 1                                                           # :75
+                while len(out_start) < e:                                                            # MATLAB grows the cell on assignment
+                    out_start.append([[] for _ in range(parms.n_initial)])
+                for row in range(s, e + 1):                                                          # :78-80
+                    out_start[row - 1][0] = ii
+                    out_start[row - 1][1] = jj
+                    out_start[row - 1][2] = kk
+                s = e + 1                                                                            # :88
+    return out_start
+
+
 def dbn_tracks(parms, n_samples, sample_time, U, *, first_sample=0, prior=0, start=None, strict_quirks=False):
     """The sampling loop of em_sample.m:78-85 (dbn_hierarchical_sample + events2samples, no
     rejection) for any model with a transition network, e.g. the correlated model cor_v1.txt.

@@ -79,6 +79,8 @@ int emu_sample_initial(void* h, uint64_t seed, uint64_t first, int64_t n, const 
         g_err = e.msg;
         return e.code;
     }
+    P.start_ps = o->start_per_sample;      // host memory: the emulation runs the device code on the host
+    P.start_stride = n;
     const DevModel D = host_dev(H);
     int status = 0;
     g_last_fast = 0;
@@ -106,7 +108,7 @@ int emu_sample_initial(void* h, uint64_t seed, uint64_t first, int64_t n, const 
         double vals[MAXV];
         int attempt = sample_initial(D, P, P.first_sample + (uint64_t)s, x, vals);
         if (attempt < 0) {
-            status = 1;
+            status = attempt == -2 ? 2 : 1;
             attempt = P.max_attempts;
         }
         if (attempts) attempts[s] = (uint16_t)(attempt + 1);
@@ -115,7 +117,8 @@ int emu_sample_initial(void* h, uint64_t seed, uint64_t first, int64_t n, const 
             if (values) values[(int64_t)i * n + s] = vals[i];
         }
     }
-    return status ? EMB_E_REJECT : 0;
+    if (status == 2) g_err = "Attempt to preset a dependent variable (or a preset bin out of range) in start_per_sample";
+    return status == 2 ? EMB_E_ARG : status ? EMB_E_REJECT : 0;
 }
 
 int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t T, const emb_sample_opts* o,

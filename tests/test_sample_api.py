@@ -180,3 +180,104 @@ def test_model_from_arrays_packs_the_same_thresholds_as_the_file_model(model_pat
     assert m.order_initial == ref.order_initial and m.order_transition == ref.order_transition
     assert m.zero_bins == ref.zero_bins and np.array_equal(m.resample_rates, ref.resample_rates)
     assert all(np.array_equal(a, b) for a, b in zip(m.boundaries, ref.boundaries))
+
+
+# ---- @CorTerminalModel/InitStartTerminal.m and per-sample presets (RUN_terminal.m:28-44) ---------------------------------------
+def test_init_start_terminal_matches_the_oracle_restatement(model_paths):
+    """Combination order (class slowest, intruder intent fastest), n_enc_per_comb = ceil(n / n_combs), the row count of the
+    grown cell, and the n_combs > nSamples case (InitStartTerminal.m:47-56)."""
+    from oracle.drivers import init_start_terminal
+    p = em_read(model_paths["terminal_v3_radar_encounter_model"])
+    m = M.CorTerminalModel(model_paths["terminal_v3_radar_encounter_model"])
+    for kw in (dict(nSamples=18), dict(nSamples=40), dict(nSamples=5),
+               dict(nSamples=25, airspace_class=(True, False, False, True), own_intent=(False, True), int_intent=(True, False, True))):
+        got = m.InitStartTerminal(**kw)
+        okw = dict(kw)
+        okw["n_samples"] = okw.pop("nSamples")
+        want = init_start_terminal(p, **okw)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert [None if v is None else int(v) for v in a] == [None if (isinstance(v, list) and not v) else int(v) for v in b]
+    rows = m.InitStartTerminal(nSamples=18)
+    assert len(rows) == 18 and rows[0][:3] == [2, 1, 1] and rows[1][:3] == [2, 1, 2] and rows[17][:3] == [4, 2, 3]   # RUN_terminal.m:29-32
+    with pytest.raises(Exception):
+        m.InitStartTerminal(nSamples=10, own_intent=(True,))
+
+
+def test_per_sample_presets_on_the_host_emulation(model_paths):
+    """start_per_sample through the device code (host emulation): sample i uses row i of the InitStartTerminal cell -- equal
+    to the oracle's bn_sample called with that row as `start` at global index i; a row that presets a variable whose parent
+    is free is refused like bn_sample.m:46-47."""
+    import helpers as H
+    from em_model_manned_bayes_b200 import _lib as L
+    from oracle.drivers import init_start_terminal, initial_sample
+    path = model_paths["terminal_v3_radar_encounter_model"]
+    p = em_read(path)
+    rows = init_start_terminal(p, 18)
+    em = H.EmuModel(path)
+    sps = np.ascontiguousarray(np.array([[0 if (isinstance(v, list) and not v) else int(v) for v in r] for r in rows], dtype=np.int8).T)
+    o = H.EmuModel.opts(p.n_initial)
+    o.start_per_sample = sps.ctypes.data
+    bins, vals, att = em.sample_initial(p.n_initial, 18, 4, 100, o)
+    for i, r in enumerate(rows):
+        S, V = initial_sample(p, 1, KeyedPhilox(4), first_sample=100 + i, start=r)
+        assert np.array_equal(bins[i], S[0]) and np.array_equal(vals[i], V[0])
+    bad = sps.copy()
+    bad[0, 3] = 0                      # own_intent preset, its parent airspace_class free
+    o.start_per_sample = bad.ctypes.data
+    with pytest.raises(L.EmbError) as ei:
+        em.sample_initial(p.n_initial, 18, 4, 100, o)
+    assert ei.value.code == L.EMB_E_ARG
+
+
+@pytest.mark.gpu
+def test_run_terminal_start_combinations(model_paths):
+    """RUN_terminal.m:28-44: the 18 start rows of InitStartTerminal, each used as mdl.start for mdl.sample(500, 'seed', 1)
+    (the reference's loop), and all of them in ONE batched call with per-sample presets -- both against the oracle."""
+    from oracle.drivers import init_start_terminal
+    name = "terminal_v3_radar_encounter_model"
+    p = em_read(model_paths[name])
+    m = M.CorTerminalModel(model_paths[name])
+    m.acType1 = "RTCA228_A1"                                                             # RUN_terminal.m:25
+    starts = m.InitStartTerminal(nSamples=18)
+    want_rows = init_start_terminal(p, 18)
+    lim1 = M.CorTerminalModel.DYN_LIMITS["RTCA228_A1"]
+    for ii in (0, 7, 17):
+        m.start = starts[ii]
+        out_inits, out_samples = m.sample(60, seed=1)
+        want, _, _ = terminal_sample(p, 60, KeyedPhilox(1), start=want_rows[ii], dyn_limits1=lim1)
+        assert np.array_equal(out_inits, want)
+        assert np.all(out_inits[:, 0] == starts[ii][0]) and np.all(out_inits[:, 1] == starts[ii][1])
+    m.start = [None] * m.n_initial
+    rows = [starts[k % 18] for k in range(90)]
+    for device in (None, "cuda:0"):
+        vals, bins, att = m.sample_raw(90, seed=3, first_sample=11, device=device, start_per_sample=rows)
+        vals = vals.cpu().numpy() if device else vals
+        for k in (0, 5, 17, 18, 44, 89):
+            want, _, _ = terminal_sample(p, 1, KeyedPhilox(3), first_sample=11 + k, start=want_rows[k % 18], dyn_limits1=lim1)
+            assert np.array_equal(vals[k], want[0])
+
+
+@pytest.mark.gpu
+def test_per_sample_presets_on_tracks_and_bad_rows(model_paths):
+    """emb_sample_tracks / emb_sample_track_events with start_per_sample: track i starts from row i (compared with one call
+    per distinct row using the uniform `start`), and an invalid row is reported as EMB_E_ARG."""
+    from em_model_manned_bayes_b200 import _lib as L
+    m = M.UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    rows = [[1, 4, 2, None, None, None, None], [None] * 7, [2, 1, 1, 3, None, None, None]]
+    n, T = 30, 50
+    sps = [rows[k % 3] for k in range(n)]
+    o = m.uncor_opts()
+    o2 = m._opts(start_per_sample=np.array([[np.nan if v is None else v for v in r] for r in sps]))
+    for f in ("reject_mode", "idx_v", "idx_dh", "idx_L"):
+        setattr(o2, f, getattr(o, f))
+    got = m.sample_tracks(n, T, seed=8, first_sample=5, opts=o2)
+    for j, r in enumerate(rows):
+        ref = m.sample_tracks(n, T, seed=8, first_sample=5, opts=m.uncor_opts(start=r))
+        pick = np.arange(j, n, 3)
+        assert np.array_equal(got.bins[pick], ref.bins[pick]) and np.array_equal(got.values[pick], ref.values[pick])
+        assert np.array_equal(got.init_values[:, pick], ref.init_values[:, pick])
+    bad = m._opts(start_per_sample=np.array([[np.nan, np.nan, np.nan, 2, np.nan, np.nan, np.nan]] * n))   # v preset, parents free
+    with pytest.raises(L.EmbError) as ei:
+        m.sample_tracks(n, T, seed=8, opts=bad)
+    assert ei.value.code == L.EMB_E_ARG
