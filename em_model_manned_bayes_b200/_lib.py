@@ -140,6 +140,7 @@ def lib():
         "emb_set_prior": (C.c_int, [vp, C.c_int, C.c_int, C.c_double]),
         "emb_sample_opts_init": (None, [P(SampleOpts)]),
         "emb_sample_initial": (C.c_int, [vp, P(Rng), i64, P(SampleOpts), vp, vp, vp]),
+        "emb_sample_initial_f32": (C.c_int, [vp, P(Rng), i64, P(SampleOpts), vp, vp, vp]),
         "emb_sample_tracks": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), P(TrackOut)]),
         "emb_sample_track_events": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i64, vp, vp, P(TrackOut), P(i64)]),
         "emb_sample_track_events_packed": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i64, vp, vp, vp, P(TrackOut), P(i64)]),
@@ -163,7 +164,7 @@ def lib():
 
 EXPORTED = [
     "emb_abi_version", "emb_last_error", "emb_launch_count", "emb_debug_force_generic", "emb_debug_last_kernel_fast", "emb_device_count", "emb_host_alloc", "emb_host_free", "emb_trim_device_memory", "emb_async_status",
-    "emb_rng_word", "emb_sample_track_events_packed", "emb_model_get_gated", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
+    "emb_rng_word", "emb_sample_initial_f32", "emb_sample_track_events_packed", "emb_model_get_gated", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
     "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",

@@ -483,8 +483,9 @@ void emb_sample_opts_init(emb_sample_opts* o) {
     }
 }
 
-int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts, int8_t* bins,
-                       double* values, uint16_t* attempts) {
+// values: double (values64) or float (values32), at most one of them
+static int sample_initial_impl(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts, int8_t* bins,
+                               double* values64, float* values32, uint16_t* attempts) {
     if (!m || !rng || !opts || n < 0) return set_err(EMB_E_ARG, "null or negative argument");
     const HostModel& H = *m->h;
     emb::SampleParams P;
@@ -500,26 +501,33 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    const int tw = (int)H.thr_initial.size();
+    auto launch = [&](int8_t* b, double* v64, float* v32, uint16_t* a, int32_t* word) {
+        return v32 ? (cudaError_t)emb::launch_initial_f32(D, P, tw, b, v32, a, nullptr, word, st)
+                   : (cudaError_t)emb::launch_initial(D, P, tw, b, v64, a, nullptr, word, st);
+    };
     P.start_ps = opts->start_per_sample;   // device pointer in the enqueue-only path; staged below otherwise
     P.start_stride = n;
     if (opts->mem & EMB_MEM_ASYNC) {   // enqueue only (device buffers): see emb_sample_tracks
         int32_t* word = nullptr;
         if ((rc = async_status_word(device, &word))) return rc;
-        const cudaError_t ea = (cudaError_t)emb::launch_initial(D, P, (int)H.thr_initial.size(), bins, values, attempts, nullptr, word, st);
+        const cudaError_t ea = launch(bins, values64, values32, attempts, word);
         return ea == cudaSuccess ? 0 : cuda_fail(ea, "launch k_initial");
     }
     Stager sg{opts->mem, st, {}};
     int8_t* d_bins;
-    double* d_vals;
+    double* d_v64;
+    float* d_v32;
     uint16_t* d_att;
     if ((rc = sg.out(bins, (size_t)n * H.n_initial, false, (void**)&d_bins))) return rc;
-    if ((rc = sg.out(values, (size_t)n * H.n_initial * 8, false, (void**)&d_vals))) return rc;
+    if ((rc = sg.out(values64, (size_t)n * H.n_initial * 8, false, (void**)&d_v64))) return rc;
+    if ((rc = sg.out(values32, (size_t)n * H.n_initial * 4, false, (void**)&d_v32))) return rc;
     if ((rc = sg.out(attempts, (size_t)n * 2, false, (void**)&d_att))) return rc;
     if ((rc = stage_start(sg, opts, H, n, P))) return rc;
     int32_t* d_status = nullptr;
     CU(tmp_alloc((void**)&d_status, 4, st));
     CU(cudaMemsetAsync(d_status, 0, 4, st));
-    cudaError_t e = (cudaError_t)emb::launch_initial(D, P, (int)H.thr_initial.size(), d_bins, d_vals, d_att, nullptr, d_status, st);
+    cudaError_t e = launch(d_bins, d_v64, d_v32, d_att, d_status);
     if (e != cudaSuccess) {
         tmp_free(d_status);
         return cuda_fail(e, "launch k_initial");
@@ -531,6 +539,16 @@ int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const 
     if (e != cudaSuccess) return cuda_fail(e, "k_initial");
     if ((rc = sg.finish())) return rc;
     return status_error(status);
+}
+
+int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts, int8_t* bins,
+                       double* values, uint16_t* attempts) {
+    return sample_initial_impl(m, rng, n, opts, bins, values, nullptr, attempts);
+}
+int emb_sample_initial_f32(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts, int8_t* bins,
+                           float* values, uint16_t* attempts) {
+    if (!values) return set_err(EMB_E_ARG, "emb_sample_initial_f32: values must not be null (use emb_sample_initial for bins only)");
+    return sample_initial_impl(m, rng, n, opts, bins, nullptr, values, attempts);
 }
 
 int64_t emb_tracks_bins_len(const emb_model* m, int64_t n, int32_t T) {

@@ -65,6 +65,8 @@ struct DevModel {
     uint64_t gate_G[MAXG];         // fires iff k*GATE_MULT mod 2^32 < G (0 for rate 0)
     int32_t gate_of_dyn[MAXD];     // gated ordinal of the d-th dynamic variable
     int32_t dd_off[MAXG];          // first entry of gated ordinal g in dd32
+    int32_t ddi_off[MAXV];         // first entry of initial variable i in dd32 (entries of ALL initial variables follow the gated ones)
+    int32_t init32_ok;             // every bin of every initial variable can be de-discretised in fp32 within 1e-6 relative
     int32_t fast32_ok;             // every gated bin can be de-discretised in fp32 within 1e-6 relative
     int32_t two23;                 // 2^23 as a run-time value (keeps IMAD.HI from being strength-reduced)
     int32_t tv_var[MAXV];          // time-varying variables (dynamic(t) or gated), ascending
@@ -490,21 +492,24 @@ EMB_HD int sample_initial(const DevModel& M, const SampleParams& P, uint64_t sam
                 for (int q = 0; q < M.init[i].np; ++q)
                     if (!st[M.init[i].par[q]]) return -2;
     for (int attempt = 0; attempt <= P.max_attempts; ++attempt) {
-        WordStream ws;
-        ws.init(P.seed, sample, (uint32_t)attempt, P_INIT);
+        // stream spec v5, INIT: one word per variable; four consecutive samples share a call (sample >> 2, lane sample & 3)
+        uint32_t kw[MAXV + 1];
+        const int nwords = n > 1 ? n : 2;
+        for (int i = 0; i < nwords; ++i)
+            kw[i] = keyed_word(P.seed, sample >> 2, (uint32_t)attempt, P_INIT, (uint32_t)i, 0, (uint32_t)(sample & 3u));
         for (int oi = 0; oi < n; ++oi) {
             const int i = M.order_initial[oi];
             if (st[i]) {
                 x[i] = (uint8_t)(st[i] - 1);                                        // bn_sample.m:49
             } else {
                 const Node& nd = M.init[i];
-                x[i] = (uint8_t)select_bin(node_column(nd, M.thr_init, x), nd.rp, ws.at((uint32_t)i));
+                x[i] = (uint8_t)select_bin(node_column(nd, M.thr_init, x), nd.rp, kw[i]);
             }
         }
         for (int i = 0; i < n; ++i) {
             const int b = x[i];
             double u = 0.5;
-            if (needs_uniform(M, i, b)) u = u01(ws.at((uint32_t)(n + i)));
+            if (needs_uniform(M, i, b)) u = u_dd(kw[i], kw[i + 1 < nwords ? i + 1 : 0]);
             vals[i] = dedisc(M, i, b, u);
         }
         bool good = true;

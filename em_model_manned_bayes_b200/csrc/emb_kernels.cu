@@ -51,9 +51,10 @@ __device__ __forceinline__ void flush_hist(const uint32_t* sh, const DevModel& M
 }
 
 // ---- initial network only (bn_sample.m batch; config 2; terminal geometry) ----------------------
+template <class VT>
 __global__ void __launch_bounds__(BLOCK)
 k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P, int8_t* __restrict__ bins,
-          double* __restrict__ values, uint16_t* __restrict__ attempts, unsigned long long* hist, int32_t* status) {
+          VT* __restrict__ values, uint16_t* __restrict__ attempts, unsigned long long* hist, int32_t* status) {
     __shared__ uint32_t sh[MAXV * HIST_STRIDE];
     if (hist) {
         for (int q = threadIdx.x; q < MAXV * HIST_STRIDE; q += blockDim.x) sh[q] = 0;
@@ -71,7 +72,7 @@ k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SamplePara
         if (attempts) attempts[s] = (uint16_t)(attempt + 1);
         for (int i = 0; i < M.n_initial; ++i) {
             if (bins) bins[(int64_t)i * P.n + s] = (int8_t)(x[i] + 1);
-            if (values) values[(int64_t)i * P.n + s] = vals[i];
+            if (values) values[(int64_t)i * P.n + s] = (VT)vals[i];
             if (hist) atomicAdd(&sh[i * HIST_STRIDE + x[i]], 1u);
         }
     }
@@ -85,22 +86,44 @@ k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SamplePara
 #ifndef EMB_INIT_MINBLOCKS_V    // resident blocks asked of the values variant (its fp64 tail otherwise takes 102 registers)
 #define EMB_INIT_MINBLOCKS_V 3
 #endif
-template <int NV, bool VALUES, bool SMEM>
-__global__ void __launch_bounds__(256, VALUES ? EMB_INIT_MINBLOCKS_V : 1)
+#ifndef EMB_INIT_MINBLOCKS_B
+#define EMB_INIT_MINBLOCKS_B 3
+#endif
+template <int NV, bool VALUES, bool SMEM, class VT, bool ALIGNED>
+__global__ void __launch_bounds__(256, VALUES ? EMB_INIT_MINBLOCKS_V : EMB_INIT_MINBLOCKS_B)
 k_initial_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
-               const __grid_constant__ InitStrides ST, int table_words, int8_t* __restrict__ bins,
-               double* __restrict__ values, uint16_t* __restrict__ attempts) {
+               const __grid_constant__ InitStrides ST, const __grid_constant__ InitCalls IC, int table_words,
+               int8_t* __restrict__ bins, VT* __restrict__ values, uint16_t* __restrict__ attempts) {
     extern __shared__ uint4 smem_table[];
     const uint32_t* table = M.thr_init;
-    if (SMEM) {
+    if (SMEM) {   // copy with a pitch of rp + pad words per column (emb_initial.cuh: fill_init_strides)
         const uint4* src = reinterpret_cast<const uint4*>(M.thr_init);
-        for (int q = threadIdx.x; q < table_words / 4; q += blockDim.x) smem_table[q] = __ldg(src + q);
-        __syncthreads();
+        for (int q = threadIdx.x; q < table_words / 4; q += blockDim.x) {
+            const uint32_t w = 4u * (uint32_t)q;
+            int i = 0;
+#pragma unroll
+            for (int v = 1; v < NV; ++v) i += w >= ST.src_off[v] ? 1 : 0;
+            const uint32_t rel = w - ST.src_off[i], c = rel / ST.rp[i], r = rel - c * ST.rp[i];
+            smem_table[(ST.off[i] + c * (ST.rp[i] + ST.pad) + r) / 4] = __ldg(src + q);
+        }
         table = reinterpret_cast<const uint32_t*>(smem_table);
     }
+    // fp32 de-discretisation entries of the initial variables (16 bytes per bin): shared memory as well
+    __shared__ float4 s_ent[VALUES && sizeof(VT) == 4 ? 256 : 1];
+    const float* ent = M.dd32 + 4 * M.ddi_off[0];
+    if (VALUES && sizeof(VT) == 4) {
+        int total = 0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) total += M.init[v].r;
+        if (total <= 256) {
+            for (int q = threadIdx.x; q < total; q += blockDim.x) s_ent[q] = __ldg(reinterpret_cast<const float4*>(ent) + q);
+            ent = reinterpret_cast<const float*>(s_ent);
+        }
+    }
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * INIT_SPT;
     for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * INIT_SPT; s0 < P.n; s0 += stride)
-        initial_fast4<NV, VALUES>(M, P, ST, table, s0, bins, values, attempts);
+        initial_fast4<NV, VALUES, VT, ALIGNED>(M, P, ST, IC, table, ent, s0, bins, values, attempts);
 }
 
 // ---- tracks, generic (any model, both dbn_sample.m branches) ------------------------------------
@@ -267,22 +290,30 @@ int launch_scan_counts(const uint32_t* counts, long long* offsets, long long n, 
 }
 
 // ------------------------------------------------------------------------------------------------
-int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
-                   uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream) {
+template <class VT>
+static int launch_initial_t(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, VT* values,
+                            uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream) {
     if (P.n <= 0) return 0;
-    if (!g_force_generic && !hist && initial_fast_ok(M, P)) {
+    const bool f32 = sizeof(VT) == 4;
+    if (!g_force_generic && !hist && initial_fast_ok(M, P) && (!f32 || !values || M.init32_ok)) {
         InitStrides st;
-        fill_init_strides(M, st);
+        fill_init_strides(M, table_words, 4, st);
+        InitCalls ic;
+        fill_init_calls(P, M.n_initial, ic);
         const int64_t need = (P.n + 256 * INIT_SPT - 1) / (256 * INIT_SPT);
-        const size_t tbytes = (size_t)table_words * 4;
-        const bool smem = tbytes > 0 && tbytes <= 96 * 1024 && need >= 2 * 148;   // staging pays only for large batches
+        size_t tbytes = (size_t)st.words * 4;
+        const bool smem = table_words > 0 && tbytes <= 96 * 1024 && need >= 2 * 148;   // staging pays only for large batches
+        if (!smem) {
+            fill_init_strides(M, table_words, 0, st);
+            tbytes = (size_t)table_words * 4;
+        }
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         bool done = false;
 #define EMB_LAUNCH_INIT(NV_, VAL_, SM_)                                                                          \
     do {                                                                                                         \
-        auto kern = k_initial_fast<NV_, VAL_, SM_>;                                                              \
+        auto kern = (P.first_sample & 3) ? k_initial_fast<NV_, VAL_, SM_, VT, false> : k_initial_fast<NV_, VAL_, SM_, VT, true>; \
         unsigned g4 = (unsigned)need;                                                                            \
         if (SM_) {   /* persistent grid: one table copy per resident block */                                    \
             int occ = 1;                                                                                         \
@@ -290,7 +321,7 @@ int launch_initial(const DevModel& M, const SampleParams& P, int table_words, in
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, tbytes);                              \
             g4 = (unsigned)std::min<int64_t>(need, (int64_t)sms * std::max(occ, 1));                             \
         }                                                                                                        \
-        kern<<<g4, 256, SM_ ? tbytes : 0, (cudaStream_t)stream>>>(M, P, st, table_words, bins, values, attempts); \
+        kern<<<g4, 256, SM_ ? tbytes : 0, (cudaStream_t)stream>>>(M, P, st, ic, table_words, bins, values, attempts); \
     } while (0)
 #define EMB_X(NV_)                                                          \
     if (!done && M.n_initial == (NV_)) {                                    \
@@ -311,9 +342,18 @@ int launch_initial(const DevModel& M, const SampleParams& P, int table_words, in
     }
     g_last_kernel_fast = 0;
     const unsigned grid = (unsigned)((P.n + BLOCK - 1) / BLOCK);
-    k_initial<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, bins, values, attempts, hist, status);
+    k_initial<VT><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, bins, values, attempts, hist, status);
     g_launch_count.fetch_add(1);
     return (int)cudaGetLastError();
+}
+
+int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
+                   uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream) {
+    return launch_initial_t<double>(M, P, table_words, bins, values, attempts, hist, status, stream);
+}
+int launch_initial_f32(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, float* values,
+                       uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream) {
+    return launch_initial_t<float>(M, P, table_words, bins, values, attempts, hist, status, stream);
 }
 
 int launch_tracks(const DevModel& M, const SampleParams& P0, const TrackOut& O, void* stream) {

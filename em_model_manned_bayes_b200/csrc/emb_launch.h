@@ -15,6 +15,8 @@ extern int g_last_kernel_fast;
 // table_words = length of the initial threshold table (decides shared-memory staging)
 int launch_initial(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, double* values,
                    uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream);
+int launch_initial_f32(const DevModel& M, const SampleParams& P, int table_words, int8_t* bins, float* values,
+                       uint16_t* attempts, unsigned long long* hist, int32_t* status, void* stream);
 int launch_tracks(const DevModel& M, const SampleParams& P, const TrackOut& O, void* stream);
 // offsets[0..n] = carry + exclusive prefix sums of counts[0..n), offsets[n] = carry + total; carry = *carry_in (device pointer,
 // may alias offsets) or 0; scratch: scan_scratch_len(n) long longs

@@ -455,9 +455,8 @@ void HostModel::pack() {
     // so that every term has the sign of the result and fp32 rounding stays <= ~2e-7 relative.
     dd32.clear();
     D.fast32_ok = 1;
-    for (int g = 0; g < D.n_gated; ++g) {
-        const int v = gated[g];
-        D.dd_off[g] = (int32_t)(dd32.size() / 4);
+    D.init32_ok = 1;
+    auto entries_of = [&](int v, int32_t& ok) {
         for (int b = 0; b < r_initial[v]; ++b) {
             float e[4] = {0.0f, 0.0f, 1.0f, -1.0f};
             if (boundaries[v].empty()) {
@@ -467,7 +466,7 @@ void HostModel::pack() {
             } else {
                 const double a = boundaries[v][b], bb = boundaries[v][b + 1];
                 volatile double w = bb - a;
-                if (a < 0.0 && bb > 0.0) D.fast32_ok = 0;               // value can cancel to ~0: fp64 only
+                if (a < 0.0 && bb > 0.0) ok = 0;                        // value can cancel to ~0: fp64 only
                 if (a + bb < 0.0) {
                     e[0] = (float)(-(double)w);
                     e[1] = (float)(bb - (double)w * 5.9604644775390625e-08);
@@ -480,6 +479,14 @@ void HostModel::pack() {
             }
             dd32.insert(dd32.end(), e, e + 4);
         }
+    };
+    for (int g = 0; g < D.n_gated; ++g) {
+        D.dd_off[g] = (int32_t)(dd32.size() / 4);
+        entries_of(gated[g], D.fast32_ok);
+    }
+    for (int i = 0; i < n_initial; ++i) {                               // all initial variables (emb_initial.cuh, fp32 values)
+        D.ddi_off[i] = (int32_t)(dd32.size() / 4);
+        entries_of(i, D.init32_ok);
     }
     ++version;
 }

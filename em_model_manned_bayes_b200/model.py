@@ -312,7 +312,7 @@ class EncounterModel:
 
     # -- sampling ----------------------------------------------------------------------------------
     def sample_initial(self, n: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,
-                       want_values=True, want_attempts=True, out=None, enqueue_only: bool = False):
+                       want_values=True, want_attempts=True, out=None, enqueue_only: bool = False, values_fp32: bool = False):
         """bn_sample.m:25-58 over n samples + de-discretisation.  Returns (bins (n, n_initial) int8,
         values (n, n_initial) float64 or None, attempts (n,) or None).  `device`: torch device string
         to keep the outputs in HBM; default host numpy."""
@@ -333,10 +333,11 @@ class EncounterModel:
             bins, vals, att = out[0].T, (out[1].T if out[1] is not None else None), out[2]
         else:
             bins = self._alloc((ni, n), np.int8, device)
-            vals = self._alloc((ni, n), np.float64, device) if want_values else None
+            vals = self._alloc((ni, n), np.float32 if values_fp32 else np.float64, device) if want_values else None
             att = self._alloc((n,), np.uint16, device) if want_attempts else None
         rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
-        L.check(L.lib().emb_sample_initial(self._h, C.byref(rng), n, C.byref(o), _ptr(bins), _ptr(vals), _ptr(att)))
+        fn = L.lib().emb_sample_initial_f32 if (values_fp32 and vals is not None) else L.lib().emb_sample_initial
+        L.check(fn(self._h, C.byref(rng), n, C.byref(o), _ptr(bins), _ptr(vals), _ptr(att)))
         return bins.T, (vals.T if vals is not None else None), att
 
     def sample_tracks(self, n: int, T: int, seed: int = 0, first_sample: int = 0, start=None, opts=None, device=None,

@@ -143,6 +143,10 @@ void emb_sample_opts_init(emb_sample_opts* o);
  * attempts: uint16[n]             (rejection attempts used)      nullable */
 int emb_sample_initial(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts,
                        int8_t* bins, double* values, uint16_t* attempts);
+/* the same with fp32 values [n_initial][n]: the compact contract (1 + 4 bytes per variable); within 1e-6 relative of the fp64
+ * values (the de-discretisation uniform has 23 bits, its conversion is exact in fp32; emb_model.cpp: pack) */
+int emb_sample_initial_f32(const emb_model* m, const emb_rng* rng, int64_t n, const emb_sample_opts* opts,
+                           int8_t* bins, float* values, uint16_t* attempts);
 
 /* ---- tracks: replaces UncorEncounterModel.m:244-307 loop around dbn_hierarchical_sample.m:9-37
  *      (dbn_sample.m both branches, resample_events.m, dediscretize.m, events2samples.m) ---------- */

@@ -80,6 +80,20 @@ static uint32_t word(ukey* k, uint32_t purpose, uint32_t index, uint32_t sub, ui
     return k->c_o[q][lane];
 }
 static uint32_t word_at(ukey* k, uint32_t purpose, uint64_t p) { return word(k, purpose, (uint32_t)(p >> 2), 0, (uint32_t)(p & 3)); }
+/* select word of initial variable i (0-based) (stream spec v5): four consecutive samples share a call (lane = sample & 3);
+ * the cache slot of purpose 1 holds one call, so a variable's word is recomputed when the index changes */
+static uint32_t init_word(ukey* k, int i) {
+    const uint64_t s = k->sample;
+    k->sample = s >> 2;
+    const uint32_t w = word(k, 1, (uint32_t)i, 0, (uint32_t)(s & 3));
+    k->sample = s;
+    k->c_ok[1] = 0;   /* the cached call belongs to the shifted sample: never reuse it under the real one */
+    return w;
+}
+static double init_dd_u(ukey* k, int i, int n) {
+    const uint32_t a = init_word(k, i), b = init_word(k, (i + 1) % (n > 2 ? n : 2));
+    return ((double)((uint32_t)(a * 0x85EBCA6Bu + b) >> 9) + 0.5) * 1.1920928955078125e-07; /* 23 bits, like the step values */
+}
 /* step word of second e, gated ordinal g (stream spec v5): one call = four consecutive seconds of one variable */
 static uint32_t step_word(ukey* k, int e, int g) { return word(k, 2, (uint32_t)((e >> 2) * k->nw + g), 0, (uint32_t)(e & 3)); }
 static double u01(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
@@ -143,7 +157,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
             if (M->start && M->start[i - 1]) { x[i - 1] = (double)M->start[i - 1]; continue; }
             int64_t j = parent_index(M->G_initial, n, i - 1, M->r, x);
             const double* w = M->W_initial + M->off_initial[i - 1] + (j - 1) * M->r[i - 1];
-            x[i - 1] = (double)select_random(w, M->r[i - 1], u01(word_at(&K, 1, (uint64_t)(i - 1))));
+            x[i - 1] = (double)select_random(w, M->r[i - 1], u01(init_word(&K, i - 1)));
         }
         for (int i = 0; i < n; ++i) init_bins[i] = x[i];
         /* dbn_sample.m:38-166 */
@@ -230,7 +244,7 @@ static int sample_one(const oc_model* M, uint64_t seed, uint64_t sample, int T, 
         /* dbn_hierarchical_sample.m:25-37 */
         for (int i = 1; i <= n; ++i) {
             double rnd = 0.5;
-            if (dd_needs_u(M, i, x[i - 1] * 0 + init_bins[i - 1])) rnd = u01(word_at(&K, 1, (uint64_t)(n + i - 1)));
+            if (dd_needs_u(M, i, x[i - 1] * 0 + init_bins[i - 1])) rnd = init_dd_u(&K, i - 1, n);
             initial[i - 1] = dediscretize(M, i, init_bins[i - 1], rnd);
         }
         for (int e = 0; e + 1 < n2; ++e) {
@@ -372,12 +386,12 @@ int oc_sample_initial(const oc_model* M, uint64_t seed, uint64_t first_sample, i
                 if (M->start && M->start[i - 1]) { x[i - 1] = (double)M->start[i - 1]; continue; }
                 int64_t j = parent_index(M->G_initial, ni, i - 1, M->r, x);
                 const double* w = M->W_initial + M->off_initial[i - 1] + (j - 1) * M->r[i - 1];
-                x[i - 1] = (double)select_random(w, M->r[i - 1], u01(word_at(&K, 1, (uint64_t)(i - 1))));
+                x[i - 1] = (double)select_random(w, M->r[i - 1], u01(init_word(&K, i - 1)));
             }
             int good = 1;
             for (int i = 1; i <= ni; ++i) {
                 double rnd = 0.5;
-                if (dd_needs_u(M, i, x[i - 1])) rnd = u01(word_at(&K, 1, (uint64_t)(ni + i - 1)));
+                if (dd_needs_u(M, i, x[i - 1])) rnd = init_dd_u(&K, i - 1, ni);
                 v[i - 1] = dediscretize(M, i, x[i - 1], rnd);
                 if (box_lo && !(v[i - 1] >= box_lo[i - 1] && v[i - 1] <= box_hi[i - 1])) good = 0;
             }

@@ -20,9 +20,14 @@ depends on the track and a part that only depends on the index -- the CUDA kerne
 the 10 rounds per call, csrc/emb_device.cuh: philox_track / philox_call / philox_finish.  The words are the plain
 Philox4x32-10 words of that counter.)
 
-purpose INIT (1):    word position p;  p = i            -> select word of initial variable i (0-based)
-                                      p = n_initial + i -> dediscretize word of initial variable i
-                     index = p // 4, lane = p % 4
+purpose INIT (1):    ONE word per initial variable, and four consecutive samples share a call:
+                         k_i(s) = philox(counter with sample := s >> 2, index = i)[lane = s & 3],   i = 0 .. n_initial-1
+                     (a thread that samples four consecutive samples consumes whole calls: n_initial calls per four
+                     samples).  The word selects the variable, u_sel = (k_i + 0.5) 2**-32 (bn_sample.m:55), and the
+                     de-discretisation of the initial value (dbn_hierarchical_sample.m:29) takes
+                         u_dd = ((((k_i * B + k_j) mod 2**32) >> 9) + 0.5) 2**-23,   j = (i + 1) mod max(n_initial, 2)
+                     (B as below; k_j is an independent full-entropy word, so u_dd is exactly uniform and independent of
+                     the select of variable i; for a single-variable network j = 1 is one extra word).
 purpose STEP (2):    ONE word per (second, variable): k(e, g), e = 1..T the second, g the ordinal of the variable
                      among the *gated* variables -- in increasing id, the initial variables that have a resample
                      rate > 0 or are dynamic (temporal_map column 1); nw = their number.  One Philox call holds four
@@ -148,6 +153,21 @@ DD_MULT = 0x85EBCA6B
 def gate_word(k):
     """step word -> the 32-bit word the resample gate compares (stream spec v5)."""
     return (int(k) * GATE_MULT) & 0xFFFFFFFF
+
+
+def init_word(seed, sample, attempt, i):
+    """select word k_i of initial variable i (0-based) for `sample` (stream spec v5: four consecutive samples share a call)."""
+    return int(word(seed, int(sample) >> 2, attempt, P_INIT, int(i), int(sample) & 3))
+
+
+def init_partner(i, n_initial):
+    """index of the word mixed into the de-discretisation word of initial variable i"""
+    return (int(i) + 1) % max(int(n_initial), 2)
+
+
+def init_dd_uniform(k, k_partner):
+    """de-discretisation uniform of an initial variable: the same 23-bit construction as dd_uniform"""
+    return dd_uniform(k, k_partner)
 
 
 def step_position(e, g, nw):

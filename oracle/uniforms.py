@@ -69,10 +69,12 @@ class KeyedPhilox(_Base):
 
     # -- draws ---------------------------------------------------------------------------------
     def select_init(self, var):                      # bn_sample.m:55 -> select_random.m:14
-        return self._rec(("init_sel", var), px.u01(self._w(px.P_INIT, var - 1)))
+        return self._rec(("init_sel", var), px.u01(px.init_word(self.seed, self.sample, self.attempt, var - 1)))
 
     def dedisc_init(self, var):                      # dbn_hierarchical_sample.m:29 -> dediscretize.m:39
-        return self._rec(("init_dd", var), px.u01(self._w(px.P_INIT, self.n_initial + var - 1)))
+        k = px.init_word(self.seed, self.sample, self.attempt, var - 1)
+        kp = px.init_word(self.seed, self.sample, self.attempt, px.init_partner(var - 1, self.n_initial))
+        return self._rec(("init_dd", var), px.init_dd_uniform(k, kp))
 
     def _step(self, e, g):
         """step word of second e, gated ordinal g (spec v5: no attempt in the step stream)"""

@@ -86,13 +86,16 @@ int emu_sample_initial(void* h, uint64_t seed, uint64_t first, int64_t n, const 
     g_last_fast = 0;
     if (g_use_fast && initial_fast_ok(D, P)) {
         InitStrides st;
-        fill_init_strides(D, st);
+        fill_init_strides(D, (int)H.thr_initial.size(), 0, st);
+        InitCalls ic;
+        fill_init_calls(P, D.n_initial, ic);
         bool done = false;
 #define EMB_X(NV_)                                                                                      \
     if (!done && D.n_initial == (NV_)) {                                                                \
         for (int64_t s0 = 0; s0 < n; s0 += INIT_SPT) {                                                  \
-            if (values) initial_fast4<NV_, true>(D, P, st, D.thr_init, s0, bins, values, attempts);                 \
-            else initial_fast4<NV_, false>(D, P, st, D.thr_init, s0, bins, values, attempts);                       \
+            if (values) initial_fast4<NV_, true, double, false>(D, P, st, ic, D.thr_init, D.dd32 + 4 * D.ddi_off[0], s0, bins, values, attempts); \
+            else if (first & 3) initial_fast4<NV_, false, double, false>(D, P, st, ic, D.thr_init, D.dd32 + 4 * D.ddi_off[0], s0, bins, values, attempts); \
+            else initial_fast4<NV_, false, double, true>(D, P, st, ic, D.thr_init, D.dd32 + 4 * D.ddi_off[0], s0, bins, values, attempts);    \
         }                                                                                               \
         done = true;                                                                                    \
     }

@@ -94,18 +94,21 @@ def test_initial_matches_golden(model_paths, golden, name, fast):
     ("balloon_v1", 37, None), ("glider_v1", 1001, None), ("glider_v1", 64, [2, None, None, None, None]),
     ("littoral_uncor_v1", 130, None), ("uncor_1200code_v2p1", 203, [1, 4, 2, None, None, None, None]),
     ("terminal_v3_radar_encounter_model", 95, None), ("cor_v1", 50, None)])
-def test_initial_specialised_equals_generic(model_paths, model, n, start):
+@pytest.mark.parametrize("first", [5, 8, 2 ** 34 - 6], ids=["unaligned", "aligned", "group-high-word-changes"])
+def test_initial_specialised_equals_generic(model_paths, model, n, start, first):
     """initial_fast4 (4 samples per thread, register state) == sample_initial, ragged n and presets included;
-    cor_v1 has a non-identity topological order and must fall back to the generic routine."""
+    cor_v1 has a non-identity topological order and must fall back to the generic routine.  Stream spec v5 lets four
+    consecutive samples share their Philox calls: first_sample not a multiple of four (two calls per variable) and a
+    batch whose sample >> 2 crosses a multiple of 2^32 (the shared call table no longer applies) are the edge cases."""
     from helpers import emu_lib
     lib = emu_lib()
     p = em_read(model_paths[model])
     em = EmuModel(model_paths[model])
     o = EmuModel.opts(p.n_initial, start=start)
-    ref = em.sample_initial(p.n_initial, n, 21, 5, o)
+    ref = em.sample_initial(p.n_initial, n, 21, first, o)
     lib.emu_use_fast(1)
     try:
-        got = em.sample_initial(p.n_initial, n, 21, 5, o)
+        got = em.sample_initial(p.n_initial, n, 21, first, o)
         assert lib.emu_last_fast() == (0 if model == "cor_v1" else 1)
     finally:
         lib.emu_use_fast(0)

@@ -201,6 +201,27 @@ def test_initial_specialised_equals_generic_at_scale(model_paths, model, n):
         assert torch.equal(x, y)
 
 
+def test_initial_fp32_values_match_fp64(model_paths):
+    """emb_sample_initial_f32 (the compact 1 + 4 bytes per variable of SURVEY 8d): same bins, values within 1e-6 relative of
+    the fp64 values, specialised and generic kernel, aligned and unaligned first_sample."""
+    lib = L.lib()
+    for name in ("glider_v1", "uncor_1200code_v2p1", "terminal_v3_radar_encounter_model"):
+        m = EncounterModel(model_paths[name])
+        for first in (0, 7):
+            b64, v64, _ = m.sample_initial(100_003, seed=3, first_sample=first, device="cuda:0")
+            b32, v32, _ = m.sample_initial(100_003, seed=3, first_sample=first, device="cuda:0", values_fp32=True)
+            assert lib.emb_debug_last_kernel_fast() == 1
+            assert b32.equal(b64)
+            a, b = v32.double().cpu().numpy(), v64.cpu().numpy()
+            assert np.all(np.abs(a - b) <= 1e-6 * np.abs(b))
+            lib.emb_debug_force_generic(1)
+            try:
+                bg, vg, _ = m.sample_initial(100_003, seed=3, first_sample=first, device="cuda:0", values_fp32=True)
+            finally:
+                lib.emb_debug_force_generic(0)
+            assert bg.equal(b64) and np.all(np.abs(vg.double().cpu().numpy() - b) <= 1e-6 * np.abs(b))
+
+
 def test_tracks_device_buffers_match_host_buffers(model_paths, golden):
     name = "uncor_v2p1_n24_T300_seed1"
     got = _run_tracks(model_paths, cases.TRACK_CASES[name], device="cuda:0")

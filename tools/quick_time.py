@@ -49,19 +49,19 @@ def time_events(name, n, T, reps=3):
           (name, n, T, best, n * T / best * 1e3, r.total / n, r.total * 8 / 1e6), flush=True)
 
 
-def time_initial(name, n, reps=3, want_values=True):
+def time_initial(name, n, reps=3, want_values=True, fp32=False):
     m = EncounterModel(paths[name])
-    m.sample_initial(n, seed=1, device=dev, want_attempts=False, want_values=want_values)
+    m.sample_initial(n, seed=1, device=dev, want_attempts=False, want_values=want_values, values_fp32=fp32)
     torch.cuda.synchronize()
     best = 1e9
     for r in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        m.sample_initial(n, seed=2 + r, device=dev, want_attempts=False, want_values=want_values)
+        m.sample_initial(n, seed=2 + r, device=dev, want_attempts=False, want_values=want_values, values_fp32=fp32)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    print("%s initial n=%d values=%s: %.3f ms  %.3e samples/s" % (name, n, want_values, best, n / best * 1e3), flush=True)
+    print("%s initial n=%d values=%s%s: %.3f ms  %.3e samples/s" % (name, n, want_values, " fp32" if fp32 else "", best, n / best * 1e3), flush=True)
 
 
 if __name__ == "__main__":
@@ -74,6 +74,7 @@ if __name__ == "__main__":
     time_tracks("glider_v1", 1 << 20, 300)
     time_events("uncor_allcode_fwsingle_v1", 1 << 20, 600)
     time_initial("glider_v1", 1 << 24)
+    time_initial("glider_v1", 1 << 24, fp32=True)
     time_initial("glider_v1", 1 << 24, want_values=False)
     time_initial("uncor_allcode_fwsingle_v1", 1 << 24, want_values=False)
     time_initial("terminal_v3_radar_encounter_model", 1 << 22)
