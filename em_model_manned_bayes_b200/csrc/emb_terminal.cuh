@@ -74,11 +74,17 @@ struct TermOut {
 // ---- MATLAB built-ins as restated by the oracle (oracle/terminal.py) --------------------------------
 // Not inlined on the device: three call sites of a ~300-instruction body made the chain kernel 60 KB of code and
 // `no_instruction` its third stall reason; as a call the kernel is 15 % smaller and 3 % faster.
+// The pair comes back by value (two register pairs): reference parameters of a non-inlined function live on the local-memory
+// stack, which was most of the chain kernel's 21.8 M local loads.
+struct SinCos {
+    double s, c;
+};
 #if defined(__CUDACC__)
-inline __host__ __device__ __noinline__ void sincosd(double x, double& s, double& c) {
+inline __host__ __device__ __noinline__ SinCos sincosd_pair(double x) {
 #else
-EMB_HD void sincosd(double x, double& s, double& c) {
+EMB_HD SinCos sincosd_pair(double x) {
 #endif
+    double s, c;
     // fmod(x, 360) is x itself for |x| < 360 (every angle this path produces); fmod proper is a long software loop on the GPU
     const double r = ::fabs(x) < 360.0 ? x : ::fmod(x, 360.0);
     const double a = dmul(r, 0.017453292519943295);     // pi/180
@@ -95,6 +101,15 @@ EMB_HD void sincosd(double x, double& s, double& c) {
         c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
         s = q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
     }
+    SinCos r2;
+    r2.s = s;
+    r2.c = c;
+    return r2;
+}
+EMB_HD void sincosd(double x, double& s, double& c) {
+    const SinCos r = sincosd_pair(x);
+    s = r.s;
+    c = r.c;
 }
 EMB_HD double atan2d(double y, double x) { return dmul(::atan2(y, x), 57.29577951308232); }   // 180/pi
 // wrapTo360(atan2d(y, x)): atan2d lies in [-180, 180], where mod(a, 360) is a + 360 for a < 0 and a otherwise (the
@@ -205,8 +220,11 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     // Three quantities the reference re-derives every second are carried instead, because they only change at events:
     //  * curr_hdg = wrapTo360(atan2d(vy, vx)) (:176): (vx, vy) is only ever set to v*(cosd h, sind h) (:150, :228-229) or rotated by
     //    delta (:252-255), so its direction is h resp. the previous direction + delta (equal to the atan2d value to ~1e-14 deg);
-    //  * speed = norm(v) (:168, :290): rotations keep it to an ulp; re-taken after a speed event;
-    //  * the cells of heading_deg, z_ft and speed (:278-293): re-discretised when an event changed the value.
+    //  * speed = norm(v) (:168, :290): re-taken from (vx, vy) whenever v changed (speed event or rotation), like the reference;
+    //  * the cells of heading_deg, z_ft and speed (:278-293): re-discretised when the value changed.
+    // a turn toward the desired heading runs at exactly +-maxTurn for all but its last second (:246-256): its sine and cosine
+    // are taken once per chain (sind(-x) = -sind(x), cosd(-x) = cosd(x) exactly)
+    const SinCos turn_sc = sincosd_pair(L.maxTurn);
     double curr_hdg = (vx == 0.0 && vy == 0.0) ? 0.0 : wrap360(heading_deg);
     double speed = norm2(vx, vy);
     uint32_t b_hdg = 0, b_alt = 0, b_spd = 0;
@@ -306,23 +324,37 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         const double turn1 = round2(dadd(heading_deg, -curr_hdg));
         const double mag = ::fmin(::fabs(turn1), L.maxTurn);
         const double delta = turn1 > 0.0 ? mag : turn1 < 0.0 ? -mag : dmul(mag, 0.0);
-        if (ev_v) {                                                               // v was re-pointed along heading_deg (:228-229)
-            curr_hdg = wrap360(heading_deg);
-            speed = norm2(vx, vy);
-        }
+        bool v_changed = ev_v;
+        if (ev_v) curr_hdg = wrap360(heading_deg);                                // v was re-pointed along heading_deg (:228-229)
         if (delta != 0.0) {                                                       // rotation by 0 degrees is the identity
             double sd, cd;
-            sincosd(delta, sd, cd);
+            if (delta == L.maxTurn) {
+                sd = turn_sc.s;
+                cd = turn_sc.c;
+            } else if (delta == -L.maxTurn) {
+                sd = -turn_sc.s;
+                cd = turn_sc.c;
+            } else {
+                sincosd(delta, sd, cd);
+            }
             const double nvx = dadd(dmul(cd, vx), -dmul(sd, vy)), nvy = dadd(dmul(sd, vx), dmul(cd, vy));
             vx = nvx;
             vy = nvy;
             curr_hdg = wrap360(dadd(curr_hdg, delta));
+            v_changed = true;
         }
         if (vx == 0.0 && vy == 0.0) curr_hdg = 0.0;                               // atan2d(0, 0) = 0
+        // The next state records norm(v) (:168) and discretises it (:290).  Whenever v changed -- a speed event (clamped to
+        // minVel/maxVel, :221-226) or a rotation, whose result can differ from the old norm in the last bit -- both are taken
+        // again from (vx, vy) exactly as the reference does, so a speed that sits on a bin edge (the dynamic limits are round
+        // numbers) lands in the same cell as in the reference given the same sind/cosd; an unchanged v gives the same norm.
+        if (v_changed) {
+            speed = norm2(vx, vy);
+            b_spd = (uint32_t)term_discretize(M, 5, speed);
+        }
         if (ev_any) {                                                             // cells of the values the events changed
             b_hdg = (uint32_t)term_discretize(M, 3, heading_deg);
             b_alt = (uint32_t)term_discretize(M, 4, z_ft);
-            if (ev_v) b_spd = (uint32_t)term_discretize(M, 5, speed);
         }
         t_s = dadd(t_s, dt_s);
         // CheckTrajectoryConditions (:296-329)

@@ -31,10 +31,11 @@ ALT_EDGES = [0, 200, 500, 1000, 1500, 2000, 2500, 3000, 5000, 10000]
 SPEED_EDGES = [0, 40, 100, 150, 200, 300, 400, 520, 600]
 
 
-def terminal_trajectory_model_arrays(seed: int = 0, direction: int = +1):
+def terminal_trajectory_model_arrays(seed: int = 0, direction: int = +1, speed_edges=None):
     rs = np.random.RandomState(1000 + 2 * int(seed) + (1 if direction > 0 else 0))
     names = ["intent", "distance", "bearing", "heading", "altitude", "speed"]
-    r_init = [3, len(DIST_EDGES) - 1, 36, 36, len(ALT_EDGES) - 1, len(SPEED_EDGES) - 1]
+    speed_edges = SPEED_EDGES if speed_edges is None else list(speed_edges)
+    r_init = [3, len(DIST_EDGES) - 1, 36, 36, len(ALT_EDGES) - 1, len(speed_edges) - 1]
     suffix = "(t+1)" if direction > 0 else "(t-1)"
     labels_initial = ['"%s"' % n for n in names]
     labels_transition = ['"%s(t)"' % n for n in names] + ['"%s%s"' % (n, suffix) for n in ("heading", "altitude", "speed")]
@@ -61,15 +62,15 @@ def terminal_trajectory_model_arrays(seed: int = 0, direction: int = +1):
                 if 0 <= nb < r:
                     c[nb, cols] += rs.randint(0, 120, size=block)
         N_t[child] = c
-    boundaries = [[], DIST_EDGES, ANGLE_EDGES, ANGLE_EDGES, ALT_EDGES, SPEED_EDGES]
+    boundaries = [[], DIST_EDGES, ANGLE_EDGES, ANGLE_EDGES, ALT_EDGES, speed_edges]
     return dict(labels_initial=labels_initial, G_initial=G_i, r_initial=r_init, N_initial=N_i,
                 labels_transition=labels_transition, G_transition=G_t, r_transition=r_t, N_transition=N_t,
                 boundaries=[np.asarray(b, dtype=np.float64) for b in boundaries], resample_rates=np.zeros(n))
 
 
-def write_terminal_trajectory_model(path: str, seed: int = 0, direction: int = +1) -> str:
+def write_terminal_trajectory_model(path: str, seed: int = 0, direction: int = +1, speed_edges=None) -> str:
     """Write a synthetic forward (`direction=+1`) or reverse (`-1`) trajectory model in the reference's file format."""
-    return em_write(path, **terminal_trajectory_model_arrays(seed, direction))
+    return em_write(path, **terminal_trajectory_model_arrays(seed, direction, speed_edges))
 
 
 # CorTerminalModel.m:62 file-name stems of the ten trajectory models
@@ -79,7 +80,7 @@ TRAJECTORY_STEMS = ("ownship_landing_model", "ownship_takeoff_model", "ownship_l
                     "intruder_transit_model_reverse")
 
 
-def write_terminal_model_set(directory: str, prefix: str = "terminal_v3_synthetic", seed: int = 0) -> dict:
+def write_terminal_model_set(directory: str, prefix: str = "terminal_v3_synthetic", seed: int = 0, speed_edges=None) -> dict:
     """Write the ten trajectory models a CorTerminalModel loads (`<prefix>_<stem>.txt`); returns {stem: path}."""
     import os
     os.makedirs(directory, exist_ok=True)
@@ -88,7 +89,8 @@ def write_terminal_model_set(directory: str, prefix: str = "terminal_v3_syntheti
         path = os.path.join(directory, "%s_%s.txt" % (prefix, stem))
         if not os.path.exists(path):
             tmp = path + ".tmp%d" % os.getpid()
-            write_terminal_trajectory_model(tmp, seed=10 * int(seed) + k, direction=-1 if stem.endswith("_reverse") else +1)
+            write_terminal_trajectory_model(tmp, seed=10 * int(seed) + k, direction=-1 if stem.endswith("_reverse") else +1,
+                                            speed_edges=speed_edges)
             os.replace(tmp, path)
         paths[stem] = path
     return paths

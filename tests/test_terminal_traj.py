@@ -125,6 +125,26 @@ def test_emu_chains_match_oracle(traj_paths, golden, types, tmax_s, seed, first)
     check_traj(traj, ln, want, want_len)
 
 
+def test_speed_edges_on_the_dynamic_limits(tmp_path, golden):
+    """createEncounter.m:221-226 clamps a sampled speed to minVel / maxVel; the next state records norm(v) (:168) and
+    discretises it (:290) after v was rotated.  With speed bin edges ON those limits the cell depends on the last bit of
+    norm(R v): the device code must take norm(v) from (vx, vy) whenever v changed, as the reference does, instead of carrying
+    the clamped value (same libm on both sides here, so the comparison is exact in the chain lengths and cells)."""
+    edges = [0, 50, 68, 100, 169, 186, 338, 491, 506, 600]
+    paths = write_terminal_model_set(str(tmp_path / "edge_models"), seed=7, speed_edges=edges)
+    geo = geo_from_golden(golden, 24)
+    for types, seed in ((("RTCA228_A3", "TEST"), 41), (("RTCA228_A1", "GENERIC"), 42), (("TEST", "RTCA228_A3"), 43)):
+        g = geo.copy()
+        g[5] = np.clip(g[5], 70.0, 180.0)
+        g[11] = np.clip(g[11], 70.0, 180.0)
+        rc, traj, ln = emu_propagate(paths, g, seed, 0, 90, types)
+        assert rc == 0
+        want, want_len = oracle_propagate(paths, g, seed, 0, 90, types)
+        check_traj(traj, ln, want, want_len)
+        spd = traj[4][~np.isnan(traj[4])]
+        assert any(np.any(np.abs(spd - e) < 1e-3) for e in (68.0, 169.0, 186.0, 338.0)), "no speed was clamped to a limit"
+
+
 def test_emu_chains_match_golden(traj_paths, golden):
     g = golden["terminal_traj_n16_T120_seed31"]
     rc, traj, ln = emu_propagate(traj_paths, np.ascontiguousarray(g["geo"]), 31, int(g["first"]), 120)
