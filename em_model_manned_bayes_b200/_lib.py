@@ -65,6 +65,7 @@ class SampleOpts(C.Structure):
         ("device", C.c_int32),
         ("stream", C.c_void_p),
         ("start_per_sample", C.c_void_p),
+        ("correct_dbn", C.c_int32),
     ]
 
 

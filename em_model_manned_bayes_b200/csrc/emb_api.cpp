@@ -582,6 +582,7 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     if ((rc = pick_device(opts, device, true))) return rc;
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
+    if (opts->correct_dbn) D.fast = 0;      // parents re-evaluated every second (emb_sample_opts::correct_dbn)
     cudaStream_t st = (cudaStream_t)opts->stream;
     const bool async = (opts->mem & EMB_MEM_ASYNC) != 0;
     Stager sg{opts->mem & 0xFF, st, {}};
@@ -661,6 +662,7 @@ static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n,
     if ((rc = pick_device(opts, device))) return rc;
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
+    if (opts->correct_dbn) D.fast = 0;
     cudaStream_t st = (cudaStream_t)opts->stream;
     if (total_rows) *total_rows = 0;
     if (n == 0) {

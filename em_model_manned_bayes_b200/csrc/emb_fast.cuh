@@ -537,6 +537,7 @@ constexpr uint32_t order_code_of(int a, int b, int c, int d) { return (uint32_t)
 #define EMB_FAST_SHAPES(X)                                                                         \
     X(0x070705u, 3, true, 0u) X(0x070705u, 4, true, 0u) X(0x070705u, 5, true, 0u)                   \
     X(0x070705u, 3, false, order_code_of(1, 2, 0, 0)) X(0x070705u, 3, false, order_code_of(1, 0, 2, 0)) \
+    X(0x070705u, 4, false, order_code_of(0, 1, 2, 0))   /* 7-variable uncor models with emb_sample_opts::correct_dbn */ \
     X(0x070905u, 5, true, 0u) X(0x050707u, 7, true, 0u)                                             \
     X(0x09090909u, 4, false, order_code_of(0, 1, 2, 3)) X(0x09090909u, 4, true, 0u)                 \
     X(0x07u, 1, true, 0u)

@@ -652,7 +652,7 @@ class UncorEncounterModel(EncounterModel):
         self.idxDH = _find(self.labels_initial, '"\\dot h"')
         self.idxDPsi = _find(self.labels_initial, '"\\dot \\psi"')
 
-    def uncor_opts(self, isQuantize500=False, layers=None, start=None, max_attempts=0):
+    def uncor_opts(self, isQuantize500=False, layers=None, start=None, max_attempts=0, correct_dbn=False):
         if not (self.idxDV and self.idxDH and self.idxDPsi):                   # :231-234
             raise L.EmbError(L.EMB_E_ARG, "dynvar:empty Model does not have a dynamic variable for either "
                              "acceleration, vertical rate, or turn rate")
@@ -660,6 +660,7 @@ class UncorEncounterModel(EncounterModel):
         o.reject_mode = L.EMB_REJECT_UNCOR
         o.idx_v, o.idx_dh, o.idx_L = self.idxV, self.idxDH, self.idxL
         o.is_quantize500 = int(bool(isQuantize500))
+        o.correct_dbn = int(bool(correct_dbn))       # not the reference's behaviour: parents re-evaluated every second
         if layers is not None and len(layers):
             layers = np.asarray(layers, dtype=np.float64).reshape(-1, 2)
             o.n_layers = layers.shape[0]

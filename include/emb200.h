@@ -133,6 +133,10 @@ typedef struct emb_sample_opts {
      * sample): int8 [n_initial][n], 1-based bins, 0 = free; NULL = use `start` for every sample.  Host or device memory
      * like the outputs (`mem`).  A preset variable with a free parent is refused like bn_sample.m:46-47 does (EMB_E_ARG). */
     const int8_t* start_per_sample;
+    /* NOT the reference's behaviour (default 0): for a model without a dynamic -> dynamic edge dbn_sample.m:110-135 freezes
+     * the parent configuration of every dynamic variable at t = 1; 1 re-evaluates the parents every second, as
+     * dbn_sample.m:66-79 does for the other models -- the Markov chain the transition tables were trained for. */
+    int32_t correct_dbn;
 } emb_sample_opts;
 void emb_sample_opts_init(emb_sample_opts* o);
 

@@ -45,7 +45,7 @@ def round500(num):
 
 
 def uncor_sample(parms, n_samples, sample_time, U, *, first_sample=0, prior=0, isQuantize500=False,
-                 layers=None, start=None, strict_quirks=False, max_attempts=65535) -> List[UncorSample]:
+                 layers=None, start=None, strict_quirks=False, max_attempts=65535, correct_dbn=False) -> List[UncorSample]:
     """UncorEncounterModel.m:192-313 (rng seeding is the provider's business)."""
     labels = parms.labels_initial
     idxL = _find_label(labels, '"L"')
@@ -67,7 +67,7 @@ def uncor_sample(parms, n_samples, sample_time, U, *, first_sample=0, prior=0, i
             U.begin(first_sample + ii, attempt)
             initial, events, prov, ibins, ebins = sp.dbn_hierarchical_sample(
                 parms, alpha_i, alpha_t, sample_time, parms.boundaries, parms.zero_bins,
-                parms.resample_rates, start, U, strict_quirks)
+                parms.resample_rates, start, U, strict_quirks, correct_dbn)
             if layers is not None and len(layers):                               # :259-263
                 L = int(initial[idxL - 1])
                 h_ft = layers[L - 1][0] + U.layer() * (layers[L - 1][1] - layers[L - 1][0])

@@ -122,7 +122,7 @@ def set_transition_priors(G, r, temporal_map, prior):
 
 
 # ------------------------------------------------------------------------------------------------
-def dbn_sample(parms, dirichlet_initial, dirichlet_transition, t_max, start, U, strict_quirks=False):
+def dbn_sample(parms, dirichlet_initial, dirichlet_transition, t_max, start, U, strict_quirks=False, correct_dbn=False):
     """dbn_sample.m:1-166.  Returns (initial bins 1 x n_initial, events list of [dt, var, bin],
     provenance list of ('trans', second))."""
     G_transition = np.asarray(parms.G_transition, dtype=bool)
@@ -147,7 +147,9 @@ def dbn_sample(parms, dirichlet_initial, dirichlet_transition, t_max, start, U, 
     events: List[List[float]] = []
     prov: List[tuple] = []
 
-    if is_dynvar_depend:                                              # :65-93 "slow" branch
+    # correct_dbn (not in the reference): take the per-step branch also for models without a dynamic -> dynamic
+    # edge, i.e. re-evaluate the parent configuration every second instead of freezing it at t = 1 (dbn_sample.m:110-135)
+    if is_dynvar_depend or correct_dbn:                               # :65-93 "slow" branch
         for t in range(2, t_max + 1):
             delta_t += 1
             x_old = x.copy()
@@ -246,11 +248,11 @@ def dediscretize_u(d, parameters, zero_bins, u_fn):
 
 def dbn_hierarchical_sample(parms, dirichlet_initial, dirichlet_transition, sample_time,
                             dediscretize_parameters, zero_bins, resample_rates, start, U,
-                            strict_quirks=False):
+                            strict_quirks=False, correct_dbn=False):
     """dbn_hierarchical_sample.m:9-37.  Returns (initial continuous, events [[dt,var,value]],
     provenance, initial bins)."""
     initial, events, prov = dbn_sample(parms, dirichlet_initial, dirichlet_transition, sample_time,
-                                       start, U, strict_quirks)
+                                       start, U, strict_quirks, correct_dbn)
     initial_bins = initial.copy()
     total = sum(e[0] for e in events)
     events = events + [[sample_time - total, 0, 0]]                   # :15-19

@@ -134,7 +134,8 @@ int emu_sample_tracks(void* h, uint64_t seed, uint64_t first, int64_t n, int32_t
         g_err = e.msg;
         return e.code;
     }
-    const DevModel D = host_dev(H);
+    DevModel D = host_dev(H);
+    if (o->correct_dbn) D.fast = 0;
     int32_t status = 0;
     TrackOut O{};
     O.bins = out->bins;
@@ -181,7 +182,8 @@ int emu_sample_track_events(void* h, uint64_t seed, uint64_t first, int64_t n, i
         g_err = e.msg;
         return e.code;
     }
-    const DevModel D = host_dev(H);
+    DevModel D = host_dev(H);
+    if (o->correct_dbn) D.fast = 0;
     int32_t status = 0;
     std::vector<uint32_t> counts((size_t)n);
     std::vector<long long> off((size_t)n + 1);

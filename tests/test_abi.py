@@ -29,7 +29,7 @@ def test_struct_layouts_match_header_sizes():
     # sizes computed from the header's field list (natural alignment)
     assert C.sizeof(L.Rng) == 16
     assert C.sizeof(L.TrackOut) == 7 * 8
-    assert C.sizeof(L.SampleOpts) == 24 * 4 + 4 * 4 + 2 * 24 * 8 + 4 + 4 + 8 * 2 * 8 + 4 * 3 + 4 + 8 + 8
+    assert C.sizeof(L.SampleOpts) == 24 * 4 + 4 * 4 + 2 * 24 * 8 + 4 + 4 + 8 * 2 * 8 + 4 * 3 + 4 + 8 + 8 + 8
     assert C.sizeof(L.ModelInfo) % 8 == 0
 
 

@@ -260,3 +260,29 @@ def test_every_shipped_dbn_model_runs_specialised_and_matches_the_c_oracle():
         assert np.all(np.abs(got["values"].astype(np.float64) - want) <= 1e-6 * np.abs(want)), path
         seen += 1
     assert seen >= 20
+
+
+@pytest.mark.parametrize("fast", [0, 1], ids=["generic", "specialised"])
+def test_correct_dbn_option_matches_the_oracle(model_paths, fast):
+    """emb_sample_opts::correct_dbn (SURVEY 8f row 2; NOT the reference's default): for a model without a dynamic -> dynamic
+    edge the parents of the dynamic variables are re-evaluated every second (dbn_sample.m:66-79) instead of frozen at t = 1
+    (:110-135).  Against the oracle with the same option; and the option really changes the tracks."""
+    from oracle.drivers import uncor_sample
+    from oracle.uniforms import KeyedPhilox
+    p = em_read(model_paths["uncor_1200code_v2p1"])
+    n, T = 40, 120
+    want = uncor_sample(p, n, T, KeyedPhilox(6), correct_dbn=True)
+    bins, vals, dyn, tv = H.oracle_dense(p, want)
+    frozen = H.oracle_dense(p, uncor_sample(p, n, T, KeyedPhilox(6)))[0]
+    assert not np.array_equal(bins, frozen)
+    lib = H.emu_lib()
+    lib.emu_use_fast(fast)
+    m = H.EmuModel(model_paths["uncor_1200code_v2p1"])
+    lab = p.labels_initial
+    o = H.EmuModel.opts(p.n_initial, reject_mode=L.EMB_REJECT_UNCOR, idx_v=cases.label_index(lab, '"v"'),
+                        idx_dh=cases.label_index(lab, '"\\dot h"'), idx_L=cases.label_index(lab, '"L"'), correct_dbn=1)
+    got = m.sample_tracks(p.n_initial, 3, 4, n, T, 6, 0, o)
+    assert lib.emu_last_fast() == fast
+    lib.emu_use_fast(0)
+    assert np.array_equal(got["bins"], bins)
+    assert np.all(np.abs(got["values"].astype(np.float64) - vals) <= 1e-6 * np.abs(vals))

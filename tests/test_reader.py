@@ -178,3 +178,43 @@ def test_uncor_get_dynamic_limits_matches_direct_conditioning(model_paths):
     g = UncorEncounterModel(model_paths["glider_v1"])
     lim = g.getDynamicLimits([1, 1, 1, 1, 1])
     assert lim["maxVel_ft_s"] > lim["minVel_ft_s"] and lim["maxVertRate_ft_s"] > 0
+
+
+@pytest.mark.parametrize("name", ["uncor_1200code_v2p1", "uncor_allcode_fwsingle_v1", "uncor_1200only_fwse_v1p2", "glider_v1"])
+def test_uncor_get_dynamic_limits_matches_the_oracle_restatement(model_paths, name):
+    """Product (model.py, host-side table arithmetic) against oracle/dynlimits.py, the statement-by-statement restatement of
+    @UncorEncounterModel/getDynamicLimits.m:1-130: every reachable (G, A, L, v) bin combination with discretised inputs, plus
+    continuous L / v taken from a simulated track (`results`, :35-50), rotorcraft flag included."""
+    from em_model_manned_bayes_b200.model import UncorEncounterModel, _find
+    from oracle.dynlimits import get_dynamic_limits
+    from oracle.em_read import em_read
+    m = UncorEncounterModel(model_paths[name])
+    p = em_read(model_paths[name])
+    lab = p.labels_initial
+    idx = dict(idx_G=_find(lab, '"G"'), idx_A=_find(lab, '"A"'), idx_L=_find(lab, '"L"'), idx_V=_find(lab, '"v"'),
+               idx_DH=_find(lab, '"\\dot h"'))
+    r = [int(x) for x in p.r_initial]
+    disc = [True] * p.n_initial
+    rs = np.random.RandomState(5)
+    tried = 0
+    for _ in range(400):
+        init = [int(rs.randint(1, ri + 1)) for ri in r]
+        try:
+            want = get_dynamic_limits(p, init, is_discretized=disc, **idx)
+        except (IndexError, ZeroDivisionError, ValueError, FloatingPointError):
+            continue                                   # an unreachable combination (all-zero conditional table)
+        if not np.isfinite(list(want.values())).all():
+            continue
+        got = m.getDynamicLimits(init, is_discretized=disc)
+        assert got == want, (init, got, want)
+        tried += 1
+    assert tried >= 50
+    if idx["idx_G"] == 1 and idx["idx_DH"] == 6:
+        for rot in (False, True):
+            m.isRotorcraft = rot
+            init = [1, r[1], 1650.0, 120.0, 0, 0, 0][:p.n_initial]
+            res = dict(up_ft=[700.0, 2900.0], speed_ftps=[90.0, 330.0])
+            nd = [len(b) == 0 for b in p.boundaries]
+            got = m.getDynamicLimits(init, results=res)
+            want = get_dynamic_limits(p, init, results=res, is_discretized=nd, is_rotorcraft=rot, **idx)
+            assert got == want

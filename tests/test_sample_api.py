@@ -281,3 +281,25 @@ def test_per_sample_presets_on_tracks_and_bad_rows(model_paths):
     with pytest.raises(L.EmbError) as ei:
         m.sample_tracks(n, T, seed=8, opts=bad)
     assert ei.value.code == L.EMB_E_ARG
+
+
+@pytest.mark.gpu
+def test_correct_dbn_option_on_the_gpu(model_paths):
+    """emb_sample_opts::correct_dbn on the device (specialised per-step kernel for the 7-variable shape): dense tracks and
+    event lists against the oracle run with the same option; default stays the reference's frozen-parent behaviour."""
+    import helpers as H
+    from em_model_manned_bayes_b200 import _lib as L
+    p = em_read(model_paths["uncor_1200code_v2p1"])
+    n, T = 48, 150
+    want = uncor_sample(p, n, T, KeyedPhilox(6), correct_dbn=True)
+    bins, vals, dyn, tv = H.oracle_dense(p, want)
+    m = M.UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    got = m.sample_tracks(n, T, seed=6, opts=m.uncor_opts(correct_dbn=True), device="cuda:0")
+    assert L.lib().emb_debug_last_kernel_fast() == 1
+    assert np.array_equal(got.bins.cpu().numpy(), bins)
+    assert np.all(np.abs(got.values.cpu().numpy().astype(np.float64) - vals) <= 1e-6 * np.abs(vals))
+    ev = m.sample_events(n, T, seed=6, opts=m.uncor_opts(correct_dbn=True))
+    for k, s in enumerate(want):
+        assert np.array_equal(ev.track(k)[:, :2], s.events[:, :2])
+    ref = m.sample_tracks(n, T, seed=6, opts=m.uncor_opts(), device="cuda:0")
+    assert not np.array_equal(ref.bins.cpu().numpy(), bins)
