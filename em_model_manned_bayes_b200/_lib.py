@@ -146,6 +146,11 @@ def lib():
         "emb_sample_track_events": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i64, vp, vp, P(TrackOut), P(i64)]),
         "emb_sample_track_events_packed": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i64, vp, vp, vp, P(TrackOut), P(i64)]),
         "emb_model_get_gated": (i64, [vp, vp, i64]),
+        "emb_shard_range": (None, [i64, i32, i32, P(i64), P(i64)]),
+        "emb_sample_tracks_multi": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), i32, vp, vp, vp]),
+        "emb_allreduce_histograms": (C.c_int, [i32, vp, vp, i64]),
+        "emb_nccl_available": (C.c_int, []),
+        "emb_multi_last_error": (C.c_char_p, []),
         "emb_dyn_limits_named": (C.c_int, [C.c_char_p, P(DynLimits)]),
         "emb_terminal_propagate": (C.c_int, [P(TerminalModels), P(Rng), i64, vp, i64, P(i32), C.c_double, P(DynLimits),
                                              P(SampleOpts), P(TrajOut)]),
@@ -165,7 +170,7 @@ def lib():
 
 EXPORTED = [
     "emb_abi_version", "emb_last_error", "emb_launch_count", "emb_debug_force_generic", "emb_debug_last_kernel_fast", "emb_device_count", "emb_host_alloc", "emb_host_free", "emb_trim_device_memory", "emb_async_status",
-    "emb_rng_word", "emb_sample_initial_f32", "emb_sample_track_events_packed", "emb_model_get_gated", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
+    "emb_rng_word", "emb_shard_range", "emb_sample_tracks_multi", "emb_allreduce_histograms", "emb_nccl_available", "emb_multi_last_error", "emb_sample_initial_f32", "emb_sample_track_events_packed", "emb_model_get_gated", "emb_model_load", "emb_model_from_arrays", "emb_model_free", "emb_model_get_info",
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
     "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",

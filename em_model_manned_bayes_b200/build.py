@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libemb200.so")
 
 CU_SOURCES = ["emb_kernels.cu", "emb_terminal.cu"]
-CXX_SOURCES = ["emb_model.cpp", "emb_api.cpp"]
+CXX_SOURCES = ["emb_model.cpp", "emb_api.cpp", "emb_multi.cpp"]
 HEADERS = ["emb_device.cuh", "emb_fast.cuh", "emb_initial.cuh", "emb_terminal.cuh", "emb_integrate.cuh", "emb_model.h", "emb_launch.h", os.path.join(ROOT, "include", "emb200.h")]
 
 NVCC_FLAGS = [
@@ -70,7 +70,7 @@ def build_variant(name: str, defines) -> str:
         objs.append(o)
     for src in CXX_SOURCES:
         objs.append(os.path.join(OBJ, src + ".o"))
-    _run([_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"], False)
+    _run([_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread", "-ldl"], False)
     return out
 
 
@@ -99,7 +99,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             for r in results:
                 sys.stdout.write(r.stderr)
     if jobs or force or _stale(LIB, objs):
-        _run([_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"], verbose)
+        _run([_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread", "-ldl"], verbose)
     return LIB
 
 

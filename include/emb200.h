@@ -209,6 +209,23 @@ int emb_sample_track_events_packed(const emb_model* m, const emb_rng* rng, int64
 /* 1-based ids of the time-varying ("gated") variables, ascending: resample rate > 0 or dynamic.  Returns their number. */
 int64_t emb_model_get_gated(const emb_model* m, int32_t* buf, int64_t cap);
 
+/* ---- every GPU of the box from ONE call: one host thread per device, tracks sharded by global sample index (device
+ *      d owns emb_shard_range(n, d, n_devices); the stream is keyed by the global index, so the union over the devices equals the
+ *      single-device result), no traffic between the devices on the data path, and ONE collective at the end: the verification
+ *      histograms are summed over the devices with ncclAllReduce (NCCL is bound at run time; the few KB go through the host when
+ *      it is not there).  outs[d] describes the buffers of device d's shard (host memory, or device memory ON device d when
+ *      opts->mem is EMB_MEM_DEVICE), sized for that shard (emb_tracks_bins_len(m, count_d, T), ...); their histogram fields are
+ *      ignored: hist_initial [n_initial][64] / hist_transition [n_dyn][64] (host, nullable, accumulated +=) receive the global
+ *      counts.  n_devices = 0: all visible devices.  opts->device, opts->stream and opts->start_per_sample are ignored. */
+void emb_shard_range(int64_t n, int32_t shard, int32_t n_shards, int64_t* first, int64_t* count);
+int emb_sample_tracks_multi(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                            int32_t n_devices, const emb_track_out* outs, unsigned long long* hist_initial,
+                            unsigned long long* hist_transition);
+/* counts[d]: `len` uint64 counters in device memory of devices[d] (NULL: device d); on return every buffer holds the sum */
+int emb_allreduce_histograms(int32_t n_devices, const int32_t* devices, unsigned long long* const* counts, int64_t len);
+int emb_nccl_available(void);              /* 1 when libnccl could be bound */
+const char* emb_multi_last_error(void);    /* message of the first failing device of the last emb_sample_tracks_multi */
+
 /* ---- terminal trajectory chains: replaces @CorTerminalModel/createEncounter.m:1-329 over a batch of encounters
  *      (PropagateTrajectory :93-265 = per state one dbn_sample.m:95-166 call with t_max = 2 and every initial
  *      variable preset by CreateStartDistribution :268-294, the dynamic-limit resample loop :192-243, the kinematic

@@ -222,6 +222,31 @@ def test_initial_fp32_values_match_fp64(model_paths):
             assert bg.equal(b64) and np.all(np.abs(vg.double().cpu().numpy() - b) <= 1e-6 * np.abs(b))
 
 
+@pytest.mark.parametrize("n_devices", [1, 2, 0], ids=["one", "two", "all"])
+def test_in_library_multi_gpu_equals_single_device(model_paths, n_devices):
+    """emb_sample_tracks_multi: one process, one host thread per device, shards by global sample index, ONE collective
+    (ncclAllReduce of the verification histograms inside the library).  The shards concatenated equal the single-device call
+    bit for bit, and the reduced histograms equal the single-device histograms.  (Two-device case: skipped on a 1-GPU box.)"""
+    from em_model_manned_bayes_b200.shard import sample_tracks_multi
+    lib = L.lib()
+    have = lib.emb_device_count()
+    if n_devices > have:
+        pytest.skip("needs %d GPUs" % n_devices)
+    assert lib.emb_nccl_available() == 1
+    m = UncorEncounterModel(model_paths["uncor_1200code_v2p1"])
+    n, T = 5003, 96
+    res, hi, ht = sample_tracks_multi(m, n, T, seed=19, first_sample=100, opts=m.uncor_opts(), n_devices=n_devices)
+    hi1 = np.zeros((m.n_initial, 64), dtype=np.uint64)
+    ht1 = np.zeros((m.n_dyn, 64), dtype=np.uint64)
+    one = m.sample_tracks(n, T, seed=19, first_sample=100, opts=m.uncor_opts(), hist_initial=hi1, hist_transition=ht1)
+    assert sum(r.n for r in res) == n and len(res) == (n_devices or have)
+    assert np.array_equal(np.concatenate([r.bins for r in res]), one.bins)
+    assert np.array_equal(np.concatenate([r.values for r in res]), one.values)
+    assert np.array_equal(np.concatenate([r.init_values for r in res], axis=1), one.init_values)
+    assert np.array_equal(hi, hi1) and np.array_equal(ht, ht1)
+    assert int(hi.sum()) == n * m.n_initial and int(ht.sum()) == n * (T - 1) * m.n_dyn
+
+
 def test_tracks_device_buffers_match_host_buffers(model_paths, golden):
     name = "uncor_v2p1_n24_T300_seed1"
     got = _run_tracks(model_paths, cases.TRACK_CASES[name], device="cuda:0")
