@@ -86,6 +86,12 @@ k_initial(const __grid_constant__ DevModel M, const __grid_constant__ SamplePara
 #ifndef EMB_INIT_MINBLOCKS_V    // resident blocks asked of the values variant (its fp64 tail otherwise takes 102 registers)
 #define EMB_INIT_MINBLOCKS_V 3
 #endif
+#ifndef EMB_INIT_TMA            // 1: stage the threshold table with TMA bulk copies (unpadded); 0: __ldg loop into the padded layout
+#define EMB_INIT_TMA 0
+#endif
+#ifndef EMB_INIT_PAD            // words between consecutive columns of the shared-memory copy (0 with EMB_INIT_TMA)
+#define EMB_INIT_PAD (EMB_INIT_TMA ? 0 : 4)
+#endif
 #ifndef EMB_INIT_MINBLOCKS_B
 #define EMB_INIT_MINBLOCKS_B 3
 #endif
@@ -96,7 +102,34 @@ k_initial_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sampl
                int8_t* __restrict__ bins, VT* __restrict__ values, uint16_t* __restrict__ attempts) {
     extern __shared__ uint4 smem_table[];
     const uint32_t* table = M.thr_init;
-    if (SMEM) {   // copy with a pitch of rp + pad words per column (emb_initial.cuh: fill_init_strides)
+    if (SMEM) {
+#if EMB_INIT_TMA
+        // A/B variant (profiles/r2_init_staging_tma_vs_ldg.txt): the table as ONE linear image, moved by the TMA unit with
+        // 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier -- requires the unpadded layout
+        // (ST.pad == 0: the bulk copy cannot re-pitch columns), which costs more in LDS bank conflicts than the copy saves.
+        __shared__ __align__(8) unsigned long long mbar;
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_table);
+        const uint32_t bytes = (uint32_t)table_words * 4u;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            for (uint32_t o = 0; o < bytes; o += 16384u) {
+                const uint32_t len = bytes - o < 16384u ? bytes - o : 16384u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + o), "l"(reinterpret_cast<const char*>(M.thr_init) + o), "r"(len), "r"(mb) : "memory");
+            }
+        }
+        __syncthreads();
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mb) : "memory");
+        }
+#else
+        // copy with a pitch of rp + pad words per column (emb_initial.cuh: fill_init_strides)
         const uint4* src = reinterpret_cast<const uint4*>(M.thr_init);
         for (int q = threadIdx.x; q < table_words / 4; q += blockDim.x) {
             const uint32_t w = 4u * (uint32_t)q;
@@ -106,6 +139,8 @@ k_initial_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sampl
             const uint32_t rel = w - ST.src_off[i], c = rel / ST.rp[i], r = rel - c * ST.rp[i];
             smem_table[(ST.off[i] + c * (ST.rp[i] + ST.pad) + r) / 4] = __ldg(src + q);
         }
+        __syncthreads();
+#endif
         table = reinterpret_cast<const uint32_t*>(smem_table);
     }
     // fp32 de-discretisation entries of the initial variables (16 bytes per bin): shared memory as well
@@ -297,7 +332,7 @@ static int launch_initial_t(const DevModel& M, const SampleParams& P, int table_
     const bool f32 = sizeof(VT) == 4;
     if (!g_force_generic && !hist && initial_fast_ok(M, P) && (!f32 || !values || M.init32_ok)) {
         InitStrides st;
-        fill_init_strides(M, table_words, 4, st);
+        fill_init_strides(M, table_words, EMB_INIT_PAD, st);
         InitCalls ic;
         fill_init_calls(P, M.n_initial, ic);
         const int64_t need = (P.n + 256 * INIT_SPT - 1) / (256 * INIT_SPT);
