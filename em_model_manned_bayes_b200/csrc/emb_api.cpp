@@ -134,8 +134,13 @@ cudaError_t tmp_alloc(void** p, size_t bytes, cudaStream_t st) {
     }
     return cudaMallocAsync(p, bytes, st);
 }
+// Temporaries die when an entry point returns.  On the normal path every stream that touched them has been synchronised;
+// on an early error return a kernel may still be running on the caller's (possibly non-blocking) stream, so the free is
+// stream-ordered on THAT stream (the legacy stream would not wait for a non-blocking one); the second stream of the event
+// pipeline is drained by its owner (Guard) before the buffers it reads are released.
+thread_local cudaStream_t g_call_stream = nullptr;   // the caller's stream of the entry point running on this thread
 void tmp_free(void* p) {
-    if (p) cudaFreeAsync(p, 0);   // every entry point has synchronised its streams before temporaries die
+    if (p) cudaFreeAsync(p, g_call_stream);
 }
 
 struct Staged {
@@ -501,6 +506,7 @@ static int sample_initial_impl(const emb_model* m, const emb_rng* rng, int64_t n
     DevModel D;
     if ((rc = ensure_device(H, device, D))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
     const int tw = (int)H.thr_initial.size();
     auto launch = [&](int8_t* b, double* v64, float* v32, uint16_t* a, int32_t* word) {
         return v32 ? (cudaError_t)emb::launch_initial_f32(D, P, tw, b, v32, a, nullptr, word, st)
@@ -584,6 +590,7 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     if ((rc = ensure_device(H, device, D))) return rc;
     if (opts->correct_dbn) D.fast = 0;      // parents re-evaluated every second (emb_sample_opts::correct_dbn)
     cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
     const bool async = (opts->mem & EMB_MEM_ASYNC) != 0;
     Stager sg{opts->mem & 0xFF, st, {}};
     emb::TrackOut O{};
@@ -593,6 +600,10 @@ int emb_sample_tracks(const emb_model* m, const emb_rng* rng, int64_t n, int32_t
     if ((rc = sg.out(out->init_bins, (size_t)n * ni, false, (void**)&O.init_bins))) return rc;
     if ((rc = sg.out(out->init_values, (size_t)n * ni * 8, false, (void**)&O.init_values))) return rc;
     if ((rc = sg.out(out->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
+    if (out->hist_initial || out->hist_transition) {   // the histograms have 64 counters per variable
+        for (int i = 0; i < H.n_initial; ++i)
+            if (H.r_initial[i] > 64) return set_err(EMB_E_LIMIT, "verification histograms hold 64 bins per variable; this model has a variable with more");
+    }
     if ((rc = sg.out(out->hist_initial, ni * 64 * 8, true, (void**)&O.hist_initial))) return rc;
     if ((rc = sg.out(out->hist_transition, H.temporal_map.size() * 64 * 8, true, (void**)&O.hist_transition))) return rc;
     if ((rc = stage_start(sg, opts, H, n, P))) return rc;
@@ -664,6 +675,7 @@ static int sample_events_impl(const emb_model* m, const emb_rng* rng, int64_t n,
     if ((rc = ensure_device(H, device, D))) return rc;
     if (opts->correct_dbn) D.fast = 0;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
     if (total_rows) *total_rows = 0;
     if (n == 0) {
         const int64_t zero = 0;
@@ -921,6 +933,7 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
         P.m[k].edges = D.edges;
     }
     cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
     Stager sg{opts->mem, st, {}};
     struct Scratch {
         void* p = nullptr;
@@ -987,6 +1000,7 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
     int device, rc = 0;
     if ((rc = pick_device(&so, device))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
     Stager sg{opts->mem, st, {}};
     struct Scratch {
         void* p = nullptr;
@@ -1021,6 +1035,7 @@ int emb_terminal_screen(const float* traj, const int16_t* len, int64_t n, double
     int device, rc = 0;
     if ((rc = pick_device(opts, device))) return rc;
     cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
     emb::ScreenParams P;
     std::memset(&P, 0, sizeof(P));
     P.n = n;

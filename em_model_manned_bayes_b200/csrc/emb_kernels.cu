@@ -16,8 +16,8 @@
 namespace emb {
 
 std::atomic<long long> g_launch_count{0};
-int g_force_generic = 0;      // emb_debug_force_generic(): tests compare both kernels
-int g_last_kernel_fast = 0;
+std::atomic<int> g_force_generic{0};      // emb_debug_force_generic(): tests compare both kernels
+std::atomic<int> g_last_kernel_fast{0};
 
 namespace {
 

@@ -8,8 +8,8 @@
 namespace emb {
 
 extern std::atomic<long long> g_launch_count;
-extern int g_force_generic;
-extern int g_last_kernel_fast;
+extern std::atomic<int> g_force_generic;
+extern std::atomic<int> g_last_kernel_fast;
 
 // all return a cudaError_t value (0 = success); pointers are device pointers
 // table_words = length of the initial threshold table (decides shared-memory staging)

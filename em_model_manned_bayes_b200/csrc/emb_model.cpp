@@ -512,8 +512,8 @@ void fill_params(const HostModel& H, uint64_t seed, uint64_t first_sample, int64
     P.idx_L = o->idx_L - 1;
     P.is_quantize500 = o->is_quantize500;
     P.n_layers = o->n_layers;
-    P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 65535;
-    if (P.max_attempts > 65535) P.max_attempts = 65535;
+    P.max_attempts = o->max_attempts > 0 ? o->max_attempts : 65534;
+    if (P.max_attempts > 65534) P.max_attempts = 65534;   // `attempts` is uint16 and holds attempt + 1
     const int nv = H.n_initial;
     // bn_sample.m:45-50 preset validation
     for (int i = 0; i < nv; ++i) {

@@ -86,7 +86,9 @@ class TrackResult:
 
 
 class EncounterModel:
-    """@EncounterModel/EncounterModel.m:75-153 (file-backed form) -- same property names."""
+    """@EncounterModel/EncounterModel.m:75-153 (file-backed form) -- same property names.  `idxZeroBoundaries` defaults to
+    empty like the class constructor's own inputParser (:87); `em_read` called directly defaults to [1 2 3] (em_read.m:34-40),
+    which is what UncorEncounterModel below passes."""
 
     def __init__(self, parameters_filename: str = "", idxZeroBoundaries: Sequence[int] = (),
                  isOverwriteZeroBoundaries: bool = False, prior=0, _handle=None):

@@ -1,9 +1,12 @@
 """Packed model archives (.npz) <-> reference-format model/*.txt files.
 
-The reference's model files are not vendored in this repository.  Tests and bench.py on a GPU box
-(where /root/reference does not exist) materialise the models they need from the packed fixture
-`tests/golden/models.npz` (written by tests/golden/make_fixtures.py) and then read them through the
-normal reader, exactly as a user would read `model/*.txt`."""
+The reference's model FILES are not vendored in this repository.  Tests and bench.py on a GPU box
+(where /root/reference does not exist) materialise the models they need from a packed fixture of their
+count tables, `tests/golden/models.npz` (written by tests/golden/make_fixtures.py; the data is the
+reference's, BSD-2-Clause, notice in tests/golden/MODELS_NOTICE.txt), and then read them through the
+normal reader, exactly as a user would read `model/*.txt`.  The archive is test/bench data, not part of
+the product: `EMB200_MODEL_ARCHIVE` overrides its location, and a user of the library passes real
+`model/*.txt` paths."""
 from __future__ import annotations
 
 import os
@@ -12,7 +15,8 @@ import numpy as np
 
 from .em_write import em_write
 
-DEFAULT_ARCHIVE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "models.npz")
+DEFAULT_ARCHIVE = os.environ.get("EMB200_MODEL_ARCHIVE") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "models.npz")
 
 
 def _cells(flat, G, r, first):

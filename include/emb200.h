@@ -101,6 +101,8 @@ int64_t emb_model_get_boundaries(const emb_model* m, double* buf, int64_t cap);
 int64_t emb_model_get_packed(const emb_model* m, int which, uint32_t* buf, int64_t cap);
 
 /* ---- priors: replaces EncounterModel.m:249-257 -> bn_dirichlet_prior.m, setTransitionPriors.m --- */
+/* Repacks the model's threshold tables: must not run concurrently with a sampling call on the SAME model (distinct models,
+ * and sampling calls among themselves, are independent). */
 int emb_set_prior(emb_model* m, int which /*0 initial, 1 transition*/, int kind, double value);
 
 /* ---- random stream --------------------------------------------------------------------------- */

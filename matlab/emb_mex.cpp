@@ -14,6 +14,8 @@
 //          emb_mex('set_prior', h, which, kind, value)
 //   [bins, values, attempts] = emb_mex('sample_initial', h, seed, first, n, opts)
 //   [out_inits, bins, values, attempts] = emb_mex('sample_tracks', h, seed, first, n, T, opts)
+//   [out_inits, bins, values, hist_i, hist_t] = emb_mex('sample_tracks_multi', h, seed, first, n, T, opts, n_devices)
+//          all GPUs of the box from one call (emb_sample_tracks_multi): bins / values are 1 x D cells of per-device tiles
 //   [events, offsets, out_inits, attempts] = emb_mex('sample_events', h, seed, first, n, T, opts)
 //          events: 4 x rows double [dt; var; value; bin], offsets: (n+1) x 1 (0-based first row of each track)
 //   [traj, len] = emb_mex('terminal_propagate', hs, seed, first, geo, tmax_s, limits, opts)
@@ -284,6 +286,54 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (nlhs > 1) plhs[1] = bins; else mxDestroyArray(bins);
         if (nlhs > 2) plhs[2] = vals; else mxDestroyArray(vals);
         if (nlhs > 3) plhs[3] = att; else mxDestroyArray(att);
+    } else if (c == "sample_tracks_multi") {                      // every GPU of the box from one MATLAB process
+        // [out_inits, bins, values, hist_initial, hist_transition] = emb_mex('sample_tracks_multi', h, seed, first, n, T, opts, n_devices)
+        // out_inits n x n_initial; bins / values: 1 x D cells of the per-device tiled arrays (shard d = emb_shard_range(n, d, D))
+        emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
+        const int64_t n = (int64_t)mxGetScalar(prhs[4]);
+        const int32_t T = (int32_t)mxGetScalar(prhs[5]);
+        emb_sample_opts o;
+        fill_opts(nrhs > 6 ? prhs[6] : nullptr, ni, &o);
+        int D = nrhs > 7 ? (int)mxGetScalar(prhs[7]) : 0;
+        if (D <= 0) D = emb_device_count();
+        if (D <= 0) mexErrMsgIdAndTxt("emb200:cuda", "no CUDA device available");
+        const mwSize nch = (mwSize)((T + 3) / 4);
+        std::vector<emb_track_out> outs((size_t)D);
+        std::vector<std::vector<double>> inits((size_t)D);
+        mxArray* cb = mxCreateCellMatrix(1, (mwSize)D);
+        mxArray* cv = mxCreateCellMatrix(1, (mwSize)D);
+        for (int d = 0; d < D; ++d) {
+            int64_t first = 0, cnt = 0;
+            emb_shard_range(n, d, D, &first, &cnt);
+            const mwSize ntile = (mwSize)((cnt + 127) / 128);
+            const mwSize db[5] = {4, 128, (mwSize)info.n_dyn, ntile, nch}, dv[5] = {4, 128, (mwSize)info.n_timevarying, ntile, nch};
+            mxArray* b = mxCreateNumericArray(5, db, mxINT8_CLASS, mxREAL);
+            mxArray* v = mxCreateNumericArray(5, dv, mxSINGLE_CLASS, mxREAL);
+            mxSetCell(cb, (mwSize)d, b);
+            mxSetCell(cv, (mwSize)d, v);
+            inits[(size_t)d].assign((size_t)cnt * (size_t)ni + 1, 0.0);
+            outs[(size_t)d] = emb_track_out{};
+            outs[(size_t)d].bins = (int8_t*)mxGetData(b);
+            outs[(size_t)d].values = (float*)mxGetData(v);
+            outs[(size_t)d].init_values = inits[(size_t)d].data();
+        }
+        mxArray* hi = mxCreateNumericMatrix(64, ni, mxUINT64_CLASS, mxREAL);          // [n_initial][64] == 64 x n_initial
+        mxArray* ht = mxCreateNumericMatrix(64, info.n_dyn, mxUINT64_CLASS, mxREAL);
+        const int rc = emb_sample_tracks_multi(m, &rng, n, T, &o, D, outs.data(), (unsigned long long*)mxGetData(hi),
+                                               (unsigned long long*)mxGetData(ht));
+        if (rc != 0) mexErrMsgIdAndTxt("emb200:error", "%s", emb_multi_last_error());
+        plhs[0] = mxCreateDoubleMatrix(n, ni, mxREAL);                                // shards back to back: out_inits
+        for (int d = 0; d < D; ++d) {
+            int64_t first = 0, cnt = 0;
+            emb_shard_range(n, d, D, &first, &cnt);
+            for (int i = 0; i < ni; ++i)
+                std::memcpy(mxGetPr(plhs[0]) + (size_t)i * (size_t)n + (size_t)first, inits[(size_t)d].data() + (size_t)i * (size_t)cnt,
+                            (size_t)cnt * 8);
+        }
+        if (nlhs > 1) plhs[1] = cb; else mxDestroyArray(cb);
+        if (nlhs > 2) plhs[2] = cv; else mxDestroyArray(cv);
+        if (nlhs > 3) plhs[3] = hi; else mxDestroyArray(hi);
+        if (nlhs > 4) plhs[4] = ht; else mxDestroyArray(ht);
     } else if (c == "tracks_integrate") {                         // sample2track.m:188-244
         const int64_t n = (int64_t)mxGetM(prhs[2]);
         const int32_t T = (int32_t)mxGetScalar(prhs[4]);
@@ -316,8 +366,44 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         init.init_values = mxGetPr(inits);
         init.attempts = (uint16_t*)mxGetData(att);
         int64_t total = 0;
+        // 5-byte packed rows (what the device writes and what crosses PCIe); the value of a row is evaluated here in fp64 from
+        // its bin and 23-bit uniform exactly as dediscretize.m:39 does.  Models outside the packed format (more than 7
+        // time-varying variables or T > 1023) take the 8-byte rows.
+        int rc = emb_sample_track_events_packed(m, &rng, n, T, &o, 0, nullptr, nullptr, off.data(), &init, &total);   // sizes the list
+        const bool packed = rc == 0 || (rc == EMB_E_LIMIT && total > 0);
+        if (packed) {
+            std::vector<uint32_t> words((size_t)total + 1);
+            std::vector<uint8_t> dts((size_t)total + 1);
+            CHECK(emb_sample_track_events_packed(m, &rng, n, T, &o, total, words.data(), dts.data(), off.data(), &init, &total));
+            int32_t gated[EMB_MAX_GATED];
+            const int ng = (int)emb_model_get_gated(m, gated, EMB_MAX_GATED);
+            std::vector<double> bnd((size_t)emb_model_get_boundaries(m, nullptr, 0) + 1);
+            emb_model_get_boundaries(m, bnd.data(), (int64_t)bnd.size());
+            std::vector<int64_t> boff((size_t)ni + 1, 0);
+            for (int i = 0; i < ni; ++i) boff[(size_t)i + 1] = boff[(size_t)i] + info.boundaries_len[i];
+            plhs[0] = mxCreateDoubleMatrix(4, (mwSize)total, mxREAL);
+            double* e = mxGetPr(plhs[0]);
+            for (int64_t k = 0; k < total; ++k) {
+                const uint32_t w = words[(size_t)k], gord = (w >> 27) & 7u;
+                const double dt = (double)(dts[(size_t)k] | ((w >> 30) << 8));
+                double var = 0, val = 0, bin = 0;
+                if (gord > 0 && (int)gord <= ng) {
+                    const int v = gated[gord - 1];                       // 1-based variable id
+                    const int b = (int)((w >> 23) & 15u) + 1;
+                    var = v; bin = b;
+                    if (info.boundaries_len[v - 1] == 0) val = b;                                   // dediscretize.m:7-10
+                    else if (info.zero_bins[v - 1] == b) val = 0.0;                                 // :24-25
+                    else {
+                        const double* ed = bnd.data() + boff[(size_t)v - 1];
+                        const double u = ((double)(w & 0x7FFFFFu) + 0.5) * 1.1920928955078125e-07;  // (frac + 0.5) 2^-23
+                        val = ed[b - 1] + (ed[b] - ed[b - 1]) * u;                                  // :39
+                    }
+                }
+                e[4 * k] = dt; e[4 * k + 1] = var; e[4 * k + 2] = val; e[4 * k + 3] = bin;
+            }
+        } else {
         std::vector<emb_event> ev;
-        int rc = emb_sample_track_events(m, &rng, n, T, &o, 0, nullptr, off.data(), &init, &total);   // sizes the list
+        rc = emb_sample_track_events(m, &rng, n, T, &o, 0, nullptr, off.data(), &init, &total);   // sizes the list
         if (rc != 0 && rc != EMB_E_LIMIT) fail(rc);
         ev.resize((size_t)total + 1);
         CHECK(emb_sample_track_events(m, &rng, n, T, &o, total, ev.data(), off.data(), &init, &total));
@@ -325,6 +411,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         double* e = mxGetPr(plhs[0]);
         for (int64_t k = 0; k < total; ++k) {
             e[4 * k] = ev[(size_t)k].dt; e[4 * k + 1] = ev[(size_t)k].var; e[4 * k + 2] = ev[(size_t)k].value; e[4 * k + 3] = ev[(size_t)k].bin;
+        }
         }
         mxArray* offs = mxCreateDoubleMatrix(n + 1, 1, mxREAL);
         for (int64_t k = 0; k <= n; ++k) mxGetPr(offs)[k] = (double)off[(size_t)k];

@@ -11,3 +11,4 @@ void mxSetField(mxArray*, int, const char*, mxArray*); mxArray* mxCreateDoubleSc
 mxArray* mxCreateNumericArray(int, const mwSize*, mxClassID, mxComplexity); void mxDestroyArray(mxArray*);
 [[noreturn]] void mexErrMsgIdAndTxt(const char*, const char*, ...);
 typedef bool mxLogical; bool mxIsLogical(const mxArray*); mxLogical* mxGetLogicals(const mxArray*); mxArray* mxGetCell(const mxArray*, size_t);
+mxArray* mxCreateCellMatrix(size_t, size_t); void mxSetCell(mxArray*, size_t, mxArray*);

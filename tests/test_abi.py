@@ -64,7 +64,7 @@ def test_mex_gateway_source_matches_the_header():
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     src = open(os.path.join(ROOT, "matlab", "emb_mex.cpp")).read()
-    for fn in ("emb_model_load", "emb_model_from_arrays", "emb_set_prior", "emb_sample_initial", "emb_sample_tracks", "emb_sample_track_events",
+    for fn in ("emb_model_load", "emb_model_from_arrays", "emb_sample_track_events_packed", "emb_sample_tracks_multi", "emb_set_prior", "emb_sample_initial", "emb_sample_tracks", "emb_sample_track_events",
                "emb_terminal_propagate", "emb_terminal_screen", "emb_tracks_integrate"):
         assert fn + "(" in src, fn
 
