@@ -132,6 +132,11 @@ EMB_HD uint32_t add_gtd(uint32_t acc, double kb, double td) {
 // variables of the (5,7,7) shapes; the 5-bin variable stays on the carry chain, which balances the alu, fma and fp64 pipes
 // (tools/ubench/ubench3.cu and profiles/r1_ubench_fp64_compare.txt hold the measurements, including an all-fp64
 // DADD + DFMA.RZ accumulator that needs no integer instruction but was slower)
+#ifndef EMB_SLOW_INLINE_PHILOX   // 1: the per-step branch computes whole Philox calls in the thread (no call table): it is bound by
+                                 // the latency of its column gathers, and the extra shared-memory round trip per call cost 5-11 %
+                                 // (glider_v1 2.47 -> 2.22 ms, cor_v1 10.0 -> 9.6 ms) where the fast branch gains 8 % from the table
+#define EMB_SLOW_INLINE_PHILOX 1
+#endif
 #ifndef EMB_F64CMP
 #define EMB_F64CMP 6
 #endif
@@ -181,6 +186,7 @@ struct FastTrack {
     int ebase[NG];            // entry-table bases (uniform)
     uint32_t G[NG];           // gate thresholds (uniform)
     PhiloxTrack pt;           // track-invariant part of the step stream's Philox calls
+    uint32_t c0w, c1w;        // EMB_SLOW_INLINE_PHILOX: counter words 0, 1 (sample_hi, sample_lo)
     uint32_t sbin1[NS > 0 ? NS : 1];   // EV: 1-based bins of the static gated variables
     uint32_t ev_last, ev_n;            // EV: second of the last row, rows so far
     long long ev_i;                    // EV == 2: next row of this track
@@ -209,8 +215,13 @@ struct FastTrack {
     EMB_HD void group(int grp, int T, uint32_t (&bout)[ND], float (&vout)[NG][4], const uint4* ut, uint32_t ut_s) {
         uint32_t W[4 * NW];
 #pragma unroll
-        for (int c = 0; c < NW; ++c)
+        for (int c = 0; c < NW; ++c) {
+#if EMB_SLOW_INLINE_PHILOX
+            if (!FAST) philox4x32_10_rk(c0w, c1w, P_STEP << 8, (uint32_t)(grp * NW + c), P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
+            else
+#endif
             philox_finish(pt, lds_call(ut, ut_s, c), P.rk, W[4 * c], W[4 * c + 1], W[4 * c + 2], W[4 * c + 3]);
+        }
 #pragma unroll
         for (int d = 0; d < ND; ++d) bout[d] = 0;
 #pragma unroll
@@ -346,9 +357,11 @@ EMB_HD void fast_groups(FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>& ft, con
     const int64_t bstep = ntile * (ND * TRACK_TILE * 4), vstep = ntile * (NG * TRACK_TILE * 4);
     for (int grp0 = 0; grp0 < ngrp; grp0 += UT_GROUPS) {
         const int gcount = ngrp - grp0 < UT_GROUPS ? ngrp - grp0 : UT_GROUPS;
-        if (grp0 > 0) block_sync();
-        fill_call_table<NG>(U, P, c0, c2, grp0, gcount, tid, nthreads);
-        block_sync();
+        if (FAST || !EMB_SLOW_INLINE_PHILOX) {
+            if (grp0 > 0) block_sync();
+            fill_call_table<NG>(U, P, c0, c2, grp0, gcount, tid, nthreads);
+            block_sync();
+        }
         if (!valid) continue;
 #if defined(__CUDA_ARCH__)
         uint32_t ut_s = (uint32_t)__cvta_generic_to_shared(U.e);
@@ -488,6 +501,8 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                     }
             }
             ft.pt = philox_track(c0, (uint32_t)sample, c2, P.rk);
+            ft.c0w = c0;
+            ft.c1w = (uint32_t)sample;
         }
     }
     if (!steps) return;
