@@ -912,13 +912,15 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
     for (int a = 0; a < 2; ++a)
         P.lim[a] = emb::TermLimits{limits[a].minVel_ft_s, limits[a].maxVel_ft_s, limits[a].maxTurnRate_deg_s,
                                    limits[a].maxAltitude_ft, limits[a].maxVertRate_ft_s};
+    constexpr size_t cuts_per_model = (size_t)emb::TERM_NCUT * emb::TERM_CUT_MAX;
+    std::vector<double> cuts(cuts_per_model * emb::TERM_NMODELS);
     const emb_model* slot[emb::TERM_NMODELS] = {
         models->own_fwd[0], models->own_bck[0], models->own_fwd[1], models->own_bck[1], models->int_fwd[0],
         models->int_bck[0], models->int_fwd[1], models->int_bck[1], models->int_fwd[2], models->int_bck[2]};
     try {
         for (int k = 0; k < emb::TERM_NMODELS; ++k) {
             if (!slot[k]) return set_err(EMB_E_ARG, "emb_terminal_models: null model");
-            emb::make_term_model(*slot[k]->h, P.lim[k < 4 ? 0 : 1], P.m[k]);
+            emb::make_term_model(*slot[k]->h, P.lim[k < 4 ? 0 : 1], P.m[k], cuts.data() + (size_t)k * cuts_per_model);
         }
     } catch (const emb::Error& e) {
         return set_err(e.code, e.msg);
@@ -938,7 +940,10 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
     struct Scratch {
         void* p = nullptr;
         ~Scratch() { tmp_free(p); }
-    } d_geo, d_status;
+    } d_geo, d_status, d_cuts;
+    CU(tmp_alloc(&d_cuts.p, cuts.size() * 8, st));
+    CU(cudaMemcpyAsync(d_cuts.p, cuts.data(), cuts.size() * 8, cudaMemcpyHostToDevice, st));   // pageable: staged before return
+    P.cuts = (const double*)d_cuts.p;
     if (opts->mem == EMB_MEM_DEVICE) {
         P.geo = geo;
     } else {   // stage the rows that are read

@@ -565,7 +565,19 @@ bool named_dyn_limits(const char* ac_type, TermLimits& out) {
     return true;
 }
 
-void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M) {
+// min{s >= 0 : sqrt(s) >= c} for c > 0: sqrt is monotone and correctly rounded, so "norm >= c" is exactly "x*x + y*y >= s"
+static double sq_threshold(double c) {
+    const double inf = std::numeric_limits<double>::infinity();
+    if (!(c > 0.0)) return 0.0;
+    if (std::isinf(c)) return inf;
+    double s = c * c;
+    if (std::isinf(s)) return inf;
+    while (s > 0.0 && std::sqrt(std::nextafter(s, 0.0)) >= c) s = std::nextafter(s, 0.0);
+    while (std::sqrt(s) < c) s = std::nextafter(s, inf);
+    return s;
+}
+
+void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M, double* cuts) {
     std::memset(&M, 0, sizeof(M));
     auto find = [&](const char* name) {
         const std::string q = std::string("\"") + name + "\"";
@@ -625,24 +637,38 @@ void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M) {
         M.spd_lo = s1;
         M.spd_hi = e1;
     }
-    M.dist_max = H.bounds_initial[M.i_dist].second;
-    // pseudo-angles of the bearing cutpoints (emb_terminal.cuh: term_bearing_bin); bearings live in [0, 360)
-    const auto& eb = H.boundaries[M.i_bear];
-    const int rb = H.r_initial[M.i_bear];
-    M.n_bear_pc = -1;
-    if (!eb.empty() && rb - 1 <= TERM_PC_MAX) {
-        M.n_bear_pc = rb - 1;
-        for (int j = 1; j < rb; ++j) {
-            const double c = eb[(size_t)j];
-            double pc;
-            if (c <= 0.0) pc = -1.0;                                            // every bearing is >= this cutpoint
-            else if (c >= 360.0) pc = std::numeric_limits<double>::infinity();  // none is
-            else {
-                double sn, cs;
-                sincosd(c, sn, cs);
-                pc = pseudo_angle(cs, sn);
+    // tests on d_nm as tests on x*x + y*y (emb_terminal.cuh: TC_DIST2)
+    M.dist_max_sq = sq_threshold(std::nextafter(H.bounds_initial[M.i_dist].second, std::numeric_limits<double>::infinity()));
+    M.quarter_sq = sq_threshold(std::nextafter(0.25, 1.0));
+    // cutpoint tables (emb_terminal.cuh: term_cell)
+    const double inf = std::numeric_limits<double>::infinity();
+    const int var_of[TERM_NCUT] = {M.i_dist, M.i_bear, 3, 4, 5};
+    for (int t = 0; t < TERM_NCUT; ++t) {
+        const int i = var_of[t], r = H.r_initial[i];
+        if (r > TERM_CUT_MAX)
+            fail(EMB_E_LIMIT, "createEncounter: a trajectory model variable has more than 64 bins");
+        double* row = cuts ? cuts + t * TERM_CUT_MAX : nullptr;
+        int step = r > 1 ? 1 : 0;                           // smallest power of two whose 2*step - 1 slots hold the r - 1 cutpoints
+        while (2 * step - 1 < r - 1) step *= 2;
+        M.cut_step[t] = step;
+        if (!row) continue;
+        for (int j = 0; j < TERM_CUT_MAX; ++j) row[j] = inf;
+        const auto& e = H.boundaries[i];
+        for (int j = 1; j < r; ++j) {
+            const double c = e.empty() ? (double)(j + 1) : e[(size_t)j];   // no boundaries: cutpoints 2..r (em_read.m:128-136)
+            double v = c;
+            if (t == TC_DIST2) {
+                v = c <= 0.0 ? -inf : sq_threshold(c);                     // a norm is never negative
+            } else if (t == TC_BEAR) {                                      // bearings live in [0, 360)
+                if (c <= 0.0) v = -inf;                                     // every bearing is >= this cutpoint
+                else if (c >= 360.0) v = inf;                               // none is
+                else {
+                    double sn, cs;
+                    sincosd(c, sn, cs);
+                    v = pseudo_angle(cs, sn);
+                }
             }
-            M.bear_pc[j - 1] = pc;
+            row[j - 1] = v;
         }
     }
 }

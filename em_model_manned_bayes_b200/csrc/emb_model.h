@@ -90,8 +90,9 @@ void fill_params(const HostModel& H, uint64_t seed, uint64_t first_sample, int64
 uint64_t gate_threshold(double rate);
 
 // Terminal trajectory chains: checks the layout createEncounter.m:107-116 asserts and fills the per-chain model
-// descriptor (table pointers left null; valid altitude/speed bins of :118-125 for `lim`); throws Error.
-void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M);
+// descriptor (table pointers left null; valid altitude/speed bins of :118-125 for `lim`) and, when `cuts` is given, its
+// [TERM_NCUT][TERM_CUT_MAX] cutpoint tables (emb_terminal.cuh: term_cell); throws Error.
+void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M, double* cuts = nullptr);
 // @CorTerminalModel/getDynamicLimits.m:14-62; false if the aircraft type is unknown
 bool named_dyn_limits(const char* ac_type, TermLimits& out);
 

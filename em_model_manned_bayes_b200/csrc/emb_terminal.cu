@@ -22,17 +22,18 @@ constexpr int TERM_BLOCK = 128;
 #endif
 __global__ void __launch_bounds__(TERM_BLOCK, EMB_TERM_MINBLOCKS)
 k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ TermOut O) {
-    // the bearing cutpoints of the (up to three) models this block's chain can use: the binary search of every lane reads them
-    // at its own index, which shared memory serves and the constant bank would serialise
-    __shared__ double pc[3 * TERM_PC_MAX];
+    // the cutpoint tables of the (up to three) models this block's chain id can use: every lane searches them at its own
+    // index, which shared memory serves and the constant bank would serialise
+    __shared__ double cuts[3 * TERM_NCUT * TERM_CUT_MAX];
     const int chain = (int)blockIdx.y, ac = chain >> 1, dir = chain & 1;
-    for (int q = threadIdx.x; q < 3 * TERM_PC_MAX; q += blockDim.x) {
-        const int it = q / TERM_PC_MAX, j = q % TERM_PC_MAX;
-        pc[q] = it < (ac ? 3 : 2) ? P.m[(ac ? 4 : 0) + it * 2 + dir].bear_pc[j] : 0.0;
+    constexpr int per_model = TERM_NCUT * TERM_CUT_MAX;
+    for (int q = threadIdx.x; q < (ac ? 3 : 2) * per_model; q += blockDim.x) {
+        const int it = q / per_model, j = q % per_model;
+        cuts[q] = __ldg(P.cuts + ((ac ? 4 : 0) + it * 2 + dir) * per_model + j);
     }
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) terminal_chain(P, O, s, chain, pc);
+    if (s < P.n) terminal_chain(P, O, s, chain, cuts);
 }
 
 // first-order track integration (emb_integrate.cuh): thread = track, HBM-bound (12 B read + 12 B written per track-second)

@@ -21,7 +21,16 @@ constexpr uint32_t P_TERM_SEL = 5, P_TERM_DD = 6;
 constexpr int TERM_NMODELS = 10;   // own {landing, takeoff} x {fwd, bck}, intruder {landing, takeoff, transit} x {fwd, bck}
 constexpr int TERM_FIELDS = 5;     // x_nm, y_nm, z_ft, heading_deg, v_ft_s  (t_s is the slot index)
 constexpr double TERM_FT_PER_NM = 6076.1154855643;   // createEncounter.m:172
-constexpr int TERM_PC_MAX = 48;    // bearing cutpoints held as pseudo-angles (r - 1 <= 47)
+constexpr double TERM_NM_PER_FT = 1.0 / TERM_FT_PER_NM;   // correctly rounded reciprocal (div_const)
+// Cutpoint tables of one trajectory model, searched without branches (term_cell): TERM_NCUT tables of TERM_CUT_MAX slots, the
+// cutpoints ascending and padded with +inf.  The chain never needs the distance or the bearing themselves, only their cells:
+//   TC_DIST2: norm([x y]) >= cut (createEncounter.m:277 on d_nm)  <=>  x*x + y*y >= min{s : sqrt(s) >= cut}  (sqrt is monotone
+//             and correctly rounded, so the threshold in s is exact and the fp64 square root leaves the per-second path);
+//   TC_BEAR : wrapTo360(atan2d(y, x)) >= cut  <=>  pseudo-angle(x, y) >= pseudo-angle(cosd cut, sind cut), see pseudo_angle();
+//   TC_HDG, TC_ALT, TC_SPD: cutpoints_initial{4..6} as they are (em_read.m:128-136).
+constexpr int TERM_CUT_MAX = 64;   // at most 63 cutpoints (64 bins) per variable of a trajectory model
+constexpr int TERM_NCUT = 5;
+enum { TC_DIST2 = 0, TC_BEAR = 1, TC_HDG = 2, TC_ALT = 3, TC_SPD = 4 };
 
 // what a chain needs from one trajectory model (built on the host from HostModel::dev)
 struct TermModel {
@@ -37,15 +46,10 @@ struct TermModel {
     int32_t i_dist, i_bear;   // 0-based positions of "distance" and "bearing" (createEncounter.m:112-113)
     int32_t alt_hi;           // discreteValidAlt = 1..alt_hi        (createEncounter.m:120), 0 = empty
     int32_t spd_lo, spd_hi;   // discreteValidV   = spd_lo..spd_hi   (:123-125), lo > hi = empty
-    int32_t pad_;
-    double dist_max;          // bounds_initial(idx.dist, 2)         (:263, :310)
-    // Bearing cell without atan2 (CreateStartDistribution :277/:293 only needs the *bin* of wrapTo360(atan2d(y, x))): the
-    // pseudo-angle p(x, y) = y >= 0 ? 1 - x/(|x|+|y|) : 3 + x/(|x|+|y|) is strictly increasing in the bearing over [0, 360),
-    // so #{j : bearing >= cut_j} = #{j : p(x, y) >= p(cosd cut_j, sind cut_j)}.  n_bear_pc = r - 1 cutpoints, or -1 when the
-    // variable has no boundaries or too many bins (then the bin comes from atan2d as in the reference).
-    int32_t n_bear_pc;
-    int32_t pad2_;
-    double bear_pc[TERM_PC_MAX];
+    int32_t cut_step[TERM_NCUT];   // first stride of term_cell over each cutpoint table (a power of two, 0 = no cutpoint)
+    // tests on d_nm = norm([x y]) taken on s = x*x + y*y (TC_DIST2 above):
+    double dist_max_sq;       // d_nm > bounds_initial(idx.dist, 2)  <=>  s >= dist_max_sq   (:263, :310)
+    double quarter_sq;        // d_nm <= 0.25                        <=>  s <  quarter_sq    (:312)
 };
 
 struct TermLimits {           // @CorTerminalModel/getDynamicLimits.m:14-62
@@ -62,6 +66,7 @@ struct TermParams {
     int64_t geo_stride;
     int32_t geo_row[12];      // own_{intent, distance, bearing, alt, heading, speed}, int_{...}
     TermLimits lim[2];
+    const double* cuts;       // [TERM_NMODELS][TERM_NCUT][TERM_CUT_MAX] cutpoint tables (make_term_cuts), same order as m[]
     TermModel m[TERM_NMODELS];// [aircraft 0: (intent-1)*2 + dir | aircraft 1: 4 + (intent-1)*2 + dir], dir 0 fwd / 1 bck
 };
 
@@ -72,39 +77,59 @@ struct TermOut {
 };
 
 // ---- MATLAB built-ins as restated by the oracle (oracle/terminal.py) --------------------------------
-// Not inlined on the device: three call sites of a ~300-instruction body made the chain kernel 60 KB of code and
-// `no_instruction` its third stall reason; as a call the kernel is 15 % smaller and 3 % faster.
-// The pair comes back by value (two register pairs): reference parameters of a non-inlined function live on the local-memory
-// stack, which was most of the chain kernel's 21.8 M local loads.
+EMB_HD double fma_rn(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+// a / c for a compile-time divisor, correctly rounded like the IEEE division it replaces (rc = 1/c correctly rounded): the
+// reciprocal product is corrected twice with the exact FMA residual (Markstein: with rc = RN(1/c) and q within one ulp of a/c,
+// RN(q + RN(a - q*c)*rc) is the correctly rounded quotient; the first correction makes q faithful, the second applies the
+// theorem).  Five fp64 instructions instead of the ~25 of a division; finite operands far from the subnormal range only.
+EMB_HD double div_const(double a, double c, double rc) {
+    const double q0 = dmul(a, rc);
+    const double q1 = fma_rn(fma_rn(-q0, c, a), rc, q0);
+    return fma_rn(fma_rn(-q1, c, a), rc, q1);
+}
+
+// sind/cosd the way MATLAB evaluates them: the argument is reduced in DEGREES (exactly) to t in [-45, 45] plus a quadrant, and
+// only t is converted to radians; the two kernels are the fdlibm polynomials for |a| <= pi/4 (error < 1 ulp).  Multiples of 90
+// degrees give exactly 0 and +-1.  ~45 fp64 instructions where sincos() of a radian argument costs several hundred (it cannot
+// know the argument is below 2*pi and carries a Payne-Hanek path through local memory).
 struct SinCos {
     double s, c;
 };
-#if defined(__CUDACC__)
-inline __host__ __device__ __noinline__ SinCos sincosd_pair(double x) {
-#else
 EMB_HD SinCos sincosd_pair(double x) {
-#endif
-    double s, c;
     // fmod(x, 360) is x itself for |x| < 360 (every angle this path produces); fmod proper is a long software loop on the GPU
     const double r = ::fabs(x) < 360.0 ? x : ::fmod(x, 360.0);
-    const double a = dmul(r, 0.017453292519943295);     // pi/180
-#if defined(__CUDA_ARCH__)
-    ::sincos(a, &s, &c);
-#else
-    s = ::sin(a);
-    c = ::cos(a);
-#endif
-    // exact at multiples of 90 degrees (cosd/sind): |r| < 360, so fmod(r, 90) == 0 means r is one of 0, +-90, +-180, +-270
-    const double ar = ::fabs(r);
-    if (ar == 0.0 || ar == 90.0 || ar == 180.0 || ar == 270.0) {
-        const int q = ((int)(r / 90.0)) & 3;            // two's complement: -1 -> 3, -2 -> 2, -3 -> 1
-        c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
-        s = q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
-    }
-    SinCos r2;
-    r2.s = s;
-    r2.c = c;
-    return r2;
+    // nearest quadrant, |qn| <= 4 (round to nearest through the 1.5 * 2^52 shift: two exact-by-construction additions)
+    const double qn = dadd(dadd(dmul(r, 0.011111111111111112), 6755399441055744.0), -6755399441055744.0);
+    const double t = fma_rn(-90.0, qn, r);                      // exact: a multiple of ulp(r) that is smaller than r
+    const double a = dmul(t, 0.017453292519943295);             // pi/180
+    const double z = dmul(a, a);
+    // sin(a) = a + a*z*(S1 + z*(S2 + ... z*S6))
+    double ps = fma_rn(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma_rn(z, ps, 2.75573137070700676789e-06);
+    ps = fma_rn(z, ps, -1.98412698298579493134e-04);
+    ps = fma_rn(z, ps, 8.33333333332248946124e-03);
+    ps = fma_rn(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma_rn(dmul(a, z), ps, a);
+    // cos(a) = w + ((1 - w) - z/2 + z*z*(C1 + z*(C2 + ... z*C6))),  w = 1 - z/2
+    double pc = fma_rn(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma_rn(z, pc, -2.75573143513906633035e-07);
+    pc = fma_rn(z, pc, 2.48015872894767294178e-05);
+    pc = fma_rn(z, pc, -1.38888888888741095749e-03);
+    pc = fma_rn(z, pc, 4.16666666666666019037e-02);
+    const double hz = dmul(0.5, z), w = dadd(1.0, -hz);
+    const double cs = dadd(w, fma_rn(dmul(z, z), pc, dadd(dadd(1.0, -w), -hz)));
+    // sin(t + 90 q), cos(t + 90 q); "+ 0.0" turns a -0 of the negated kernel value into the +0 of the reference's table
+    const int q = (int)qn & 3;                                  // two's complement: -1 -> 3, -2 -> 2, -3 -> 1
+    SinCos o;
+    o.s = dadd((q & 1) ? ((q & 2) ? -cs : cs) : ((q & 2) ? -sn : sn), 0.0);
+    o.c = dadd((q & 1) ? ((q & 2) ? sn : -sn) : ((q & 2) ? -cs : cs), 0.0);
+    return o;
 }
 EMB_HD void sincosd(double x, double& s, double& c) {
     const SinCos r = sincosd_pair(x);
@@ -133,35 +158,17 @@ EMB_HD double pseudo_angle(double x, double y) {        // [0, 4), increasing wi
 EMB_HD double round2(double x) {                        // round(x, 2), half away from zero
     const double y = dmul(x, 100.0);
     const double m = ::floor(dadd(::fabs(y), 0.5));
-    return (y >= 0.0 ? m : -m) / 100.0;
+    return div_const(y >= 0.0 ? m : -m, 100.0, 0.01);
 }
 EMB_HD double norm2(double a, double b) { return ::sqrt(dadd(dmul(a, a), dmul(b, b))); }
 
-// discretize_bayes.m:14-22 against cutpoints_initial{i} (em_read.m:128-136); returns the 0-based bin
-EMB_HD int term_discretize(const TermModel& M, int i, double x) {
-    const int r = M.r[i];
-    if (M.edge_off[i] < 0) {                            // no boundaries: cutpoints 2..r
-        int b = 0;
-        for (int j = 2; j <= r; ++j) b += (x >= (double)j) ? 1 : 0;
-        return b;
-    }
-    const double* e = M.edges + M.edge_off[i];          // lower edge of bin j at e[2j]; cutpoints are e[2], e[4], ...
-    int lo = 0, hi = r - 1;                             // result = #{j in 1..r-1 : x >= cut_j}
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (x >= ldg64(e + 2 * mid)) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-// bin of the bearing of (x, y) from the pseudo-angle cutpoints `pc` (TermModel::bear_pc, or its shared-memory copy)
-EMB_HD int term_bearing_bin(const double* pc, int n, double x, double y) {
-    const double p = pseudo_angle(x, y);
-    int lo = 0, hi = n;                                 // result = #{j in 0..n-1 : p >= pc[j]}
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (p >= pc[mid - 1]) lo = mid; else hi = mid - 1;
-    }
-    return lo;
+// discretize_bayes.m:14-22, 0-based: #{j : v >= cut[j]} over an ascending table padded with +inf up to 2*step0 - 1 slots
+// (make_term_cuts).  No branch and no data-dependent trip count: log2 steps of one load, one compare and one predicated add.
+EMB_HD int term_cell(const double* cut, int step0, double v) {
+    int pos = 0;
+    for (int step = step0; step > 0; step >>= 1)
+        if (v >= cut[pos + step - 1]) pos += step;
+    return pos;
 }
 EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // dediscretize.m:39, two-argument call
     if (M.edge_off[i] < 0) return (double)(b + 1);
@@ -179,8 +186,9 @@ EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // d
 #endif
 
 // One chain.  `s` = encounter index within this call, chain = 2*aircraft + direction.
-// pc_rows: per-intent copies of TermModel::bear_pc in shared memory ([3][TERM_PC_MAX], device) or nullptr (host emulation)
-EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain, const double* pc_rows = nullptr) {
+// cuts_sh: the cutpoint tables of the (up to three) models this chain id can use, one per intent, in shared memory
+// ([3][TERM_NCUT][TERM_CUT_MAX], device) or nullptr (host emulation: read from TermParams::cuts)
+EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain, const double* cuts_sh = nullptr) {
     const int ac = chain >> 1, dir = chain & 1;
     const double dt_s = dir ? -1.0 : 1.0;
     const int64_t N = P.n;
@@ -206,8 +214,10 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
 #endif
     const bool bad_intent = intent < 1 || intent > (ac ? 3 : 2);                 // createEncounter.m:14-38
     if (bad_intent && O.status) EMB_FLAG_OR(O.status, 2);
-    const TermModel& M = P.m[(ac ? 4 : 0) + ((bad_intent ? 1 : intent) - 1) * 2 + dir];
-    const double* bear_pc = pc_rows ? pc_rows + ((bad_intent ? 1 : intent) - 1) * TERM_PC_MAX : M.bear_pc;
+    const int islot = (bad_intent ? 1 : intent) - 1, mi = (ac ? 4 : 0) + islot * 2 + dir;
+    const TermModel& M = P.m[mi];
+    const double* cuts = cuts_sh ? cuts_sh + islot * (TERM_NCUT * TERM_CUT_MAX) : P.cuts + mi * (TERM_NCUT * TERM_CUT_MAX);
+    const int step_dist = M.cut_step[TC_DIST2], step_bear = M.cut_step[TC_BEAR];
 
     double sb, cb, sh, ch;
     sincosd(bearing, sb, cb);
@@ -229,9 +239,9 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     double speed = norm2(vx, vy);
     uint32_t b_hdg = 0, b_alt = 0, b_spd = 0;
     if (go) {
-        b_hdg = (uint32_t)term_discretize(M, 3, heading_deg);
-        b_alt = (uint32_t)term_discretize(M, 4, z_ft);
-        b_spd = (uint32_t)term_discretize(M, 5, speed);
+        b_hdg = (uint32_t)term_cell(cuts + TC_HDG * TERM_CUT_MAX, M.cut_step[TC_HDG], heading_deg);
+        b_alt = (uint32_t)term_cell(cuts + TC_ALT * TERM_CUT_MAX, M.cut_step[TC_ALT], z_ft);
+        b_spd = (uint32_t)term_cell(cuts + TC_SPD * TERM_CUT_MAX, M.cut_step[TC_SPD], speed);
     }
 
     for (int ii = 1; ii <= K; ++ii) {
@@ -257,16 +267,16 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
             put(3, (float)curr_hdg);
             put(4, (float)speed);
         }
-        x = dadd(x, dmul(vx, dt_s) / TERM_FT_PER_NM);                             // :171-173
-        y = dadd(y, dmul(vy, dt_s) / TERM_FT_PER_NM);
+        x = dadd(x, div_const(dmul(vx, dt_s), TERM_FT_PER_NM, TERM_NM_PER_FT));   // :171-173
+        y = dadd(y, div_const(dmul(vy, dt_s), TERM_FT_PER_NM, TERM_NM_PER_FT));
 
-        // CreateStartDistribution (:268-294), 0-based bins
-        const double d_nm = norm2(x, y);
+        // CreateStartDistribution (:268-294), 0-based bins; the cells of d_nm = norm([x y]) and of the bearing
+        // wrapTo360(atan2d(y, x)) (:277, :293) come from x*x + y*y and the pseudo-angle (TC_DIST2, TC_BEAR)
+        const double d_sq = dadd(dmul(x, x), dmul(y, y));
         uint32_t st[6];
         st[0] = (uint32_t)(intent - 1);
-        st[1] = (uint32_t)term_discretize(M, M.i_dist, d_nm);                     // positional cell, cutpoints by label (:277,:293)
-        st[2] = M.n_bear_pc >= 0 ? (uint32_t)term_bearing_bin(bear_pc, M.n_bear_pc, x, y)
-                                 : (uint32_t)term_discretize(M, M.i_bear, heading_of(y, x));
+        st[1] = (uint32_t)term_cell(cuts + TC_DIST2 * TERM_CUT_MAX, step_dist, d_sq);
+        st[2] = (uint32_t)term_cell(cuts + TC_BEAR * TERM_CUT_MAX, step_bear, pseudo_angle(x, y));
         st[3] = b_hdg;
         st[4] = b_alt;
         st[5] = b_spd;
@@ -350,15 +360,15 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         // numbers) lands in the same cell as in the reference given the same sind/cosd; an unchanged v gives the same norm.
         if (v_changed) {
             speed = norm2(vx, vy);
-            b_spd = (uint32_t)term_discretize(M, 5, speed);
+            b_spd = (uint32_t)term_cell(cuts + TC_SPD * TERM_CUT_MAX, M.cut_step[TC_SPD], speed);
         }
         if (ev_any) {                                                             // cells of the values the events changed
-            b_hdg = (uint32_t)term_discretize(M, 3, heading_deg);
-            b_alt = (uint32_t)term_discretize(M, 4, z_ft);
+            b_hdg = (uint32_t)term_cell(cuts + TC_HDG * TERM_CUT_MAX, M.cut_step[TC_HDG], heading_deg);
+            b_alt = (uint32_t)term_cell(cuts + TC_ALT * TERM_CUT_MAX, M.cut_step[TC_ALT], z_ft);
         }
         t_s = dadd(t_s, dt_s);
         // CheckTrajectoryConditions (:296-329)
-        const bool violate = ::fabs(t_s) > P.tmax_s || d_nm > M.dist_max || ((intent == 1 || intent == 2) && d_nm <= 0.25) ||
+        const bool violate = ::fabs(t_s) > P.tmax_s || d_sq >= M.dist_max_sq || ((intent == 1 || intent == 2) && d_sq < M.quarter_sq) ||
                              (ac == 0 && y > 0.25);
         go = !violate;
     }

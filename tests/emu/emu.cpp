@@ -266,10 +266,12 @@ int emu_terminal_propagate(void** models, uint64_t seed, uint64_t first, int64_t
     for (int a = 0; a < 2; ++a)
         P.lim[a] = TermLimits{limits[a].minVel_ft_s, limits[a].maxVel_ft_s, limits[a].maxTurnRate_deg_s,
                               limits[a].maxAltitude_ft, limits[a].maxVertRate_ft_s};
+    std::vector<double> cuts((size_t)TERM_NMODELS * TERM_NCUT * TERM_CUT_MAX);
+    P.cuts = cuts.data();
     try {
         for (int k = 0; k < TERM_NMODELS; ++k) {
             const HostModel& H = *static_cast<HostModel*>(models[k]);
-            make_term_model(H, P.lim[k < 4 ? 0 : 1], P.m[k]);
+            make_term_model(H, P.lim[k < 4 ? 0 : 1], P.m[k], cuts.data() + (size_t)k * TERM_NCUT * TERM_CUT_MAX);
             P.m[k].thr = H.thr_transition.data();
             P.m[k].edges = H.edges.data();
         }
@@ -285,24 +287,51 @@ int emu_terminal_propagate(void** models, uint64_t seed, uint64_t first, int64_t
     return (status & 1) ? EMB_E_REJECT : 0;
 }
 
-// bearing cells of n points: cells_pc = term_bearing_bin on the pseudo-angle cutpoints the chain kernel uses, cells_ref = the
-// reference's own route, discretize_bayes(wrapTo360(atan2d(y, x))) (createEncounter.m:277, :293)
-int emu_bearing_cells(void* model, int64_t n, const double* x, const double* y, int32_t* cells_pc, int32_t* cells_ref) {
+// discretize_bayes.m:14-22 against cutpoints_initial{i} (em_read.m:128-136), 0-based, straight from the model's boundaries
+static int ref_discretize(const HostModel& H, int i, double x) {
+    const int r = H.r_initial[i];
+    const auto& e = H.boundaries[i];
+    int b = 0;
+    for (int j = 1; j < r; ++j) b += x >= (e.empty() ? (double)(j + 1) : e[(size_t)j]) ? 1 : 0;
+    return b;
+}
+
+// bearing and distance cells of n points: cells_pc / cells_d2 = term_cell on the pseudo-angle and squared-norm tables the chain
+// kernel uses, cells_ref / cells_dref = the reference's own route, discretize_bayes(wrapTo360(atan2d(y, x))) and
+// discretize_bayes(norm([x y])) (createEncounter.m:277, :293); near[2] = dist_max_sq, quarter_sq
+int emu_bearing_cells(void* model, int64_t n, const double* x, const double* y, int32_t* cells_pc, int32_t* cells_ref,
+                      int32_t* cells_d2, int32_t* cells_dref, double* near) {
     const HostModel& H = *static_cast<HostModel*>(model);
     TermModel M;
+    std::vector<double> cuts((size_t)TERM_NCUT * TERM_CUT_MAX);
     try {
-        make_term_model(H, TermLimits{0.0, 1e9, 3.0, 1e9, 1e9}, M);
+        make_term_model(H, TermLimits{0.0, 1e9, 3.0, 1e9, 1e9}, M, cuts.data());
     } catch (const Error& e) {
         g_err = e.msg;
         return e.code;
     }
-    M.edges = H.edges.data();
-    if (M.n_bear_pc < 0) return EMB_E_MODEL;
     for (int64_t i = 0; i < n; ++i) {
-        cells_pc[i] = term_bearing_bin(M.bear_pc, M.n_bear_pc, x[i], y[i]);
-        cells_ref[i] = term_discretize(M, M.i_bear, heading_of(y[i], x[i]));
+        cells_pc[i] = term_cell(cuts.data() + TC_BEAR * TERM_CUT_MAX, M.cut_step[TC_BEAR], pseudo_angle(x[i], y[i]));
+        cells_ref[i] = ref_discretize(H, M.i_bear, heading_of(y[i], x[i]));
+        if (cells_d2) cells_d2[i] = term_cell(cuts.data() + TC_DIST2 * TERM_CUT_MAX, M.cut_step[TC_DIST2], dadd(dmul(x[i], x[i]), dmul(y[i], y[i])));
+        if (cells_dref) cells_dref[i] = ref_discretize(H, M.i_dist, norm2(x[i], y[i]));
+    }
+    if (near) {
+        near[0] = M.dist_max_sq;
+        near[1] = M.quarter_sq;
     }
     return 0;
+}
+
+// sind/cosd and the constant-divisor division of the chain kernel, for comparison with libm / IEEE division
+void emu_sincosd(int64_t n, const double* x, double* s, double* c) {
+    for (int64_t i = 0; i < n; ++i) sincosd(x[i], s[i], c[i]);
+}
+void emu_div_const(int64_t n, const double* a, double* by_ft, double* by_100) {
+    for (int64_t i = 0; i < n; ++i) {
+        by_ft[i] = div_const(a[i], TERM_FT_PER_NM, TERM_NM_PER_FT);
+        by_100[i] = div_const(a[i], 100.0, 0.01);
+    }
 }
 
 // host emulation of emb_tracks_integrate (same per-track code as k_tracks_integrate); g_* = tile ordinals

@@ -68,7 +68,11 @@ def emu_lib():
                                            C.POINTER(L.DynLimits), i32, vp, vp]
     lib.emu_terminal_screen.argtypes = [vp, vp, i64, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     lib.emu_tracks_integrate.argtypes = [i64, i32, i32, i32, i32, i32, i32, i32] + [C.c_double] * 5 + [vp, vp, vp, vp]
-    lib.emu_bearing_cells.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.emu_bearing_cells.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.emu_sincosd.argtypes = [i64, vp, vp, vp]
+    lib.emu_sincosd.restype = None
+    lib.emu_div_const.argtypes = [i64, vp, vp, vp]
+    lib.emu_div_const.restype = None
     lib.emu_use_fast.argtypes = [C.c_int]
     lib.emu_last_fast.restype = C.c_int
     _emu = lib

@@ -125,11 +125,23 @@ def test_emu_chains_match_oracle(traj_paths, golden, types, tmax_s, seed, first)
     check_traj(traj, ln, want, want_len)
 
 
-def test_speed_edges_on_the_dynamic_limits(tmp_path, golden):
+def test_speed_edges_on_the_dynamic_limits(tmp_path, golden, monkeypatch):
     """createEncounter.m:221-226 clamps a sampled speed to minVel / maxVel; the next state records norm(v) (:168) and
     discretises it (:290) after v was rotated.  With speed bin edges ON those limits the cell depends on the last bit of
     norm(R v): the device code must take norm(v) from (vx, vy) whenever v changed, as the reference does, instead of carrying
-    the clamped value (same libm on both sides here, so the comparison is exact in the chain lengths and cells)."""
+    the clamped value.  The last bit of sind/cosd decides these cells (MATLAB's own are closed source), so for this test the
+    oracle is given the chain kernel's sind/cosd (checked against libm in
+    test_sind_cosd_and_constant_division_of_the_chain_kernel): everything else must then agree exactly."""
+    from oracle import terminal as T
+    lib = H.emu_lib()
+
+    def _sc(x):
+        a, s1, c1 = np.array([float(x)]), np.zeros(1), np.zeros(1)
+        lib.emu_sincosd(1, a.ctypes.data, s1.ctypes.data, c1.ctypes.data)
+        return float(s1[0]), float(c1[0])
+
+    monkeypatch.setattr(T, "sind", lambda x: _sc(x)[0])
+    monkeypatch.setattr(T, "cosd", lambda x: _sc(x)[1])
     edges = [0, 50, 68, 100, 169, 186, 338, 491, 506, 600]
     paths = write_terminal_model_set(str(tmp_path / "edge_models"), seed=7, speed_edges=edges)
     geo = geo_from_golden(golden, 24)
@@ -221,7 +233,7 @@ def test_bearing_cell_from_pseudo_angle_equals_atan2_route(traj_paths):
     y = np.ascontiguousarray(np.concatenate([y, ax[:, 1], ye]))
     got = np.zeros(x.size, dtype=np.int32)
     ref = np.zeros(x.size, dtype=np.int32)
-    assert lib.emu_bearing_cells(m.h, x.size, x.ctypes.data, y.ctypes.data, got.ctypes.data, ref.ctypes.data) == 0
+    assert lib.emu_bearing_cells(m.h, x.size, x.ctypes.data, y.ctypes.data, got.ctypes.data, ref.ctypes.data, None, None, None) == 0
     bearing = np.mod(np.degrees(np.arctan2(y, x)), 360.0)
     near = np.min(np.abs(bearing[:, None] - cuts[None, :]), axis=1) < 1e-9
     assert np.array_equal(got[~near], ref[~near])
@@ -229,6 +241,78 @@ def test_bearing_cell_from_pseudo_angle_equals_atan2_route(traj_paths):
     assert near.sum() < 200 and len(np.unique(got)) == len(cuts) + 1
     # and the reference route agrees with NumPy's own digitize on the same angles
     assert np.array_equal(ref[~near], np.searchsorted(cuts, bearing[~near], side="right"))
+
+
+def test_distance_cell_from_the_squared_norm_is_exact(traj_paths):
+    """The chain kernel takes the cell of d_nm = norm([x y]) (createEncounter.m:277) and the tests d_nm > dist_max, d_nm <= 0.25
+    (:310-312) on x*x + y*y against thresholds min{s : sqrt(s) >= c}: identical to the square-root route on every point,
+    including points placed within a few ulps of every cutpoint."""
+    lib = H.emu_lib()
+    m = H.EmuModel(traj_paths["intruder_transit_model"])
+    m.set_prior(1, L.EMB_PRIOR_STAY, 1.0)
+    from oracle.em_read import em_read
+    p = em_read(traj_paths["intruder_transit_model"])
+    idist = [k for k, lab in enumerate(p.labels_initial) if lab == '"distance"'][0]
+    cuts = np.asarray(p.boundaries[idist], dtype=np.float64)[1:-1]
+    rng = np.random.default_rng(6)
+    n = 1_000_000
+    r = np.concatenate([10.0 ** rng.uniform(-3, 1.2, n), rng.uniform(0.0, 9.0, n)])
+    th = rng.uniform(0.0, 2 * np.pi, r.size)
+    x, y = r * np.cos(th), r * np.sin(th)
+    # points whose norm lands within a few ulps of a cutpoint (and of 0.25 and the upper bound), on axes and off them
+    edge = np.concatenate([cuts, [0.25, float(p.boundaries[idist][-1])]])
+    xe, ye = [], []
+    for c in edge:
+        for k in range(-6, 7):
+            ck = c
+            for _ in range(abs(k)):
+                ck = np.nextafter(ck, np.inf if k > 0 else -np.inf)
+            xe += [ck, 0.0, ck * 0.6, ck * np.cos(1.0)]
+            ye += [0.0, -ck, ck * 0.8, ck * np.sin(1.0)]
+    x = np.ascontiguousarray(np.concatenate([x, xe, [0.0]]))
+    y = np.ascontiguousarray(np.concatenate([y, ye, [0.0]]))
+    pc = np.zeros(x.size, dtype=np.int32)
+    pr = np.zeros(x.size, dtype=np.int32)
+    d2 = np.zeros(x.size, dtype=np.int32)
+    dr = np.zeros(x.size, dtype=np.int32)
+    near = np.zeros(2)
+    assert lib.emu_bearing_cells(m.h, x.size, x.ctypes.data, y.ctypes.data, pc.ctypes.data, pr.ctypes.data, d2.ctypes.data,
+                                 dr.ctypes.data, near.ctypes.data) == 0
+    assert np.array_equal(d2, dr)
+    d = np.sqrt(x * x + y * y)
+    assert np.array_equal(dr, np.searchsorted(cuts, d, side="right"))
+    s = x * x + y * y
+    assert np.array_equal(s >= near[0], d > float(p.boundaries[idist][-1]))
+    assert np.array_equal(s < near[1], d <= 0.25)
+    assert len(np.unique(d2)) == len(cuts) + 1
+
+
+def test_sind_cosd_and_constant_division_of_the_chain_kernel():
+    """sincosd (degree reduction + fdlibm kernels) against libm within 2 ulp, exact at multiples of 90 degrees; div_const
+    bit-identical to IEEE division."""
+    lib = H.emu_lib()
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(-360.0, 360.0, 2_000_000), rng.uniform(-1e-3, 1e-3, 1000), np.arange(-720.0, 721.0, 45.0),
+                        [1e-300, -1e-300, 359.99999999999994, -359.99999999999994, 44.99999999999999, 45.00000000000001, 1000.5]])
+    x = np.ascontiguousarray(x)
+    s, c = np.zeros_like(x), np.zeros_like(x)
+    lib.emu_sincosd(x.size, x.ctypes.data, s.ctypes.data, c.ctypes.data)
+    r = np.fmod(x, 360.0)
+    sr, cr = np.sin(np.radians(r)), np.cos(np.radians(r))
+    # reference error budget: the radian conversion of the unreduced angle alone moves sin/cos by |a| * 2^-53 ~ 7e-16
+    assert np.max(np.abs(s - sr)) < 1.5e-15 and np.max(np.abs(c - cr)) < 1.5e-15
+    small = np.abs(r) < 1.0
+    assert np.max(np.abs(s[small] - sr[small]) / np.maximum(np.abs(sr[small]), 1e-300)) < 4.5e-16
+    m90 = np.fmod(r, 90.0) == 0.0
+    q = np.round(r[m90] / 90.0).astype(int) % 4
+    assert np.array_equal(s[m90], np.array([0.0, 1.0, 0.0, -1.0])[q]) and np.array_equal(c[m90], np.array([1.0, 0.0, -1.0, 0.0])[q])
+    assert not np.any(np.signbit(s[m90] * 0.0 + s[m90]) & (s[m90] == 0.0)) and not np.any(np.signbit(c[m90]) & (c[m90] == 0.0))
+    assert np.max(np.abs(s * s + c * c - 1.0)) < 5e-16
+    a = np.concatenate([rng.uniform(-1e4, 1e4, 2_000_000), 10.0 ** rng.uniform(-12, 9, 1_000_000), np.arange(-36000.0, 36001.0), [0.0]])
+    a = np.ascontiguousarray(a)
+    qf, qh = np.zeros_like(a), np.zeros_like(a)
+    lib.emu_div_const(a.size, a.ctypes.data, qf.ctypes.data, qh.ctypes.data)
+    assert np.array_equal(qf, a / 6076.1154855643) and np.array_equal(qh, a / 100.0)
 
 
 def test_stay_prior_is_required(traj_paths):
