@@ -648,9 +648,6 @@ void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M, do
         if (r > TERM_CUT_MAX)
             fail(EMB_E_LIMIT, "createEncounter: a trajectory model variable has more than 64 bins");
         double* row = cuts ? cuts + t * TERM_CUT_MAX : nullptr;
-        int step = r > 1 ? 1 : 0;                           // smallest power of two whose 2*step - 1 slots hold the r - 1 cutpoints
-        while (2 * step - 1 < r - 1) step *= 2;
-        M.cut_step[t] = step;
         if (!row) continue;
         for (int j = 0; j < TERM_CUT_MAX; ++j) row[j] = inf;
         const auto& e = H.boundaries[i];

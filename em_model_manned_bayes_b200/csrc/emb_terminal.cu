@@ -25,15 +25,17 @@ k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ 
     // the cutpoint tables of the (up to three) models this block's chain id can use: every lane searches them at its own
     // index, which shared memory serves and the constant bank would serialise
     __shared__ double cuts[3 * TERM_NCUT * TERM_CUT_MAX];
+    __shared__ TermLane lanes[3];
     const int chain = (int)blockIdx.y, ac = chain >> 1, dir = chain & 1;
     constexpr int per_model = TERM_NCUT * TERM_CUT_MAX;
-    for (int q = threadIdx.x; q < (ac ? 3 : 2) * per_model; q += blockDim.x) {
-        const int it = q / per_model, j = q % per_model;
-        cuts[q] = __ldg(P.cuts + ((ac ? 4 : 0) + it * 2 + dir) * per_model + j);
+    for (int it = 0; it < (ac ? 3 : 2); ++it) {
+        const int mi = (ac ? 4 : 0) + it * 2 + dir;
+        for (int j = threadIdx.x; j < per_model; j += blockDim.x) cuts[it * per_model + j] = __ldg(P.cuts + mi * per_model + j);
+        if (threadIdx.x == 32 * it) term_lane_fill(P.m[mi], lanes[it]);
     }
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.n) terminal_chain(P, O, s, chain, cuts);
+    if (s < P.n) terminal_chain(P, O, s, chain, cuts, lanes);
 }
 
 // first-order track integration (emb_integrate.cuh): thread = track, HBM-bound (12 B read + 12 B written per track-second)

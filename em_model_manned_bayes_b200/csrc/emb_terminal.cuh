@@ -17,6 +17,9 @@
 
 namespace emb {
 
+#ifndef EMB_TERM_PREFETCH
+#define EMB_TERM_PREFETCH 0
+#endif
 constexpr uint32_t P_TERM_SEL = 5, P_TERM_DD = 6;
 constexpr int TERM_NMODELS = 10;   // own {landing, takeoff} x {fwd, bck}, intruder {landing, takeoff, transit} x {fwd, bck}
 constexpr int TERM_FIELDS = 5;     // x_nm, y_nm, z_ft, heading_deg, v_ft_s  (t_s is the slot index)
@@ -46,7 +49,6 @@ struct TermModel {
     int32_t i_dist, i_bear;   // 0-based positions of "distance" and "bearing" (createEncounter.m:112-113)
     int32_t alt_hi;           // discreteValidAlt = 1..alt_hi        (createEncounter.m:120), 0 = empty
     int32_t spd_lo, spd_hi;   // discreteValidV   = spd_lo..spd_hi   (:123-125), lo > hi = empty
-    int32_t cut_step[TERM_NCUT];   // first stride of term_cell over each cutpoint table (a power of two, 0 = no cutpoint)
     // tests on d_nm = norm([x y]) taken on s = x*x + y*y (TC_DIST2 above):
     double dist_max_sq;       // d_nm > bounds_initial(idx.dist, 2)  <=>  s >= dist_max_sq   (:263, :310)
     double quarter_sq;        // d_nm <= 0.25                        <=>  s <  quarter_sq    (:312)
@@ -162,19 +164,63 @@ EMB_HD double round2(double x) {                        // round(x, 2), half awa
 }
 EMB_HD double norm2(double a, double b) { return ::sqrt(dadd(dmul(a, a), dmul(b, b))); }
 
-// discretize_bayes.m:14-22, 0-based: #{j : v >= cut[j]} over an ascending table padded with +inf up to 2*step0 - 1 slots
-// (make_term_cuts).  No branch and no data-dependent trip count: log2 steps of one load, one compare and one predicated add.
-EMB_HD int term_cell(const double* cut, int step0, double v) {
-    int pos = 0;
-    for (int step = step0; step > 0; step >>= 1)
-        if (v >= cut[pos + step - 1]) pos += step;
-    return pos;
+// discretize_bayes.m:14-22, 0-based: #{j : v >= cut[j]} over an ascending table of 63 slots padded with +inf (make_term_model).
+// No branch, no loop, no data-dependent trip count: six steps of one load at an immediate offset, one compare and one
+// predicated pointer bump.
+EMB_HD int term_cell(const double* cut, double v) {
+    const double* p = cut;
+    if (v >= p[31]) p += 32;
+    if (v >= p[15]) p += 16;
+    if (v >= p[7]) p += 8;
+    if (v >= p[3]) p += 4;
+    if (v >= p[1]) p += 2;
+    if (v >= p[0]) p += 1;
+    return (int)(p - cut);
 }
-EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // dediscretize.m:39, two-argument call
-    if (M.edge_off[i] < 0) return (double)(b + 1);
+
+// What a chain reads from its model in every state, gathered in one place: in shared memory on the device (one per intent of the
+// block's chain id; lanes of a warp differ in intent, and a lane-indexed read of the kernel parameters is an address computation
+// plus a replayed constant load per field), a local copy in the host emulation.
+struct TermLane {
+    uint32_t off[3], rp[3], stride[3][6];
+    int32_t edge_off[3];      // heading, altitude, speed
+    int32_t alt_hi, spd_lo, spd_hi;
+    const uint32_t* thr;
+    const double* edges;
+    double dist_max_sq, quarter_sq;
+};
+EMB_HD void term_lane_fill(const TermModel& M, TermLane& C) {
+    for (int d = 0; d < 3; ++d) {
+        C.off[d] = M.off[d];
+        C.rp[d] = M.rp[d];
+        for (int i = 0; i < 6; ++i) C.stride[d][i] = M.stride[d][i];
+        C.edge_off[d] = M.edge_off[3 + d];
+    }
+    C.alt_hi = M.alt_hi;
+    C.spd_lo = M.spd_lo;
+    C.spd_hi = M.spd_hi;
+    C.thr = M.thr;
+    C.edges = M.edges;
+    C.dist_max_sq = M.dist_max_sq;
+    C.quarter_sq = M.quarter_sq;
+}
+EMB_HD double term_dedisc(const TermLane& C, int d, int b, uint32_t k) {   // dediscretize.m:39, two-argument call; d = 0..2
+    if (C.edge_off[d] < 0) return (double)(b + 1);
     double a, w;
-    ldg_pair(M.edges + M.edge_off[i] + 2 * b, a, w);
+    ldg_pair(C.edges + C.edge_off[d] + 2 * b, a, w);
     return dadd(a, dmul(w, u01(k)));
+}
+
+// request the cache lines of a packed column (rp <= 64 words, 16-byte aligned: at most three 128-byte lines)
+EMB_HD void prefetch_column(const uint32_t* col, uint32_t rp) {
+#if defined(__CUDA_ARCH__) && EMB_TERM_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(col));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(col + rp - 1));
+    if (rp > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(col + (rp >> 1)));
+#else
+    (void)col;
+    (void)rp;
+#endif
 }
 
 #if defined(__CUDA_ARCH__)
@@ -186,9 +232,16 @@ EMB_HD double term_dedisc(const TermModel& M, int i, int b, uint32_t k) {   // d
 #endif
 
 // One chain.  `s` = encounter index within this call, chain = 2*aircraft + direction.
-// cuts_sh: the cutpoint tables of the (up to three) models this chain id can use, one per intent, in shared memory
-// ([3][TERM_NCUT][TERM_CUT_MAX], device) or nullptr (host emulation: read from TermParams::cuts)
-EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain, const double* cuts_sh = nullptr) {
+// cuts_sh / lanes_sh: the cutpoint tables ([3][TERM_NCUT][TERM_CUT_MAX]) and per-state constants ([3]) of the (up to three)
+// models this chain id can use, one per intent, in shared memory; nullptr in the host emulation (read from TermParams).
+//
+// The walk is ONE loop whose trip is a (state, attempt) pair: createEncounter.m's `while is_resample` (:192-243) inside its
+// `for ii` (:160) would make a warp repeat the select for as long as ANY of its lanes is re-drawing (1.7 passes per state on
+// the bench models, the extra ones with three lanes active); flattened, a lane that must re-draw simply does not advance its state
+// in this trip while its neighbours move on.  Lanes of a warp then sit at most a few states apart, so their stores touch a few
+// neighbouring rows of the [slot][n] output instead of one (L2 merges the sectors before they leave for HBM).
+EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int chain, const double* cuts_sh = nullptr,
+                           const TermLane* lanes_sh = nullptr) {
     const int ac = chain >> 1, dir = chain & 1;
     const double dt_s = dir ? -1.0 : 1.0;
     const int64_t N = P.n;
@@ -205,6 +258,7 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     const TermLimits& L = P.lim[ac];
 
     const int64_t fstride = 2 * S * N;                   // between fields
+    const int64_t sstep = dir ? -N : N;                  // between consecutive states of this chain
     float* slotp = O.traj ? O.traj + ((int64_t)ac * S + P.tmax) * N + s : nullptr;   // slot of t_s = 0, field 0
     auto put = [&](int f, float v) { EMB_STREAM_F32(slotp + f * fstride, v); };
 #if defined(__CUDA_ARCH__)
@@ -215,9 +269,15 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     const bool bad_intent = intent < 1 || intent > (ac ? 3 : 2);                 // createEncounter.m:14-38
     if (bad_intent && O.status) EMB_FLAG_OR(O.status, 2);
     const int islot = (bad_intent ? 1 : intent) - 1, mi = (ac ? 4 : 0) + islot * 2 + dir;
-    const TermModel& M = P.m[mi];
+#if defined(__CUDA_ARCH__)
+    const TermLane& C = lanes_sh[islot];
+    const double* cuts = cuts_sh + islot * (TERM_NCUT * TERM_CUT_MAX);
+#else
+    TermLane C_;
+    term_lane_fill(P.m[mi], C_);
+    const TermLane& C = lanes_sh ? lanes_sh[islot] : C_;
     const double* cuts = cuts_sh ? cuts_sh + islot * (TERM_NCUT * TERM_CUT_MAX) : P.cuts + mi * (TERM_NCUT * TERM_CUT_MAX);
-    const int step_dist = M.cut_step[TC_DIST2], step_bear = M.cut_step[TC_BEAR];
+#endif
 
     double sb, cb, sh, ch;
     sincosd(bearing, sb, cb);
@@ -239,22 +299,24 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     double speed = norm2(vx, vy);
     uint32_t b_hdg = 0, b_alt = 0, b_spd = 0;
     if (go) {
-        b_hdg = (uint32_t)term_cell(cuts + TC_HDG * TERM_CUT_MAX, M.cut_step[TC_HDG], heading_deg);
-        b_alt = (uint32_t)term_cell(cuts + TC_ALT * TERM_CUT_MAX, M.cut_step[TC_ALT], z_ft);
-        b_spd = (uint32_t)term_cell(cuts + TC_SPD * TERM_CUT_MAX, M.cut_step[TC_SPD], speed);
+        b_hdg = (uint32_t)term_cell(cuts + TC_HDG * TERM_CUT_MAX, heading_deg);
+        b_alt = (uint32_t)term_cell(cuts + TC_ALT * TERM_CUT_MAX, z_ft);
+        b_spd = (uint32_t)term_cell(cuts + TC_SPD * TERM_CUT_MAX, speed);
     }
 
-    for (int ii = 1; ii <= K; ++ii) {
-        const bool store = O.traj && !(dir && ii == 1);                          // [fwd, bck(2:end)] (:77)
-        if (ii > 1 && slotp) slotp += dir ? -N : N;
-        if (!go) {
-            if (store) for (int f = 0; f < TERM_FIELDS; ++f) put(f, qnan);
-            continue;
-        }
+    int ii = 1;                       // state being produced (:160)
+    uint32_t attempt = 0;             // pass of the resample loop of this state (:192)
+    uint32_t co0 = 0, co1 = 0, co2 = 0;   // columns of heading', altitude', speed' for this state (frozen parents, dbn_sample.m:110-135)
+    double d_sq = 0.0;
+    bool ev_any = false, ev_v = false;
+    // Opening of state ii (:163-187): record it, step the position, take the cells of the new position and the three columns.
+    // It runs at the END of the previous trip (and once before the loop): everything it reads is known there, so the columns'
+    // cache lines are requested (prefetch into L1) a whole state opening before the select reads them.
+    auto open_state = [&]() {
+        const bool store = O.traj && !(dir && ii == 1);                              // [fwd, bck(2:end)] (:77)
         ++len;
-        // state ii (:163-184)
         double z_rec = z_ft;
-        if (ii > 1) {                                                             // :180-184
+        if (ii > 1) {                                                                 // :180-184
             const double diff = dadd(z_ft, -z_prev);
             const double lim = ::fmin(L.maxVR, ::fabs(diff));
             z_rec = dadd(z_prev, diff > 0.0 ? lim : diff < 0.0 ? -lim : dmul(0.0, lim));
@@ -267,110 +329,117 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
             put(3, (float)curr_hdg);
             put(4, (float)speed);
         }
-        x = dadd(x, div_const(dmul(vx, dt_s), TERM_FT_PER_NM, TERM_NM_PER_FT));   // :171-173
+        x = dadd(x, div_const(dmul(vx, dt_s), TERM_FT_PER_NM, TERM_NM_PER_FT));       // :171-173
         y = dadd(y, div_const(dmul(vy, dt_s), TERM_FT_PER_NM, TERM_NM_PER_FT));
-
         // CreateStartDistribution (:268-294), 0-based bins; the cells of d_nm = norm([x y]) and of the bearing
         // wrapTo360(atan2d(y, x)) (:277, :293) come from x*x + y*y and the pseudo-angle (TC_DIST2, TC_BEAR)
-        const double d_sq = dadd(dmul(x, x), dmul(y, y));
+        d_sq = dadd(dmul(x, x), dmul(y, y));
         uint32_t st[6];
         st[0] = (uint32_t)(intent - 1);
-        st[1] = (uint32_t)term_cell(cuts + TC_DIST2 * TERM_CUT_MAX, step_dist, d_sq);
-        st[2] = (uint32_t)term_cell(cuts + TC_BEAR * TERM_CUT_MAX, step_bear, pseudo_angle(x, y));
+        st[1] = (uint32_t)term_cell(cuts + TC_DIST2 * TERM_CUT_MAX, d_sq);
+        st[2] = (uint32_t)term_cell(cuts + TC_BEAR * TERM_CUT_MAX, pseudo_angle(x, y));
         st[3] = b_hdg;
         st[4] = b_alt;
         st[5] = b_spd;
-        const uint32_t* col[3];                                                   // frozen parents (dbn_sample.m:110-135)
+        co0 = C.off[0];
+        co1 = C.off[1];
+        co2 = C.off[2];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            uint32_t o = M.off[d];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) o += M.stride[d][i] * st[i];
-            col[d] = M.thr + o;
+        for (int i = 0; i < 6; ++i) {
+            co0 += C.stride[0][i] * st[i];
+            co1 += C.stride[1][i] * st[i];
+            co2 += C.stride[2][i] * st[i];
+        }
+        prefetch_column(C.thr + co0, C.rp[0]);
+        prefetch_column(C.thr + co1, C.rp[1]);
+        prefetch_column(C.thr + co2, C.rp[2]);
+        ev_any = false;
+        ev_v = false;
+    };
+    if (go) open_state();
+    while (ii <= K) {
+        if (!go) {                                                                    // the chain has ended: NaN in its slots
+            if (O.traj && !(dir && ii == 1)) for (int f = 0; f < TERM_FIELDS; ++f) put(f, qnan);
+            ++ii;
+            if (slotp) slotp += sstep;
+            continue;
         }
 
-        bool ev_any = false, ev_v = false;
-        for (uint32_t attempt = 0;; ++attempt) {                                  // while is_resample (:192-243)
-            uint32_t w0, w1, w2, w3;
-            philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample,
-                          (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain, (uint32_t)ii, (uint32_t)P.seed,
-                          (uint32_t)(P.seed >> 32), w0, w1, w2, w3);
-            const int nh = select_bin(col[0], (int)M.rp[0], w0);
-            const int na = select_bin(col[1], (int)M.rp[1], w1);
-            const int nv = select_bin(col[2], (int)M.rp[2], w2);
-            bool redo = false;
-            if (nh != (int)st[3] || na != (int)st[4] || nv != (int)st[5]) {
-                ev_any = true;                      // events in variable order 4, 5, 6
-                uint32_t d0, d1, d2, d3;
-                philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample,
-                              (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain, (uint32_t)ii, (uint32_t)P.seed,
-                              (uint32_t)(P.seed >> 32), d0, d1, d2, d3);
-                if (nh != (int)st[3]) heading_deg = term_dedisc(M, 3, nh, d0);         // :200-205
-                if (na != (int)st[4]) {                                                // :206-212
-                    if (na + 1 <= M.alt_hi) z_ft = term_dedisc(M, 4, na, d1);
-                    else redo = true;
-                }
-                if (!redo && nv != (int)st[5]) {                                       // :213-233
-                    if (nv + 1 >= M.spd_lo && nv + 1 <= M.spd_hi) {
-                        double v1 = term_dedisc(M, 5, nv, d2);
-                        if (v1 < L.minVel) v1 = L.minVel;
-                        if (v1 > L.maxVel) v1 = L.maxVel;
-                        sincosd(heading_deg, sh, ch);
-                        vx = dadd(dmul(ch, v1), -dmul(sh, 0.0));                  // :228-229
-                        vy = dadd(dmul(sh, v1), dmul(ch, 0.0));
-                        ev_v = true;
-                    } else {
-                        redo = true;
-                    }
-                }
-            }
-            if (!redo) break;
-            if (attempt >= (uint32_t)P.max_attempts) {
-                if (O.status) EMB_FLAG_OR(O.status, 1);
-                break;
-            }
+        // One pass of `while is_resample` (:192-243) and the turn (:246-256), written without branches: in a warp of 32 chains
+        // some lane has an event, a rejected bin, the last second of a turn ... in practically every trip, so every branch body
+        // is executed anyway -- one after the other, each with a handful of lanes and its own dependent chain of fp64 latencies.
+        // As straight-line code with selects the same instructions interleave.  Values that only change at an event are
+        // recomputed from unchanged inputs in the other trips, which reproduces them bit for bit.
+        uint32_t w0, w1, w2, w3, d0, d1, d2, d3;
+        philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain,
+                      (uint32_t)ii, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), w0, w1, w2, w3);
+        philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain,
+                      (uint32_t)ii, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), d0, d1, d2, d3);
+        const int nh = select_bin(C.thr + co0, (int)C.rp[0], w0);
+        const int na = select_bin(C.thr + co1, (int)C.rp[1], w1);
+        const int nv = select_bin(C.thr + co2, (int)C.rp[2], w2);
+        const bool e_h = nh != (int)b_hdg, e_a = na != (int)b_alt, e_v = nv != (int)b_spd;   // events in variable order 4, 5, 6
+        const double h_new = term_dedisc(C, 0, nh, d0), z_new = term_dedisc(C, 1, na, d1);
+        double v1 = term_dedisc(C, 2, nv, d2);
+        ev_any = ev_any || e_h || e_a || e_v;
+        if (e_h) heading_deg = h_new;                                                 // :200-205
+        const bool alt_ok = na + 1 <= C.alt_hi;                                       // :206-212
+        if (e_a && alt_ok) z_ft = z_new;
+        bool redo = e_a && !alt_ok;
+        const bool spd_ev = !redo && e_v;                                             // :213-233
+        const bool spd_ok = nv + 1 >= C.spd_lo && nv + 1 <= C.spd_hi;
+        redo = redo || (spd_ev && !spd_ok);
+        if (v1 < L.minVel) v1 = L.minVel;
+        if (v1 > L.maxVel) v1 = L.maxVel;
+        const SinCos hsc = sincosd_pair(heading_deg);
+        if (spd_ev && spd_ok) {
+            vx = dadd(dmul(hsc.c, v1), -dmul(hsc.s, 0.0));                            // :228-229
+            vy = dadd(dmul(hsc.s, v1), dmul(hsc.c, 0.0));
+            ev_v = true;
         }
+        if (redo) {
+            if (attempt < (uint32_t)P.max_attempts) {
+                ++attempt;
+                continue;
+            }
+            if (O.status) EMB_FLAG_OR(O.status, 1);
+        }
+
         // turn to the desired heading at the maximum rate (:246-256); curr_hdg is still the heading at the top of this state
         const double turn1 = round2(dadd(heading_deg, -curr_hdg));
         const double mag = ::fmin(::fabs(turn1), L.maxTurn);
         const double delta = turn1 > 0.0 ? mag : turn1 < 0.0 ? -mag : dmul(mag, 0.0);
-        bool v_changed = ev_v;
         if (ev_v) curr_hdg = wrap360(heading_deg);                                // v was re-pointed along heading_deg (:228-229)
-        if (delta != 0.0) {                                                       // rotation by 0 degrees is the identity
-            double sd, cd;
-            if (delta == L.maxTurn) {
-                sd = turn_sc.s;
-                cd = turn_sc.c;
-            } else if (delta == -L.maxTurn) {
-                sd = -turn_sc.s;
-                cd = turn_sc.c;
-            } else {
-                sincosd(delta, sd, cd);
-            }
+        {
+            // a turn runs at exactly +-maxTurn for all but its last second: that sine and cosine were taken once per chain
+            const SinCos dsc = sincosd_pair(delta);
+            const bool full = mag == L.maxTurn;
+            const double sd = full ? (delta < 0.0 ? -turn_sc.s : turn_sc.s) : dsc.s, cd = full ? turn_sc.c : dsc.c;
             const double nvx = dadd(dmul(cd, vx), -dmul(sd, vy)), nvy = dadd(dmul(sd, vx), dmul(cd, vy));
-            vx = nvx;
-            vy = nvy;
-            curr_hdg = wrap360(dadd(curr_hdg, delta));
-            v_changed = true;
+            const double nh2 = wrap360(dadd(curr_hdg, delta));
+            if (delta != 0.0) {                                                       // rotation by 0 degrees is the identity
+                vx = nvx;
+                vy = nvy;
+                curr_hdg = nh2;
+            }
         }
         if (vx == 0.0 && vy == 0.0) curr_hdg = 0.0;                               // atan2d(0, 0) = 0
-        // The next state records norm(v) (:168) and discretises it (:290).  Whenever v changed -- a speed event (clamped to
-        // minVel/maxVel, :221-226) or a rotation, whose result can differ from the old norm in the last bit -- both are taken
-        // again from (vx, vy) exactly as the reference does, so a speed that sits on a bin edge (the dynamic limits are round
-        // numbers) lands in the same cell as in the reference given the same sind/cosd; an unchanged v gives the same norm.
-        if (v_changed) {
-            speed = norm2(vx, vy);
-            b_spd = (uint32_t)term_cell(cuts + TC_SPD * TERM_CUT_MAX, M.cut_step[TC_SPD], speed);
-        }
-        if (ev_any) {                                                             // cells of the values the events changed
-            b_hdg = (uint32_t)term_cell(cuts + TC_HDG * TERM_CUT_MAX, M.cut_step[TC_HDG], heading_deg);
-            b_alt = (uint32_t)term_cell(cuts + TC_ALT * TERM_CUT_MAX, M.cut_step[TC_ALT], z_ft);
-        }
+        // The next state records norm(v) (:168) and discretises it (:290) from (vx, vy) exactly as the reference does, so a
+        // speed that was clamped to minVel/maxVel (:221-226) and sits on a bin edge (the dynamic limits are round numbers) lands
+        // in the same cell as in the reference given the same sind/cosd; likewise the cells of heading_deg and z_ft (:278-289).
+        speed = norm2(vx, vy);
+        b_spd = (uint32_t)term_cell(cuts + TC_SPD * TERM_CUT_MAX, speed);
+        b_hdg = (uint32_t)term_cell(cuts + TC_HDG * TERM_CUT_MAX, heading_deg);
+        b_alt = (uint32_t)term_cell(cuts + TC_ALT * TERM_CUT_MAX, z_ft);
         t_s = dadd(t_s, dt_s);
-        // CheckTrajectoryConditions (:296-329)
-        const bool violate = ::fabs(t_s) > P.tmax_s || d_sq >= M.dist_max_sq || ((intent == 1 || intent == 2) && d_sq < M.quarter_sq) ||
+        // CheckTrajectoryConditions (:296-329); the tests on d_nm are taken on d_sq (TermModel::dist_max_sq, quarter_sq)
+        const bool violate = ::fabs(t_s) > P.tmax_s || d_sq >= C.dist_max_sq || ((intent == 1 || intent == 2) && d_sq < C.quarter_sq) ||
                              (ac == 0 && y > 0.25);
         go = !violate;
+        ++ii;
+        attempt = 0;
+        if (slotp) slotp += sstep;
+        if (go && ii <= K) open_state();
     }
     if (O.len) O.len[(int64_t)chain * N + s] = (int16_t)len;
 }

@@ -311,9 +311,9 @@ int emu_bearing_cells(void* model, int64_t n, const double* x, const double* y, 
         return e.code;
     }
     for (int64_t i = 0; i < n; ++i) {
-        cells_pc[i] = term_cell(cuts.data() + TC_BEAR * TERM_CUT_MAX, M.cut_step[TC_BEAR], pseudo_angle(x[i], y[i]));
+        cells_pc[i] = term_cell(cuts.data() + TC_BEAR * TERM_CUT_MAX, pseudo_angle(x[i], y[i]));
         cells_ref[i] = ref_discretize(H, M.i_bear, heading_of(y[i], x[i]));
-        if (cells_d2) cells_d2[i] = term_cell(cuts.data() + TC_DIST2 * TERM_CUT_MAX, M.cut_step[TC_DIST2], dadd(dmul(x[i], x[i]), dmul(y[i], y[i])));
+        if (cells_d2) cells_d2[i] = term_cell(cuts.data() + TC_DIST2 * TERM_CUT_MAX, dadd(dmul(x[i], x[i]), dmul(y[i], y[i])));
         if (cells_dref) cells_dref[i] = ref_discretize(H, M.i_dist, norm2(x[i], y[i]));
     }
     if (near) {
