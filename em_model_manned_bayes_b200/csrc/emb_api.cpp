@@ -900,6 +900,7 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
     P.first_sample = rng->first_sample;
     P.n = n;
     P.tmax_s = tmax_s;
+    emb::term_round_keys(P.seed, P.rk);
     P.tmax = (int32_t)tmax_s;
     P.max_attempts = opts->max_attempts > 0 ? std::min(opts->max_attempts, 65535) : 65535;
     P.geo_stride = geo_stride;

@@ -596,6 +596,8 @@ void make_term_model(const HostModel& H, const TermLimits& lim, TermModel& M, do
     if (H.temporal_map.size() != 3 || H.temporal_map[0].first != 3 || H.temporal_map[1].first != 4 ||
         H.temporal_map[2].first != 5)
         fail(EMB_E_MODEL, "createEncounter: the dynamic variables must be heading, altitude and speed");
+    if (H.thr_transition.size() >= (1u << 26))
+        fail(EMB_E_LIMIT, "createEncounter: transition table of a trajectory model exceeds 2^26 words");
     if (H.is_dynvar_depend)
         fail(EMB_E_MODEL, "createEncounter: trajectory models have no dynamic->dynamic edge (dbn_sample.m:95-166 branch)");
     if (H.prior_transition.kind != EMB_PRIOR_STAY || H.prior_transition.value != 1.0)

@@ -64,6 +64,7 @@ struct TermParams {
     double tmax_s;
     int32_t tmax;             // floor(tmax_s): a chain has at most tmax + 1 states
     int32_t max_attempts;
+    uint32_t rk[20];          // Philox round keys of `seed` (k0 + i*W0, k1 + i*W1; term_round_keys), constant operands of the rounds
     const double* geo;        // sample_geo fields, row geo_row[k] of a [rows][geo_stride] array
     int64_t geo_stride;
     int32_t geo_row[12];      // own_{intent, distance, bearing, alt, heading, speed}, int_{...}
@@ -211,6 +212,60 @@ EMB_HD double term_dedisc(const TermLane& C, int d, int b, uint32_t k) {   // de
     return dadd(a, dmul(w, u01(k)));
 }
 
+// select_bin (emb_device.cuh) with the loads of twelve thresholds in flight at a time: the plain loop waits for one 16-byte load
+// per trip (nine in a row for a 36-bin heading column, the first stall of the chain kernel).  Every slot is counted, the
+// padding (0xFFFFFFFF, never exceeded) and the last one, which holds `lead`; that one is taken out again at the end.
+EMB_HD int select_bin3(const uint32_t* col, uint32_t rp, uint32_t k, uint32_t& lead_out) {
+    uint32_t neg = 0;             // minus the number of slots below k
+    for (uint32_t q = 0; q < rp; q += 12) {
+#if defined(__CUDA_ARCH__)
+        const uint4 none = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(col + q));
+        const uint4 b = q + 4 < rp ? __ldg(reinterpret_cast<const uint4*>(col + q + 4)) : none;
+        const uint4 c = q + 8 < rp ? __ldg(reinterpret_cast<const uint4*>(col + q + 8)) : none;
+        neg = sub_gt(sub_gt(sub_gt(sub_gt(neg, k, a.x), k, a.y), k, a.z), k, a.w);
+        neg = sub_gt(sub_gt(sub_gt(sub_gt(neg, k, b.x), k, b.y), k, b.z), k, b.w);
+        neg = sub_gt(sub_gt(sub_gt(sub_gt(neg, k, c.x), k, c.y), k, c.z), k, c.w);
+#else
+        for (uint32_t m = q; m < q + 12 && m < rp; ++m) neg = sub_gt(neg, k, col[m]);
+#endif
+    }
+    const uint32_t lead = ldg32(col + rp - 1);
+    lead_out = lead;
+    return (int)sub_gt(lead - neg, k, lead);
+}
+
+// The select of one dynamic variable with a one-entry cache in registers.  With the stay prior most seconds keep the bin, and
+// the column only changes when a parent's cell does, so a lane remembers for which (column, bin) it last selected and the
+// interval of words (T'[bin-1], T'[bin]] that gives that bin again (thresholds ascend from slot `lead` on, pack_column); a word
+// inside it needs no memory access at all.  What this buys is L1 tag bandwidth: every lane's column is its own cache line, so a
+// 16-byte load of a warp is 32 tag lookups -- 519 per warp and state before, the busiest unit of the SM (0.75 per clock).
+struct SelectCache {
+    uint32_t key = 0xFFFFFFFFu, lo1 = 0, width = 0;   // key = column offset * 64 + bin (tables < 2^26 words, bins <= 64)
+};
+EMB_HD int select_cached(const uint32_t* thr, uint32_t co, uint32_t rp, uint32_t b, uint32_t k, SelectCache& c) {
+#if !defined(EMB_TERM_NOCACHE)
+    if (co * 64u + b == c.key && k - c.lo1 <= c.width) return (int)b;
+#endif
+    const uint32_t* col = thr + co;
+    uint32_t lead;
+    const int n = select_bin3(col, rp, k, lead);
+#if !defined(EMB_TERM_NOCACHE)
+    const uint32_t lo1 = (uint32_t)n > lead ? ldg32(col + n - 1) + 1u : 0u;
+    const uint32_t hi = (uint32_t)n + 1u < rp ? ldg32(col + n) : 0xFFFFFFFFu;
+    c.key = co * 64u + (uint32_t)n;
+    c.lo1 = lo1;
+    c.width = hi - lo1;
+#endif
+    return n;
+}
+EMB_HD void term_round_keys(uint64_t seed, uint32_t (&rk)[20]) {
+    for (int i = 0; i < 10; ++i) {
+        rk[2 * i] = (uint32_t)seed + (uint32_t)i * PHILOX_W0;
+        rk[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * PHILOX_W1;
+    }
+}
+
 // request the cache lines of a packed column (rp <= 64 words, 16-byte aligned: at most three 128-byte lines)
 EMB_HD void prefetch_column(const uint32_t* col, uint32_t rp) {
 #if defined(__CUDA_ARCH__) && EMB_TERM_PREFETCH
@@ -309,6 +364,7 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
     uint32_t co0 = 0, co1 = 0, co2 = 0;   // columns of heading', altitude', speed' for this state (frozen parents, dbn_sample.m:110-135)
     double d_sq = 0.0;
     bool ev_any = false, ev_v = false;
+    SelectCache sc0, sc1, sc2;
     // Opening of state ii (:163-187): record it, step the position, take the cells of the new position and the three columns.
     // It runs at the END of the previous trip (and once before the loop): everything it reads is known there, so the columns'
     // cache lines are requested (prefetch into L1) a whole state opening before the select reads them.
@@ -371,13 +427,13 @@ EMB_HD void terminal_chain(const TermParams& P, const TermOut& O, int64_t s, int
         // As straight-line code with selects the same instructions interleave.  Values that only change at an event are
         // recomputed from unchanged inputs in the other trips, which reproduces them bit for bit.
         uint32_t w0, w1, w2, w3, d0, d1, d2, d3;
-        philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain,
-                      (uint32_t)ii, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), w0, w1, w2, w3);
-        philox4x32_10((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain,
-                      (uint32_t)ii, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), d0, d1, d2, d3);
-        const int nh = select_bin(C.thr + co0, (int)C.rp[0], w0);
-        const int na = select_bin(C.thr + co1, (int)C.rp[1], w1);
-        const int nv = select_bin(C.thr + co2, (int)C.rp[2], w2);
+        philox4x32_10_rk((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (P_TERM_SEL << 8) | (uint32_t)chain,
+                         (uint32_t)ii, P.rk, w0, w1, w2, w3);
+        philox4x32_10_rk((uint32_t)(sample >> 32), (uint32_t)sample, (attempt << 16) | (P_TERM_DD << 8) | (uint32_t)chain,
+                         (uint32_t)ii, P.rk, d0, d1, d2, d3);
+        const int nh = select_cached(C.thr, co0, C.rp[0], b_hdg, w0, sc0);
+        const int na = select_cached(C.thr, co1, C.rp[1], b_alt, w1, sc1);
+        const int nv = select_cached(C.thr, co2, C.rp[2], b_spd, w2, sc2);
         const bool e_h = nh != (int)b_hdg, e_a = na != (int)b_alt, e_v = nv != (int)b_spd;   // events in variable order 4, 5, 6
         const double h_new = term_dedisc(C, 0, nh, d0), z_new = term_dedisc(C, 1, na, d1);
         double v1 = term_dedisc(C, 2, nv, d2);

@@ -258,6 +258,7 @@ int emu_terminal_propagate(void** models, uint64_t seed, uint64_t first, int64_t
     P.first_sample = first;
     P.n = n;
     P.tmax_s = tmax_s;
+    term_round_keys(P.seed, P.rk);
     P.tmax = (int32_t)tmax_s;
     P.max_attempts = max_attempts > 0 ? max_attempts : 65535;
     P.geo = geo;
