@@ -303,8 +303,11 @@ EMB_HD uint4 philox_call(uint32_t c0, uint32_t c2, uint32_t index, const uint32_
 EMB_HD void philox_finish(const PhiloxTrack& t, const uint4& e, const uint32_t (&rk)[20],
                           uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
     uint32_t c0 = t.r1h ^ e.x, c1 = t.r1l, c2 = e.y ^ t.q0l, c3 = e.z;
+#ifndef EMB_PHILOX_ROUNDS   // measurement only: the stream spec, the oracle and every golden are 10 rounds
+#define EMB_PHILOX_ROUNDS 10
+#endif
 #pragma unroll
-    for (int i = 3; i < 10; ++i) {
+    for (int i = 3; i < EMB_PHILOX_ROUNDS; ++i) {
         uint32_t h0, l0, h1, l1;
         mulhilo(PHILOX_M0, c0, h0, l0);
         mulhilo(PHILOX_M1, c2, h1, l1);
