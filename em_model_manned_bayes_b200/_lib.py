@@ -157,6 +157,7 @@ def lib():
         "emb_terminal_traj_len": (i64, [i64, C.c_double]),
         "emb_terminal_screen": (C.c_int, [vp, vp, i64, C.c_double, C.c_double, C.c_double, P(SampleOpts), P(ScreenOut)]),
         "emb_tracks_integrate": (C.c_int, [vp, i64, i32, vp, vp, P(IntegrateOpts), vp, vp]),
+        "emb_sample_tracks_xyz": (C.c_int, [vp, P(Rng), i64, i32, P(SampleOpts), P(IntegrateOpts), P(TrackOut), vp, vp]),
         "emb_tracks_bins_len": (i64, [vp, i64, i32]),
         "emb_tracks_values_len": (i64, [vp, i64, i32]),
     }
@@ -174,7 +175,7 @@ EXPORTED = [
     "emb_model_get_labels", "emb_model_get_G", "emb_model_get_N", "emb_model_get_boundaries",
     "emb_model_get_packed", "emb_set_prior", "emb_sample_opts_init", "emb_sample_initial", "emb_sample_tracks",
     "emb_tracks_bins_len", "emb_tracks_values_len", "emb_sample_track_events",
-    "emb_dyn_limits_named", "emb_terminal_propagate", "emb_terminal_traj_len", "emb_tracks_integrate",
+    "emb_dyn_limits_named", "emb_terminal_propagate", "emb_terminal_traj_len", "emb_tracks_integrate", "emb_sample_tracks_xyz",
     "emb_terminal_screen",
 ]
 TRAJ_FIELDS = ("x_nm", "y_nm", "z_ft", "heading_deg", "v_ft_s")

@@ -970,12 +970,8 @@ int emb_terminal_propagate(const emb_terminal_models* models, const emb_rng* rng
     return 0;
 }
 
-int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double* init_values, const float* values,
-                         const emb_integrate_opts* opts, float* xyz, uint8_t* is_good) {
-    if (!m || !opts || n < 0 || T < 1 || (n > 0 && (!init_values || !values)))
-        return set_err(EMB_E_ARG, "null or out-of-range argument");
-    const HostModel& H = *m->h;
-    emb::IntegrateParams P;
+// IntegrateParams from emb_integrate_opts (labels -> tile ordinals, unit ratios); 0 or an error code
+static int fill_integrate(const HostModel& H, const emb_integrate_opts* opts, int64_t n, int32_t T, emb::IntegrateParams& P) {
     std::memset(&P, 0, sizeof(P));
     P.n = n;
     P.T = T;
@@ -999,6 +995,16 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
     P.ur_heading = opts->ur_heading;
     P.min_speed = opts->min_speed;
     P.max_speed = opts->max_speed;
+    return 0;
+}
+
+int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double* init_values, const float* values,
+                         const emb_integrate_opts* opts, float* xyz, uint8_t* is_good) {
+    if (!m || !opts || n < 0 || T < 1 || (n > 0 && (!init_values || !values)))
+        return set_err(EMB_E_ARG, "null or out-of-range argument");
+    const HostModel& H = *m->h;
+    emb::IntegrateParams P;
+    if (int rcf = fill_integrate(H, opts, n, T, P)) return rcf;
     if (n == 0) return 0;
     emb_sample_opts so;
     emb_sample_opts_init(&so);
@@ -1031,6 +1037,87 @@ int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double*
     if (e != cudaSuccess) return cuda_fail(e, "launch k_tracks_integrate");
     CU(cudaStreamSynchronize(st));
     return sg.finish();
+}
+
+int emb_sample_tracks_xyz(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                          const emb_integrate_opts* iopts, const emb_track_out* out, float* xyz, uint8_t* is_good) {
+    if (!m || !rng || !opts || !iopts || n < 0 || T < 1) return set_err(EMB_E_ARG, "null or out-of-range argument");
+    if (out && (out->hist_initial || out->hist_transition))
+        return set_err(EMB_E_ARG, "emb_sample_tracks_xyz: histograms belong to emb_sample_tracks");
+    if (opts->mem & EMB_MEM_ASYNC) return set_err(EMB_E_ARG, "emb_sample_tracks_xyz: EMB_MEM_ASYNC is not supported");
+    const HostModel& H = *m->h;
+    if (!H.has_transition || H.temporal_map.empty())
+        return set_err(EMB_E_ARG, "dynvar:empty: model has no transition network");
+    if ((int64_t)T * (int64_t)H.gated.size() >= (1ll << 33))
+        return set_err(EMB_E_LIMIT, "T too large for the 32-bit stream index");
+    emb::SampleParams P;
+    emb::IntegrateParams IP;
+    int rc = 0;
+    try {
+        emb::fill_params(H, rng->seed, rng->first_sample, n, T, *opts, P);
+    } catch (const emb::Error& e) {
+        return set_err(e.code, e.msg);
+    }
+    if ((rc = fill_integrate(H, iopts, n, T, IP))) return rc;
+    if (n == 0) return 0;
+    int device;
+    if ((rc = pick_device(opts, device, true))) return rc;
+    DevModel D;
+    if ((rc = ensure_device(H, device, D))) return rc;
+    if (opts->correct_dbn) D.fast = 0;
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    g_call_stream = st;
+    Stager sg{opts->mem & 0xFF, st, {}};
+    emb::TrackOut O{};
+    const size_t ni = (size_t)H.n_initial;
+    const emb_track_out none{};
+    const emb_track_out* o = out ? out : &none;
+    if ((rc = sg.out(o->bins, (size_t)emb_tracks_bins_len(m, n, T), false, (void**)&O.bins))) return rc;
+    if ((rc = sg.out(o->values, (size_t)emb_tracks_values_len(m, n, T) * 4, false, (void**)&O.values))) return rc;
+    if ((rc = sg.out(o->init_bins, (size_t)n * ni, false, (void**)&O.init_bins))) return rc;
+    if ((rc = sg.out(o->init_values, (size_t)n * ni * 8, false, (void**)&O.init_values))) return rc;
+    if ((rc = sg.out(o->attempts, (size_t)n * 2, false, (void**)&O.attempts))) return rc;
+    if ((rc = sg.out(xyz, (size_t)3 * (size_t)(T + 1) * (size_t)n * 4, false, (void**)&O.x.xyz))) return rc;
+    if ((rc = sg.out(is_good, (size_t)n, false, (void**)&O.x.is_good))) return rc;
+    if (!O.x.xyz && !O.x.is_good) return set_err(EMB_E_ARG, "emb_sample_tracks_xyz: xyz and is_good are both null");
+    O.x.g_acc = IP.g_acc; O.x.g_vr = IP.g_vr; O.x.g_turn = IP.g_turn; O.x.i_alt = IP.i_alt; O.x.i_speed = IP.i_speed;
+    O.x.ur_speed = IP.ur_speed; O.x.ur_vertrate = IP.ur_vertrate; O.x.ur_heading = IP.ur_heading;
+    O.x.min_speed = IP.min_speed; O.x.max_speed = IP.max_speed;
+    if ((rc = stage_start(sg, opts, H, n, P))) return rc;
+    struct Scratch {
+        void* p = nullptr;
+        ~Scratch() { tmp_free(p); }
+    } d_status, d_values, d_inits;
+    CU(tmp_alloc(&d_status.p, 4, st));
+    CU(cudaMemsetAsync(d_status.p, 0, 4, st));
+    O.status = (int32_t*)d_status.p;
+    int le = emb::launch_tracks(D, P, O, st);
+    if (le == -1) {   // no fused kernel for this shape: sample the dense values (into a temporary if the caller wants none), then integrate
+        emb::TrackOut O2 = O;
+        O2.x = emb::XyzOut{};
+        if (!O2.values) {
+            CU(tmp_alloc(&d_values.p, (size_t)emb_tracks_values_len(m, n, T) * 4, st));
+            O2.values = (float*)d_values.p;
+        }
+        if (!O2.init_values) {
+            CU(tmp_alloc(&d_inits.p, (size_t)n * ni * 8, st));
+            O2.init_values = (double*)d_inits.p;
+        }
+        le = emb::launch_tracks(D, P, O2, st);
+        if (le == 0) {
+            IP.init_values = O2.init_values;
+            IP.values = O2.values;
+            IP.xyz = O.x.xyz;
+            IP.is_good = O.x.is_good;
+            le = emb::launch_integrate(IP, st);
+        }
+    }
+    if (le != 0) return cuda_fail((cudaError_t)le, "launch k_tracks (xyz)");
+    int32_t status = 0;
+    CU(cudaMemcpyAsync(&status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((rc = sg.finish())) return rc;
+    return status_error(status);
 }
 
 int emb_terminal_screen(const float* traj, const int16_t* len, int64_t n, double tmax_s, double thres_dist_ft,

@@ -134,6 +134,16 @@ inline int64_t next_segment(uint64_t first_sample, int64_t s0, int64_t n) {
     return (uint64_t)(n - s0) <= room ? n : s0 + (int64_t)room;
 }
 
+// fused first-order integration (emb_fast.cuh, mode 3 of k_tracks_fast): the Euler loop of sample2track.m:199-244 on the values of a
+// group of four seconds while they are still in registers; same fields and meaning as IntegrateParams (emb_integrate.cuh)
+struct XyzOut {
+    float* xyz;                    // [3][T+1][n]  x_ft, y_ft, z_ft at time_s = 0..T (nullable)
+    uint8_t* is_good;              // [n]  ~is_cfit & ~is_reject_speed (nullable)
+    int32_t g_acc, g_vr, g_turn;   // ordinals of \dot v, \dot h, \dot\psi among the time-varying variables
+    int32_t i_alt, i_speed;        // 0-based initial variables: altitude layer value, airspeed
+    double ur_speed, ur_vertrate, ur_heading, min_speed, max_speed;
+};
+
 struct TrackOut {
     int8_t* bins;
     float* values;
@@ -151,6 +161,7 @@ struct TrackOut {
     int32_t ev_gord_bits, ev_dt_bytes;   // EventFormat of the write pass
     int64_t init_stride;           // samples between consecutive variables of init_bins / init_values; 0 = P.n (a chunk of
                                    // a larger call writes into the whole call's [n_initial][n] arrays)
+    XyzOut x;                      // fused integration (both pointers null: off)
 };
 
 // ---- packed event rows: what the write pass produces and emb_sample_track_events_packed returns --------------------------------

@@ -19,6 +19,7 @@
 // straddles zero without being the zero bin (DevModel::fast32_ok).
 #pragma once
 #include "emb_device.cuh"
+#include "emb_terminal.cuh"   // sincosd (fused integration)
 
 namespace emb {
 
@@ -158,7 +159,9 @@ EMB_HD float fmaf_rn(float a, float b, float c) {
 #endif
 }
 
-// EV: 0 = dense outputs only, 1 = also count the rows of the event list, 2 = also write them (see emb200.h: emb_event)
+// EV: 0 = dense outputs only, 1 = also count the rows of the event list, 2 = also write them (see emb200.h: emb_event),
+//     3 = dense outputs (if present) + the fused Euler loop of sample2track.m:199-244 (TrackOut::x)
+constexpr bool ev_list(int EV) { return EV == 1 || EV == 2; }
 // ORD (slow branch only): the order in which dbn_sample.m:66-79 samples the dynamic variables, two bits per position
 // (order_code below); a compile-time order keeps the per-second code straight-line (no jump table, a third of the code)
 template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD, class HistInc>
@@ -190,6 +193,8 @@ struct FastTrack {
     uint32_t sbin1[NS > 0 ? NS : 1];   // EV: 1-based bins of the static gated variables
     uint32_t ev_last, ev_n;            // EV: second of the last row, rows so far
     long long ev_i;                    // EV == 2: next row of this track
+    double ix, iy, iz, ispeed, ihead;  // EV == 3: state of the Euler loop (emb_integrate.cuh: integrate_track, same arithmetic)
+    bool icfit, ibad;
     uint32_t* O_words;                 // EV == 2: TrackOut::ev_words / ev_dts
     uint8_t* O_dts;
     EventFormat O_fmt;
@@ -305,7 +310,7 @@ struct FastTrack {
                 const bool fired = (k * GATE_MULT) < G[g];
                 const bool changed = g >= NS && nb[d >= 0 ? d : 0] != bin[d >= 0 ? d : 0];
                 if ((fired || changed) && act) val[g] = cand;
-                if (EV) {
+                if (ev_list(EV)) {
                     // gate row: the re-emitted *current* bin (resample_events.m:26-29); when the variable also changes
                     // in this second the row is hidden in the dense output but present in the list.  A row carries the 23
                     // value bits, not the value (pack_event_word): gate and transition row of a second share them.
@@ -320,7 +325,7 @@ struct FastTrack {
                 if (g >= NS) bin[d >= 0 ? d : 0] = nb[d >= 0 ? d : 0];
                 vout[g][j] = live ? val[g] : 0.0f;
             }
-            if (EV) {   // transition rows follow the gate rows of the same second, variables ascending (dbn_sample.m:84-92)
+            if (ev_list(EV)) {   // transition rows follow the gate rows of the same second, variables ascending (dbn_sample.m:84-92)
 #pragma unroll
                 for (int d = 0; d < ND; ++d)
                     emit(ev_chg[d], (uint32_t)e, (uint32_t)(NS + d) + 1u, bin[d] - (uint32_t)ebase[NS + d] + 1u, ev_frac[d]);
@@ -337,6 +342,48 @@ struct FastTrack {
             for (int d = 0; d < ND; ++d) bout[d] += 0x01010101u * (1u - (uint32_t)ebase[NS + d]);
         }
     }
+
+    // EV == 3: the four seconds of a group through the Euler loop of sample2track.m:199-218 (integrate_track statement for
+    // statement, on the same fp32 values the dense output holds, so both routes give identical points).  The caller runs it one
+    // group BEHIND the sampling (fast_groups): the fp64 chain of four dependent sincosd evaluations and the integer work of the
+    // next group's Philox calls and selects are independent and interleave.
+    EMB_HD void pick_rates(const float (&vout)[NG][4], const XyzOut& X, float (&a)[4], float (&v)[4], float (&t)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a[j] = 0.0f; v[j] = 0.0f; t[j] = 0.0f;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (g == X.g_acc) a[j] = vout[g][j];
+                if (g == X.g_vr) v[j] = vout[g][j];
+                if (g == X.g_turn) t[j] = vout[g][j];
+            }
+        }
+    }
+    EMB_HD void integrate4(int grp, int T, const float (&a)[4], const float (&v)[4], const float (&t)[4], const XyzOut& X, float* out,
+                           int64_t N) {
+        const int64_t fs = (int64_t)(T + 1) * N;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * grp + j;
+            if (c >= T) break;
+            double sh, ch;
+            sincosd(ihead, sh, ch);
+            const double nx = dadd(ix, dmul(ispeed, ch)), ny = dadd(iy, dmul(ispeed, sh));   // :212-213 (old speed, old heading)
+            iz = dadd(iz, dmul((double)v[j], X.ur_vertrate));                               // :208 (+ unit conversion :134)
+            ispeed = dadd(ispeed, dmul((double)a[j], X.ur_speed));                          // :209 (:135)
+            ihead = dadd(ihead, dmul((double)t[j], X.ur_heading));                          // :210 (:136)
+            ix = nx;
+            iy = ny;
+            icfit = icfit || iz < 0.0;
+            ibad = ibad || ispeed <= X.min_speed || ispeed >= X.max_speed;
+            if (out) {
+                float* o = out + (int64_t)(c + 1) * N;
+                EMB_STREAM_F32(o, (float)ix);
+                EMB_STREAM_F32(o + fs, (float)iy);
+                EMB_STREAM_F32(o + 2 * fs, (float)iz);
+            }
+        }
+    }
 };
 
 // the loop over the four-second groups of one track; BOTH = both dense outputs are present (no per-group pointer tests)
@@ -348,13 +395,15 @@ EMB_HD void fast_groups(FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>& ft, con
     const int64_t N = P.n;
     const int nch4 = (T + 3) >> 2;
     const int nfull = T >> 2;       // groups 1 .. nfull-1 contain only seconds 1 <= e < T
-    const int ngrp = EV ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
+    const int ngrp = ev_list(EV) ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
     const int64_t ntile = num_tiles(N);
     // (a null output only predicates the stores off: its pointer is advanced but never dereferenced)
     const bool wb = BOTH || O.bins != nullptr, wv = BOTH || O.values != nullptr;
     int8_t* pb = O.bins + tile_offset(ND, ntile, 0, 0, s);
     float* pv = O.values + tile_offset(NG, ntile, 0, 0, s);
     const int64_t bstep = ntile * (ND * TRACK_TILE * 4), vstep = ntile * (NG * TRACK_TILE * 4);
+    float xa[4], xv[4], xt[4];      // EV == 3: rates of the group the Euler loop has not taken yet
+    int xgrp = -1;
     for (int grp0 = 0; grp0 < ngrp; grp0 += UT_GROUPS) {
         const int gcount = ngrp - grp0 < UT_GROUPS ? ngrp - grp0 : UT_GROUPS;
         if (FAST || !EMB_SLOW_INLINE_PHILOX) {
@@ -374,7 +423,12 @@ EMB_HD void fast_groups(FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>& ft, con
             float vout[NG][4];
             if (grp > 0 && grp < nfull) ft.template group<false>(grp, T, bout, vout, ut, ut_s);
             else ft.template group<true>(grp, T, bout, vout, ut, ut_s);
-            if (EV && grp >= nch4) break;
+            if (ev_list(EV) && grp >= nch4) break;
+            if (EV == 3) {   // the Euler loop runs one group behind (see integrate4)
+                if (xgrp >= 0) ft.integrate4(xgrp, T, xa, xv, xt, O.x, O.x.xyz ? O.x.xyz + s : nullptr, N);
+                ft.pick_rates(vout, O.x, xa, xv, xt);
+                xgrp = grp;
+            }
             if (wv) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
@@ -401,6 +455,7 @@ EMB_HD void fast_groups(FastTrack<RS, NG, FAST, HIST, EV, ORD, HistInc>& ft, con
             pb += bstep;
         }
     }
+    if (EV == 3 && valid && xgrp >= 0) ft.integrate4(xgrp, T, xa, xv, xt, O.x, O.x.xyz ? O.x.xyz + s : nullptr, N);
 }
 
 // `valid` = this thread owns track s (s < P.n); the other threads of a block only help filling the call table U.
@@ -420,7 +475,7 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     const uint32_t c0 = (uint32_t)((P.first_sample + (uint64_t)P.s_begin) >> 32), c2 = P_STEP << 8;
     const int nch4 = (T + 3) >> 2;
     const int nfull = T >> 2;       // groups 1 .. nfull-1 contain only seconds 1 <= e < T
-    const int ngrp = EV ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
+    const int ngrp = ev_list(EV) ? (T + 4) >> 2 : nch4;   // the event list also needs the gates of second T
     const bool steps = T > 0 && (EV || O.bins || O.values || O.hist_transition);   // uniform
 
     // ---- initial network (once per track; generic code, cost amortised over T seconds) -----------
@@ -450,6 +505,22 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
                 if (g < NS) {
                     ft.sent[g] = S.ent[ft.ebase[g] + (int)x[M.gated_var[g]]];
                     ft.sbin1[g] = (uint32_t)x[M.gated_var[g]] + 1u;
+                }
+            }
+            if (EV == 3) {                                                               // sample2track.m:190-194
+                ft.iz = vals[O.x.i_alt];
+                ft.ispeed = dmul(vals[O.x.i_speed], O.x.ur_speed);
+                ft.ihead = 0.0;
+                ft.ix = 0.0;
+                ft.iy = 0.0;
+                ft.icfit = ft.iz < 0.0;
+                ft.ibad = ft.ispeed <= O.x.min_speed || ft.ispeed >= O.x.max_speed;
+                if (O.x.xyz) {
+                    float* o = O.x.xyz + s;
+                    const int64_t fs = (int64_t)(T + 1) * N;
+                    EMB_STREAM_F32(o, 0.0f);
+                    EMB_STREAM_F32(o + fs, 0.0f);
+                    EMB_STREAM_F32(o + 2 * fs, (float)ft.iz);
                 }
             }
             ft.ev_last = 0;
@@ -511,7 +582,8 @@ EMB_HD void track_fast(const DevModel& M, const SampleParams& P, const TrackOut&
     // (the loop is instantiated for "both dense outputs present", the bench case, and for the general case)
     if (O.bins && O.values) fast_groups<RS, NG, FAST, HIST, EV, ORD, HistInc, true>(ft, P, O, U, s, valid, tid, nthreads, c0, c2);
     else fast_groups<RS, NG, FAST, HIST, EV, ORD, HistInc, false>(ft, P, O, U, s, valid, tid, nthreads, c0, c2);
-    if (EV && valid) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
+    if (EV == 3 && valid && O.x.is_good) O.x.is_good[s] = (uint8_t)(!ft.icfit && !ft.ibad);   // sample2track.m:234-244
+    if (ev_list(EV) && valid) {   // closing row [T - sum(dt), 0, 0] (dbn_hierarchical_sample.m:15-19)
         ft.emit(true, (uint32_t)T, 0u, 0u, 0u);
         if (EV == 1) O.ev_counts[s] = ft.ev_n;
     }

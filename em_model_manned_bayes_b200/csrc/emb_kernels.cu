@@ -27,6 +27,9 @@ namespace {
 #ifndef EMB_MINBLOCKS
 #define EMB_MINBLOCKS 4
 #endif
+#ifndef EMB_MINBLOCKS_XYZ       // fused integration (mode 3): five more fp64 state words and a sincosd per second
+#define EMB_MINBLOCKS_XYZ 4
+#endif
 #ifndef EMB_MINBLOCKS_SLOW      // slow branch (per-second column gathers): latency-bound, more resident warps help -- as long as
 #define EMB_MINBLOCKS_SLOW 5    // the columns of all dynamic variables still fit in registers (four 9-bin variables need 128)
 #endif
@@ -179,7 +182,7 @@ k_tracks_generic(const __grid_constant__ DevModel M, const __grid_constant__ Sam
 
 // ---- tracks, register-resident specialisation (emb_fast.cuh) --------------------------------------
 template <uint32_t RS, int NG, bool FAST, bool HIST, int EV, uint32_t ORD>
-__global__ void __launch_bounds__(BLOCK, FAST ? EMB_MINBLOCKS : (DynShape<RS>::ND >= 4 ? EMB_MINBLOCKS : EMB_MINBLOCKS_SLOW))
+__global__ void __launch_bounds__(BLOCK, EV == 3 ? EMB_MINBLOCKS_XYZ : FAST ? EMB_MINBLOCKS : (DynShape<RS>::ND >= 4 ? EMB_MINBLOCKS : EMB_MINBLOCKS_SLOW))
 k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ SampleParams P,
               const __grid_constant__ TrackOut O) {
     __shared__ FastShared S;
@@ -191,7 +194,7 @@ k_tracks_fast(const __grid_constant__ DevModel M, const __grid_constant__ Sample
     __syncthreads();
     const int64_t s = P.s_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     track_fast<RS, NG, FAST, HIST, EV, ORD>(M, P, O, s, s < P.s_end, S, U, (int)threadIdx.x, (int)blockDim.x, SmemHist{sh});
-    if (!EV && s >= P.s_end && P.s_end == P.n) zero_padding_track(O, M.n_dyn, NG, P.T, P.n, s);
+    if (!ev_list(EV) && s >= P.s_end && P.s_end == P.n) zero_padding_track(O, M.n_dyn, NG, P.T, P.n, s);
     if (HIST) flush_hist(sh, M, O.hist_initial, O.hist_transition);
 }
 
@@ -397,7 +400,7 @@ int launch_tracks(const DevModel& M, const SampleParams& P0, const TrackOut& O, 
     const bool fast = M.fast != 0;
     const uint32_t ord = order_code(M);
     const bool hist = O.hist_initial || O.hist_transition;
-    const int ev = O.ev_counts ? 1 : O.ev_words ? 2 : 0;   // event passes never carry histograms (emb_api.cpp)
+    const int ev = O.ev_counts ? 1 : O.ev_words ? 2 : (O.x.xyz || O.x.is_good) ? 3 : 0;   // event / fused passes never carry histograms (emb_api.cpp)
     bool done = false;
     // one launch per run of tracks whose global sample index shares its high word (spec v5: counter word 0 is launch-uniform)
     SampleParams P = P0;
@@ -410,12 +413,14 @@ int launch_tracks(const DevModel& M, const SampleParams& P0, const TrackOut& O, 
     if (!done && rs == (RS_) && M.n_gated == (NG_) && fast == (FAST_) && ord == (ORD_)) {               \
         if (ev == 1) k_tracks_fast<RS_, NG_, FAST_, false, 1, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);      \
         else if (ev == 2) k_tracks_fast<RS_, NG_, FAST_, false, 2, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
+        else if (ev == 3) k_tracks_fast<RS_, NG_, FAST_, false, 3, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O); \
         else if (hist) k_tracks_fast<RS_, NG_, FAST_, true, 0, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);     \
         else k_tracks_fast<RS_, NG_, FAST_, false, 0, ORD_><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);              \
         done = true;                                                                                    \
     }
         EMB_FAST_SHAPES(EMB_X)
 #undef EMB_X
+        if (!done && ev == 3) return -1;   // no fused kernel for this model shape: the caller integrates in a second pass
         if (!done) k_tracks_generic<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(M, P, O);
         g_launch_count.fetch_add(1);
     }

@@ -79,6 +79,33 @@ def integrate_tracks(model: EncounterModel, res: TrackResult, opts: Optional[L.I
     return xyz, good
 
 
+def sample_tracks_xyz(model: EncounterModel, n: int, T: int, seed: int = 0, first_sample: int = 0, sample_opts=None,
+                      opts: Optional[L.IntegrateOpts] = None, device=None, want_xyz: bool = True, dense: Optional[TrackResult] = None):
+    """Sampling and the Euler loop of sample2track.m:188-244 in ONE kernel pass (emb200.h: emb_sample_tracks_xyz): the same
+    (xyz, is_good) as `integrate_tracks(model, model.sample_tracks(...))` without the dense tiles' round trip through HBM.
+    `sample_opts`: e.g. `UncorEncounterModel.uncor_opts()`; `dense`: a TrackResult whose buffers are filled as well."""
+    io = opts if opts is not None else integrate_opts(model)
+    so = sample_opts if sample_opts is not None else model._opts()
+    if device is not None:
+        import torch
+        dev = torch.device(device)
+        so.mem, so.device = L.EMB_MEM_DEVICE, dev.index if dev.index is not None else torch.cuda.current_device()
+        so.stream = torch.cuda.current_stream(dev).cuda_stream
+        xyz = torch.empty((3, T + 1, n), dtype=torch.float32, device=dev) if want_xyz else None
+        good = torch.empty((n,), dtype=torch.uint8, device=dev)
+    else:
+        xyz = np.empty((3, T + 1, n), dtype=np.float32) if want_xyz else None
+        good = np.empty((n,), dtype=np.uint8)
+    to = None
+    if dense is not None:
+        to = L.TrackOut(_ptr(dense.bins_tiled), _ptr(dense.values_tiled), _ptr(dense.init_bins), _ptr(dense.init_values),
+                        _ptr(dense.attempts), None, None)
+    rng = L.Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample))
+    L.check(L.lib().emb_sample_tracks_xyz(model._h, C.byref(rng), n, T, C.byref(so), C.byref(io),
+                                          C.byref(to) if to is not None else None, _ptr(xyz), _ptr(good)))
+    return xyz, good
+
+
 def _read_table(path):
     with open(path, encoding="utf-8") as f:
         f.readline()

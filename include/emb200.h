@@ -299,6 +299,15 @@ typedef struct emb_integrate_opts {
 int emb_tracks_integrate(const emb_model* m, int64_t n, int32_t T, const double* init_values, const float* values,
                          const emb_integrate_opts* opts, float* xyz, uint8_t* is_good);
 
+/* Sampling and integration in ONE pass (sample2track.m:188-244 fused into the track kernel): the Euler loop runs on the values of
+ * four seconds while they are in registers, so (x, y, z) leave the device without the dense tiles making a round trip through HBM.
+ * `out` may be NULL or carry any of emb_sample_tracks' outputs except the histograms (dense bins / values are then written as well);
+ * xyz, is_good as in emb_tracks_integrate, in opts->mem memory; iopts->mem / device / stream are ignored (opts' are used).
+ * Identical results to emb_sample_tracks followed by emb_tracks_integrate.  Models without a specialised track kernel run
+ * exactly that two-pass route internally. */
+int emb_sample_tracks_xyz(const emb_model* m, const emb_rng* rng, int64_t n, int32_t T, const emb_sample_opts* opts,
+                          const emb_integrate_opts* iopts, const emb_track_out* out, float* xyz, uint8_t* is_good);
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 int emb_host_alloc(void** p, int64_t bytes); /* pinned host memory */
 int emb_host_free(void* p);

@@ -123,6 +123,69 @@ def test_gpu_integration_matches_oracle_and_host_equals_device(model_paths):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("model,uncor,n,T", [("uncor_1200code_v2p1", True, 3000, 150), ("uncor_allcode_fwsingle_v1", True, 2000, 601),
+                                             ("glider_v1", True, 1500, 90), ("cor_v1", False, 0, 0)])
+def test_gpu_fused_xyz_equals_sample_then_integrate(model_paths, model, uncor, n, T):
+    """emb_sample_tracks_xyz (the Euler loop of sample2track.m:199-244 fused into the track kernel) against emb_sample_tracks followed
+    by emb_tracks_integrate: points, is_good and every dense output identical, on the fast branch, the per-step branch, with the
+    rejection loop of UncorEncounterModel.sample, with host buffers, against the oracle, and through the two-pass fallback of a
+    model shape without a specialised kernel (forced generic)."""
+    import torch
+    from em_model_manned_bayes_b200.model import EncounterModel, UncorEncounterModel
+    from em_model_manned_bayes_b200.sample2track import integrate_tracks, sample_tracks_xyz
+    if not uncor:
+        pytest.skip("cor_v1 has no altitude-layer / airspeed pair to integrate")
+    m = UncorEncounterModel(model_paths[model])
+    opts = lambda: m.uncor_opts()
+    res = m.sample_tracks(n, T, seed=77, first_sample=123, opts=opts(), device="cuda:0")
+    xyz, good = integrate_tracks(m, res, device="cuda:0")
+    fx, fg = sample_tracks_xyz(m, n, T, seed=77, first_sample=123, sample_opts=opts(), device="cuda:0")
+    torch.cuda.synchronize()
+    assert L.lib().emb_debug_last_kernel_fast() == 1
+    assert torch.equal(fx, xyz) and torch.equal(fg, good)
+    assert 0 < int(good.sum()) < n
+    # with the dense outputs requested as well
+    dense = m.sample_tracks(1, T, seed=0, opts=opts(), device="cuda:0")      # a TrackResult to size the buffers from
+    dense = m.sample_tracks(n, T, seed=1, opts=opts(), device="cuda:0")
+    fx2, fg2 = sample_tracks_xyz(m, n, T, seed=77, first_sample=123, sample_opts=opts(), device="cuda:0", dense=dense)
+    torch.cuda.synchronize()
+    assert torch.equal(fx2, xyz) and torch.equal(fg2, good)
+    for a, b in ((dense.bins_tiled, res.bins_tiled), (dense.values_tiled, res.values_tiled), (dense.init_bins, res.init_bins),
+                 (dense.init_values, res.init_values), (dense.attempts, res.attempts)):
+        assert torch.equal(a, b)
+    # host buffers
+    hx, hg = sample_tracks_xyz(m, 257, T, seed=77, first_sample=123, sample_opts=opts())
+    assert np.array_equal(hx, xyz[:, :, :257].cpu().numpy()) and np.array_equal(hg, good[:257].cpu().numpy())
+    # is_good only
+    _, g3 = sample_tracks_xyz(m, n, T, seed=77, first_sample=123, sample_opts=opts(), device="cuda:0", want_xyz=False)
+    assert torch.equal(g3, good)
+    # a shape without a specialised kernel: the library runs the two passes itself (the generic kernel's fp32 values may differ
+    # from the specialised kernel's in the last bit, so the reference is the generic two-pass route)
+    L.lib().emb_debug_force_generic(1)
+    try:
+        gx, gg = sample_tracks_xyz(m, 500, T, seed=77, first_sample=123, sample_opts=opts(), device="cuda:0")
+        rx, rg = integrate_tracks(m, m.sample_tracks(500, T, seed=77, first_sample=123, opts=opts(), device="cuda:0"), device="cuda:0")
+        torch.cuda.synchronize()
+        assert L.lib().emb_debug_last_kernel_fast() == 0
+    finally:
+        L.lib().emb_debug_force_generic(0)
+    assert torch.equal(gx, rx) and torch.equal(gg, rg)
+
+
+@pytest.mark.gpu
+def test_gpu_fused_xyz_matches_oracle(model_paths):
+    from em_model_manned_bayes_b200.model import EncounterModel
+    from em_model_manned_bayes_b200.sample2track import sample_tracks_xyz
+    model, n, T = "uncor_1200code_v2p1", 40, 150
+    p = em_read(model_paths[model])
+    out = dbn_tracks(p, n, T, KeyedPhilox(56))
+    ref, _ = oracle_tracks(p, out, T, from_fp32=False)
+    m = EncounterModel(model_paths[model])
+    xyz, good = sample_tracks_xyz(m, n, T, seed=56)
+    check_xyz(xyz, good, ref)
+
+
+@pytest.mark.gpu
 def test_gpu_integration_full_size_properties(model_paths):
     """1e5 tracks x 600 s in HBM: integration invariants that do not need the oracle."""
     import torch

@@ -28,3 +28,30 @@ for r in range(3):
     best = min(best, e0.elapsed_time(e1))
 print("emb_tracks_integrate n=%d T=%d: %.3f ms  %.3e track-timesteps/s (reads 12 B + writes 12 B per unit: %.0f GB/s), good %.3f"
       % (n, T, best, n * T / best * 1e3, 24.0 * n * T / best / 1e6, float(good.float().mean())))
+
+from em_model_manned_bayes_b200.sample2track import sample_tracks_xyz  # noqa: E402
+
+
+def timed(fn):
+    fn()
+    torch.cuda.synchronize()
+    b = 1e9
+    for r in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        b = min(b, e0.elapsed_time(e1))
+    return b
+
+
+del xyz, good
+t2 = timed(lambda: integrate_tracks(m, m.sample_compact(n, T, seed=5, device="cuda:0", out=res, want_init=True), device="cuda:0"))
+print("two passes (emb_sample_tracks + emb_tracks_integrate, incl. output allocation): %.3f ms" % t2)
+del res
+torch.cuda.empty_cache()
+tf = timed(lambda: sample_tracks_xyz(m, n, T, seed=5, sample_opts=m.uncor_opts(), device="cuda:0"))
+print("fused (emb_sample_tracks_xyz, xyz + is_good only, incl. output allocation): %.3f ms  %.3e track-timesteps/s" % (tf, n * T / tf * 1e3))
+tg = timed(lambda: sample_tracks_xyz(m, n, T, seed=5, sample_opts=m.uncor_opts(), device="cuda:0", want_xyz=False))
+print("fused, is_good only: %.3f ms" % tg)
