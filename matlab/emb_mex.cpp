@@ -29,6 +29,8 @@
 //          out_inits n x n_initial double and values 4 x 128 x n_tv x ceil(n/128) x ceil(T/4) single as returned by 'sample_tracks';
 //          iopts: struct idx_altitude, idx_speed, idx_acceleration, idx_vertrate, idx_turnrate, ur_speed, ur_vertrate,
 //          ur_heading, min_speed, max_speed;  xyz: n x (T+1) x 3 single, is_good: n x 1 uint8
+//   [xyz, is_good, out_inits] = emb_mex('sample_tracks_xyz', h, seed, first, n, T, opts, iopts)
+//          sampling and the loop of sample2track.m:188-244 in one kernel pass (no dense tiles); outputs as above
 //          emb_mex('free', h)
 // opts: struct with optional fields start (1 x n_initial, 0/NaN = free), reject_mode, idx_v, idx_dh,
 // idx_L, is_quantize500, layers (r_L x 2), box_lo, box_hi, max_attempts, device, start_per_sample (n x n_initial, 0/NaN = free:
@@ -353,6 +355,30 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         CHECK(emb_tracks_integrate(m, n, T, mxGetPr(prhs[2]), (const float*)mxGetData(prhs[3]), &o, (float*)mxGetData(plhs[0]),
                                    (uint8_t*)mxGetData(good)));
         if (nlhs > 1) plhs[1] = good; else mxDestroyArray(good);
+    } else if (c == "sample_tracks_xyz") {                        // sample2track.m:150-244 in one pass
+        emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
+        const int64_t n = (int64_t)mxGetScalar(prhs[4]);
+        const int32_t T = (int32_t)mxGetScalar(prhs[5]);
+        emb_sample_opts so;
+        fill_opts(nrhs > 6 ? prhs[6] : nullptr, ni, &so);
+        const mxArray* io = nrhs > 7 ? prhs[7] : nullptr;
+        emb_integrate_opts o;
+        std::memset(&o, 0, sizeof(o));
+        o.idx_altitude = (int)field_or(io, "idx_altitude", 0); o.idx_speed = (int)field_or(io, "idx_speed", 0);
+        o.idx_acceleration = (int)field_or(io, "idx_acceleration", 0); o.idx_vertrate = (int)field_or(io, "idx_vertrate", 0);
+        o.idx_turnrate = (int)field_or(io, "idx_turnrate", 0);
+        o.ur_speed = field_or(io, "ur_speed", 6076.1154855643 / 3600); o.ur_vertrate = field_or(io, "ur_vertrate", 1.0 / 60);
+        o.ur_heading = field_or(io, "ur_heading", 1.0);
+        o.min_speed = field_or(io, "min_speed", 0); o.max_speed = field_or(io, "max_speed", 1e300);
+        const mwSize dx[3] = {(mwSize)n, (mwSize)(T + 1), 3};      // [3][T+1][n] == n x (T+1) x 3 column-major
+        plhs[0] = mxCreateNumericArray(3, dx, mxSINGLE_CLASS, mxREAL);
+        mxArray* good = mxCreateNumericMatrix(n, 1, mxUINT8_CLASS, mxREAL);
+        mxArray* inits = mxCreateDoubleMatrix(n, ni, mxREAL);
+        emb_track_out out{};
+        out.init_values = mxGetPr(inits);
+        CHECK(emb_sample_tracks_xyz(m, &rng, n, T, &so, &o, &out, (float*)mxGetData(plhs[0]), (uint8_t*)mxGetData(good)));
+        if (nlhs > 1) plhs[1] = good; else mxDestroyArray(good);
+        if (nlhs > 2) plhs[2] = inits; else mxDestroyArray(inits);
     } else if (c == "sample_events") {                            // out_events of UncorEncounterModel.m:253-300
         emb_rng rng{(uint64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])};
         const int64_t n = (int64_t)mxGetScalar(prhs[4]);
