@@ -419,7 +419,7 @@ def main():
     config4 = {"value": states / dt_traj, "unit": "trajectory states/s", "ms_chains": dt_traj * 1e3, "ms_geometry": dt_geo * 1e3,
                "encounters_per_s": world * n5 / (dt_traj + dt_geo), "encounters": world * n5, "n_gpus": world, "scaling": "weak",
                "states_per_encounter": states / (world * n5),
-               # 5 fp32 fields per state written; the chains are fp64-trigonometry bound, not HBM bound
+               # 5 fp32 fields per state written; the chains are bound by the latency of their per-lane column gathers and fp64 chains, not by HBM
                "algorithmic_bytes_per_unit": 20.0, "roofline_frac": states / dt_traj * 20.0 / 1e9 / (peaks()[0] * world)}
     del r5, geo, vals5, tm
     torch.cuda.empty_cache()
