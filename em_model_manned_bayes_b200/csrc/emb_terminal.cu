@@ -15,7 +15,10 @@
 namespace emb {
 namespace {
 
-constexpr int TERM_BLOCK = 128;
+#ifndef EMB_TERM_BLOCK
+#define EMB_TERM_BLOCK 128
+#endif
+constexpr int TERM_BLOCK = EMB_TERM_BLOCK;
 
 #ifndef EMB_TERM_MINBLOCKS
 #define EMB_TERM_MINBLOCKS 6
@@ -31,7 +34,7 @@ k_terminal_chains(const __grid_constant__ TermParams P, const __grid_constant__ 
     for (int it = 0; it < (ac ? 3 : 2); ++it) {
         const int mi = (ac ? 4 : 0) + it * 2 + dir;
         for (int j = threadIdx.x; j < per_model; j += blockDim.x) cuts[it * per_model + j] = __ldg(P.cuts + mi * per_model + j);
-        if (threadIdx.x == 32 * it) term_lane_fill(P.m[mi], lanes[it]);
+        if (threadIdx.x == it) term_lane_fill(P.m[mi], lanes[it]);
     }
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
