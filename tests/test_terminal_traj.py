@@ -373,6 +373,39 @@ def test_gpu_chains_match_live_oracle_mixed_limits(model_paths, traj_paths, gold
 
 
 @pytest.mark.gpu
+def test_gpu_chains_equal_the_host_emulation_bit_for_bit(model_paths, traj_paths, tmp_path):
+    """The chain code is one source for the device and the host emulation, and everything in it is now exactly specified
+    arithmetic (own sind/cosd, correctly rounded division and square root, no library transcendental): trajectories, NaN
+    pattern and chain lengths must be IDENTICAL, on 3 000 sampled encounters and on the models whose speed edges sit on the
+    dynamic limits (the cells that depend on the last bit of norm(R v), test_speed_edges_on_the_dynamic_limits)."""
+    from em_model_manned_bayes_b200.model import CorTerminalModel
+    m = _product_model(model_paths, traj_paths, ("RTCA228_A3", "GENERIC"))
+    vals, _, _ = m.sample_raw(3000, seed=4)
+    labels = [l.strip('"') for l in m.labels_initial]
+    fields = ("own_intent", "own_distance", "own_bearing", "own_alt", "own_heading", "own_speed",
+              "int_intent", "int_distance", "int_bearing", "int_alt", "int_heading", "int_speed")
+    geo = np.ascontiguousarray(np.stack([np.asarray(vals)[:, labels.index(f)] for f in fields]))
+    geo[5] = np.clip(geo[5], 70.0, 180.0)
+    for paths, mm, tmax in ((traj_paths, m, 120),):
+        res = mm.create_encounters(geo, tmax, seed=9, first_sample=2 ** 33 + 1, geo_rows=range(12))
+        rc, traj, ln = emu_propagate(paths, geo, 9, 2 ** 33 + 1, tmax, ("RTCA228_A3", "GENERIC"))
+        assert rc == 0
+        assert np.array_equal(np.asarray(res.len), ln)
+        assert np.array_equal(np.asarray(res.traj).view(np.uint32), traj.view(np.uint32))
+    edges = [0, 50, 68, 100, 169, 186, 338, 491, 506, 600]
+    epaths = write_terminal_model_set(str(tmp_path / "edge_models"), seed=7, speed_edges=edges)
+    me = CorTerminalModel(model_paths["terminal_v3_radar_encounter_model"], acType1="RTCA228_A3", acType2="TEST")
+    me.load_trajectory_models(os.path.dirname(epaths[TRAJECTORY_STEMS[0]]))
+    g2 = geo[:, :600].copy()
+    g2[11] = np.clip(g2[11], 70.0, 180.0)
+    res = me.create_encounters(g2, 90, seed=41, geo_rows=range(12))
+    rc, traj, ln = emu_propagate(epaths, g2, 41, 0, 90, ("RTCA228_A3", "TEST"))
+    assert rc == 0
+    assert np.array_equal(np.asarray(res.len), ln)
+    assert np.array_equal(np.asarray(res.traj).view(np.uint32), traj.view(np.uint32))
+
+
+@pytest.mark.gpu
 def test_gpu_limits_golden(model_paths, traj_paths, golden):
     g = golden["terminal_traj_n12_T45_seed32_test_a1"]
     m = _product_model(model_paths, traj_paths, ("TEST", "RTCA228_A1"))
